@@ -1,0 +1,124 @@
+/*
+ * sfengine.h - C ABI of the B200-native force-evaluation engine for Starflood.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no reference structs, no
+ * torch types.  The reference-side shims (starflood_b200/shim/) unpack sim_t / tree_t
+ * and call these; INTEGRATION.md shows the Makefile change.  All file:line citations are
+ * into the reference tree (/root/reference/src).
+ *
+ * Conventions
+ *   - return 0 (STARFLOOD_SUCCESS, common.h:31) or -1 (STARFLOOD_FAILURE, common.h:32);
+ *     diagnostics go to stderr as "<fn>() error: ..." like the reference (tree.c:181),
+ *     and the text of the last one is available from sfe_last_error();
+ *   - fp32 only (STARFLOOD_DOUBLE_PRECISION, config.h:221, is out of scope);
+ *   - positions are xyz-interleaved (pos[3*i+k]) exactly as in sim.mem;
+ *   - the *host* entry points are synchronous: inputs are read from and outputs are
+ *     completely written to HOST memory when the call returns (simulation.c:423-451
+ *     consumes acc/pot on the host right after sim_solv());
+ *   - the *device* entry points (sfe_dev_*) take device pointers and a cudaStream_t
+ *     passed as void*, enqueue work and return without synchronising;
+ *   - there is NO CPU fallback: every entry point fails with -1 when no sm_100 device
+ *     is usable.
+ */
+#ifndef SFENGINE_H
+#define SFENGINE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFE_SUCCESS 0
+#define SFE_FAILURE (-1)
+
+/* Same memory layout as the reference's node_t (tree.h:18-24): 80 bytes. */
+typedef struct {
+    uint32_t parent;
+    uint32_t bodies;
+    uint32_t branch[8];
+    float    bounds[6];
+    float    params[4];
+} sfe_node_t;
+
+/* Per-phase device timings (CUDA events on the engine's stream) of the last host entry point. */
+typedef struct {
+    float h2d_ms;      /* host -> device copies + packing */
+    float build_ms;    /* tree build (0 for PP / SPH) */
+    float solve_ms;    /* force kernels */
+    float d2h_ms;      /* device -> host copies */
+    float total_ms;    /* first event to last event */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t launches; /* kernels launched by the call */
+} sfe_timings_t;
+
+/* Walk flavours for sfe_bh / sfe_dev_bh. */
+#define SFE_WALK_EXACT 0u /* IEEE div/sqrt + the reference's Kahan order: bit-identical to gravity.c:273-660 */
+#define SFE_WALK_FAST  1u /* rsqrt.approx, plain fp32 sums in the same visit order (<=1e-6 rel-RMS from EXACT) */
+
+/* ---------------------------------------------------------------- lifecycle */
+/* Bind the calling process to one CUDA device and create the engine context.  device < 0 picks
+ * $SFE_DEVICE, else $LOCAL_RANK, else 0.  Idempotent.  Replaces nothing in the reference (it has no
+ * accelerator runtime); the shims call it lazily from the first solver call. */
+int sfe_init(int device);
+int sfe_shutdown(void);
+const char* sfe_last_error(void);
+/* Pin a host range (e.g. the whole sim.mem block, simulation.c:89) so that the copies of the host entry
+ * points run at full PCIe rate.  Optional: unpinned ranges are staged through an internal pinned buffer. */
+int sfe_host_register(void* ptr, uint64_t bytes);
+int sfe_host_unregister(void* ptr);
+int sfe_get_timings(sfe_timings_t* out);
+/* SM count, SM clock (kHz), and the FP32 FMA peak 2*128*SMs*clock in TFLOP/s of the bound device. */
+int sfe_device_info(int* sm_count, int* clock_khz, double* fp32_peak_tflops);
+
+/* ---------------------------------------------------------------- host entry points */
+/* Replaces solve_gravity_part_part() (gravity.h:22, gravity.c:667-819): all-pairs softened gravity
+ * including j == i; acc[3N] = -G m_i sum(...), pot[N] = -G sum(m_j / r). */
+int sfe_pp(const float* pos, const float* mas, float* acc, float* pot, uint32_t N, float G, float eps2);
+/* Same, for the target slice [i0, i0+ni) only; acc/pot are still indexed by global i. */
+int sfe_pp_slice(const float* pos, const float* mas, float* acc, float* pot, uint32_t N,
+                 uint32_t i0, uint32_t ni, float G, float eps2);
+
+/* Replaces tree_build() (tree.h:44, tree.c:74-318).  bounds = tree_ptr->bounds as set by sim_solv()
+ * (simulation.c:298-301).  The tree stays on the device; nothing is written to host memory.
+ * Fails like the reference on node overflow (tree.c:180-183) or depth overflow (tree.c:186-189). */
+int sfe_tree_build(const float bounds[6], const float* pos, const float* mas, uint32_t N,
+                   int depth_max, uint32_t nodes_max);
+/* Replaces solve_gravity_part_tree() (gravity.h:14-18, gravity.c:245-663) using the tree of the last
+ * sfe_tree_build() on the same pos/mas.  theta is TREE_THETA (config.h:44), compared against
+ * width^2/dist^2 exactly as gravity.c:377,448. */
+int sfe_bh(const float* pos, const float* mas, float* acc, float* pot, uint32_t N,
+           float G, float eps2, float theta, uint32_t flavour);
+int sfe_bh_slice(const float* pos, const float* mas, float* acc, float* pot, uint32_t N,
+                 uint32_t i0, uint32_t ni, float G, float eps2, float theta, uint32_t flavour);
+/* Test / debug hooks: copy the device tree out in the reference's node_t layout with canonical
+ * (breadth-first) numbering, and the 48-bit path keys + sorted permutation of the last build. */
+int sfe_tree_download(sfe_node_t* nodes, uint32_t max_nodes, uint32_t* num_nodes);
+int sfe_tree_keys_download(uint64_t* keys, uint32_t* perm, uint32_t N, uint32_t* num_inbox);
+
+/* Replaces solve_sph() (sph.h:6, sph.c:14-283): density (all pairs, no cutoff), EOS
+ * P = (eos_k rho)^(1/eos_n + 1), pressure force added to acc (read-modify-write) for r^2 <= cutoff2. */
+int sfe_sph(const float* pos, const float* mas, const float* rad, float* rho, float* prs, float* acc,
+            uint32_t N, float eos_k, float eos_n, float cutoff2);
+
+/* ---------------------------------------------------------------- device entry points */
+/* Particle records on the device are float4 {x, y, z, m} ("pm4"): the 16-byte unit that the
+ * ncclAllGather of SURVEY 8(e) moves.  All pointers below are device pointers. */
+int sfe_dev_pack_pm4(const float* pos, const float* mas, void* pm4, uint32_t n, void* stream);
+int sfe_dev_pp(const void* pm4, uint32_t N, uint32_t i0, uint32_t ni, float* acc, float* pot,
+               float G, float eps2, void* stream);
+int sfe_dev_tree_build(const float bounds[6], const void* pm4, uint32_t N, int depth_max,
+                       uint32_t nodes_max, void* stream);
+/* Raises the deferred build status (node / depth overflow) after synchronising the stream. */
+int sfe_dev_tree_status(void* stream, uint32_t* num_nodes, uint32_t* num_inbox, uint32_t* depth);
+int sfe_dev_bh(const void* pm4, uint32_t N, uint32_t i0, uint32_t ni, float* acc, float* pot,
+               float G, float eps2, float theta, uint32_t flavour, void* stream);
+int sfe_dev_sph_density(const void* pm4, const float* rad, uint32_t N, uint32_t i0, uint32_t ni,
+                        float* rho, void* stream);
+int sfe_dev_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float eos_n, void* stream);
+int sfe_dev_sph_force(const void* pm4, const float* rad, const float* rho, const float* prs, uint32_t N,
+                      uint32_t i0, uint32_t ni, float cutoff2, float* acc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,178 @@
+// sfe_internal.cuh - engine context, error plumbing and small device helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include "../../include/sfengine.h"
+
+namespace sfe {
+
+// ---------------------------------------------------------------------------- errors
+void set_error(const char* fn, const char* fmt, ...);
+#define SFE_CUDA(fn, call)                                                              \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            sfe::set_error(fn, "%s failed: %s", #call, cudaGetErrorString(e__));        \
+            return SFE_FAILURE;                                                         \
+        }                                                                               \
+    } while (0)
+
+// ---------------------------------------------------------------------------- growable device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes, const char* fn) {
+        if (bytes <= cap) return SFE_SUCCESS;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { set_error(fn, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); return SFE_FAILURE; }
+        cap = want;
+        return SFE_SUCCESS;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ---------------------------------------------------------------------------- tree (host-side handle)
+constexpr int SFE_MAX_LEVELS = 21;   // deepest supported TREE_DEPTH_MAX (21 * 3 = 63 key bits; the reference uses 16)
+
+struct Tree {
+    // configuration of the last build
+    uint32_t N = 0, nodes_max = 0;
+    int depth_max = 0;
+    float bounds[6] = {0, 0, 0, 0, 0, 0};
+    bool valid = false;
+    // results, fetched lazily by tree_status()
+    uint32_t num_nodes = 0, num_inbox = 0, depth = 0;
+    int status = 0;  // 0 ok, 1 node overflow, 2 depth overflow
+    bool status_fetched = false;
+    const void* pm4_of_build = nullptr;
+    int final_perm = 0;
+    // device storage
+    DevBuf nodes;        // sfe_node_t[nodes_max]  reference layout, canonical (breadth-first) numbering
+    DevBuf seg;          // uint2[nodes_max]       slot range of each node
+    DevBuf next;         // uint32_t[nodes_max]    depth-first successor when a node is not opened
+    DevBuf child_base;   // uint32_t[nodes_max]    first child of internal nodes
+    DevBuf counts;       // uint32_t[8*nodes_max]  per-octant member counts of internal nodes
+    DevBuf keys;         // uint64_t[N]            48-bit path keys
+    DevBuf perm[SFE_MAX_LEVELS + 2];   // uint32_t[N] slot -> particle index, one array per level
+    DevBuf spm4[SFE_MAX_LEVELS + 2];   // float4[N]  slot-ordered particle records, one array per level
+    DevBuf perm_out;     // uint32_t[N]            out-of-box particles in ascending index
+    DevBuf slot_node[2]; // uint32_t[N]            node owning each slot (ping-pong between levels)
+    DevBuf oct;          // uint8_t[N]
+    DevBuf rank;         // uint32_t[N]            stable rank inside (node, octant)
+    DevBuf tile_agg;     // uint32_t[9*tiles]
+    DevBuf scan_tmp;
+    DevBuf slice_count;  // uint32_t[1]
+    DevBuf root_gate;    // uint32_t[1]  set when some target evaluates the root as a monopole
+    DevBuf meta;         // uint32_t[M_WORDS]
+    DevBuf rec0, rec1, rec2;   // walk records
+    uint32_t* meta_host = nullptr;     // pinned, (SFE_MAX_LEVELS + 2) snapshots of meta
+    cudaEvent_t ev_level[SFE_MAX_LEVELS + 2], ev_perm[SFE_MAX_LEVELS + 2], ev_side;
+    bool ev_init = false;
+};
+
+// ---------------------------------------------------------------------------- context
+struct Ctx {
+    int device = -1;
+    int sm_count = 0;
+    int clock_khz = 0;
+    cudaStream_t stream = nullptr;     // engine stream for the host entry points
+    cudaStream_t side = nullptr;       // overlapped work (long moment folds)
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // device copies of the host arrays
+    DevBuf d_pos, d_mas, d_pm4, d_acc, d_pot, d_rad, d_rho, d_prs;
+    // PP / SPH scratch
+    DevBuf pp_src, pp_partial, sph_src, sph_partial;
+    // pinned bounce buffer for unregistered host memory
+    void* bounce = nullptr; size_t bounce_cap = 0;
+    Tree tree;
+    sfe_timings_t timings;
+    uint32_t launches = 0;
+};
+
+Ctx* ctx();                 // nullptr before sfe_init
+int ensure_init(const char* fn);
+
+// host <-> device staging that copes with pinned and pageable host memory
+int h2d(const char* fn, void* dst, const void* src, size_t bytes, cudaStream_t s);
+int d2h(const char* fn, void* dst, const void* src, size_t bytes, cudaStream_t s);
+
+// ---------------------------------------------------------------------------- kernels (launchers)
+int launch_pack_pm4(const float* pos, const float* mas, float4* pm4, uint32_t n, cudaStream_t s);
+int launch_pp(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, float* acc, float* pot,
+              float G, float eps2, cudaStream_t s);
+int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t N, int depth_max,
+                      uint32_t nodes_max, cudaStream_t s);
+int tree_status(Ctx* c, cudaStream_t s);
+int launch_bh(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, float* acc, float* pot,
+              float G, float eps2, float theta, uint32_t flavour, cudaStream_t s);
+int launch_sph_density(Ctx* c, const float4* pm4, const float* rad, uint32_t N, uint32_t i0, uint32_t ni,
+                       float* rho, cudaStream_t s);
+int launch_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float eos_n, cudaStream_t s);
+int launch_sph_force(Ctx* c, const float4* pm4, const float* rad, const float* rho, const float* prs,
+                     uint32_t N, uint32_t i0, uint32_t ni, float cutoff2, float* acc, cudaStream_t s);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------- mbarrier / bulk-copy PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+
+// bare MUFU.RSQ / MUFU.EX2 (rsqrtf()/exp2f() add denormal fix-up code around the MUFU)
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Compensated accumulator (same recurrence as the reference's Kahan blocks, gravity.c:771-799)
+struct Kahan {
+    float s, c;
+    __device__ __forceinline__ void add(float x) {
+        float y = __fsub_rn(x, c);
+        float t = __fadd_rn(s, y);
+        c = __fsub_rn(__fsub_rn(t, s), y);
+        s = t;
+    }
+};
+#endif  // __CUDACC__
+
+inline int check_launch(const char* fn) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error(fn, "kernel launch failed: %s", cudaGetErrorString(e)); return SFE_FAILURE; }
+    if (ctx()) ctx()->launches++;
+    return SFE_SUCCESS;
+}
+
+}  // namespace sfe

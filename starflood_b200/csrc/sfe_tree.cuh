@@ -1,0 +1,63 @@
+// sfe_tree.cuh - device-side view of the octree shared by the build (sfe_tree.cu) and the walk (sfe_walk.cu).
+#pragma once
+#include "sfe_internal.cuh"
+
+namespace sfe {
+
+constexpr uint32_t NODE_END = 0xFFFFFFFFu;
+
+// meta[] words (device-side counters of one build)
+enum : int {
+    M_COUNT = 0,       // nodes allocated so far
+    M_STATUS = 1,      // 0 ok, 1 node overflow (tree.c:180-183), 2 depth overflow (tree.c:186-189)
+    M_NUM_INBOX = 2,   // particles inside the root box
+    M_DEPTH = 3,       // deepest level that holds nodes
+    M_LV_BEGIN = 4,                        // [SFE_MAX_LEVELS + 2] first node id of each level
+    M_LV_END = M_LV_BEGIN + SFE_MAX_LEVELS + 2,   // [SFE_MAX_LEVELS + 2] one past the last node id of each level
+    M_WORDS = M_LV_END + SFE_MAX_LEVELS + 2
+};
+
+// walk records --------------------------------------------------------------------------------------
+constexpr uint32_t KIND_EMPTY = 0u, KIND_SINGLE = 1u, KIND_LEAF = 2u, KIND_INTERNAL = 3u;
+
+struct __align__(16) WalkRec0 {   // 32 B: everything the traversal decision needs
+    float cx, cy, cz;             // geometric centre (gravity.c:353-357)
+    float w2;                     // fl(width^2)     (gravity.c:368-372,377)
+    uint32_t next;                // next node in depth-first order when this node is not opened
+    uint32_t child_kind;          // kind << 30 | first child (internal nodes)
+    float rin2;                   // beyond this squared distance from the centre a point is surely outside the box
+    float pad;
+};
+struct __align__(16) WalkRec2 {   // 32 B: bounds, only for the self-subtraction test (gravity.c:473-476)
+    float lo[3], hi[3], pad[2];
+};
+static_assert(sizeof(WalkRec0) == 32 && sizeof(WalkRec2) == 32, "walk records are 32 bytes");
+
+struct TreeDev {
+    float bounds[6];
+    uint32_t nodes_max;
+    sfe_node_t* nodes;
+    uint2* seg;
+    uint32_t* next;
+    uint32_t* child_base;
+    uint32_t* counts;
+    uint64_t* keys;
+    uint32_t* perm[SFE_MAX_LEVELS + 2];
+    float4* spm4[SFE_MAX_LEVELS + 2];   // slot-ordered copy of pm4 per level
+    uint32_t* perm0;
+    uint32_t* perm_out;
+    uint32_t* slot_node[2];
+    uint32_t* slot_node0;
+    uint8_t* oct;
+    uint32_t* rank;
+    uint32_t* tile_agg;
+    uint32_t* meta;
+    WalkRec0* rec0;
+    float4* rec1;      // {com x, y, z, mass}
+    WalkRec2* rec2;
+};
+
+TreeDev tree_dev(Ctx* c);
+int tree_root_moments(Ctx* c, const float4* pm4, uint32_t i0, uint32_t ni, float theta, bool force, cudaStream_t s);
+
+}  // namespace sfe

@@ -1,0 +1,168 @@
+// sfe_walk.cu - Barnes-Hut tree walk (replaces solve_gravity_part_tree, gravity.c:245-663).
+//
+// The reference walks a parent-pointer tree with a per-particle path stack, visiting the children of an
+// opened node in octant order 0..7 and taking every leaf (1..8 bodies) and every accepted internal node as
+// one monopole.  Here the same depth-first visit order is produced without a stack: every
+// node carries `next`, its successor when it is not opened (the next sibling, or the parent's successor
+// after octant 7), built top-down by the tree build.  Since children are allocated 8 at a time the
+// successor of child o < 7 is simply the next record.
+//
+// Targets are processed in Morton (slot) order, so the lanes of a warp hold neighbouring particles and
+// follow nearly the same path: node records are fetched through L1 by all lanes at once and control flow
+// stays mostly converged.  The 32-byte decision record {centre, width^2, next, child|kind} is the only thing
+// touched for an opened or empty node; the monopole {com, mass} is a second 16-byte record and the bounds
+// (self-subtraction test, gravity.c:473-490) a third one that is read only when the target can be inside.
+//
+// Arithmetic:
+//   * the opening decision reproduces gravity.c:353-377,448 exactly (no FMA contraction; the IEEE division
+//     w^2/d^2 is only evaluated when the cheap comparison is within 1e-5 of the threshold), so the
+//     interaction list of every particle is identical to the reference's;
+//   * SFE_WALK_EXACT evaluates the monopole with IEEE div / sqrt and the reference's Kahan recurrence in the
+//     same order: acc and pot are bit-identical to the reference;
+//   * SFE_WALK_FAST uses rsqrt.approx and plain fp32 accumulation in the same visit order.
+//
+// Bound: HBM/L2 bandwidth by the SURVEY 8(d) model (32 B x node visits + particle I/O).
+#include "sfe_internal.cuh"
+#include "sfe_tree.cuh"
+#include "sfe_scan.cuh"
+
+namespace sfe {
+
+constexpr int WALK_THREADS = 128;
+
+struct KahanRef {   // gravity.c:771-799: y = F - com; t = sum + y; z = t - sum; com = z - y; sum = t
+    float s, c;
+    __device__ __forceinline__ void add(float x) {
+        const float y = __fsub_rn(x, c);
+        const float t = __fadd_rn(s, y);
+        const float z = __fsub_rn(t, s);
+        c = __fsub_rn(z, y);
+        s = t;
+    }
+};
+
+// theta <= (d2 > 0 ? fl(w2 / d2) : 0)      (gravity.c:377,448)
+__device__ __forceinline__ bool opens(float w2, float d2, float theta) {
+    if (!(0.0f < d2)) return theta <= 0.0f;
+    const float rhs = theta * d2;
+    if (w2 > rhs * 1.00001f) return true;
+    if (w2 < rhs * 0.99999f) return false;
+    return theta <= __fdiv_rn(w2, d2);
+}
+
+template <int FLAVOUR>
+__global__ void __launch_bounds__(WALK_THREADS)
+walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restrict__ slots /* null: all */,
+            uint32_t nslots, uint32_t final_perm, float G, float eps2, float theta,
+            float* __restrict__ acc, float* __restrict__ pot) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nslots) return;
+    const uint32_t M = t.meta[M_NUM_INBOX];
+    const uint32_t s = slots ? slots[k] : k;
+    const uint32_t idx = s < M ? t.perm[final_perm][s] : t.perm_out[s - M];
+    const float4 me = s < M ? t.spm4[final_perm][s] : pm4[idx];
+    const float x = me.x, y = me.y, z = me.z, mi = me.w;
+
+    KahanRef ax = {0.f, 0.f}, ay = {0.f, 0.f}, az = {0.f, 0.f}, ap = {0.f, 0.f};
+    float fx = 0.f, fy = 0.f, fz = 0.f, fp = 0.f;
+
+    const WalkRec0* __restrict__ rec0 = t.rec0;
+    const float4* __restrict__ rec1 = t.rec1;
+    const WalkRec2* __restrict__ rec2 = t.rec2;
+
+    uint32_t n = 0u;
+    while (n != NODE_END) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(&rec0[n]));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(&rec0[n]) + 1);
+        const uint32_t next = b.x, kind = b.y >> 30;
+        if (kind == KIND_EMPTY) { n = next; continue; }                           // gravity.c:324-328
+        const float ox = __fsub_rn(a.x, x), oy = __fsub_rn(a.y, y), oz = __fsub_rn(a.z, z);
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ox, ox), __fmul_rn(oy, oy)), __fmul_rn(oz, oz));
+        if (kind == KIND_INTERNAL && opens(a.w, d2, theta)) { n = b.y & 0x3FFFFFFFu; continue; }   // gravity.c:448-453
+        // monopole (gravity.c:463-548)
+        const float4 cm = __ldg(&rec1[n]);
+        float rx = cm.x, ry = cm.y, rz = cm.z, mj = cm.w;
+        if (kind != KIND_SINGLE && d2 <= __uint_as_float(b.z)) {
+            const float4 lo = __ldg(reinterpret_cast<const float4*>(&rec2[n]));
+            const float4 hi = __ldg(reinterpret_cast<const float4*>(&rec2[n]) + 1);
+            // lo = {lo.x, lo.y, lo.z, hi.x}, hi = {hi.y, hi.z, -, -}
+            if (lo.x <= x && x <= lo.w && lo.y <= y && y <= hi.x && lo.z <= z && z <= hi.y) {
+                rx = __fsub_rn(__fmul_rn(rx, mj), __fmul_rn(mi, x));              // gravity.c:478-484
+                ry = __fsub_rn(__fmul_rn(ry, mj), __fmul_rn(mi, y));
+                rz = __fsub_rn(__fmul_rn(rz, mj), __fmul_rn(mi, z));
+                mj = __fsub_rn(mj, mi);
+                const float inv = 0.0f < mj ? __fdiv_rn(1.0f, mj) : 1.0f;
+                rx = __fmul_rn(rx, inv); ry = __fmul_rn(ry, inv); rz = __fmul_rn(rz, inv);
+            }
+        }
+        const float dx = __fsub_rn(x, rx), dy = __fsub_rn(y, ry), dz = __fsub_rn(z, rz);
+        const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const float q = __fadd_rn(r2, eps2);
+        if (FLAVOUR == (int)SFE_WALK_EXACT) {
+            const float inv_r2 = __fdiv_rn(1.0f, q);
+            const float inv_r1 = __fdiv_rn(1.0f, __fsqrt_rn(q));
+            const float pj = __fmul_rn(mj, inv_r1);
+            const float w = __fmul_rn(pj, inv_r2);
+            ax.add(__fmul_rn(w, dx)); ay.add(__fmul_rn(w, dy)); az.add(__fmul_rn(w, dz));
+            ap.add(pj);
+        } else {
+            const float inv = rsqrt_approx(q);
+            const float pj = mj * inv;
+            const float w = pj * (inv * inv);
+            fx = fmaf(w, dx, fx); fy = fmaf(w, dy, fy); fz = fmaf(w, dz, fz);
+            fp += pj;
+        }
+        n = next;
+    }
+    if (FLAVOUR == (int)SFE_WALK_EXACT) { fx = ax.s; fy = ay.s; fz = az.s; fp = ap.s; }
+    const float gm = __fmul_rn(-G, mi);                                            // gravity.c:656-659
+    acc[3u * idx + 0u] = __fmul_rn(gm, fx);
+    acc[3u * idx + 1u] = __fmul_rn(gm, fy);
+    acc[3u * idx + 2u] = __fmul_rn(gm, fz);
+    pot[idx] = __fmul_rn(-G, fp);
+}
+
+// slots whose particle index lies in [i0, i0+ni), in slot order (multi-GPU target slices)
+struct SliceOp {
+    TreeDev t; uint32_t N, i0, i1, final_perm; uint32_t* out; uint32_t* count;
+    __device__ uint32_t n() const { return N; }
+    __device__ uint32_t idx_of(uint32_t s) const {
+        const uint32_t M = t.meta[M_NUM_INBOX];
+        return s < M ? t.perm[final_perm][s] : t.perm_out[s - M];
+    }
+    __device__ uint32_t load(uint32_t s) const { const uint32_t i = idx_of(s); return (i >= i0 && i < i1) ? 1u : 0u; }
+    __device__ void store(uint32_t s, uint32_t ex) const { const uint32_t i = idx_of(s); if (i >= i0 && i < i1) out[ex] = s; }
+    __device__ void total(uint32_t c) const { *count = c; }
+};
+
+// compacted slot list of a target slice; lives in the tree's rank buffer (free once the build is done)
+static int walk_slice_slots(Ctx* c, uint32_t N, uint32_t i0, uint32_t ni, cudaStream_t s, uint32_t** slots_out) {
+    Tree& t = c->tree;
+    if (t.slice_count.reserve(4, "sfe_bh")) return SFE_FAILURE;
+    SliceOp op{tree_dev(c), N, i0, i0 + ni, (uint32_t)t.final_perm, t.rank.as<uint32_t>(), t.slice_count.as<uint32_t>()};
+    if (run_scan(c, op, N, s, "sfe_bh")) return SFE_FAILURE;
+    *slots_out = t.rank.as<uint32_t>();
+    return SFE_SUCCESS;
+}
+
+int launch_bh(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, float* acc, float* pot,
+              float G, float eps2, float theta, uint32_t flavour, cudaStream_t s) {
+    const char* fn = "sfe_bh";
+    Tree& t = c->tree;
+    if (!t.valid || t.N != N) { set_error(fn, "no tree for N=%u: call sfe_tree_build() first", N); return SFE_FAILURE; }
+    if ((uint64_t)i0 + ni > N) { set_error(fn, "target slice [%u,%u) exceeds N=%u", i0, i0 + ni, N); return SFE_FAILURE; }
+    if (flavour != SFE_WALK_EXACT && flavour != SFE_WALK_FAST) { set_error(fn, "unknown walk flavour %u", flavour); return SFE_FAILURE; }
+    if (ni == 0) return SFE_SUCCESS;
+    if (tree_root_moments(c, pm4, i0, ni, theta, false, s)) return SFE_FAILURE;
+    TreeDev dv = tree_dev(c);
+    uint32_t* slots = nullptr;
+    if (ni != N && walk_slice_slots(c, N, i0, ni, s, &slots)) return SFE_FAILURE;
+    const uint32_t grid = (ni + WALK_THREADS - 1) / WALK_THREADS;
+    if (flavour == SFE_WALK_EXACT)
+        walk_kernel<(int)SFE_WALK_EXACT><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, ni, (uint32_t)t.final_perm, G, eps2, theta, acc, pot);
+    else
+        walk_kernel<(int)SFE_WALK_FAST><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, ni, (uint32_t)t.final_perm, G, eps2, theta, acc, pot);
+    return check_launch(fn);
+}
+
+}  // namespace sfe

@@ -1,0 +1,275 @@
+"""Python host binding over the C ABI (include/sfengine.h) of libsfengine.so.
+
+The product is the C ABI + the reference-side C shims (starflood_b200/shim/); this module exists so
+that tests and bench.py can drive the same entry points, and it mirrors the reference's solver
+interface for this path (same names, argument meaning and error behaviour):
+
+    solve_gravity_part_part(sim)   gravity.h:22     tree_init / tree_free / tree_build   tree.h:38-44
+    solve_gravity_part_tree(sim)   gravity.h:14-18  solve_sph(sim)                        sph.h:6
+
+`Sim` is the reference's sim_t over one RAW-layout state block (simulation.h:17-67).
+There is no CPU fallback: importing works without a GPU (so the symbol table can be checked), but
+every compute call fails with SFE_FAILURE / raises when the CUDA library or device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsfengine.so")
+
+STARFLOOD_SUCCESS = 0   # common.h:31
+STARFLOOD_FAILURE = -1  # common.h:32
+
+# macro values the reference passes on this path (config.h:38-44,170-178; gravity.c:754; sph.c:148-149,231)
+G = 1.000
+EPSILON = 1.000e-3
+EPS2 = np.float32(EPSILON * EPSILON)
+TREE_THETA = 0.5
+TREE_DEPTH_MAX = 16
+TREE_NODES_MAX = 262144
+EOS_K = 0.100
+EOS_N = 1.000
+SPH_CUTOFF2 = 1.000 * 1.000
+
+WALK_EXACT = 0
+WALK_FAST = 1
+
+NODE_DTYPE = np.dtype([
+    ("parent", "<u4"), ("bodies", "<u4"), ("branch", "<u4", (8,)),
+    ("bounds", "<f4", (6,)), ("params", "<f4", (4,)),
+])
+
+
+class Timings(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("build_ms", C.c_float), ("solve_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("total_ms", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("launches", C.c_uint32)]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_P = C.c_void_p
+_u32 = C.c_uint32
+_f = C.c_float
+SIGNATURES = {
+    "sfe_init": ([C.c_int], C.c_int),
+    "sfe_shutdown": ([], C.c_int),
+    "sfe_last_error": ([], C.c_char_p),
+    "sfe_host_register": ([_P, C.c_uint64], C.c_int),
+    "sfe_host_unregister": ([_P], C.c_int),
+    "sfe_get_timings": ([C.POINTER(Timings)], C.c_int),
+    "sfe_device_info": ([C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)], C.c_int),
+    "sfe_pp": ([_P, _P, _P, _P, _u32, _f, _f], C.c_int),
+    "sfe_pp_slice": ([_P, _P, _P, _P, _u32, _u32, _u32, _f, _f], C.c_int),
+    "sfe_tree_build": ([_P, _P, _P, _u32, C.c_int, _u32], C.c_int),
+    "sfe_bh": ([_P, _P, _P, _P, _u32, _f, _f, _f, _u32], C.c_int),
+    "sfe_bh_slice": ([_P, _P, _P, _P, _u32, _u32, _u32, _f, _f, _f, _u32], C.c_int),
+    "sfe_tree_download": ([_P, _u32, C.POINTER(_u32)], C.c_int),
+    "sfe_tree_keys_download": ([_P, _P, _u32, C.POINTER(_u32)], C.c_int),
+    "sfe_sph": ([_P, _P, _P, _P, _P, _P, _u32, _f, _f, _f], C.c_int),
+    "sfe_dev_pack_pm4": ([_P, _P, _P, _u32, _P], C.c_int),
+    "sfe_dev_pp": ([_P, _u32, _u32, _u32, _P, _P, _f, _f, _P], C.c_int),
+    "sfe_dev_tree_build": ([_P, _P, _u32, C.c_int, _u32, _P], C.c_int),
+    "sfe_dev_tree_status": ([_P, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)], C.c_int),
+    "sfe_dev_bh": ([_P, _u32, _u32, _u32, _P, _P, _f, _f, _f, _u32, _P], C.c_int),
+    "sfe_dev_sph_density": ([_P, _P, _u32, _u32, _u32, _P, _P], C.c_int),
+    "sfe_dev_sph_eos": ([_P, _P, _u32, _f, _f, _P], C.c_int),
+    "sfe_dev_sph_force": ([_P, _P, _P, _P, _u32, _u32, _u32, _f, _P, _P], C.c_int),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libsfengine.so (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError("libsfengine.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(or make -C starflood_b200); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, (args, res) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = res
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return (lib().sfe_last_error() or b"").decode()
+
+
+def _check(rc, what):
+    if rc != STARFLOOD_SUCCESS:
+        raise EngineError("%s failed: %s" % (what, last_error()))
+
+
+def init(device=-1):
+    _check(lib().sfe_init(device), "sfe_init")
+
+
+def shutdown():
+    lib().sfe_shutdown()
+
+
+def timings():
+    t = Timings()
+    lib().sfe_get_timings(C.byref(t))
+    return t
+
+
+def device_info():
+    sm = C.c_int(); khz = C.c_int(); peak = C.c_double()
+    _check(lib().sfe_device_info(C.byref(sm), C.byref(khz), C.byref(peak)), "sfe_device_info")
+    return {"sm_count": sm.value, "clock_khz": khz.value, "fp32_peak_tflops": peak.value}
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Tree:
+    """tree_t (tree.h:27-35).  `node` is host memory in the reference; the engine keeps the real tree on
+    the device and fills `node` only on download()."""
+    def __init__(self):
+        self.max_nodes = 0
+        self.num_nodes = 0
+        self.bounds = np.zeros(6, np.float32)
+        self.node = None
+
+
+class Sim:
+    """sim_t (simulation.h:53-67) over one RAW-layout block: real[N * SIM_DOF], sim_find(p) = mem + N*p."""
+    OFFSETS = {"pos": (0, 3), "vel": (3, 3), "acc": (6, 3), "mas": (9, 1), "pot": (10, 1), "ken": (11, 1),
+               "pen": (12, 1), "rad": (13, 1), "rho": (14, 1), "prs": (15, 1)}
+
+    def __init__(self, N, sph=False, mem=None, pinned=False):
+        self.N = int(N)
+        self.step_number = 0
+        self.sph = sph
+        self.dof = 16 if sph else 13
+        if mem is None:
+            mem = np.zeros(self.N * self.dof, np.float32)
+        assert mem.dtype == np.float32 and mem.size == self.N * self.dof and mem.flags.c_contiguous
+        self.mem = mem
+        self.tree = Tree()
+        if pinned:
+            _check(lib().sfe_host_register(self.mem.ctypes.data, self.mem.nbytes), "sfe_host_register")
+
+    def find(self, name):
+        first, width = self.OFFSETS[name]
+        return self.mem[first * self.N:(first + width) * self.N]
+
+    pos = property(lambda s: s.find("pos")); vel = property(lambda s: s.find("vel"))
+    acc = property(lambda s: s.find("acc")); mas = property(lambda s: s.find("mas"))
+    pot = property(lambda s: s.find("pot")); rad = property(lambda s: s.find("rad"))
+    rho = property(lambda s: s.find("rho")); prs = property(lambda s: s.find("prs"))
+
+
+# ---------------------------------------------------------------------------------- reference interface
+def solve_gravity_part_part(sim, i0=0, ni=None):
+    """gravity.h:22 / gravity.c:667-819.  Returns STARFLOOD_SUCCESS / STARFLOOD_FAILURE like the reference."""
+    ni = sim.N - i0 if ni is None else ni
+    return lib().sfe_pp_slice(_ptr(sim.pos), _ptr(sim.mas), _ptr(sim.acc), _ptr(sim.pot), sim.N, i0, ni,
+                              G, EPS2)
+
+
+def tree_init(tree, max_nodes):
+    """tree.h:38 / tree.c:14-55."""
+    tree.max_nodes = int(max_nodes)
+    tree.num_nodes = 0
+    tree.bounds[:] = 0
+    tree.node = np.zeros(tree.max_nodes, NODE_DTYPE)
+    return STARFLOOD_SUCCESS
+
+
+def tree_free(tree):
+    """tree.h:41 / tree.c:57-72."""
+    tree.max_nodes = 0
+    tree.num_nodes = 0
+    tree.bounds[:] = 0
+    tree.node = None
+    return STARFLOOD_SUCCESS
+
+
+def tree_build(tree, num_parts, pos, mas, depth_max=TREE_DEPTH_MAX):
+    """tree.h:44 / tree.c:74-318.  tree.bounds must have been set by the caller (simulation.c:298-301)."""
+    return lib().sfe_tree_build(_ptr(tree.bounds), _ptr(pos), _ptr(mas), num_parts, depth_max, tree.max_nodes)
+
+
+def tree_download(tree):
+    """Test hook: copy the device tree into tree.node (reference node_t layout, canonical numbering)."""
+    n = _u32()
+    rc = lib().sfe_tree_download(_ptr(tree.node), tree.max_nodes, C.byref(n))
+    tree.num_nodes = n.value
+    return rc
+
+
+def tree_keys(N):
+    keys = np.zeros(N, np.uint64); perm = np.zeros(N, np.uint32); nin = _u32()
+    _check(lib().sfe_tree_keys_download(_ptr(keys), _ptr(perm), N, C.byref(nin)), "sfe_tree_keys_download")
+    return keys, perm, nin.value
+
+
+def solve_gravity_part_tree(sim, flavour=WALK_EXACT, i0=0, ni=None, theta=TREE_THETA):
+    """gravity.h:14-18 / gravity.c:245-663 (the SOLVER_VIS render-buffer arguments are ignored)."""
+    ni = sim.N - i0 if ni is None else ni
+    return lib().sfe_bh_slice(_ptr(sim.pos), _ptr(sim.mas), _ptr(sim.acc), _ptr(sim.pot), sim.N, i0, ni,
+                              G, EPS2, theta, flavour)
+
+
+def solve_sph(sim):
+    """sph.h:6 / sph.c:14-283."""
+    return lib().sfe_sph(_ptr(sim.pos), _ptr(sim.mas), _ptr(sim.rad), _ptr(sim.rho), _ptr(sim.prs), _ptr(sim.acc),
+                         sim.N, EOS_K, EOS_N, SPH_CUTOFF2)
+
+
+def root_box(sim):
+    """Caller-side root box of sim_solv() (simulation.c:245-301): stays host code in the reference; this is
+    the same arithmetic in numpy for hosts that do not link the reference (bench.py, tests)."""
+    p = sim.pos.reshape(-1, 3).astype(np.float64)
+    r = np.sqrt((p[:, 0] * p[:, 0]) + (p[:, 1] * p[:, 1]) + (p[:, 2] * p[:, 2]))
+    # Kahan-compensated left fold == exactly rounded sum to well below fp32 resolution of the box
+    import math
+    rbar = math.fsum(r.tolist()) * (1.0 / sim.N)
+    s = _pcg4d(np.array([0x638FE17B + sim.step_number, 0xB10BDCE7, 0x7B8ADB9B, 0xD8C5850E], np.uint64))
+    inv = 2.3283062977608182109179324470460414886474609375e-10
+    b = np.zeros(6, np.float32)
+    for k in range(3):
+        jitter = 2.0 * (inv * float(s[k])) - 1.0
+        b[k] = np.float32(-2.0 * rbar + 0.5 * jitter * rbar)
+        b[3 + k] = np.float32(2.0 * rbar + 0.5 * jitter * rbar)
+    return b
+
+
+def _pcg4d(v):
+    """rng.h:13-40 on uint32 lanes."""
+    M = np.uint64(0xFFFFFFFF)
+    v = [(int(x) * 1664525 + 1013904223) & 0xFFFFFFFF for x in v]
+    for rnd in range(2):
+        v[0] = (v[0] + v[1] * v[3]) & 0xFFFFFFFF
+        v[1] = (v[1] + v[2] * v[0]) & 0xFFFFFFFF
+        v[2] = (v[2] + v[0] * v[1]) & 0xFFFFFFFF
+        v[3] = (v[3] + v[1] * v[2]) & 0xFFFFFFFF
+        if rnd == 0:
+            v = [x ^ (x >> 16) for x in v]
+    return v
+
+
+def sim_solv(sim, tree=True, sph=False, flavour=WALK_EXACT):
+    """The dispatch of sim_solv() (simulation.c:231-345) over the engine: root box -> tree_build ->
+    solve_gravity_part_tree, or solve_gravity_part_part; then solve_sph."""
+    if tree:
+        sim.tree.bounds[:] = root_box(sim)
+        tree_build(sim.tree, sim.N, sim.pos, sim.mas)      # return value ignored like simulation.c:312
+        rc = solve_gravity_part_tree(sim, flavour)
+    else:
+        rc = solve_gravity_part_part(sim)
+    if sph:
+        rc = solve_sph(sim)
+    return rc
