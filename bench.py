@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the force-evaluation hot path (BASELINE.json).
+
+Workload (config.workload): C2 = Barnes-Hut gravity, N = 2^20 uniform sphere from the reference's
+initcond_generate(), theta = 0.5 monopole, root box of sim_solv().  One "step" = one pass of the hot path over
+one snapshot: tree_build + solve_gravity_part_tree for all N particles (the root box is caller-side code that
+stays in the reference, simulation.c:245-308, and is computed once per snapshot at set-up).
+
+    value   particle-steps/s with the snapshot already resident in HBM (device entry points, sfe_dev_*)
+    e2e     the same through the host C ABI (sfe_tree_build + sfe_bh on pinned HOST buffers): every step copies
+            pos/mas host->device and acc/pot device->host inside the timed region
+    pp      PP direct-sum interactions/s at the same N (second half of BASELINE.json's metric), FP32-bound
+    roofline  the walk kernel against measured HBM bandwidth with SURVEY 8(d)'s algorithmic bytes
+    cpu_baseline  the unmodified reference (oracle/_ref/libsfref_tree.so) timed on this box's host cores
+
+N > 1 (torchrun, one rank per GPU): strong scaling at the same total N.  Every rank owns a target slice,
+all-gathers the {x,y,z,m} records over NCCL/NVLink (torch.distributed), builds the full tree locally and walks
+its own slice.  Time is the max over ranks.
+
+Timing hygiene: W >= 3 warm-up steps; the timed steps rotate through a ring of distinct snapshots whose total
+footprint exceeds L2 (config.l2), so no step finds its inputs cached; CUDA events on the launching stream;
+nvidia-smi clocks sampled during the timed region.
+
+--impl reference times the reference's own CPU implementation (all host threads) on the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DEFAULT = 1 << 20
+THETA = 0.5
+L2_BYTES = 126 << 20
+# distinct node visits per particle of the reference walk on C2 (opened + evaluated + empty),
+# re-measured by the oracle in tests/test_gpu_walk.py::test_full_size
+V_C2 = 514.3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--flavour", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--no-pp", action="store_true", help="skip the PP leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if not (self.t0 - 0.05 <= ts <= self.t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": max(pw),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def snapshots(N, count):
+    """Ring of distinct snapshots: the reference ICs rotated about z by different angles (same density profile and
+    walk statistics), each with the root box sim_solv() would compute at step_number = k."""
+    from starflood_b200 import engine as e, ics
+    pos, vel, mas = ics.uniform_ball(N)
+    p = pos.reshape(-1, 3)
+    out = []
+    for k in range(count):
+        a = 0.37 * k
+        c, s = np.float32(np.cos(a)), np.float32(np.sin(a))
+        q = np.empty_like(p)
+        q[:, 0] = c * p[:, 0] - s * p[:, 1]; q[:, 1] = s * p[:, 0] + c * p[:, 1]; q[:, 2] = p[:, 2]
+        sim = e.Sim(N, mem=None)
+        sim.pos[:] = q.ravel(); sim.mas[:] = mas; sim.step_number = k
+        out.append((sim, e.root_box(sim)))
+    return out
+
+
+def ref_lib_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libsfref_tree.so"))
+
+
+def cpu_reference_steps(N, steps, warmup):
+    """The reference's own sim_solv() (root box + tree_build + solve_gravity_part_tree) from oracle/_ref on all
+    host threads; falls back to the oracle port when the reference library did not travel."""
+    from oracle import sfo
+    cores = os.cpu_count()
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ.setdefault("OMP_PROC_BIND", "true")
+    times = []
+    if ref_lib_available() and N <= 2 * sfo.REF_NODES_MAX["tree"]:
+        kind = "reference"
+        r = sfo.RefSim("tree", N); r.initcond()
+        for s in range(warmup + steps):
+            t0 = time.perf_counter(); r.solv(s); dt = time.perf_counter() - t0
+            if s >= warmup:
+                times.append(dt)
+        r.close()
+    else:
+        kind = "port"
+        pos, vel, mas = sfo.initcond(N)
+        for s in range(warmup + steps):
+            t0 = time.perf_counter()
+            b = sfo.root_box(pos, s)
+            rc, nodes, n = sfo.tree_build_insert(b, pos, mas, N)
+            sfo.bh_walk(nodes[:n], pos, mas)
+            dt = time.perf_counter() - t0
+            if s >= warmup:
+                times.append(dt)
+    return kind, cores, times
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N = args.n
+    kind, cores, times = cpu_reference_steps(N, args.steps, args.warmup)
+    ms = 1e3 * float(np.mean(times))
+    value = N / (ms * 1e-3)
+    sample = "%d full sim_solv() steps (root box + tree_build + BH walk) at N=%d, %d OpenMP threads" % (args.steps, N, cores)
+    line = {
+        "impl": "reference", "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: Barnes-Hut gravity N=%d uniform sphere, theta=0.5 monopole (CPU, OpenMP)" % N,
+                   "N": N, "theta": THETA},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ engine arm
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    from starflood_b200 import engine as e
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    e.init(local)
+    L = e.lib()
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    flavour = e.WALK_EXACT if args.flavour == "exact" else e.WALK_FAST
+
+    N = args.n
+    G = world
+    # target slices: rank g owns [g*N/G, (g+1)*N/G)
+    i0 = (N * rank) // G
+    i1 = (N * (rank + 1)) // G
+    ni = i1 - i0
+    ring = max(3, (2 * L2_BYTES) // (16 * N) + 1)
+    snaps = snapshots(N, ring)
+    nodes_max = max(N, 1024)
+
+    # device-resident state: per snapshot the rank's slice of pm4 records; full pm4 + outputs shared
+    pm4_full = torch.empty(N * 4, dtype=torch.float32, device=dev)
+    acc = torch.zeros(3 * N, dtype=torch.float32, device=dev)
+    pot = torch.zeros(N, dtype=torch.float32, device=dev)
+    slices, boxes = [], []
+    for sim, box in snaps:
+        pm = np.empty((N, 4), np.float32)
+        pm[:, :3] = sim.pos.reshape(-1, 3); pm[:, 3] = sim.mas
+        slices.append(torch.from_numpy(pm[i0:i1].copy()).to(dev).reshape(-1))
+        boxes.append(np.ascontiguousarray(box, np.float32))
+    import ctypes as C
+
+    def gather(k):
+        if world > 1:
+            dist.all_gather_into_tensor(pm4_full, slices[k])
+        else:
+            pm4_full.copy_(slices[k])      # at N=1 the "gather" is a device copy of the resident snapshot
+
+    def step_dev(k, ev=None):
+        gather(k)
+        rc = L.sfe_dev_tree_build(boxes[k].ctypes.data, pm4_full.data_ptr(), N, e.TREE_DEPTH_MAX, nodes_max, sptr)
+        if ev is not None:
+            ev[0].record(stream)
+        rc |= L.sfe_dev_bh(pm4_full.data_ptr(), N, i0, ni, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, THETA, flavour, sptr)
+        if ev is not None:
+            ev[1].record(stream)
+        if rc != 0:
+            raise SystemExit("bench.py: engine call failed: " + e.last_error())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up
+    for w in range(max(args.warmup, 3)):
+        step_dev(w % ring)
+    barrier()
+    st = (C.c_uint32(), C.c_uint32(), C.c_uint32())
+    if L.sfe_dev_tree_status(sptr, C.byref(st[0]), C.byref(st[1]), C.byref(st[2])) != 0:
+        raise SystemExit("bench.py: tree build failed: " + e.last_error())
+
+    # ---- timed region: K steps, device resident
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        time.sleep(0.3)
+    walk_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = L.sfe_launch_count()
+    t_wall0 = time.time()
+    e0.record(stream)
+    for s in range(args.steps):
+        step_dev((args.warmup + s) % ring, walk_ev[s])
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    launches = int(L.sfe_launch_count() - launches0)
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    value = N / (ms_step * 1e-3)
+    walk_ms = float(np.mean([a.elapsed_time(b) for a, b in walk_ev]))
+    walk_ms = max_over_ranks(walk_ms)
+
+    # ---- e2e: host buffers through the host C ABI (N=1) / pinned slices + collective + device ABI (N>1)
+    e2e_ms = None
+    h2d_b = d2h_b = 0
+    if world == 1:
+        for sim, box in snaps:
+            L.sfe_host_register(sim.mem.ctypes.data, sim.mem.nbytes)
+        def step_host(k):
+            sim, box = snaps[k]
+            rc = L.sfe_tree_build(boxes[k].ctypes.data, sim.pos.ctypes.data, sim.mas.ctypes.data, N, e.TREE_DEPTH_MAX, nodes_max)
+            rc |= L.sfe_bh(sim.pos.ctypes.data, sim.mas.ctypes.data, sim.acc.ctypes.data, sim.pot.ctypes.data, N,
+                           e.G, e.EPS2, THETA, flavour)
+            if rc != 0:
+                raise SystemExit("bench.py: engine call failed: " + e.last_error())
+        for w in range(3):
+            step_host(w % ring)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            step_host((args.warmup + s) % ring)
+        torch.cuda.synchronize()
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+        h2d_b, d2h_b = 16 * N, 16 * N
+    else:
+        host_in = [torch.from_numpy(np.ascontiguousarray(
+            np.concatenate([snaps[k][0].pos.reshape(-1, 3)[i0:i1], snaps[k][0].mas[i0:i1, None]], axis=1))).pin_memory()
+            for k in range(ring)]
+        host_acc = torch.empty(3 * ni, dtype=torch.float32).pin_memory()
+        host_pot = torch.empty(ni, dtype=torch.float32).pin_memory()
+        def step_host(k):
+            slices[k].copy_(host_in[k].reshape(-1), non_blocking=True)
+            step_dev(k)
+            host_acc.copy_(acc[3 * i0:3 * i1], non_blocking=True)
+            host_pot.copy_(pot[i0:i1], non_blocking=True)
+            stream.synchronize()
+        for w in range(3):
+            step_host(w % ring)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            step_host((args.warmup + s) % ring)
+        barrier()
+        e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / args.steps)
+        h2d_b, d2h_b = 16 * ni, 16 * ni
+    if sampler:
+        sampler.window(t_wall0, t_wall1)
+        clocks = sampler.stop()
+    else:
+        clocks = None
+
+    # ---- PP leg: interactions/s at the same N, target-sliced the same way
+    pp = None
+    if not args.no_pp:
+        gather(0)
+        reps = 2 if N >= (1 << 19) else 5
+        L.sfe_dev_pp(pm4_full.data_ptr(), N, i0, ni, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, sptr)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for r in range(reps):
+            gather(r % ring)
+            L.sfe_dev_pp(pm4_full.data_ptr(), N, i0, ni, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, sptr)
+        p1.record(stream)
+        barrier()
+        pp_ms = max_over_ranks(p0.elapsed_time(p1)) / reps
+        info = e.device_info()
+        inter = float(N) * float(N) / (pp_ms * 1e-3)
+        tf = 20.0 * inter / 1e12
+        pp = {"metric": "PP interactions/s", "value": inter, "ms_per_solve": pp_ms, "N": N,
+              "flop_per_interaction": 20, "achieved_tflops": tf,
+              "fp32_peak_tflops": info["fp32_peak_tflops"] * world,
+              "peak_note": "2*128 lanes*%d SMs*%.0f MHz per GPU (cudaDevAttrClockRate)" % (info["sm_count"], info["clock_khz"] / 1e3),
+              "frac": tf / (info["fp32_peak_tflops"] * world)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the walk): algorithmic bytes per launch / measured launch time
+    hbm, hbm_src = measured_peaks()
+    walk_bytes = (32.0 * V_C2 + 32.0) * ni            # 32 B per node visit + 32 B particle I/O
+    step_bytes = (32.0 * V_C2 + 32.0 + 16.0 + 24.0 * 8 + 32.0 * 0.382) * N
+    achieved = walk_bytes / (walk_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "walk_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "walk_kernel (sfe_dev_bh)", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                "frac": achieved / hbm, "traffic": traffic, "peak_source": hbm_src,
+                "algorithmic_bytes_per_launch": walk_bytes, "launch_ms": walk_ms,
+                "model": "32 B x V(=%.1f node visits/particle, oracle-counted) + 32 B particle I/O, x %d targets" % (V_C2, ni),
+                "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
+                               "frac": step_bytes / (ms_step * 1e-3) / 1e9 / hbm,
+                               "model": "SURVEY 8(d) B = 32 V + 32 + B_build = 16710 B per particle-step"}}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only, bounded sample)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        kind, cores, times = cpu_reference_steps(N, 4, 1)
+        cms = 1e3 * float(np.median(times))
+        cpu = {"value": N / (cms * 1e-3), "unit": "particle-steps/s", "cores": cores, "kind": kind,
+               "sample": "4 full sim_solv() steps at N=%d after 1 warm-up (%.2f s each, median), %d OpenMP threads" % (N, cms / 1e3, cores)}
+
+    line = {
+        "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: Barnes-Hut gravity N=%d uniform sphere (reference initcond), theta=0.5 monopole, "
+                               "tree_build + solve_gravity_part_tree per step" % N,
+                   "N": N, "theta": THETA, "depth_max": 16, "walk": args.flavour,
+                   "partition": "target slices, tree per GPU, all-gather of {x,y,z,m}" if world > 1 else "single GPU",
+                   "l2": "ring of %d distinct snapshots (%d MiB of inputs > L2) rotated between steps" % (ring, ring * 16 * N >> 20),
+                   "tree_nodes": int(st[0].value), "tree_depth": int(st[2].value)},
+        "e2e": {"value": N / (e2e_ms * 1e-3), "unit": "particle-steps/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+                "api": "sfe_tree_build + sfe_bh on pinned host arrays" if world == 1 else
+                       "pinned slice H2D + all_gather + sfe_dev_tree_build + sfe_dev_bh + slice D2H"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "pp": pp,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_engine(a)

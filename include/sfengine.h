@@ -69,6 +69,8 @@ int sfe_host_unregister(void* ptr);
 int sfe_get_timings(sfe_timings_t* out);
 /* SM count, SM clock (kHz), and the FP32 FMA peak 2*128*SMs*clock in TFLOP/s of the bound device. */
 int sfe_device_info(int* sm_count, int* clock_khz, double* fp32_peak_tflops);
+/* Cumulative number of engine kernels launched by this process (host and device entry points). */
+uint64_t sfe_launch_count(void);
 
 /* ---------------------------------------------------------------- host entry points */
 /* Replaces solve_gravity_part_part() (gravity.h:22, gravity.c:667-819): all-pairs softened gravity

@@ -228,6 +228,8 @@ extern "C" int sfe_device_info(int* sm_count, int* clock_khz, double* fp32_peak_
     return SFE_SUCCESS;
 }
 
+extern "C" uint64_t sfe_launch_count(void) { return g_ctx ? g_ctx->total_launches : 0; }
+
 // ============================================================================ host entry points
 extern "C" int sfe_pp_slice(const float* pos, const float* mas, float* acc, float* pot, uint32_t N,
                             uint32_t i0, uint32_t ni, float G, float eps2) {

@@ -94,6 +94,7 @@ struct Ctx {
     Tree tree;
     sfe_timings_t timings;
     uint32_t launches = 0;
+    uint64_t total_launches = 0;
 };
 
 Ctx* ctx();                 // nullptr before sfe_init
@@ -171,7 +172,7 @@ struct Kahan {
 inline int check_launch(const char* fn) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error(fn, "kernel launch failed: %s", cudaGetErrorString(e)); return SFE_FAILURE; }
-    if (ctx()) ctx()->launches++;
+    if (ctx()) { ctx()->launches++; ctx()->total_launches++; }
     return SFE_SUCCESS;
 }
 

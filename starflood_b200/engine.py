@@ -63,6 +63,7 @@ SIGNATURES = {
     "sfe_host_unregister": ([_P], C.c_int),
     "sfe_get_timings": ([C.POINTER(Timings)], C.c_int),
     "sfe_device_info": ([C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)], C.c_int),
+    "sfe_launch_count": ([], C.c_uint64),
     "sfe_pp": ([_P, _P, _P, _P, _u32, _f, _f], C.c_int),
     "sfe_pp_slice": ([_P, _P, _P, _P, _u32, _u32, _u32, _f, _f], C.c_int),
     "sfe_tree_build": ([_P, _P, _P, _u32, C.c_int, _u32], C.c_int),

@@ -1,0 +1,99 @@
+"""PP gravity parity (solve_gravity_part_part, gravity.c:667-819) through the C ABI.  Gate: rel-RMS <= 1e-5
+for acc and pot (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_rms
+from oracle import sfo
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def run_pp(engine, pos, mas, **kw):
+    sim = engine.Sim(len(mas)); sim.pos[:] = pos; sim.mas[:] = mas
+    assert engine.solve_gravity_part_part(sim, **kw) == engine.STARFLOOD_SUCCESS, engine.last_error()
+    return sim
+
+
+def test_golden(engine):
+    g = np.load(os.path.join(G, "pp_n1024.npz"))
+    sim = run_pp(engine, g["pos"], g["mas"])
+    assert rel_rms(sim.acc, g["acc"]) <= TOL and rel_rms(sim.pot, g["pot"]) <= TOL
+
+
+@pytest.mark.parametrize("N", [1, 2, 31, 513, 4097, 65536])
+def test_sizes_vs_oracle(engine, N):
+    pos, vel, mas = sfo.initcond(N)
+    sim = run_pp(engine, pos, mas)
+    acc, pot = sfo.pp(pos, mas)
+    if N == 1:
+        assert np.array_equal(sim.acc, acc) and rel_rms(sim.pot, pot) <= TOL     # self term only: 0 force, m/eps
+    else:
+        assert rel_rms(sim.acc, acc) <= TOL and rel_rms(sim.pot, pot) <= TOL
+
+
+def test_empty(engine):
+    sim = engine.Sim(0)
+    assert engine.solve_gravity_part_part(sim) == engine.STARFLOOD_SUCCESS
+
+
+def test_unequal_masses_and_clustering(engine):
+    rng = np.random.default_rng(7)
+    N = 3000
+    pos = (rng.normal(size=(N, 3)) * np.array([1.0, 0.05, 1.0])).astype(np.float32).ravel()
+    pos[:30] = pos[30:60]                       # coincident pairs: r = 0 -> softened, finite
+    mas = rng.uniform(0.0, 2.0, N).astype(np.float32)
+    mas[5] = 0.0
+    sim = run_pp(engine, pos, mas)
+    acc, pot = sfo.pp(pos, mas)
+    assert np.isfinite(sim.acc).all() and np.isfinite(sim.pot).all()
+    assert rel_rms(sim.acc, acc) <= TOL and rel_rms(sim.pot, pot) <= TOL
+
+
+def test_slice_writes_only_its_targets(engine):
+    N = 5000
+    pos, vel, mas = sfo.initcond(N)
+    acc, pot = sfo.pp(pos, mas)
+    sim = engine.Sim(N); sim.pos[:] = pos; sim.mas[:] = mas
+    sim.acc[:] = 123.0; sim.pot[:] = 456.0
+    i0, ni = 1234, 2500
+    assert engine.solve_gravity_part_part(sim, i0=i0, ni=ni) == 0
+    assert (sim.acc[:3 * i0] == 123.0).all() and (sim.acc[3 * (i0 + ni):] == 123.0).all()
+    assert (sim.pot[:i0] == 456.0).all() and (sim.pot[i0 + ni:] == 456.0).all()
+    assert rel_rms(sim.acc[3 * i0:3 * (i0 + ni)], acc[3 * i0:3 * (i0 + ni)]) <= TOL
+    # slices tile the full answer exactly (same kernel, same order)
+    full = run_pp(engine, pos, mas)
+    assert np.array_equal(sim.acc[3 * i0:3 * (i0 + ni)], full.acc[3 * i0:3 * (i0 + ni)])
+
+
+def test_deterministic(engine):
+    pos, vel, mas = sfo.initcond(20000)
+    a = run_pp(engine, pos, mas); b = run_pp(engine, pos, mas)
+    assert np.array_equal(a.acc, b.acc) and np.array_equal(a.pot, b.pot)
+
+
+def test_bad_arguments(engine):
+    sim = engine.Sim(16)
+    assert engine.solve_gravity_part_part(sim, i0=10, ni=10) == engine.STARFLOOD_FAILURE
+    assert "exceeds N" in engine.last_error()
+
+
+def test_full_size_properties(engine):
+    """N = 2^20 (BASELINE.json metric size): sampled targets against the oracle + size-independent
+    properties (Newton's third law: the `acc` the reference stores is a force, so it sums to zero;
+    pairwise symmetry of the potential energy)."""
+    N = 1 << 20
+    pos, vel, mas = sfo.initcond(N)
+    sim = engine.Sim(N, pinned=True); sim.pos[:] = pos; sim.mas[:] = mas
+    assert engine.solve_gravity_part_part(sim) == 0
+    i0, i1 = 500000, 500000 + 1024
+    acc, pot = sfo.pp(pos, mas, i0, i1)
+    assert rel_rms(sim.acc[3 * i0:3 * i1], acc[3 * i0:3 * i1]) <= TOL
+    assert rel_rms(sim.pot[i0:i1], pot[i0:i1]) <= TOL
+    f = sim.acc.reshape(-1, 3).astype(np.float64)
+    assert np.abs(f.sum(axis=0)).max() <= 1e-5 * np.abs(f).sum(axis=0).max()
+    assert np.isfinite(sim.acc).all() and (sim.pot < 0).all()

@@ -1,0 +1,97 @@
+"""Barnes-Hut walk parity (solve_gravity_part_tree, gravity.c:245-663) through the C ABI.  Gate from
+BASELINE.json: acc within 1e-4 rel-RMS of the reference's BH at the same theta; the EXACT flavour is held to
+the stronger bar it was built for: bit-identical acc and pot."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_rms
+from oracle import sfo
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def solve(engine, pos, mas, bounds, flavour, theta=0.5, max_nodes=None, **kw):
+    N = len(mas)
+    sim = engine.Sim(N); sim.pos[:] = pos; sim.mas[:] = mas
+    engine.tree_init(sim.tree, max_nodes or N + 64); sim.tree.bounds[:] = bounds
+    assert engine.tree_build(sim.tree, N, sim.pos, sim.mas) == 0, engine.last_error()
+    assert engine.solve_gravity_part_tree(sim, flavour, theta=theta, **kw) == 0, engine.last_error()
+    return sim
+
+
+@pytest.mark.parametrize("name", ["bh_n4096.npz", "bh_n4096_step7.npz"])
+def test_golden(engine, name):
+    g0 = np.load(os.path.join(G, "bh_n4096.npz")); g = np.load(os.path.join(G, name))
+    sim = solve(engine, g0["pos"], g0["mas"], g["bounds"], engine.WALK_EXACT)
+    assert np.array_equal(sim.acc, g["acc"]) and np.array_equal(sim.pot, g["pot"])
+    sim = solve(engine, g0["pos"], g0["mas"], g["bounds"], engine.WALK_FAST)
+    assert rel_rms(sim.acc, g["acc"]) <= 1e-4 and rel_rms(sim.pot, g["pot"]) <= 1e-4
+
+
+@pytest.mark.parametrize("N", [1, 9, 100, 5000, 65536])
+@pytest.mark.parametrize("theta", [0.5, 0.2, 1.0, 2.5])
+def test_sizes_and_thetas(engine, N, theta):
+    if N == 65536 and theta == 0.2:
+        pytest.skip("slow on the CPU oracle")
+    pos, vel, mas = sfo.initcond(N)
+    b = sfo.root_box(pos, 0)
+    rc, onodes, oc, *_ = sfo.tree_build_sorted(b, pos, mas, N + 64)
+    acc, pot, st = sfo.bh_walk(onodes[:oc], pos, mas, theta=np.float32(theta))
+    sim = solve(engine, pos, mas, b, engine.WALK_EXACT, theta=theta)
+    assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)      # theta 2.5 accepts the root itself
+    sim = solve(engine, pos, mas, b, engine.WALK_FAST, theta=theta)
+    assert rel_rms(sim.pot, pot) <= 1e-4
+    if N > 1:
+        assert rel_rms(sim.acc, acc) <= 1e-4
+
+
+def test_out_of_box_targets_and_self_subtraction(engine):
+    N = 5000
+    pos, vel, mas = sfo.initcond(N)
+    b = np.array([-0.5, -0.4, -0.6, 0.7, 0.8, 0.6], np.float32)        # elongated box, 58 % of particles outside
+    pos[3 * 17:3 * 17 + 3] = [50.0, 60.0, -70.0]                       # accepts the root as a monopole
+    rc, onodes, oc, *_ = sfo.tree_build_sorted(b, pos, mas, 8192)
+    acc, pot, st = sfo.bh_walk(onodes[:oc], pos, mas)
+    assert st.self_sub > 0
+    sim = solve(engine, pos, mas, b, engine.WALK_EXACT, max_nodes=8192)
+    assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)
+
+
+def test_slices_tile_the_answer(engine):
+    N = 30000
+    pos, vel, mas = sfo.initcond(N)
+    b = sfo.root_box(pos, 0)
+    full = solve(engine, pos, mas, b, engine.WALK_EXACT)
+    sim = engine.Sim(N); sim.pos[:] = pos; sim.mas[:] = mas
+    engine.tree_init(sim.tree, N + 64); sim.tree.bounds[:] = b
+    assert engine.tree_build(sim.tree, N, sim.pos, sim.mas) == 0
+    for i0, ni in ((0, 10000), (10000, 7), (10007, 19993)):
+        assert engine.solve_gravity_part_tree(sim, engine.WALK_EXACT, i0=i0, ni=ni) == 0
+    assert np.array_equal(sim.acc, full.acc) and np.array_equal(sim.pot, full.pot)
+
+
+def test_needs_matching_tree(engine):
+    sim = engine.Sim(64); sim.mas[:] = 1
+    engine.tree_init(sim.tree, 64); sim.tree.bounds[:] = [-1, -1, -1, 1, 1, 1]
+    assert engine.tree_build(sim.tree, 64, sim.pos, sim.mas) in (0, -1)
+    other = engine.Sim(65); other.mas[:] = 1
+    assert engine.solve_gravity_part_tree(other) == engine.STARFLOOD_FAILURE
+
+
+def test_full_size(engine):
+    """C2: N = 2^20, theta = 0.5, root box of step 0: every particle bit-identical to the oracle walk
+    (which reproduces the reference bitwise)."""
+    N = 1 << 20
+    pos, vel, mas = sfo.initcond(N)
+    b = sfo.root_box(pos, 0)
+    rc, onodes, oc, *_ = sfo.tree_build_sorted(b, pos, mas, N)
+    acc, pot, st = sfo.bh_walk(onodes[:oc], pos, mas)
+    sim = solve(engine, pos, mas, b, engine.WALK_EXACT, max_nodes=N)
+    assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)
+    fast = solve(engine, pos, mas, b, engine.WALK_FAST, max_nodes=N)
+    assert rel_rms(fast.acc, acc) <= 1e-4 and rel_rms(fast.pot, pot) <= 1e-4
+    # walk statistics that the roofline model uses: V = opened + evals + empty = 514.3
+    assert abs((st.opened + st.evals + st.empty) / N - 514.3) < 0.1

@@ -1,0 +1,105 @@
+"""Host-side logic that runs without a GPU: the numpy IC generator and root box against the oracle, the RAW
+state layout, the target-slice partition, and the N > 1 data flow (all-gather of {x,y,z,m} slices) on the gloo
+backend with world_size 2."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import sfo
+from starflood_b200 import engine, ics
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_ics_match_reference_generator():
+    for N in (1, 1000, 20000):
+        p, v, m = ics.uniform_ball(N)
+        P, V, M = sfo.initcond(N)
+        assert np.array_equal(m, M)
+        # identical up to libm rounding of cos/sin/acos/cbrt in numpy vs glibc (in practice: identical)
+        assert np.abs(p - P).max() <= 1.2e-7 and np.abs(v - V).max() <= 1e-9
+    p0, v0, m0 = ics.uniform_ball(4096, outflow=0.0)
+    P0, V0, M0 = sfo.initcond(4096, outflow=0.0)
+    assert np.abs(v0 - V0).max() <= 1e-9
+
+
+def test_pcg4d_matches_oracle():
+    seeds = np.array([0x638FE17B, 0xB10BDCE7, 0x7B8ADB9B, 0xD8C5850E], np.uint32)
+    want = sfo.pcg4d(seeds)
+    got = ics.pcg4d(*[np.array([s], np.uint32) for s in seeds])
+    assert [int(x[0]) for x in got] == [int(x) for x in want]
+    assert [int(x) for x in engine._pcg4d(seeds)] == [int(x) for x in want]
+
+
+@pytest.mark.parametrize("step", [0, 1, 999])
+def test_root_box_matches_oracle(step):
+    pos, vel, mas = sfo.initcond(30000)
+    sim = engine.Sim(30000); sim.pos[:] = pos; sim.step_number = step
+    assert np.array_equal(engine.root_box(sim), sfo.root_box(pos, step))
+
+
+def test_sim_layout_is_raw_snapshot_layout():
+    # blocks of N reals at offsets POS 0, VEL 3, ACC 6, MAS 9, POT 10, KEN 11, PEN 12, [RAD 13, RHO 14, PRS 15]
+    N = 10
+    sim = engine.Sim(N, sph=True)
+    sim.mem[:] = np.arange(16 * N, dtype=np.float32)
+    assert sim.pos[0] == 0 and sim.vel[0] == 3 * N and sim.acc[0] == 6 * N and sim.mas[0] == 9 * N
+    assert sim.pot[0] == 10 * N and sim.rad[0] == 13 * N and sim.rho[0] == 14 * N and sim.prs[0] == 15 * N
+    assert engine.Sim(N).mem.size == 13 * N
+    r = sfo.RefSim("pp", 7) if sfo.ref_available("pp") else None
+    if r is not None:
+        assert r.mem.size == 13 * 7
+
+
+def test_slices_partition_targets():
+    for N in (1, 10, 1 << 20, 12345):
+        for G in (1, 2, 4, 8):
+            cuts = [(N * g) // G for g in range(G + 1)]
+            assert cuts[0] == 0 and cuts[-1] == N and all(b >= a for a, b in zip(cuts, cuts[1:]))
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from oracle import sfo
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+N = 3000
+pos, vel, mas = sfo.initcond(N)
+pm = np.concatenate([pos.reshape(-1, 3), mas[:, None]], axis=1).astype(np.float32)
+i0, i1 = (N * rank) // world, (N * (rank + 1)) // world
+mine = torch.from_numpy(pm[i0:i1].copy())
+# ragged slices: gather with explicit sizes (N is not a multiple of world in general)
+sizes = [((N * (g + 1)) // world - (N * g) // world) for g in range(world)]
+parts = [torch.empty(s, 4) for s in sizes]
+dist.all_gather(parts, mine)
+full = torch.cat(parts).numpy()
+assert np.array_equal(full, pm)
+# each rank evaluates its own target slice over all sources with the CPU restatement; together they tile the answer
+acc, pot = sfo.pp(np.ascontiguousarray(full[:, :3]).ravel(), np.ascontiguousarray(full[:, 3]), i0, i1)
+out = torch.from_numpy(np.concatenate([acc.reshape(-1, 3)[i0:i1], pot[i0:i1, None]], axis=1).copy())
+outs = [torch.empty(s, 4) for s in sizes]
+dist.all_gather(outs, out)
+got = torch.cat(outs).numpy()
+ref_acc, ref_pot = sfo.pp(pos, mas)
+assert np.array_equal(got[:, :3].ravel(), ref_acc) and np.array_equal(got[:, 3], ref_pot)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_gloo_slice_flow(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2

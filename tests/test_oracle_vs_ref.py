@@ -1,0 +1,61 @@
+"""Oracle vs the unmodified reference libraries (oracle/_ref/, built by oracle/build_ref.sh from
+/root/reference/src).  Skipped when the libraries are absent."""
+import numpy as np
+import pytest
+
+from oracle import sfo
+
+needs_ref = pytest.mark.skipif(not (sfo.ref_available("pp") and sfo.ref_available("tree") and sfo.ref_available("pp_sph")),
+                               reason="oracle/_ref not built (needs /root/reference)")
+
+
+@needs_ref
+@pytest.mark.parametrize("N", [257, 4096])
+def test_pp_matches_reference(N):
+    r = sfo.RefSim("pp", N); r.initcond(); r.solv(0)
+    pos, vel, mas = sfo.initcond(N)
+    assert np.array_equal(pos, r.pos) and np.array_equal(vel, r.vel) and np.array_equal(mas, r.mas)
+    acc, pot = sfo.pp(pos, mas)
+    assert np.array_equal(acc, r.acc) and np.array_equal(pot, r.pot)
+
+
+@needs_ref
+@pytest.mark.parametrize("N,step", [(1000, 0), (65536, 3)])
+def test_tree_and_walk_match_reference(N, step):
+    r = sfo.RefSim("tree", N); r.initcond(); r.solv(step)
+    pos, vel, mas = sfo.initcond(N)
+    b = sfo.root_box(pos, step)
+    ref_nodes = r.nodes().copy()
+    assert np.array_equal(b, np.array(ref_nodes[0]["bounds"]))
+    rc, nodes, n = sfo.tree_build_insert(b, pos, mas, len(ref_nodes) + 9)
+    assert rc == 0 and nodes[:n].tobytes() == ref_nodes.tobytes()           # same numbering, same bits
+    rc, snodes, sn, keys, perm, nin = sfo.tree_build_sorted(b, pos, mas, len(ref_nodes) + 9)
+    canon, nc = sfo.tree_canonicalise(ref_nodes)
+    assert rc == 0 and snodes[:sn].tobytes() == canon[:nc].tobytes()
+    acc, pot, st = sfo.bh_walk(snodes[:sn], pos, mas)
+    assert np.array_equal(acc, r.acc) and np.array_equal(pot, r.pot)
+    r.close()
+
+
+@needs_ref
+def test_sph_matches_reference():
+    N = 1500
+    r = sfo.RefSim("pp_sph", N); r.initcond(); r.solv(0)
+    pos, vel, mas, rad = sfo.initcond(N, sph=True)
+    acc, pot = sfo.pp(pos, mas)
+    rho = sfo.sph_density(pos, mas, rad); prs = sfo.sph_eos(rho)
+    acc = sfo.sph_force(pos, mas, rad, rho, prs, acc)
+    assert np.array_equal(rho, r.rho) and np.array_equal(prs, r.prs) and np.array_equal(acc, r.acc)
+
+
+@needs_ref
+def test_walk_statistics_match_survey():
+    # SURVEY App. C, N = 65536: 795.2 iterations, 274.2 evaluations, 49.6 opened, 74.2 empty visits per particle
+    N = 65536
+    pos, vel, mas = sfo.initcond(N)
+    b = sfo.root_box(pos, 0)
+    rc, nodes, n, keys, perm, nin = sfo.tree_build_sorted(b, pos, mas, N)
+    assert n == 42545
+    acc, pot, st = sfo.bh_walk(nodes[:n], pos, mas)
+    assert abs(st.iterations / N - 795.2) < 0.1 and abs(st.evals / N - 274.2) < 0.1
+    assert abs(st.opened / N - 49.6) < 0.1 and abs(st.empty / N - 74.2) < 0.1
