@@ -63,7 +63,9 @@ int sfe_init(int device);
 int sfe_shutdown(void);
 const char* sfe_last_error(void);
 /* Pin a host range (e.g. the whole sim.mem block, simulation.c:89) so that the copies of the host entry
- * points run at full PCIe rate.  Optional: unpinned ranges are staged through an internal pinned buffer. */
+ * points run at full PCIe rate.  Optional: unpinned ranges are staged through an internal pinned buffer.
+ * A registered range must be unregistered BEFORE it is freed (a stale registration makes later allocations
+ * at the same address look pinned while the DMA engine still targets the old physical pages). */
 int sfe_host_register(void* ptr, uint64_t bytes);
 int sfe_host_unregister(void* ptr);
 int sfe_get_timings(sfe_timings_t* out);

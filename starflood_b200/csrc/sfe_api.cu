@@ -259,7 +259,7 @@ extern "C" int sfe_tree_build(const float bounds[6], const float* pos, const flo
                               int depth_max, uint32_t nodes_max) {
     const char* fn = "sfe_tree_build";
     if (ensure_init(fn)) return SFE_FAILURE;
-    if (!bounds || !pos || !mas) { set_error(fn, "null pointer argument"); return SFE_FAILURE; }
+    if (!bounds || ((!pos || !mas) && N > 0)) { set_error(fn, "null pointer argument"); return SFE_FAILURE; }
     Ctx* c = g_ctx;
     t_begin(c);
     if (upload_particles(c, fn, pos, mas, N)) return SFE_FAILURE;

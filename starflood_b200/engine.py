@@ -13,6 +13,7 @@ every compute call fails with SFE_FAILURE / raises when the CUDA library or devi
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -130,6 +131,11 @@ def device_info():
     return {"sm_count": sm.value, "clock_khz": khz.value, "fp32_peak_tflops": peak.value}
 
 
+def _unregister(addr):
+    if _lib is not None:
+        _lib.sfe_host_unregister(addr)
+
+
 def _ptr(a):
     return a.ctypes.data if a is not None else None
 
@@ -160,7 +166,12 @@ class Sim:
         self.mem = mem
         self.tree = Tree()
         if pinned:
-            _check(lib().sfe_host_register(self.mem.ctypes.data, self.mem.nbytes), "sfe_host_register")
+            # pin the block for full-rate PCIe copies; MUST be undone before the memory is freed, otherwise the
+            # driver keeps a stale mapping and a later allocation at the same address is copied from / to the
+            # wrong physical pages
+            addr = self.mem.ctypes.data
+            _check(lib().sfe_host_register(addr, self.mem.nbytes), "sfe_host_register")
+            weakref.finalize(self, _unregister, addr)
 
     def find(self, name):
         first, width = self.OFFSETS[name]

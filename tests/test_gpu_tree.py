@@ -55,9 +55,9 @@ def test_sizes(engine, N):
 def test_out_of_box_ties_and_non_cubic_box(engine):
     N = 5000
     pos, vel, mas = sfo.initcond(N)
-    b = np.array([-0.5, -0.4, -0.6, 0.7, 0.8, 0.6], np.float32)
-    pos[0:3] = [0.1, 0.2, 0.0]                 # exactly on the root's mid planes, resident -> low side
-    pos[3 * 4000:3 * 4000 + 3] = [0.1, 0.2, 0.0]    # same point arriving later -> high side
+    b = np.array([-0.5, -0.375, -0.625, 0.75, 0.875, 0.625], np.float32)   # mid planes 0.125, 0.25, 0 are exact in fp32
+    pos[0:3] = [0.125, 0.25, 0.0]              # exactly on the root's mid planes, resident -> low side
+    pos[3 * 4000:3 * 4000 + 3] = [0.125, 0.25, 0.0]  # same point arriving later -> high side
     pos[3 * 17:3 * 17 + 3] = [50.0, 60.0, -70.0]
     mas = (mas * np.linspace(0.5, 1.5, N)).astype(np.float32)
     sim = check_against_oracle(engine, pos, mas, b, 8192)
