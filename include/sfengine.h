@@ -76,11 +76,12 @@ uint64_t sfe_launch_count(void);
 
 /* ---------------------------------------------------------------- host entry points */
 /* Replaces solve_gravity_part_part() (gravity.h:22, gravity.c:667-819): all-pairs softened gravity
- * including j == i; acc[3N] = -G m_i sum(...), pot[N] = -G sum(m_j / r). */
-int sfe_pp(const float* pos, const float* mas, float* acc, float* pot, uint32_t N, float G, float eps2);
+ * including j == i; acc[3N] = -grav_g m_i sum(...), pot[N] = -grav_g sum(m_j / r).
+ * (Parameter names avoid the reference's config.h macros G / EPSILON, which are visible where the shims include this.) */
+int sfe_pp(const float* pos, const float* mas, float* acc, float* pot, uint32_t N, float grav_g, float eps2);
 /* Same, for the target slice [i0, i0+ni) only; acc/pot are still indexed by global i. */
 int sfe_pp_slice(const float* pos, const float* mas, float* acc, float* pot, uint32_t N,
-                 uint32_t i0, uint32_t ni, float G, float eps2);
+                 uint32_t i0, uint32_t ni, float grav_g, float eps2);
 
 /* Replaces tree_build() (tree.h:44, tree.c:74-318).  bounds = tree_ptr->bounds as set by sim_solv()
  * (simulation.c:298-301).  The tree stays on the device; nothing is written to host memory.
@@ -91,9 +92,9 @@ int sfe_tree_build(const float bounds[6], const float* pos, const float* mas, ui
  * sfe_tree_build() on the same pos/mas.  theta is TREE_THETA (config.h:44), compared against
  * width^2/dist^2 exactly as gravity.c:377,448. */
 int sfe_bh(const float* pos, const float* mas, float* acc, float* pot, uint32_t N,
-           float G, float eps2, float theta, uint32_t flavour);
+           float grav_g, float eps2, float theta, uint32_t flavour);
 int sfe_bh_slice(const float* pos, const float* mas, float* acc, float* pot, uint32_t N,
-                 uint32_t i0, uint32_t ni, float G, float eps2, float theta, uint32_t flavour);
+                 uint32_t i0, uint32_t ni, float grav_g, float eps2, float theta, uint32_t flavour);
 /* Test / debug hooks: copy the device tree out in the reference's node_t layout with canonical
  * (breadth-first) numbering, and the 48-bit path keys + sorted permutation of the last build. */
 int sfe_tree_download(sfe_node_t* nodes, uint32_t max_nodes, uint32_t* num_nodes);
@@ -109,13 +110,13 @@ int sfe_sph(const float* pos, const float* mas, const float* rad, float* rho, fl
  * ncclAllGather of SURVEY 8(e) moves.  All pointers below are device pointers. */
 int sfe_dev_pack_pm4(const float* pos, const float* mas, void* pm4, uint32_t n, void* stream);
 int sfe_dev_pp(const void* pm4, uint32_t N, uint32_t i0, uint32_t ni, float* acc, float* pot,
-               float G, float eps2, void* stream);
+               float grav_g, float eps2, void* stream);
 int sfe_dev_tree_build(const float bounds[6], const void* pm4, uint32_t N, int depth_max,
                        uint32_t nodes_max, void* stream);
 /* Raises the deferred build status (node / depth overflow) after synchronising the stream. */
 int sfe_dev_tree_status(void* stream, uint32_t* num_nodes, uint32_t* num_inbox, uint32_t* depth);
 int sfe_dev_bh(const void* pm4, uint32_t N, uint32_t i0, uint32_t ni, float* acc, float* pot,
-               float G, float eps2, float theta, uint32_t flavour, void* stream);
+               float grav_g, float eps2, float theta, uint32_t flavour, void* stream);
 int sfe_dev_sph_density(const void* pm4, const float* rad, uint32_t N, uint32_t i0, uint32_t ni,
                         float* rho, void* stream);
 int sfe_dev_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float eos_n, void* stream);
