@@ -52,7 +52,7 @@ static int do_init(int device, const char* fn) {
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
     c->clock_khz = khz;
     SFE_CUDA(fn, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    SFE_CUDA(fn, cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    for (auto& sd : c->side) SFE_CUDA(fn, cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
     for (auto& ev : c->ev) SFE_CUDA(fn, cudaEventCreate(&ev));
     memset(&c->timings, 0, sizeof c->timings);
     g_ctx = c;
@@ -180,7 +180,7 @@ extern "C" int sfe_shutdown(void) {
     if (t.ev_init) {
         for (auto& ev : t.ev_level) cudaEventDestroy(ev);
         for (auto& ev : t.ev_perm) cudaEventDestroy(ev);
-        cudaEventDestroy(t.ev_side);
+        for (auto& ev : t.ev_side) cudaEventDestroy(ev);
         t.ev_init = false;
     }
     t.valid = false;
@@ -188,7 +188,7 @@ extern "C" int sfe_shutdown(void) {
     if (c->bounce) cudaFreeHost(c->bounce);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
-    if (c->side) cudaStreamDestroy(c->side);
+    for (auto& sd : c->side) if (sd) cudaStreamDestroy(sd);
     delete c;
     g_ctx = nullptr;
     return SFE_SUCCESS;

@@ -39,6 +39,7 @@ struct DevBuf {
 };
 
 // ---------------------------------------------------------------------------- tree (host-side handle)
+constexpr int SFE_SIDE_STREAMS = 4;  // the moment folds of consecutive levels overlap with each other and with the partitioning
 constexpr int SFE_MAX_LEVELS = 21;   // deepest supported TREE_DEPTH_MAX (21 * 3 = 63 key bits; the reference uses 16)
 
 struct Tree {
@@ -73,7 +74,7 @@ struct Tree {
     DevBuf meta;         // uint32_t[M_WORDS]
     DevBuf rec0, rec1, rec2;   // walk records
     uint32_t* meta_host = nullptr;     // pinned, (SFE_MAX_LEVELS + 2) snapshots of meta
-    cudaEvent_t ev_level[SFE_MAX_LEVELS + 2], ev_perm[SFE_MAX_LEVELS + 2], ev_side;
+    cudaEvent_t ev_level[SFE_MAX_LEVELS + 2], ev_perm[SFE_MAX_LEVELS + 2], ev_side[SFE_SIDE_STREAMS];
     bool ev_init = false;
 };
 
@@ -83,7 +84,7 @@ struct Ctx {
     int sm_count = 0;
     int clock_khz = 0;
     cudaStream_t stream = nullptr;     // engine stream for the host entry points
-    cudaStream_t side = nullptr;       // overlapped work (long moment folds)
+    cudaStream_t side[SFE_SIDE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // overlapped work (moment folds)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // device copies of the host arrays
     DevBuf d_pos, d_mas, d_pm4, d_acc, d_pot, d_rad, d_rho, d_prs;

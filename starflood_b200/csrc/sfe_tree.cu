@@ -29,6 +29,8 @@
 #include "sfe_internal.cuh"
 #include "sfe_tree.cuh"
 #include "sfe_scan.cuh"
+#include <chrono>
+#include <stdlib.h>
 
 namespace sfe {
 
@@ -414,59 +416,167 @@ __global__ void __launch_bounds__(256) part_scatter_kernel(TreeDev t, int d) {
 }
 
 // ============================================================================ moments (tree.c:166-169, :302-310)
-// One warp per node of level d.  Lanes gather 32 members at a time, round the products, park them in shared
-// memory; lanes 0..3 then run the four dependent fp32 add chains (x, y, z, mass) over the chunk.
-constexpr int MOM_WARPS = 4;
-constexpr int MOM_DEPTH = 8;   // chunks of 32 members kept in flight per warp
-__global__ void __launch_bounds__(MOM_WARPS * 32) moments_kernel(TreeDev t, int d,
-                                                                 uint32_t* __restrict__ gate /* {needed, done} or null */) {
-    __shared__ float chunk[MOM_WARPS][MOM_DEPTH][32][4];
+// params += {m*x, m*y, m*z, m} is an fp32 LEFT FOLD in arrival (= slot) order, so every node is a serial
+// dependent-add chain (FADD latency: 4 cycles per member) that no reduction tree may replace.
+// One lane per (node, component): a warp carries 32 chains (8 nodes) at once and the 8 depth-1 cells - the
+// longest chains of a build, N/8 members each - share ONE warp.  The members of a node are contiguous in
+// spm4[d].  Two kernels per level:
+//   moments_long_kernel   nodes with more than ML_MIN members.  Warp-specialised CTA: eight PRODUCER warps
+//                         stream the raw float4 records into a shared-memory ring with cp.async (LDGSTS),
+//                         ML_R batches deep so HBM/L2 latency is hidden, round the products m*x, m*y, m*z
+//                         (no FMA) and park them component-major; the CONSUMER warp does nothing but
+//                         LDS.128 + 4 dependent FADDs per 4 members, i.e. the chain runs at the FADD latency.
+//   moments_short_kernel  the (many) small nodes: one lane per (node, component) straight from global memory.
+constexpr int ML_B = 128;                // members per node per batch
+constexpr int ML_R = 4;                  // raw ring depth in batches
+constexpr int ML_BP = ML_B + 4;          // padded row of the product buffer: conflict-free LDS.128 across 32 rows
+constexpr int ML_THREADS = 288;          // warp 0 consumer, warps 1-8 producers (one node each)
+constexpr uint32_t ML_MIN = 64u;         // nodes with more members than this take the pipelined kernel
+constexpr size_t ML_SMEM = (size_t)ML_R * 8 * ML_B * 16 + (size_t)2 * 32 * ML_BP * 4;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(ML_THREADS) moments_long_kernel(TreeDev t, int d,
+                                                                  uint32_t* __restrict__ gate /* {needed, done} or null */) {
+    extern __shared__ __align__(16) unsigned char ml_smem[];
+    float4 (*raw)[8][ML_B] = reinterpret_cast<float4 (*)[8][ML_B]>(ml_smem);                                  // [ML_R][8][ML_B]
+    float (*prod)[32][ML_BP] = reinterpret_cast<float (*)[32][ML_BP]>(ml_smem + (size_t)ML_R * 8 * ML_B * 16);  // [2][32][ML_BP]
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t b = t.meta[M_LV_BEGIN + d], e = t.meta[M_LV_END + d];
     const float4* __restrict__ spm4 = t.spm4[d];
-    for (uint32_t n = b + blockIdx.x * MOM_WARPS + warp; n < e; n += gridDim.x * MOM_WARPS) {
-        const uint2 sg = t.seg[n];
-        const uint32_t cnt = sg.y - sg.x;
-        const float4* __restrict__ src = spm4 + sg.x;
-        float sum = 0.f;
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (uint32_t base = 0; base < cnt; base += 32 * MOM_DEPTH) {
-            // MOM_DEPTH independent coalesced loads in flight, products rounded one by one (tree.c:166-169)
-            float4 pr[MOM_DEPTH];
+    for (uint32_t base = b + blockIdx.x * 8u; base < e; base += gridDim.x * 8u) {
+        // every thread looks at the 8 segments of the group (uniform loads) for the trip count
+        uint32_t maxcnt = 0u;
 #pragma unroll
-            for (int q = 0; q < MOM_DEPTH; q++) {
-                const uint32_t j = base + q * 32 + lane;
-                pr[q] = j < cnt ? src[j] : zero4;
-            }
-            __syncwarp();   // previous batch fully consumed
+        for (int i = 0; i < 8; i++) {
+            const uint2 sg = base + i < e ? t.seg[base + i] : make_uint2(0u, 0u);
+            const uint32_t cn = sg.y - sg.x;
+            maxcnt = max(maxcnt, cn > ML_MIN ? cn : 0u);
+        }
+        if (maxcnt == 0u) continue;
+        const uint32_t nbatch = (maxcnt + ML_B - 1) / ML_B;
+        if (warp == 0u) {
+            // ---------------------------------------------------------------- consumer: 32 chains
+            float sum = 0.f;
+            for (uint32_t k = 0; k < nbatch; k++) {
+                __syncthreads();                                   // prod[k & 1] is complete
+                const float4* row = reinterpret_cast<const float4*>(&prod[k & 1u][lane][0]);
 #pragma unroll
-            for (int q = 0; q < MOM_DEPTH; q++) {
-                float* bq = chunk[warp][q][lane];
-                bq[0] = __fmul_rn(pr[q].w, pr[q].x);
-                bq[1] = __fmul_rn(pr[q].w, pr[q].y);
-                bq[2] = __fmul_rn(pr[q].w, pr[q].z);
-                bq[3] = pr[q].w;
-            }
-            __syncwarp();
-            if (lane < 4) {
-                const uint32_t m = min((uint32_t)(32 * MOM_DEPTH), cnt - base);
-                const float* flat = &chunk[warp][0][0][0];
-                if (m == 32u * MOM_DEPTH) {
-#pragma unroll 32
-                    for (uint32_t j = 0; j < 32u * MOM_DEPTH; j++) sum = __fadd_rn(sum, flat[j * 4 + lane]);
-                } else {
-                    for (uint32_t j = 0; j < m; j++) sum = __fadd_rn(sum, flat[j * 4 + lane]);
+                for (int u = 0; u < ML_B / 4; u++) {
+                    const float4 v = row[u];                       // pads are +0: s + 0 == s
+                    sum = __fadd_rn(sum, v.x); sum = __fadd_rn(sum, v.y);   // tree.c:166-169
+                    sum = __fadd_rn(sum, v.z); sum = __fadd_rn(sum, v.w);
                 }
             }
-        }
-        __syncwarp();
-        const float mass = __shfl_sync(0xFFFFFFFFu, sum, 3);
-        if (lane < 4) {
-            const float inv = 0.f < mass ? __fdiv_rn(1.0f, mass) : 1.0f;   // tree.c:303-304
-            t.nodes[n].params[lane] = lane < 3 ? __fmul_rn(sum, inv) : sum;
+            __syncthreads();                                       // group done: buffers may be reused
+            const uint32_t q = lane >> 2, c = lane & 3u;
+            const uint2 msg = base + q < e ? t.seg[base + q] : make_uint2(0u, 0u);
+            const uint32_t mycount = (msg.y - msg.x) > ML_MIN ? (msg.y - msg.x) : 0u;
+            const float mass = __shfl_sync(0xFFFFFFFFu, sum, lane | 3u);
+            if (mycount) {
+                const float inv = 0.f < mass ? __fdiv_rn(1.0f, mass) : 1.0f;   // tree.c:303-304
+                t.nodes[base + q].params[c] = c < 3u ? __fmul_rn(sum, inv) : sum;
+            }
+        } else {
+            // ---------------------------------------------------------------- producers: one node per warp
+            const uint32_t node = warp - 1u;
+            const uint2 sg = base + node < e ? t.seg[base + node] : make_uint2(0u, 0u);
+            const uint32_t cnt = (sg.y - sg.x) > ML_MIN ? (sg.y - sg.x) : 0u;
+            const float4* __restrict__ src = spm4 + sg.x;
+            auto issue = [&](uint32_t k) {       // raw batch k -> ring slot k % ML_R
+                const uint32_t j0 = k * ML_B;
+                if (j0 < cnt) {
+                    float4* dst = &raw[k % ML_R][node][0];
+#pragma unroll
+                    for (int h = 0; h < ML_B / 32; h++) {
+                        const uint32_t j = lane + 32u * h;
+                        if (j0 + j < cnt) cp_async16(dst + j, src + j0 + j);
+                    }
+                }
+                cp_async_commit();               // one (possibly empty) group per batch index keeps the wait arithmetic uniform
+            };
+            auto transpose = [&](uint32_t k) {   // raw batch k -> prod[k & 1], products rounded one by one
+                const uint32_t j0 = k * ML_B;
+                const float4* rw = &raw[k % ML_R][node][0];
+                float* pr = &prod[k & 1u][node * 4u][0];
+#pragma unroll
+                for (int h = 0; h < ML_B / 32; h++) {
+                    const uint32_t j = lane + 32u * h;
+                    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j0 + j < cnt) r = rw[j];
+                    pr[j] = __fmul_rn(r.w, r.x);
+                    pr[ML_BP + j] = __fmul_rn(r.w, r.y);
+                    pr[2 * ML_BP + j] = __fmul_rn(r.w, r.z);
+                    pr[3 * ML_BP + j] = r.w;
+                }
+            };
+#pragma unroll 1
+            for (uint32_t k = 0; k < (uint32_t)ML_R; k++) issue(k);
+            cp_async_wait<ML_R - 1>();
+            __syncwarp();
+            transpose(0u);
+            __syncwarp();
+            issue((uint32_t)ML_R);
+#pragma unroll 1
+            for (uint32_t k = 0; k < nbatch; k++) {
+                __syncthreads();                                   // hands prod[k & 1] to the consumer
+                if (k + 1u < nbatch) {
+                    cp_async_wait<ML_R - 1>();                     // raw batch k+1 has landed
+                    __syncwarp();
+                    transpose(k + 1u);
+                    __syncwarp();
+                    issue(k + 1u + ML_R);
+                }
+            }
+            cp_async_wait<0>();
+            __syncthreads();
         }
     }
+}
+
+__global__ void __launch_bounds__(256) moments_short_kernel(TreeDev t, int d, uint32_t* __restrict__ gate) {
+    if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
+    const uint32_t c = threadIdx.x & 3u;
+    const uint32_t b = t.meta[M_LV_BEGIN + d], e = t.meta[M_LV_END + d];
+    const float4* __restrict__ spm4 = t.spm4[d];
+    const uint32_t quads = (e - b);
+    for (uint32_t qd = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; qd < ((quads + 7u) & ~7u); qd += (gridDim.x * blockDim.x) >> 2) {
+        const uint32_t n = b + qd;
+        const bool live = n < e;
+        const uint2 sg = live ? t.seg[n] : make_uint2(0u, 0u);
+        uint32_t cnt = sg.y - sg.x;
+        if (cnt > ML_MIN) cnt = 0u;                               // the pipelined kernel owns the long nodes
+        const float* __restrict__ src = reinterpret_cast<const float*>(spm4 + sg.x);
+        float sum = 0.f;
+#pragma unroll 4
+        for (uint32_t j = 0; j < cnt; j++) {
+            const float m = __ldg(src + 4u * j + 3u);
+            const float p = __fmul_rn(m, __ldg(src + 4u * j + c));  // tree.c:166-168: product rounded, then added
+            sum = __fadd_rn(sum, c == 3u ? m : p);                  // tree.c:169
+        }
+        const float mass = __shfl_sync(0xFFFFFFFFu, sum, (threadIdx.x & 31u) | 3u);
+        if (cnt) {
+            const float inv = 0.f < mass ? __fdiv_rn(1.0f, mass) : 1.0f;   // tree.c:303-304
+            t.nodes[n].params[c] = c < 3u ? __fmul_rn(sum, inv) : sum;
+        }
+    }
+}
+
+static int launch_moments(Ctx* c, const TreeDev& dv, int d, uint32_t* gate, bool single, cudaStream_t s, const char* fn) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SFE_CUDA(fn, cudaFuncSetAttribute(moments_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ML_SMEM));
+        attr_set = true;
+    }
+    moments_long_kernel<<<single ? 1 : c->sm_count * 2, ML_THREADS, ML_SMEM, s>>>(dv, d, gate);
+    if (check_launch(fn)) return SFE_FAILURE;
+    moments_short_kernel<<<single ? 1 : c->sm_count * 8, 256, 0, s>>>(dv, d, gate);
+    return check_launch(fn);
 }
 
 // ============================================================================ finalize: walk records
@@ -499,6 +609,14 @@ __global__ void finalize_kernel(TreeDev t, uint32_t* __restrict__ gate /* null: 
 }
 
 // ============================================================================ host side
+static bool trace_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SFE_TRACE"); v = (e && atoi(e) > 0) ? 1 : 0; }
+    return v == 1;
+}
+
+static cudaEvent_t g_trace_ev[2 * (SFE_MAX_LEVELS + 3)];
+
 static TreeDev make_dev(Tree& t) {
     TreeDev d;
     memset(&d, 0, sizeof d);
@@ -552,9 +670,10 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     if (!t.ev_init) {
         for (int k = 0; k < SFE_MAX_LEVELS + 2; k++) {
             SFE_CUDA(fn, cudaEventCreateWithFlags(&t.ev_level[k], cudaEventDisableTiming));
-            SFE_CUDA(fn, cudaEventCreateWithFlags(&t.ev_perm[k], cudaEventDisableTiming));
+            SFE_CUDA(fn, cudaEventCreateWithFlags(&t.ev_perm[k], trace_enabled() ? cudaEventDefault : cudaEventDisableTiming));
         }
-        SFE_CUDA(fn, cudaEventCreateWithFlags(&t.ev_side, cudaEventDisableTiming));
+        for (auto& ev : t.ev_side) SFE_CUDA(fn, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        if (trace_enabled()) for (auto& ev : g_trace_ev) SFE_CUDA(fn, cudaEventCreate(&ev));
         t.ev_init = true;
     }
 
@@ -570,7 +689,10 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     SFE_CUDA(fn, cudaEventRecord(t.ev_perm[0], s));
 
     int levels_run = 0;
+    double host_us[SFE_MAX_LEVELS + 3];
+    const auto host_t0 = std::chrono::steady_clock::now();
     for (int d = 0; d <= depth_max; d++) {
+        host_us[d] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count();
         // make sure perm[d+1] exists (first build at this depth only) and refresh the device view
         if (t.perm[d + 1].cap < n1 * 4 || t.spm4[d + 1].cap < n1 * 16) {
             if (t.perm[d + 1].reserve(n1 * 4, fn) || t.spm4[d + 1].reserve(n1 * 16, fn)) return SFE_FAILURE;
@@ -584,11 +706,13 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
             if (!more) break;   // level d-1 is empty (or the build failed): nothing left to split
         }
         levels_run = d + 1;
-        // moments of level d on the side stream (needs perm[d]); the root's fold is deferred
-        SFE_CUDA(fn, cudaStreamWaitEvent(c->side, t.ev_perm[d], 0));
+        // moments of level d on a side stream (needs perm[d]); the root's fold is deferred
         if (d > 0) {
-            moments_kernel<<<c->sm_count * 4, MOM_WARPS * 32, 0, c->side>>>(dv, d, nullptr);
-            if (check_launch(fn)) return SFE_FAILURE;
+            cudaStream_t side = c->side[d % SFE_SIDE_STREAMS];
+            SFE_CUDA(fn, cudaStreamWaitEvent(side, t.ev_perm[d], 0));
+            if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d], side);
+            if (launch_moments(c, dv, d, nullptr, false, side, fn)) return SFE_FAILURE;
+            if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d + 1], side);
         }
         // child allocation for level d
         {
@@ -611,11 +735,36 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         SFE_CUDA(fn, cudaEventRecord(t.ev_perm[d + 1], s));
     }
     t.final_perm = levels_run;   // perm[levels_run] is the last one written by a scatter
-    // join the side stream, then build the walk records
-    SFE_CUDA(fn, cudaEventRecord(t.ev_side, c->side));
-    SFE_CUDA(fn, cudaStreamWaitEvent(s, t.ev_side, 0));
+    if (trace_enabled()) {   // SFE_TRACE=1: where does the build spend its time (device time per level vs host enqueue time)
+        host_us[levels_run] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count();
+        cudaStreamSynchronize(s);
+        for (int d = 0; d < levels_run; d++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, t.ev_perm[d], t.ev_perm[d + 1]);
+            fprintf(stderr, "[sfe trace] level %2d: device %8.1f us   host enqueue at %8.1f us (+%.1f)\n", d, ms * 1e3, host_us[d], host_us[d + 1] - host_us[d]);
+        }
+    }
+    // join the side streams, then build the walk records
+    for (int k = 0; k < SFE_SIDE_STREAMS; k++) {
+        SFE_CUDA(fn, cudaEventRecord(t.ev_side[k], c->side[k]));
+        SFE_CUDA(fn, cudaStreamWaitEvent(s, t.ev_side[k], 0));
+    }
+    if (trace_enabled()) cudaEventRecord(g_trace_ev[0], s);
     finalize_kernel<<<c->sm_count * 4, 256, 0, s>>>(dv, nullptr);
     if (check_launch(fn)) return SFE_FAILURE;
+    if (trace_enabled()) {
+        cudaEventRecord(g_trace_ev[1], s);
+        cudaStreamSynchronize(s);
+        float a = 0.f, b = 0.f;
+        for (int d = 1; d < levels_run; d++) {
+            cudaEventElapsedTime(&a, t.ev_perm[0], g_trace_ev[2 * d]);
+            cudaEventElapsedTime(&b, t.ev_perm[0], g_trace_ev[2 * d + 1]);
+            fprintf(stderr, "[sfe trace] moments level %2d: start %8.1f us  end %8.1f us\n", d, a * 1e3, b * 1e3);
+        }
+        cudaEventElapsedTime(&a, t.ev_perm[0], g_trace_ev[0]);
+        cudaEventElapsedTime(&b, t.ev_perm[0], g_trace_ev[1]);
+        fprintf(stderr, "[sfe trace] finalize: start %8.1f us  end %8.1f us (relative to the end of the compaction)\n", a * 1e3, b * 1e3);
+    }
     SFE_CUDA(fn, cudaMemcpyAsync(t.meta_host + (size_t)(SFE_MAX_LEVELS + 1) * M_WORDS, t.meta.p, sizeof(uint32_t) * M_WORDS,
                                  cudaMemcpyDeviceToHost, s));
     t.pm4_of_build = pm4;
@@ -663,8 +812,7 @@ int tree_root_moments(Ctx* c, const float4* pm4, uint32_t i0, uint32_t ni, float
     if (force) root_force_kernel<<<1, 1, 0, s>>>(gate);
     else root_gate_kernel<<<(ni + 255) / 256, 256, 0, s>>>(dv, pm4, i0, ni, theta, gate);
     if (check_launch(fn)) return SFE_FAILURE;
-    moments_kernel<<<1, MOM_WARPS * 32, 0, s>>>(dv, 0, gate);
-    if (check_launch(fn)) return SFE_FAILURE;
+    if (launch_moments(c, dv, 0, gate, true, s, fn)) return SFE_FAILURE;
     finalize_kernel<<<1, 32, 0, s>>>(dv, gate);
     if (check_launch(fn)) return SFE_FAILURE;
     root_done_kernel<<<1, 1, 0, s>>>(gate);
