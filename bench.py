@@ -378,7 +378,7 @@ def run_engine(args):
     prof = os.path.join(ROOT, "profiles", "walk_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            traffic = json.load(open(prof)).get(args.flavour, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"kernel": "walk_kernel (sfe_dev_bh)", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",

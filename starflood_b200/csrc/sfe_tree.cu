@@ -382,7 +382,12 @@ __global__ void children_kernel(TreeDev t, int d) {
             for (int k = 0; k < 4; k++) ch.params[k] = 0.f;
             t.nodes[c] = ch;
             t.seg[c] = make_uint2(start, start + cnt);
-            t.next[c] = o < 7u ? c + 1u : nxt;
+            // depth-first successor when c is not opened: the next NON-EMPTY sibling, else the parent's successor.
+            // The reference only steps back to the parent at an empty node (gravity.c:324-328), so leaving empty
+            // nodes out of the walk links changes neither the visit order nor the sums.
+            uint32_t succ = nxt;
+            for (uint32_t o2 = 7u; o2 > o; o2--) if (t.counts[(size_t)n * 8u + o2] > 0u) succ = base + o2;
+            t.next[c] = succ;
             start += cnt;
         }
     }
@@ -587,17 +592,29 @@ __global__ void finalize_kernel(TreeDev t, uint32_t* __restrict__ gate /* null: 
         const sfe_node_t nd = t.nodes[n];
         const float* b = nd.bounds;
         WalkRec0 r0;
-        r0.cx = __fmul_rn(0.5f, __fadd_rn(b[0], b[3]));   // gravity.c:353-357
-        r0.cy = __fmul_rn(0.5f, __fadd_rn(b[1], b[4]));
-        r0.cz = __fmul_rn(0.5f, __fadd_rn(b[2], b[5]));
         const float ex = __fsub_rn(b[3], b[0]), ey = __fsub_rn(b[4], b[1]), ez = __fsub_rn(b[5], b[2]);
-        const float w = __fmul_rn((float)(1.0 / 3.0), __fadd_rn(__fadd_rn(ex, ey), ez));   // gravity.c:368-372
-        r0.w2 = __fmul_rn(w, w);
-        r0.next = t.next[n];
         const uint32_t kind = nd.bodies == 0u ? KIND_EMPTY : nd.bodies == 1u ? KIND_SINGLE : nd.bodies <= 8u ? KIND_LEAF : KIND_INTERNAL;
-        r0.child_kind = (kind << 30) | (kind == KIND_INTERNAL ? nd.branch[0] : 0u);
-        // conservative squared radius (about the geometric centre) outside of which a point cannot be inside the box
-        r0.rin2 = 0.25f * (ex * ex + ey * ey + ez * ez) * 1.0001f + 1e-30f;
+        // squared-distance filters in front of the exact inside-the-box test: generous by a few ulps of the
+        // coordinates, because the centre / COM are themselves rounded
+        const float slack = 4e-6f * (fabsf(b[0]) + fabsf(b[1]) + fabsf(b[2]) + fabsf(b[3]) + fabsf(b[4]) + fabsf(b[5]));
+        const float diag = sqrtf(ex * ex + ey * ey + ez * ez);
+        uint32_t child = 0u;
+        if (kind == KIND_INTERNAL) {
+            r0.a[0] = __fmul_rn(0.5f, __fadd_rn(b[0], b[3]));   // gravity.c:353-357
+            r0.a[1] = __fmul_rn(0.5f, __fadd_rn(b[1], b[4]));
+            r0.a[2] = __fmul_rn(0.5f, __fadd_rn(b[2], b[5]));
+            const float w = __fmul_rn((float)(1.0 / 3.0), __fadd_rn(__fadd_rn(ex, ey), ez));   // gravity.c:368-372
+            r0.a[3] = __fmul_rn(w, w);
+            // conservative squared radius about the geometric centre outside of which a point cannot be inside the box
+            r0.rin2 = (0.5f * diag + slack) * (0.5f * diag + slack) * 1.0001f + 1e-30f;
+            for (uint32_t o = 8u; o > 0u; o--) if (t.counts[(size_t)n * 8u + o - 1u] > 0u) child = nd.branch[o - 1u];
+        } else {
+            r0.a[0] = nd.params[0]; r0.a[1] = nd.params[1]; r0.a[2] = nd.params[2]; r0.a[3] = nd.params[3];
+            // the COM lies inside the box, so does a target that must be self-subtracted: at most one diagonal apart
+            r0.rin2 = (diag + slack) * (diag + slack) * 1.0001f + 1e-30f;
+        }
+        r0.next = t.next[n];
+        r0.child_kind = (kind << 30) | child;
         r0.pad = 0.f;
         t.rec0[n] = r0;
         t.rec1[n] = make_float4(nd.params[0], nd.params[1], nd.params[2], nd.params[3]);

@@ -20,12 +20,14 @@ enum : int {
 // walk records --------------------------------------------------------------------------------------
 constexpr uint32_t KIND_EMPTY = 0u, KIND_SINGLE = 1u, KIND_LEAF = 2u, KIND_INTERNAL = 3u;
 
-struct __align__(16) WalkRec0 {   // 32 B: everything the traversal decision needs
-    float cx, cy, cz;             // geometric centre (gravity.c:353-357)
-    float w2;                     // fl(width^2)     (gravity.c:368-372,377)
-    uint32_t next;                // next node in depth-first order when this node is not opened
-    uint32_t child_kind;          // kind << 30 | first child (internal nodes)
-    float rin2;                   // beyond this squared distance from the centre a point is surely outside the box
+struct __align__(32) WalkRec0 {   // 32 B = one L1 sector, fetched with ONE 256-bit load: everything a visit decides on
+    float a[4];                   // internal: geometric centre xyz (gravity.c:353-357), fl(width^2) (gravity.c:368-372,377)
+                                  // leaf    : centre of mass xyz, mass - a leaf is always a monopole (gravity.c:331), so
+                                  //           its visit costs exactly this one sector
+    uint32_t next;                // next NON-EMPTY node in depth-first order when this node is not opened
+    uint32_t child_kind;          // kind << 30 | first NON-EMPTY child (internal nodes)
+    float rin2;                   // beyond this squared distance (internal: from the centre; leaf: from the COM) a point
+                                  // is surely outside the box: filter in front of the exact bounds test (gravity.c:473-476)
     float pad;
 };
 struct __align__(16) WalkRec2 {   // 32 B: bounds, only for the self-subtraction test (gravity.c:473-476)

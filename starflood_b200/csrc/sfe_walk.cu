@@ -70,19 +70,32 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
     const float4* __restrict__ rec1 = t.rec1;
     const WalkRec2* __restrict__ rec2 = t.rec2;
 
-    uint32_t n = 0u;
+    uint32_t n = M == 0u ? NODE_END : 0u;   // an empty root is never evaluated (gravity.c:324-328)
     while (n != NODE_END) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(&rec0[n]));
-        const uint4 b = __ldg(reinterpret_cast<const uint4*>(&rec0[n]) + 1);
-        const uint32_t next = b.x, kind = b.y >> 30;
-        if (kind == KIND_EMPTY) { n = next; continue; }                           // gravity.c:324-328
-        const float ox = __fsub_rn(a.x, x), oy = __fsub_rn(a.y, y), oz = __fsub_rn(a.z, z);
-        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ox, ox), __fmul_rn(oy, oy)), __fmul_rn(oz, oz));
-        if (kind == KIND_INTERNAL && opens(a.w, d2, theta)) { n = b.y & 0x3FFFFFFFu; continue; }   // gravity.c:448-453
+        // one 256-bit load = one L1 sector: {a[4], next, child|kind, rin2, -}
+        uint32_t r[8];
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "l"(rec0 + n));
+        const float a0 = __uint_as_float(r[0]), a1 = __uint_as_float(r[1]), a2 = __uint_as_float(r[2]), a3 = __uint_as_float(r[3]);
+        const uint32_t next = r[4], kind = r[5] >> 30;
+        const float rin2 = __uint_as_float(r[6]);
+        float rx, ry, rz, mj;
+        bool maybe_inside;
+        if (kind == KIND_INTERNAL) {
+            const float ox = __fsub_rn(a0, x), oy = __fsub_rn(a1, y), oz = __fsub_rn(a2, z);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ox, ox), __fmul_rn(oy, oy)), __fmul_rn(oz, oz));
+            if (opens(a3, d2, theta)) { n = r[5] & 0x3FFFFFFFu; continue; }   // gravity.c:448-453 (first non-empty child)
+            const float4 cm = __ldg(&rec1[n]);                                   // accepted: monopole of the cell
+            rx = cm.x; ry = cm.y; rz = cm.z; mj = cm.w;
+            maybe_inside = d2 <= rin2;
+        } else {                                                                 // leaf: the record IS the monopole
+            rx = a0; ry = a1; rz = a2; mj = a3;
+            const float ux = x - rx, uy = y - ry, uz = z - rz;
+            maybe_inside = kind != KIND_SINGLE && (ux * ux + uy * uy + uz * uz) <= rin2;
+        }
         // monopole (gravity.c:463-548)
-        const float4 cm = __ldg(&rec1[n]);
-        float rx = cm.x, ry = cm.y, rz = cm.z, mj = cm.w;
-        if (kind != KIND_SINGLE && d2 <= __uint_as_float(b.z)) {
+        if (maybe_inside) {
             const float4 lo = __ldg(reinterpret_cast<const float4*>(&rec2[n]));
             const float4 hi = __ldg(reinterpret_cast<const float4*>(&rec2[n]) + 1);
             // lo = {lo.x, lo.y, lo.z, hi.x}, hi = {hi.y, hi.z, -, -}
