@@ -99,6 +99,10 @@ int sfe_bh_slice(const float* pos, const float* mas, float* acc, float* pot, uin
  * (breadth-first) numbering, and the 48-bit path keys + sorted permutation of the last build. */
 int sfe_tree_download(sfe_node_t* nodes, uint32_t max_nodes, uint32_t* num_nodes);
 int sfe_tree_keys_download(uint64_t* keys, uint32_t* perm, uint32_t N, uint32_t* num_inbox);
+/* Test hook: the EXACT walk evaluates 1/q, sqrt(q) and 1/sqrt(q) (gravity.c:754-759) with short Newton sequences
+ * instead of the IEEE intrinsics; this compares the two for EVERY float of the range in which the sequences are
+ * used and returns the number of mismatching bit patterns per function (must be {0, 0, 0}). */
+int sfe_selftest_exact_math(uint64_t mismatches[3]);
 
 /* Replaces solve_sph() (sph.h:6, sph.c:14-283): density (all pairs, no cutoff), EOS
  * P = (eos_k rho)^(1/eos_n + 1), pressure force added to acc (read-modify-write) for r^2 <= cutoff2. */

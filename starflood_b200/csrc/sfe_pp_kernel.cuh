@@ -138,4 +138,125 @@ pp_kernel(const float4* __restrict__ pairs,   // pair records, whole tiles
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Target-pair variant: the two packed lanes are two TARGETS, the source is a broadcast scalar record
+// {x, y, z, m} (16 B, one LDS.128 per source).  Same 13 FMA-pipe lane-ops + 1 MUFU per interaction, but half
+// the shared-memory -> register traffic per interaction of the source-pair kernel above (the LDS write-backs
+// compete with the FMA pipe for register-file ports), and no source re-packing pass: tiles are bulk-copied
+// straight from the {x,y,z,m} array the all-gather produces.  Thread t of a CTA owns targets
+// i = blockIdx.x * THREADS * 2T + k * 2 * THREADS + {t, t + THREADS}.
+template <int T, int THREADS, int TILE>
+constexpr size_t pp_tp_smem_bytes() { return (size_t)PP_STAGES * TILE * 16 + (size_t)T * 16 * THREADS * 4 + PP_STAGES * 8; }
+
+template <int T, int THREADS, int MINBLOCKS, int TILE, int UNROLL>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS)
+pp_kernel_tp(const float4* __restrict__ src,     // sources {x,y,z,m}, padded to whole tiles
+             const float4* __restrict__ pm4,     // targets are read from here
+             uint32_t N, uint32_t i0, uint32_t ni, uint32_t tiles_total, uint32_t tiles_per_split, float eps2,
+             float4* __restrict__ partial /* [gridDim.y][ni] */) {
+    constexpr int TILE_BYTES = TILE * 16;
+    extern __shared__ __align__(128) unsigned char pp_smem[];   // pp_tp_smem_bytes<T, THREADS, TILE>()
+    float4 (*tile)[TILE] = reinterpret_cast<float4 (*)[TILE]>(pp_smem);                                 // [PP_STAGES][TILE]
+    float (*stot)[THREADS] = reinterpret_cast<float (*)[THREADS]>(pp_smem + PP_STAGES * TILE_BYTES);   // [T * 16][THREADS]
+    uint64_t* full = reinterpret_cast<uint64_t*>(pp_smem + PP_STAGES * TILE_BYTES + T * 16 * THREADS * 4);
+    // stot: Kahan (sum, comp) x {x,y,z,pot} x 2 targets per pair
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t t0 = blockIdx.y * tiles_per_split;
+    const uint32_t t1 = min(t0 + tiles_per_split, tiles_total);
+    const uint32_t ntiles = t1 - t0;
+
+    if (tid == 0) {
+        for (int s = 0; s < PP_STAGES; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (uint32_t s = 0; s < PP_STAGES && s < ntiles; s++) {
+            mbar_expect_tx(&full[s], TILE_BYTES);
+            bulk_g2s(&tile[s][0], src + (size_t)(t0 + s) * TILE, TILE_BYTES, &full[s]);
+        }
+    }
+
+    float2 nx[T], ny[T], nz[T];   // negated target coordinates, {target a, target b}
+    const uint32_t ibase = blockIdx.x * (THREADS * 2 * T) + tid;
+#pragma unroll
+    for (int k = 0; k < T; k++) {
+        const uint32_t ia = ibase + k * 2 * THREADS, ib = ia + THREADS;
+        const float4 a = (ia < ni) ? pm4[i0 + ia] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b = (ib < ni) ? pm4[i0 + ib] : make_float4(0.f, 0.f, 0.f, 0.f);
+        nx[k] = make_float2(-a.x, -b.x);
+        ny[k] = make_float2(-a.y, -b.y);
+        nz[k] = make_float2(-a.z, -b.z);
+#pragma unroll
+        for (int q = 0; q < 16; q++) stot[k * 16 + q][tid] = 0.f;
+    }
+    const float2 e2 = make_float2(eps2, eps2);
+
+    for (uint32_t it = 0; it < ntiles; it++) {
+        const uint32_t s = it % PP_STAGES;
+        mbar_wait(&full[s], (it / PP_STAGES) & 1u);
+        float2 ax[T], ay[T], az[T], ap[T];
+#pragma unroll
+        for (int k = 0; k < T; k++) ax[k] = ay[k] = az[k] = ap[k] = make_float2(0.f, 0.f);
+        const float4* sm = &tile[s][0];
+#pragma unroll UNROLL
+        for (int j = 0; j < TILE; j++) {
+            const float4 S = sm[j];
+            const float2 xj = make_float2(S.x, S.x), yj = make_float2(S.y, S.y);
+            const float2 zj = make_float2(S.z, S.z), mj = make_float2(S.w, S.w);
+#pragma unroll
+            for (int k = 0; k < T; k++) {
+                const float2 dx = __fadd2_rn(nx[k], xj);
+                const float2 dy = __fadd2_rn(ny[k], yj);
+                const float2 dz = __fadd2_rn(nz[k], zj);
+                float2 r2 = __ffma2_rn(dx, dx, e2);
+                r2 = __ffma2_rn(dy, dy, r2);
+                r2 = __ffma2_rn(dz, dz, r2);
+                float2 inv;
+                inv.x = rsqrt_approx(r2.x);
+                inv.y = rsqrt_approx(r2.y);
+                const float2 u = __fmul2_rn(inv, mj);     // m_j / r          (pot_j, gravity.c:761)
+                const float2 i2 = __fmul2_rn(inv, inv);   // 1 / r^2
+                const float2 w = __fmul2_rn(u, i2);       // m_j / r^3
+                ax[k] = __ffma2_rn(w, dx, ax[k]);
+                ay[k] = __ffma2_rn(w, dy, ay[k]);
+                az[k] = __ffma2_rn(w, dz, az[k]);
+                ap[k] = __fadd2_rn(ap[k], u);
+            }
+        }
+        // fold this tile's partial sums (TILE terms per lane) into the compensated running totals
+#pragma unroll
+        for (int k = 0; k < T; k++) {
+            const float v[8] = {ax[k].x, ay[k].x, az[k].x, ap[k].x, ax[k].y, ay[k].y, az[k].y, ap[k].y};
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                Kahan a{stot[k * 16 + 2 * q][tid], stot[k * 16 + 2 * q + 1][tid]};
+                a.add(v[q]);
+                stot[k * 16 + 2 * q][tid] = a.s; stot[k * 16 + 2 * q + 1][tid] = a.c;
+            }
+        }
+        __syncthreads();  // everyone is done reading stage s
+        if (tid == 0 && it + PP_STAGES < ntiles) {
+            mbar_expect_tx(&full[s], TILE_BYTES);
+            bulk_g2s(&tile[s][0], src + (size_t)(t0 + it + PP_STAGES) * TILE, TILE_BYTES, &full[s]);
+        }
+    }
+
+#pragma unroll
+    for (int k = 0; k < T; k++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t il = ibase + k * 2 * THREADS + h * THREADS;
+            if (il < ni) {
+                float r[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) r[q] = stot[k * 16 + 8 * h + 2 * q][tid] - stot[k * 16 + 8 * h + 2 * q + 1][tid];
+                // d' = -(r_i - r_j): flip the sign of the force sums here
+                partial[(size_t)blockIdx.y * ni + il] = make_float4(-r[0], -r[1], -r[2], r[3]);
+            }
+        }
+    }
+}
+
 }  // namespace sfe

@@ -41,6 +41,56 @@ struct KahanRef {   // gravity.c:771-799: y = F - com; t = sum + y; z = t - sum;
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Correctly rounded 1/q, sqrt(q) and 1/sqrt-then-reciprocal for the EXACT flavour.  The reference computes
+// inv_r2 = 1/q and inv_r1 = 1/sqrtf(q) with IEEE division and square root (gravity.c:754-759); __fdiv_rn /
+// __fsqrt_rn reproduce them but expand to ~10 instructions each plus a slow-path guard, and the EXACT walk is
+// issue-bound.  For operands away from the denormal / overflow range the Newton / Markstein sequences below give
+// the same bits in 5 + 7 + 5 instructions.  "The same bits" is not argued, it is checked: the fast path is only
+// taken for q in [2^-24, 2^16) (the reference workloads have q = r^2 + 1e-6 < 50), and
+// sfe_selftest_exact_math() compares the sequences against the intrinsics for EVERY float of that range on the
+// device - 40 binades, 3.4e8 values (tests/test_gpu_walk.py::test_exact_math_exhaustive).
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_rn_seq(float q) {
+    float r = rcp_approx(q);
+    float e = __fmaf_rn(-q, r, 1.0f);
+    r = __fmaf_rn(r, e, r);
+    e = __fmaf_rn(-q, r, 1.0f);
+    return __fmaf_rn(r, e, r);
+}
+// s = RN(sqrt(q)).  (Seeding 1/s with the MUFU.RSQ estimate instead of a MUFU.RCP of s saves one instruction but
+// is NOT exact: the exhaustive check found 40 mismatching inputs in 3.4e8, so 1/s goes through rcp_rn_seq.)
+__device__ __forceinline__ float sqrt_rn_seq(float q) {
+    const float y = rsqrt_approx(q);
+    float s = __fmul_rn(q, y);
+    const float h = __fmul_rn(0.5f, y);
+    float e = __fmaf_rn(-s, s, q);
+    s = __fmaf_rn(e, h, s);
+    e = __fmaf_rn(-s, s, q);
+    return __fmaf_rn(e, h, s);
+}
+// the exhaustively verified operand range
+constexpr float SEQ_LO = 5.9604644775390625e-08f;   // 2^-24
+constexpr float SEQ_HI = 65536.0f;                   // 2^16
+constexpr uint32_t SEQ_LO_BITS = 0x33800000u;        // bit pattern of 2^-24
+constexpr uint32_t SEQ_BINADES = 40u;
+
+__global__ void exact_math_selftest_kernel(unsigned long long* __restrict__ bad /* [3] */) {
+    // every float in [SEQ_LO, SEQ_HI)
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < (SEQ_BINADES << 23); k += gridDim.x * blockDim.x) {
+        const float q = __uint_as_float(SEQ_LO_BITS + k);
+        const float s = sqrt_rn_seq(q);
+        const float s_ref = __fsqrt_rn(q);
+        if (__float_as_uint(rcp_rn_seq(q)) != __float_as_uint(__fdiv_rn(1.0f, q))) atomicAdd(&bad[0], 1ull);
+        if (__float_as_uint(s) != __float_as_uint(s_ref)) atomicAdd(&bad[1], 1ull);
+        if (__float_as_uint(rcp_rn_seq(s_ref)) != __float_as_uint(__fdiv_rn(1.0f, s_ref))) atomicAdd(&bad[2], 1ull);
+    }
+}
+
 // theta <= (d2 > 0 ? fl(w2 / d2) : 0)      (gravity.c:377,448)
 __device__ __forceinline__ bool opens(float w2, float d2, float theta) {
     if (!(0.0f < d2)) return theta <= 0.0f;
@@ -70,6 +120,7 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
     const float4* __restrict__ rec1 = t.rec1;
     const WalkRec2* __restrict__ rec2 = t.rec2;
 
+    const bool seq_ok = eps2 >= SEQ_LO;
     uint32_t n = M == 0u ? NODE_END : 0u;   // an empty root is never evaluated (gravity.c:324-328)
     while (n != NODE_END) {
         // one 256-bit load = one L1 sector: {a[4], next, child|kind, rin2, -}
@@ -112,8 +163,14 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
         const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
         const float q = __fadd_rn(r2, eps2);
         if (FLAVOUR == (int)SFE_WALK_EXACT) {
-            const float inv_r2 = __fdiv_rn(1.0f, q);
-            const float inv_r1 = __fdiv_rn(1.0f, __fsqrt_rn(q));
+            float inv_r2, inv_r1;
+            if (seq_ok && q < SEQ_HI) {      // q >= eps2 >= SEQ_LO here
+                inv_r2 = rcp_rn_seq(q);
+                inv_r1 = rcp_rn_seq(sqrt_rn_seq(q));
+            } else {
+                inv_r2 = __fdiv_rn(1.0f, q);
+                inv_r1 = __fdiv_rn(1.0f, __fsqrt_rn(q));
+            }
             const float pj = __fmul_rn(mj, inv_r1);
             const float w = __fmul_rn(pj, inv_r2);
             ax.add(__fmul_rn(w, dx)); ay.add(__fmul_rn(w, dy)); az.add(__fmul_rn(w, dz));
@@ -179,3 +236,21 @@ int launch_bh(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, f
 }
 
 }  // namespace sfe
+
+extern "C" int sfe_selftest_exact_math(uint64_t mismatches[3]) {
+    using namespace sfe;
+    const char* fn = "sfe_selftest_exact_math";
+    if (ensure_init(fn)) return SFE_FAILURE;
+    Ctx* c = ctx();
+    unsigned long long* d = nullptr;
+    SFE_CUDA(fn, cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+    SFE_CUDA(fn, cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), c->stream));
+    exact_math_selftest_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d);
+    if (check_launch(fn)) return SFE_FAILURE;
+    unsigned long long h[3] = {0, 0, 0};
+    SFE_CUDA(fn, cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    SFE_CUDA(fn, cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    for (int k = 0; k < 3; k++) mismatches[k] = h[k];
+    return SFE_SUCCESS;
+}

@@ -72,6 +72,7 @@ SIGNATURES = {
     "sfe_bh_slice": ([_P, _P, _P, _P, _u32, _u32, _u32, _f, _f, _f, _u32], C.c_int),
     "sfe_tree_download": ([_P, _u32, C.POINTER(_u32)], C.c_int),
     "sfe_tree_keys_download": ([_P, _P, _u32, C.POINTER(_u32)], C.c_int),
+    "sfe_selftest_exact_math": ([C.POINTER(C.c_uint64)], C.c_int),
     "sfe_sph": ([_P, _P, _P, _P, _P, _P, _u32, _f, _f, _f], C.c_int),
     "sfe_dev_pack_pm4": ([_P, _P, _P, _u32, _P], C.c_int),
     "sfe_dev_pp": ([_P, _u32, _u32, _u32, _P, _P, _f, _f, _P], C.c_int),
@@ -226,6 +227,13 @@ def tree_keys(N):
     keys = np.zeros(N, np.uint64); perm = np.zeros(N, np.uint32); nin = _u32()
     _check(lib().sfe_tree_keys_download(_ptr(keys), _ptr(perm), N, C.byref(nin)), "sfe_tree_keys_download")
     return keys, perm, nin.value
+
+
+def selftest_exact_math():
+    """Mismatch counts {1/q, sqrt(q), 1/sqrt(q)} of the EXACT walk's Newton sequences vs the IEEE intrinsics."""
+    bad = (C.c_uint64 * 3)()
+    _check(lib().sfe_selftest_exact_math(bad), "sfe_selftest_exact_math")
+    return [int(b) for b in bad]
 
 
 def solve_gravity_part_tree(sim, flavour=WALK_EXACT, i0=0, ni=None, theta=TREE_THETA):

@@ -95,3 +95,8 @@ def test_full_size(engine):
     assert rel_rms(fast.acc, acc) <= 1e-4 and rel_rms(fast.pot, pot) <= 1e-4
     # walk statistics that the roofline model uses: V = opened + evals + empty = 514.3
     assert abs((st.opened + st.evals + st.empty) / N - 514.3) < 0.1
+
+
+def test_exact_math_exhaustive(engine):
+    """The EXACT flavour's 1/q, sqrt(q), 1/sqrt(q) sequences give the IEEE result for every float in [2^-24, 2^16)."""
+    assert engine.selftest_exact_math() == [0, 0, 0]

@@ -74,6 +74,59 @@ void run(const char* name, const float4* pm4, float4* pairs, float4* partial, ui
     fflush(stdout);
 }
 
+__global__ void pad_kernel(const float4* __restrict__ pm4, float4* __restrict__ src, uint32_t N, uint32_t npad) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < npad) src[j] = j < N ? pm4[j] : make_float4(PP_PAD_POS, PP_PAD_POS, PP_PAD_POS, 0.f);
+}
+
+template <int T, int THREADS, int MINB, int TILE, int UNR>
+void run_tp(const char* name, const float4* pm4, float4* srcbuf, float4* partial, uint32_t N) {
+    const uint32_t tiles = (N + TILE - 1) / TILE, npad = tiles * TILE;
+    pad_kernel<<<(npad + 255) / 256, 256>>>(pm4, srcbuf, N, npad);
+    const uint32_t per_cta = THREADS * 2 * T;
+    const uint32_t iblocks = (N + per_cta - 1) / per_cta;
+    int occ = 0;
+    const size_t smem = pp_tp_smem_bytes<T, THREADS, TILE>();
+    cudaFuncSetAttribute(pp_kernel_tp<T, THREADS, MINB, TILE, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_kernel_tp<T, THREADS, MINB, TILE, UNR>, THREADS, smem);
+    const uint32_t wave = (uint32_t)(occ * g_sms);
+    uint32_t best = 1; double best_eff = 0;
+    for (uint32_t sp = 1; sp <= 64 && sp <= tiles; sp++) {
+        uint32_t tps = (tiles + sp - 1) / sp, rsp = (tiles + tps - 1) / tps;
+        uint64_t ctas = (uint64_t)iblocks * rsp, waves = (ctas + wave - 1) / wave;
+        double eff = (double)iblocks * tiles / ((double)waves * wave * tps);
+        if (tps < 8) eff *= 0.9;
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = rsp; }
+    }
+    uint32_t tps = (tiles + best - 1) / best, splits = (tiles + tps - 1) / tps;
+    dim3 grid(iblocks, splits);
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, pp_kernel_tp<T, THREADS, MINB, TILE, UNR>);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best_ms = 1e30f;
+    for (int r = 0; r < 4; r++) {
+        cudaEventRecord(e0);
+        pp_kernel_tp<T, THREADS, MINB, TILE, UNR><<<grid, THREADS, smem>>>(srcbuf, pm4, N, 0, N, tiles, tps, 1e-6f, partial);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best_ms) best_ms = ms;
+    }
+    cudaError_t err = cudaGetLastError();
+    std::vector<float4> h((size_t)splits * N);
+    cudaMemcpy(h.data(), partial, h.size() * sizeof(float4), cudaMemcpyDeviceToHost);
+    double num = 0, den = 0;
+    for (uint32_t i = 0; i < N; i++) {
+        double x = 0, y = 0, z = 0;
+        for (uint32_t s = 0; s < splits; s++) { float4 v = h[(size_t)s * N + i]; x += v.x; y += v.y; z += v.z; }
+        double dx = (float)x - g_ref[i].x, dy = (float)y - g_ref[i].y, dz = (float)z - g_ref[i].z;
+        num += dx * dx + dy * dy + dz * dz;
+        den += (double)g_ref[i].x * g_ref[i].x + (double)g_ref[i].y * g_ref[i].y + (double)g_ref[i].z * g_ref[i].z;
+    }
+    double tf = 20.0 * (double)N * N / (best_ms * 1e-3) / 1e12;
+    printf("%-34s regs %3d occ %d grid %ux%u eff %.3f  %8.3f ms  %6.2f TFLOP/s  relrms-vs-first %.2e  %s\n", name, fa.numRegs, occ,
+           iblocks, splits, best_eff, best_ms, tf, sqrt(num / den), err == cudaSuccess ? "" : cudaGetErrorString(err));
+    fflush(stdout);
+}
+
 int main(int argc, char** argv) {
     uint32_t N = argc > 1 ? (uint32_t)atoi(argv[1]) : 262144u;
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
@@ -107,5 +160,17 @@ int main(int argc, char** argv) {
     run<3, 256, 2, 512, false, 4>("T3 256x2 tile512 reg-tot u4", pm4, pairs, partial, N);
     run<3, 128, 6, 512, true, 4>("T3 128x6 tile512 smem-tot u4", pm4, pairs, partial, N);
     run<6, 128, 3, 512, true, 2>("T6 128x3 tile512 smem-tot u2", pm4, pairs, partial, N);
+    //      T(pairs) THR MINB TILE UNROLL
+    run_tp<2, 128, 6, 512, 4>("TP T2 128x6 tile512 u4", pm4, pairs, partial, N);
+    run_tp<2, 256, 3, 512, 4>("TP T2 256x3 tile512 u4", pm4, pairs, partial, N);
+    run_tp<3, 128, 5, 512, 4>("TP T3 128x5 tile512 u4", pm4, pairs, partial, N);
+    run_tp<4, 128, 4, 512, 4>("TP T4 128x4 tile512 u4", pm4, pairs, partial, N);
+    run_tp<4, 128, 4, 512, 2>("TP T4 128x4 tile512 u2", pm4, pairs, partial, N);
+    run_tp<4, 128, 3, 512, 4>("TP T4 128x3 tile512 u4", pm4, pairs, partial, N);
+    run_tp<4, 64, 8, 512, 4>("TP T4 64x8 tile512 u4", pm4, pairs, partial, N);
+    run_tp<4, 256, 2, 512, 4>("TP T4 256x2 tile512 u4", pm4, pairs, partial, N);
+    run_tp<6, 128, 2, 512, 2>("TP T6 128x2 tile512 u2", pm4, pairs, partial, N);
+    run_tp<6, 64, 5, 512, 2>("TP T6 64x5 tile512 u2", pm4, pairs, partial, N);
+    run_tp<8, 64, 4, 512, 2>("TP T8 64x4 tile512 u2", pm4, pairs, partial, N);
     return 0;
 }
