@@ -60,21 +60,26 @@ struct Tree {
     DevBuf next;         // uint32_t[nodes_max]    depth-first successor when a node is not opened
     DevBuf child_base;   // uint32_t[nodes_max]    first child of internal nodes
     DevBuf counts;       // uint32_t[8*nodes_max]  per-octant member counts of internal nodes
-    DevBuf keys;         // uint64_t[N]            48-bit path keys
-    DevBuf perm[SFE_MAX_LEVELS + 2];   // uint32_t[N] slot -> particle index, one array per level
-    DevBuf spm4[SFE_MAX_LEVELS + 2];   // float4[N]  slot-ordered particle records, one array per level
+    DevBuf keys;         // uint64_t[N]            48-bit path keys by particle index (on demand)
+    DevBuf skey[2];      // uint64_t[N]            path key of every slot, ping-pong between levels
+    DevBuf perm[SFE_MAX_LEVELS + 3];   // uint32_t[N] slot -> particle index, one array per level
+    DevBuf spm4[SFE_MAX_LEVELS + 3];   // float4[N]  slot-ordered particle records, one array per level
     DevBuf perm_out;     // uint32_t[N]            out-of-box particles in ascending index
     DevBuf slot_node[2]; // uint32_t[N]            node owning each slot (ping-pong between levels)
     DevBuf oct;          // uint8_t[N]
     DevBuf rank;         // uint32_t[N]            stable rank inside (node, octant)
-    DevBuf tile_agg;     // uint32_t[9*tiles]
+    DevBuf nmid;         // float4[nodes_max]      split planes of internal nodes
+    DevBuf lookback;     // tickets + look-back descriptors of one build (zeroed per build)
+    uint32_t* summary_host = nullptr;  // mapped pinned: per-level summaries written by the device
+    uint32_t* summary_dev = nullptr;
+    uint32_t build_id = 0;
     DevBuf scan_tmp;
     DevBuf slice_count;  // uint32_t[1]
     DevBuf root_gate;    // uint32_t[1]  set when some target evaluates the root as a monopole
     DevBuf meta;         // uint32_t[M_WORDS]
     DevBuf rec0, rec1, rec2;   // walk records
     uint32_t* meta_host = nullptr;     // pinned, (SFE_MAX_LEVELS + 2) snapshots of meta
-    cudaEvent_t ev_level[SFE_MAX_LEVELS + 2], ev_perm[SFE_MAX_LEVELS + 2], ev_side[SFE_SIDE_STREAMS];
+    cudaEvent_t ev_perm[SFE_MAX_LEVELS + 3], ev_side[SFE_SIDE_STREAMS];
     bool ev_init = false;
 };
 

@@ -46,8 +46,8 @@ struct CompactOp {
     __device__ uint32_t load(uint32_t i) const { return in_box(t.bounds, pm4[i]) ? 1u : 0u; }
     __device__ void store(uint32_t i, uint32_t ex) const {
         const float4 p = pm4[i];
-        if (in_box(t.bounds, p)) { t.perm0[ex] = i; t.slot_node0[ex] = 0u; t.keys[i] = 0ull; t.spm4[0][ex] = p; }
-        else { t.perm_out[i - ex] = i; t.keys[i] = ~0ull; }
+        if (in_box(t.bounds, p)) { t.perm0[ex] = i; t.slot_node0[ex] = 0u; t.skey[0][ex] = 0ull; t.spm4[0][ex] = p; }
+        else t.perm_out[i - ex] = i;
     }
     __device__ void total(uint32_t M) const {
         // root node (tree.c:113-115) and the per-build counters
@@ -55,6 +55,7 @@ struct CompactOp {
         t.meta[M_COUNT] = 1u;
         t.meta[M_STATUS] = 0u;
         t.meta[M_DEPTH] = 0u;
+        t.meta[M_FINAL] = 0u;
         t.meta[M_LV_BEGIN + 0] = 0u;
         t.meta[M_LV_END + 0] = 1u;
         sfe_node_t root;
@@ -68,49 +69,26 @@ struct CompactOp {
     }
 };
 
-// ============================================================================ per level: child allocation
-// element j of the scan = j-th node of level d; value = 1 if it is internal (more than 8 bodies).
-struct AllocOp {
-    TreeDev t; int d; int depth_max;
-    __device__ uint32_t lv_begin() const { return t.meta[M_LV_BEGIN + d]; }
-    __device__ uint32_t n() const { return t.meta[M_STATUS] ? 0u : t.meta[M_LV_END + d] - t.meta[M_LV_BEGIN + d]; }
-    __device__ uint32_t load(uint32_t j) const { uint2 s = t.seg[lv_begin() + j]; return (s.y - s.x) > 8u ? 1u : 0u; }
-    __device__ void total(uint32_t internal) const {
-        const uint32_t end = t.meta[M_LV_END + d];
-        uint32_t next_end = end + 8u * internal;
-        if (internal > 0u) {
-            // tree.c:180-189: node budget first (success iff the final count stays below max_nodes), then depth
-            if (t.nodes_max <= next_end) { t.meta[M_STATUS] = 1u; next_end = end; }
-            else if (depth_max <= d) { t.meta[M_STATUS] = 2u; next_end = end; }
-            else t.meta[M_DEPTH] = (uint32_t)d + 1u;
-        }
-        t.meta[M_LV_BEGIN + d + 1] = end;
-        t.meta[M_LV_END + d + 1] = next_end;
-        t.meta[M_COUNT] = next_end;
-    }
-    __device__ void store(uint32_t j, uint32_t rank) const {
-        if (t.meta[M_STATUS]) return;
-        const uint32_t n = lv_begin() + j;
-        const uint2 s = t.seg[n];
-        const uint32_t bodies = s.y - s.x;
-        sfe_node_t* nd = &t.nodes[n];
-        nd->bodies = bodies;
-        if (bodies > 8u) {
-            const uint32_t base = t.meta[M_LV_END + d] + 8u * rank;
-            t.child_base[n] = base;
-            for (int o = 0; o < 8; o++) nd->branch[o] = base + o;
-        } else {
-            t.child_base[n] = NODE_END;
-            const uint32_t* perm = t.perm[d];
-            for (uint32_t b = 0; b < 8u; b++) nd->branch[b] = b < bodies ? perm[s.x + b] : 0u;   // tree.c:172-175
-        }
-    }
-};
-
-// ============================================================================ per level: octants + segmented scan
+// ============================================================================ per level: three kernels
+// Level d is processed by three launches that hand over through device memory only:
+//   rank_kernel(d)      every slot of an internal level-d node picks its octant (tie rule below) and gets its
+//                       stable rank inside (node, octant): ONE pass over the slot array, a segmented scan of
+//                       eight counters with decoupled look-back between 2048-slot tiles; also the per-node
+//                       octant totals counts[n][8];
+//   children_kernel(d)  creates the eight children of every internal level-d node (tree.c:191-274) and, in the
+//                       same pass, allocates THEIR children: a look-back scan over the level counts the children
+//                       that are internal themselves (more than 8 bodies) and hands each of them a block of
+//                       eight node ids of level d+2 in parent order (breadth-first canonical numbering);
+//   scatter_kernel(d)   moves every slot to its place in level d+1 (stable 8-way partition) and appends the key digit.
+// The root plays the part of children_kernel(-1) (root_kernel).  The only host involvement is "how deep does the
+// tree go": children_kernel(d) publishes the number of internal nodes of level d+1 into mapped host memory and the
+// host stops enqueuing levels two levels after it reads a zero there (the kernels of an empty level return at once).
 constexpr int PT_THREADS = 256;
 constexpr int PT_ITEMS = 8;
 constexpr int PT_TILE = PT_THREADS * PT_ITEMS;
+constexpr uint32_t DESC_WORDS = 20u;   // tile descriptor of the segmented look-back: [0] status, [1] has_head, [2..9] agg, [10..17] incl
+constexpr uint32_t ST_NONE = 0u, ST_AGG = 1u, ST_INCL = 2u;
+constexpr int CH_THREADS = 256;
 
 struct Cnt8 {                // eight 16-bit counters (a tile holds 2048 slots)
     uint32_t w[4];
@@ -120,19 +98,22 @@ struct Cnt8 {                // eight 16-bit counters (a tile holds 2048 slots)
     __device__ __forceinline__ uint32_t get(uint32_t o) const { return (w[o >> 1] >> ((o & 1u) * 16u)) & 0xFFFFu; }
 };
 
-// Octant of a member with the reference's tie rule; also appends the key digit.
-__device__ __forceinline__ uint32_t pick_octant(const sfe_node_t* nd, float4 p, bool resident) {
-    const float mx = __fmul_rn(0.5f, __fadd_rn(nd->bounds[0], nd->bounds[3]));   // tree.c:159-163
-    const float my = __fmul_rn(0.5f, __fadd_rn(nd->bounds[1], nd->bounds[4]));
-    const float mz = __fmul_rn(0.5f, __fadd_rn(nd->bounds[2], nd->bounds[5]));
-    if (resident) return (mx < p.x ? 1u : 0u) + (my < p.y ? 2u : 0u) + (mz < p.z ? 4u : 0u);     // tree.c:244-247
-    return (mx <= p.x ? 1u : 0u) + (my <= p.y ? 2u : 0u) + (mz <= p.z ? 4u : 0u);                 // tree.c:282-285
+// Octant of a member with the reference's tie rule; mid = 0.5f*(lo+hi) (tree.c:159-163) comes from nmid[].
+__device__ __forceinline__ uint32_t pick_octant(float4 mid, float4 p, bool resident) {
+    if (resident) return (mid.x < p.x ? 1u : 0u) + (mid.y < p.y ? 2u : 0u) + (mid.z < p.z ? 4u : 0u);     // tree.c:244-247
+    return (mid.x <= p.x ? 1u : 0u) + (mid.y <= p.y ? 2u : 0u) + (mid.z <= p.z ? 4u : 0u);                 // tree.c:282-285
 }
 
-// Tile-local segmented scan shared by the two partition kernels.  On return, for each of the thread's
-// PT_ITEMS consecutive slots: oct[k] (0xFF = inactive), head[k]; `before` = counters of the open range
-// at the thread's first slot counted from the last head inside the tile (or from the tile start), and
-// `head_before` tells whether such a head exists inside the tile.
+__device__ __forceinline__ bool level_idle(const TreeDev& t, int d) {   // no internal node at level d (or the build failed)
+    return t.meta[M_STATUS] != 0u || t.meta[M_LV_END + d + 1] == t.meta[M_LV_BEGIN + d + 1];
+}
+
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+// Tile-local segmented scan.  On return, for each of the thread's PT_ITEMS consecutive slots: `before` = counters
+// of the open range at the thread's first slot counted from the last head inside the tile (or from the tile
+// start), `head_before` tells whether such a head exists inside the tile; tile_trailing / tile_has_head are the
+// tile's aggregate (same value in every thread).
 struct TileScan {
     Cnt8 before; bool head_before;
     Cnt8 tile_trailing; bool tile_has_head;
@@ -192,231 +173,348 @@ __device__ __forceinline__ void tile_segmented_scan(const uint8_t* oct, const bo
     __syncthreads();
 }
 
-// load one tile's worth of per-slot state
-__device__ __forceinline__ void load_tile_slots(const TreeDev& t, int d, uint32_t first,
-                                                uint32_t M, uint8_t* oct, bool* head, uint32_t* node) {
+// ---------------------------------------------------------------------------- rank_kernel
+// per-slot byte staged in shared memory between the coalesced load phase and the thread-contiguous scan phase
+constexpr uint32_t SB_ACTIVE = 0x08u, SB_HEAD = 0x10u, SB_LAST = 0x20u;
+
+// Warp-parallel decoupled look-back of the segmented scan: lane l inspects tile (tile-1-l) of the current window;
+// the nearest tile that either already knows its inclusive prefix or starts the open range ends the search.
+__device__ __forceinline__ void rank_lookback(const uint32_t* __restrict__ desc_base, uint32_t tile, uint32_t carry[8]) {
+    const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int o = 0; o < 8; o++) carry[o] = 0u;
+    int base = (int)tile - 1;
+    for (;;) {
+        const int j = base - (int)lane;
+        const bool valid = j >= 0;
+        const uint32_t* dj = desc_base + (size_t)(valid ? j : 0) * DESC_WORDS;
+        uint32_t st;
+        do { st = valid ? ld_volatile(&dj[0]) : ST_INCL; } while (__any_sync(0xFFFFFFFFu, st == ST_NONE));
+        __threadfence();
+        const bool stop = !valid || st == ST_INCL || ld_volatile(&dj[1]) != 0u;
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, stop);
+        const uint32_t first = ballot ? (uint32_t)__ffs(ballot) - 1u : 32u;
+        uint32_t v[8];
+#pragma unroll
+        for (int o = 0; o < 8; o++) v[o] = 0u;
+        if (valid && lane <= first) {
+            const uint32_t off = st == ST_INCL ? 10u : 2u;
+#pragma unroll
+            for (int o = 0; o < 8; o++) v[o] = ld_volatile(&dj[off + o]);
+        }
+#pragma unroll
+        for (int o = 0; o < 8; o++) {
+#pragma unroll
+            for (int sh = 16; sh >= 1; sh >>= 1) v[o] += __shfl_xor_sync(0xFFFFFFFFu, v[o], sh);
+            carry[o] += v[o];
+        }
+        if (ballot) return;
+        base -= 32;
+    }
+}
+
+__global__ void __launch_bounds__(PT_THREADS) rank_kernel(TreeDev t, int d) {
+    __shared__ uint32_t sm[48];
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_carry[8];
+    __shared__ __align__(16) uint8_t s_byte[PT_TILE];
+    __shared__ __align__(16) uint32_t s_rank[PT_TILE];
+    if (level_idle(t, d)) return;
+    const uint32_t M = t.meta[M_NUM_INBOX];
+    const uint32_t ntiles = (M + PT_TILE - 1) / PT_TILE;
     const float4* __restrict__ spm4 = t.spm4[d];
     const uint32_t* __restrict__ slot_node = t.slot_node[d & 1];
+    uint32_t* __restrict__ desc_base = t.tdesc + (size_t)d * t.tdesc_stride;
+    for (;;) {
+        // tiles are handed out in launch order, so a tile only ever waits for tiles that are already running
+        if (threadIdx.x == 0) s_tile = atomicAdd(&t.ticket[2 * d], 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= ntiles) return;
+        const uint32_t tile0 = tile * PT_TILE;
+        // phase 1, coalesced: octant of every active slot (tie rule) + range head / last-member flags
 #pragma unroll
-    for (int k = 0; k < PT_ITEMS; k++) {
-        const uint32_t s = first + k;
-        oct[k] = 0xFFu; head[k] = false; node[k] = NODE_END;
-        if (s < M) {
-            const uint32_t n = slot_node[s];
-            if (n != NODE_END) {
-                const uint2 sg = t.seg[n];
-                if (sg.y - sg.x > 8u) {
-                    node[k] = n;
-                    head[k] = (s == sg.x);
-                    oct[k] = (uint8_t)pick_octant(&t.nodes[n], spm4[s], s - sg.x < 8u);
+        for (int k = 0; k < PT_ITEMS; k++) {
+            const uint32_t i = k * PT_THREADS + threadIdx.x, s = tile0 + i;
+            uint32_t byte = 0u;
+            if (s < M) {
+                const uint32_t n = slot_node[s];
+                if (n != NODE_END) {                       // slot of an internal node (scatter marks the others)
+                    const float4 mid = t.nmid[n];
+                    const uint2 sg = t.seg[n];
+                    byte = pick_octant(mid, spm4[s], s - sg.x < 8u) | SB_ACTIVE | (s == sg.x ? SB_HEAD : 0u) | (s + 1u == sg.y ? SB_LAST : 0u);
                 }
             }
+            s_byte[i] = (uint8_t)byte;
         }
-    }
-}
-
-// S1: tile aggregates
-__global__ void __launch_bounds__(PT_THREADS) part_aggregate_kernel(TreeDev t, int d) {
-    __shared__ uint32_t sm[48];
-    if (t.meta[M_STATUS] || t.meta[M_LV_END + d + 1] == t.meta[M_LV_BEGIN + d + 1]) return;   // nothing splits
-    const uint32_t M = t.meta[M_NUM_INBOX];
-    const uint32_t ntiles = (M + PT_TILE - 1) / PT_TILE;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        uint8_t oct[PT_ITEMS]; bool head[PT_ITEMS]; uint32_t node[PT_ITEMS];
-        load_tile_slots(t, d, tile * PT_TILE + threadIdx.x * PT_ITEMS, M, oct, head, node);
+        __syncthreads();
+        // phase 2, thread-contiguous: segmented scan of eight counters
+        uint8_t oct[PT_ITEMS]; bool head[PT_ITEMS]; uint8_t raw[PT_ITEMS];
+        {
+            const uint2 w = *reinterpret_cast<const uint2*>(&s_byte[threadIdx.x * PT_ITEMS]);
+#pragma unroll
+            for (int k = 0; k < PT_ITEMS; k++) {
+                raw[k] = (uint8_t)(((k < 4 ? w.x : w.y) >> (8 * (k & 3))) & 0xFFu);
+                oct[k] = (raw[k] & SB_ACTIVE) ? (uint8_t)(raw[k] & 7u) : (uint8_t)0xFFu;
+                head[k] = (raw[k] & SB_HEAD) != 0u;
+            }
+        }
         TileScan ts;
         tile_segmented_scan(oct, head, &ts, sm);
-        if (threadIdx.x == 0) {
-            uint32_t* a = &t.tile_agg[(size_t)tile * 9];
+        // publish the aggregate, fetch the carry of the range that is open at the tile start (decoupled look-back)
+        uint32_t* desc = desc_base + (size_t)tile * DESC_WORDS;
+        if (threadIdx.x < 8) desc[2 + threadIdx.x] = ts.tile_trailing.get(threadIdx.x);
+        if (threadIdx.x == 8) desc[1] = ts.tile_has_head ? 1u : 0u;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t carry[8];
+            if (tile > 0u) {
+                if (threadIdx.x == 0) atomicExch(&desc[0], ST_AGG);
+                rank_lookback(desc_base, tile, carry);
+            } else {
 #pragma unroll
-            for (uint32_t o = 0; o < 8; o++) a[o] = ts.tile_trailing.get(o);
-            a[8] = ts.tile_has_head ? 1u : 0u;
+                for (int o = 0; o < 8; o++) carry[o] = 0u;
+            }
+            if (threadIdx.x == 0) {
+#pragma unroll
+                for (int o = 0; o < 8; o++) {
+                    s_carry[o] = carry[o];
+                    desc[10 + o] = ts.tile_trailing.get(o) + (ts.tile_has_head ? 0u : carry[o]);
+                }
+                __threadfence();
+                atomicExch(&desc[0], ST_INCL);
+            }
         }
-    }
-}
-
-// S2: exclusive segmented scan over the tile aggregates.  One CTA; thread t owns a contiguous run of tiles,
-// scans it locally, and the per-thread totals go through a warp-shuffle + shared-memory segmented scan.
-constexpr int TS_THREADS = 1024;
-struct SegVal {
-    uint32_t v[8]; uint32_t f;
-    __device__ __forceinline__ void zero() { for (int o = 0; o < 8; o++) v[o] = 0u; f = 0u; }
-    // this = earlier (+) this, where `earlier` precedes in scan order
-    __device__ __forceinline__ void absorb_earlier(const SegVal& e) {
-        if (!f) { for (int o = 0; o < 8; o++) v[o] += e.v[o]; }
-        f |= e.f;
-    }
-};
-__device__ __forceinline__ SegVal seg_shfl_up(const SegVal& x, int delta) {
-    SegVal r;
-#pragma unroll
-    for (int o = 0; o < 8; o++) r.v[o] = __shfl_up_sync(0xFFFFFFFFu, x.v[o], delta);
-    r.f = __shfl_up_sync(0xFFFFFFFFu, x.f, delta);
-    return r;
-}
-__global__ void __launch_bounds__(TS_THREADS) part_tilescan_kernel(TreeDev t, int d) {
-    __shared__ uint32_t sm[32][9];
-    if (t.meta[M_STATUS] || t.meta[M_LV_END + d + 1] == t.meta[M_LV_BEGIN + d + 1]) return;
-    const uint32_t M = t.meta[M_NUM_INBOX];
-    const uint32_t ntiles = (M + PT_TILE - 1) / PT_TILE;
-    const uint32_t per = (ntiles + TS_THREADS - 1) / TS_THREADS;
-    const uint32_t first = threadIdx.x * per, last = min(first + per, ntiles);
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // thread-local aggregate of my run of tiles
-    SegVal mine; mine.zero();
-    for (uint32_t tile = first; tile < last; tile++) {
-        const uint32_t* a = &t.tile_agg[(size_t)tile * 9];
-        SegVal x;
-#pragma unroll
-        for (int o = 0; o < 8; o++) x.v[o] = a[o];
-        x.f = a[8];
-        x.absorb_earlier(mine);
-        mine = x;
-    }
-    // inclusive scan across the warp
-    SegVal inc = mine;
-#pragma unroll
-    for (int dl = 1; dl < 32; dl <<= 1) {
-        SegVal e = seg_shfl_up(inc, dl);
-        if (lane >= (uint32_t)dl) inc.absorb_earlier(e);
-    }
-    if (lane == 31) {
-#pragma unroll
-        for (int o = 0; o < 8; o++) sm[warp][o] = inc.v[o];
-        sm[warp][8] = inc.f;
-    }
-    __syncthreads();
-    // carry from earlier warps
-    SegVal carry; carry.zero();
-    for (uint32_t w = 0; w < warp; w++) {
-        SegVal x;
-#pragma unroll
-        for (int o = 0; o < 8; o++) x.v[o] = sm[w][o];
-        x.f = sm[w][8];
-        x.absorb_earlier(carry);
-        carry = x;
-    }
-    // exclusive value for this thread = carry (+) inclusive of the previous lane
-    SegVal ex = seg_shfl_up(inc, 1);
-    if (lane == 0) ex.zero();
-    ex.absorb_earlier(carry);
-    // rewrite my tiles with their exclusive carries
-    SegVal run = ex;
-    for (uint32_t tile = first; tile < last; tile++) {
-        uint32_t* a = &t.tile_agg[(size_t)tile * 9];
-        SegVal x;
-#pragma unroll
-        for (int o = 0; o < 8; o++) x.v[o] = a[o];
-        x.f = a[8];
-#pragma unroll
-        for (int o = 0; o < 8; o++) a[o] = run.v[o];
-        x.absorb_earlier(run);
-        run = x;
-    }
-}
-
-// S3: stable rank of every active slot inside its (node, octant) group; per-node octant counts
-__global__ void __launch_bounds__(PT_THREADS) part_rank_kernel(TreeDev t, int d) {
-    __shared__ uint32_t sm[48];
-    if (t.meta[M_STATUS] || t.meta[M_LV_END + d + 1] == t.meta[M_LV_BEGIN + d + 1]) return;
-    const uint32_t M = t.meta[M_NUM_INBOX];
-    const uint32_t ntiles = (M + PT_TILE - 1) / PT_TILE;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        uint8_t oct[PT_ITEMS]; bool head[PT_ITEMS]; uint32_t node[PT_ITEMS];
-        const uint32_t first = tile * PT_TILE + threadIdx.x * PT_ITEMS;
-        load_tile_slots(t, d, first, M, oct, head, node);
-        TileScan ts;
-        tile_segmented_scan(oct, head, &ts, sm);
+        __syncthreads();
         uint32_t run[8];
-        const uint32_t* carry = &t.tile_agg[(size_t)tile * 9];
 #pragma unroll
-        for (uint32_t o = 0; o < 8; o++) run[o] = ts.before.get(o) + (ts.head_before ? 0u : carry[o]);
+        for (uint32_t o = 0; o < 8; o++) run[o] = ts.before.get(o) + (ts.head_before ? 0u : s_carry[o]);
 #pragma unroll
         for (int k = 0; k < PT_ITEMS; k++) {
             if (head[k]) {
 #pragma unroll
                 for (uint32_t o = 0; o < 8; o++) run[o] = 0u;
             }
+            uint32_t r = 0;
             if (oct[k] != 0xFFu) {
-                const uint32_t s = first + k;
-                uint32_t r = 0;
 #pragma unroll
                 for (uint32_t o = 0; o < 8; o++) if (o == oct[k]) { r = run[o]; run[o] = r + 1u; }
-                t.rank[s] = r;
-                t.oct[s] = oct[k];
-                if (s + 1u == t.seg[node[k]].y) {       // last member: the running counts are the node's totals
-#pragma unroll
-                    for (uint32_t o = 0; o < 8; o++) t.counts[(size_t)node[k] * 8u + o] = run[o];
+                if (raw[k] & SB_LAST) {                 // last member: the running counts are the node's totals
+                    const uint32_t n = slot_node[tile0 + threadIdx.x * PT_ITEMS + k];
+                    *reinterpret_cast<uint4*>(&t.counts[(size_t)n * 8u]) = make_uint4(run[0], run[1], run[2], run[3]);
+                    *reinterpret_cast<uint4*>(&t.counts[(size_t)n * 8u + 4u]) = make_uint4(run[4], run[5], run[6], run[7]);
                 }
-            } else if (first + k < M) {
-                t.oct[first + k] = 0xFFu;
+            }
+            s_rank[threadIdx.x * PT_ITEMS + k] = r;
+        }
+        __syncthreads();
+        // phase 3, coalesced: ranks and octants out
+#pragma unroll
+        for (int k = 0; k < PT_ITEMS; k++) {
+            const uint32_t i = k * PT_THREADS + threadIdx.x, s = tile0 + i;
+            if (s < M) {
+                const uint32_t byte = s_byte[i];
+                t.rank[s] = s_rank[i];
+                t.oct[s] = (byte & SB_ACTIVE) ? (uint8_t)(byte & 7u) : (uint8_t)0xFFu;
             }
         }
+        __syncthreads();   // shared buffers are reused by the next ticket
     }
 }
 
-// A3: create the eight children of every internal node of level d (tree.c:191-274)
-__global__ void children_kernel(TreeDev t, int d) {
-    if (t.meta[M_STATUS]) return;
-    const uint32_t b = t.meta[M_LV_BEGIN + d], e = t.meta[M_LV_END + d];
-    for (uint32_t n = b + blockIdx.x * blockDim.x + threadIdx.x; n < e; n += gridDim.x * blockDim.x) {
-        const uint32_t base = t.child_base[n];
-        if (base == NODE_END) continue;
-        const sfe_node_t* nd = &t.nodes[n];
-        float lo[3], hi[3], mid[3];
-        for (int k = 0; k < 3; k++) {
-            lo[k] = nd->bounds[k]; hi[k] = nd->bounds[3 + k];
-            mid[k] = __fmul_rn(0.5f, __fadd_rn(lo[k], hi[k]));
-        }
-        uint32_t start = t.seg[n].x;
-        const uint32_t nxt = t.next[n];
-        for (uint32_t o = 0; o < 8; o++) {
-            const uint32_t c = base + o, cnt = t.counts[(size_t)n * 8u + o];
-            sfe_node_t ch;
-            ch.parent = n; ch.bodies = cnt;
-            for (int k = 0; k < 8; k++) ch.branch[k] = 0u;
-            for (int k = 0; k < 3; k++) {
-                ch.bounds[k] = (o >> k) & 1u ? mid[k] : lo[k];          // tree.c:219-226
-                ch.bounds[3 + k] = (o >> k) & 1u ? hi[k] : mid[k];
-            }
-            for (int k = 0; k < 4; k++) ch.params[k] = 0.f;
-            t.nodes[c] = ch;
-            t.seg[c] = make_uint2(start, start + cnt);
-            // depth-first successor when c is not opened: the next NON-EMPTY sibling, else the parent's successor.
-            // The reference only steps back to the parent at an empty node (gravity.c:324-328), so leaving empty
-            // nodes out of the walk links changes neither the visit order nor the sums.
-            uint32_t succ = nxt;
-            for (uint32_t o2 = 7u; o2 > o; o2--) if (t.counts[(size_t)n * 8u + o2] > 0u) succ = base + o2;
-            t.next[c] = succ;
-            start += cnt;
-        }
-    }
+// ---------------------------------------------------------------------------- children_kernel
+// level summary for the host (mapped pinned memory): {build id, internal nodes of the level, status, node count}
+__device__ __forceinline__ void publish_summary(const TreeDev& t, int level, uint32_t internal, uint32_t status, uint32_t count) {
+    volatile uint32_t* h = t.summary + 4 * level;
+    h[1] = internal; h[2] = status; h[3] = count;
+    __threadfence_system();
+    h[0] = t.build_id;
 }
 
-// S4: scatter into the next level's slot order
-__global__ void __launch_bounds__(256) part_scatter_kernel(TreeDev t, int d) {
+// Bookkeeping shared by root_kernel and the last tile of children_kernel: level `lv` has `internal` internal nodes;
+// allocate their children as level lv+1 (tree.c:180-189: node budget first, then depth).
+__device__ __forceinline__ void open_level(const TreeDev& t, int lv, uint32_t internal, int depth_max) {
+    const uint32_t end = t.meta[M_LV_END + lv];
+    uint32_t next_end = end + 8u * internal;
+    if (internal > 0u) {
+        if (t.nodes_max <= next_end) { t.meta[M_STATUS] = 1u; next_end = end; }
+        else if (depth_max <= lv) { t.meta[M_STATUS] = 2u; next_end = end; }
+        else t.meta[M_DEPTH] = (uint32_t)lv + 1u;
+    }
+    t.meta[M_LV_BEGIN + lv + 1] = end;
+    t.meta[M_LV_END + lv + 1] = next_end;
+    t.meta[M_COUNT] = next_end;
+    if (next_end == end) t.meta[M_FINAL] = (uint32_t)lv;   // nothing splits at level lv: its slot order is the final one
+    __threadfence();
+    publish_summary(t, lv, next_end != end ? internal : 0u, t.meta[M_STATUS], next_end);
+}
+
+__global__ void root_kernel(TreeDev t, int depth_max) {
+    // runs after the compaction: the root is internal when it holds more than 8 bodies
     const uint32_t M = t.meta[M_NUM_INBOX];
-    const bool split = !t.meta[M_STATUS] && t.meta[M_LV_END + d + 1] != t.meta[M_LV_BEGIN + d + 1];
+    const bool internal = M > 8u;
+    t.child_base[0] = internal ? 1u : NODE_END;
+    const float* b = t.bounds;
+    t.nmid[0] = make_float4(__fmul_rn(0.5f, __fadd_rn(b[0], b[3])), __fmul_rn(0.5f, __fadd_rn(b[1], b[4])),
+                            __fmul_rn(0.5f, __fadd_rn(b[2], b[5])), __uint_as_float(0u));
+    open_level(t, 0, internal ? 1u : 0u, depth_max);
+    if (t.meta[M_STATUS] != 0u) t.child_base[0] = NODE_END;
+    else if (internal) for (int k = 0; k < 8; k++) t.nodes[0].branch[k] = 1u + k;
+}
+
+__global__ void __launch_bounds__(CH_THREADS) children_kernel(TreeDev t, int d, int depth_max) {
+    __shared__ uint32_t sm[33];
+    __shared__ uint32_t s_tile, s_prefix;
+    if (level_idle(t, d)) {
+        // nothing splits at level d: level d+1 does not exist
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (t.meta[M_STATUS] == 0u) { t.meta[M_LV_BEGIN + d + 2] = t.meta[M_LV_END + d + 1]; t.meta[M_LV_END + d + 2] = t.meta[M_LV_END + d + 1]; }
+            publish_summary(t, d + 1, 0u, t.meta[M_STATUS], t.meta[M_COUNT]);
+        }
+        return;
+    }
+    const uint32_t nb = t.meta[M_LV_BEGIN + d], ne = t.meta[M_LV_END + d];
+    const uint32_t ntiles = (ne - nb + CH_THREADS - 1) / CH_THREADS;
+    const uint32_t child_level_end = t.meta[M_LV_END + d + 1];
+    unsigned long long* __restrict__ cdesc = t.cdesc + (size_t)d * t.cdesc_stride;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(&t.ticket[2 * d + 1], 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= ntiles) return;
+        const uint32_t n = nb + tile * CH_THREADS + threadIdx.x;
+        const uint32_t base = n < ne ? t.child_base[n] : NODE_END;
+        uint32_t cnt[8], ki = 0u;
+        if (base != NODE_END) {
+            const uint4 c0 = *reinterpret_cast<const uint4*>(&t.counts[(size_t)n * 8u]);
+            const uint4 c1 = *reinterpret_cast<const uint4*>(&t.counts[(size_t)n * 8u + 4u]);
+            cnt[0] = c0.x; cnt[1] = c0.y; cnt[2] = c0.z; cnt[3] = c0.w; cnt[4] = c1.x; cnt[5] = c1.y; cnt[6] = c1.z; cnt[7] = c1.w;
+#pragma unroll
+            for (int o = 0; o < 8; o++) ki += cnt[o] > 8u ? 1u : 0u;
+        }
+        uint32_t tile_total;
+        const uint32_t ex = block_excl_scan(ki, &tile_total, sm);
+        // warp-parallel decoupled look-back over the tiles of this level: status in the high word, value in the low
+        if (threadIdx.x < 32) {
+            const uint32_t lane = threadIdx.x;
+            uint32_t prefix = 0u;
+            if (tile > 0u) {
+                if (lane == 0) atomicExch(&cdesc[tile], ((unsigned long long)ST_AGG << 32) | tile_total);
+                int jb = (int)tile - 1;
+                for (;;) {
+                    const int j = jb - (int)lane;
+                    const bool valid = j >= 0;
+                    unsigned long long v;
+                    do { v = valid ? *reinterpret_cast<volatile unsigned long long*>(&cdesc[j]) : ((unsigned long long)ST_INCL << 32); }
+                    while (__any_sync(0xFFFFFFFFu, (uint32_t)(v >> 32) == ST_NONE));
+                    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, (uint32_t)(v >> 32) == ST_INCL);
+                    const uint32_t first = ballot ? (uint32_t)__ffs(ballot) - 1u : 32u;
+                    uint32_t x = lane <= first ? (uint32_t)v : 0u;
+#pragma unroll
+                    for (int sh = 16; sh >= 1; sh >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, sh);
+                    prefix += x;
+                    if (ballot) break;
+                    jb -= 32;
+                }
+            }
+            if (lane == 0) {
+                atomicExch(&cdesc[tile], ((unsigned long long)ST_INCL << 32) | (prefix + tile_total));
+                s_prefix = prefix;
+                if (tile == ntiles - 1u) open_level(t, d + 1, prefix + tile_total, depth_max);   // level d+1 has this many internal nodes
+            }
+        }
+        __syncthreads();
+        if (base != NODE_END) {
+            const sfe_node_t* nd = &t.nodes[n];
+            float lo[3], hi[3], mid[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                lo[k] = nd->bounds[k]; hi[k] = nd->bounds[3 + k];
+                mid[k] = __fmul_rn(0.5f, __fadd_rn(lo[k], hi[k]));
+            }
+            uint32_t start = t.seg[n].x;
+            const uint32_t nxt = t.next[n];
+            uint32_t r = s_prefix + ex;                  // rank of this node's first internal child within level d+1
+#pragma unroll
+            for (uint32_t o = 0; o < 8; o++) {
+                const uint32_t c = base + o, cn = cnt[o];
+                sfe_node_t ch;
+                ch.parent = n; ch.bodies = cn;
+#pragma unroll
+                for (int k = 0; k < 8; k++) ch.branch[k] = 0u;
+                float clo[3], chi[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    clo[k] = (o >> k) & 1u ? mid[k] : lo[k];          // tree.c:219-226
+                    chi[k] = (o >> k) & 1u ? hi[k] : mid[k];
+                    ch.bounds[k] = clo[k]; ch.bounds[3 + k] = chi[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) ch.params[k] = 0.f;
+                if (cn > 8u) {
+                    const uint32_t cb = child_level_end + 8u * r; r++;
+                    t.child_base[c] = cb;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) ch.branch[k] = cb + k;
+                    t.nmid[c] = make_float4(__fmul_rn(0.5f, __fadd_rn(clo[0], chi[0])), __fmul_rn(0.5f, __fadd_rn(clo[1], chi[1])),
+                                            __fmul_rn(0.5f, __fadd_rn(clo[2], chi[2])), __uint_as_float(start));
+                } else {
+                    t.child_base[c] = NODE_END;
+                }
+                t.nodes[c] = ch;
+                t.seg[c] = make_uint2(start, start + cn);
+                // depth-first successor when c is not opened: the next NON-EMPTY sibling, else the parent's successor.
+                // The reference only steps back to the parent at an empty node (gravity.c:324-328), so leaving empty
+                // nodes out of the walk links changes neither the visit order nor the sums.
+                uint32_t succ = nxt;
+#pragma unroll
+                for (uint32_t o2 = 7u; o2 > o; o2--) if (cnt[o2] > 0u) succ = base + o2;
+                t.next[c] = succ;
+                start += cn;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------- scatter_kernel
+__global__ void __launch_bounds__(256) scatter_kernel(TreeDev t, int d) {
+    if (level_idle(t, d)) return;
+    const uint32_t M = t.meta[M_NUM_INBOX];
     const uint32_t* __restrict__ perm = t.perm[d];
     uint32_t* __restrict__ perm_next = t.perm[d + 1];
     const uint32_t* __restrict__ slot_node = t.slot_node[d & 1];
     uint32_t* __restrict__ slot_node_next = t.slot_node[(d + 1) & 1];
     const float4* __restrict__ spm4 = t.spm4[d];
     float4* __restrict__ spm4_next = t.spm4[d + 1];
+    const uint64_t* __restrict__ skey = t.skey[d & 1];
+    uint64_t* __restrict__ skey_next = t.skey[(d + 1) & 1];
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < M; s += gridDim.x * blockDim.x) {
-        const uint32_t idx = perm[s];
+        const uint32_t n = slot_node[s];
         uint32_t dest = s, owner = NODE_END;
-        if (split) {
+        uint64_t key = skey[s];
+        if (n != NODE_END) {
             const uint32_t o = t.oct[s];
-            if (o != 0xFFu) {
-                owner = t.child_base[slot_node[s]] + o;
-                dest = t.seg[owner].x + t.rank[s];
-                t.keys[idx] |= (uint64_t)o << (45 - 3 * d);
-            }
+            const uint32_t c = t.child_base[n] + o;
+            const uint2 sg = t.seg[c];
+            dest = sg.x + t.rank[s];
+            owner = (sg.y - sg.x) > 8u ? c : NODE_END;      // only slots of internal nodes stay active
+            key |= (uint64_t)o << (45 - 3 * d);             // digit d of the 48-bit path key
         }
-        perm_next[dest] = idx;
+        perm_next[dest] = perm[s];
         slot_node_next[dest] = owner;
         spm4_next[dest] = spm4[s];
+        skey_next[dest] = key;
+    }
+}
+
+// path keys by particle index (test hook): in-box particles from their final slot, the others get all ones
+__global__ void keys_gather_kernel(TreeDev t, uint32_t N) {
+    const uint32_t M = t.meta[M_NUM_INBOX], fin = t.meta[M_FINAL];
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < N; s += gridDim.x * blockDim.x) {
+        if (s < M) t.keys[t.perm[fin][s]] = t.skey[fin & 1u][s];
+        else t.keys[t.perm_out[s - M]] = ~0ull;
     }
 }
 
@@ -588,8 +686,15 @@ static int launch_moments(Ctx* c, const TreeDev& dv, int d, uint32_t* gate, bool
 __global__ void finalize_kernel(TreeDev t, uint32_t* __restrict__ gate /* null: all nodes; else root only, gated */) {
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
     const uint32_t count = gate ? 1u : t.meta[M_COUNT];
+    const uint32_t* __restrict__ perm_final = t.perm[t.meta[M_FINAL]];
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < count; n += gridDim.x * blockDim.x) {
-        const sfe_node_t nd = t.nodes[n];
+        sfe_node_t nd = t.nodes[n];
+        if (!gate && nd.bodies <= 8u) {
+            // leaf: branch[] lists the members in arrival (= ascending index) order (tree.c:172-175); a leaf's slot
+            // range does not move once the leaf exists, so the final order serves every level
+            const uint32_t sx = t.seg[n].x;
+            for (uint32_t b = 0; b < 8u; b++) { nd.branch[b] = b < nd.bodies ? perm_final[sx + b] : 0u; t.nodes[n].branch[b] = nd.branch[b]; }
+        }
         const float* b = nd.bounds;
         WalkRec0 r0;
         const float ex = __fsub_rn(b[3], b[0]), ey = __fsub_rn(b[4], b[1]), ez = __fsub_rn(b[5], b[2]);
@@ -645,20 +750,35 @@ static TreeDev make_dev(Tree& t) {
     d.child_base = t.child_base.as<uint32_t>();
     d.counts = t.counts.as<uint32_t>();
     d.keys = t.keys.as<uint64_t>();
+    d.skey[0] = t.skey[0].as<uint64_t>(); d.skey[1] = t.skey[1].as<uint64_t>();
     d.perm_out = t.perm_out.as<uint32_t>();
-    for (int k = 0; k < SFE_MAX_LEVELS + 2; k++) { d.perm[k] = t.perm[k].as<uint32_t>(); d.spm4[k] = t.spm4[k].as<float4>(); }
+    for (int k = 0; k < SFE_MAX_LEVELS + 3; k++) { d.perm[k] = t.perm[k].as<uint32_t>(); d.spm4[k] = t.spm4[k].as<float4>(); }
     d.perm0 = d.perm[0];
     d.slot_node[0] = t.slot_node[0].as<uint32_t>();
     d.slot_node[1] = t.slot_node[1].as<uint32_t>();
     d.slot_node0 = d.slot_node[0];
     d.oct = t.oct.as<uint8_t>();
     d.rank = t.rank.as<uint32_t>();
-    d.tile_agg = t.tile_agg.as<uint32_t>();
     d.meta = t.meta.as<uint32_t>();
+    d.nmid = t.nmid.as<float4>();
+    // one zero-initialised block per build: [tickets | rank_kernel descriptors | children_kernel descriptors]
+    const uint32_t levels = SFE_MAX_LEVELS + 2;
+    d.tdesc_stride = (uint32_t)(((size_t)(t.N ? t.N : 1) + PT_TILE - 1) / PT_TILE + 1) * DESC_WORDS;
+    d.cdesc_stride = (t.nodes_max + CH_THREADS - 1) / CH_THREADS + 1;
+    d.ticket = t.lookback.as<uint32_t>();
+    d.tdesc = d.ticket + 2 * levels;
+    d.cdesc = reinterpret_cast<unsigned long long*>(t.lookback.as<char>() + (((size_t)(2 * levels) + (size_t)levels * d.tdesc_stride) * 4 + 7) / 8 * 8);
+    d.summary = t.summary_dev;
+    d.build_id = t.build_id;
     d.rec0 = t.rec0.as<WalkRec0>();
     d.rec1 = t.rec1.as<float4>();
     d.rec2 = t.rec2.as<WalkRec2>();
     return d;
+}
+
+static size_t lookback_bytes(const TreeDev& d) {
+    const size_t levels = SFE_MAX_LEVELS + 2;
+    return ((2 * levels + levels * d.tdesc_stride) * 4 + 7) / 8 * 8 + levels * (size_t)d.cdesc_stride * 8;
 }
 
 TreeDev tree_dev(Ctx* c) { return make_dev(c->tree); }
@@ -675,27 +795,36 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     const size_t n1 = N ? N : 1;
     if (t.nodes.reserve((size_t)nodes_max * sizeof(sfe_node_t), fn) || t.seg.reserve((size_t)nodes_max * 8, fn) ||
         t.next.reserve((size_t)nodes_max * 4, fn) || t.child_base.reserve((size_t)nodes_max * 4, fn) ||
-        t.counts.reserve((size_t)nodes_max * 32, fn) || t.keys.reserve(n1 * 8, fn) || t.perm_out.reserve(n1 * 4, fn) ||
-        t.slot_node[0].reserve(n1 * 4, fn) || t.slot_node[1].reserve(n1 * 4, fn) || t.oct.reserve(n1, fn) ||
-        t.rank.reserve(n1 * 4, fn) || t.tile_agg.reserve(((n1 + PT_TILE - 1) / PT_TILE + 1) * 36, fn) ||
+        t.counts.reserve((size_t)nodes_max * 32, fn) || t.nmid.reserve((size_t)nodes_max * 16, fn) || t.skey[0].reserve(n1 * 8, fn) || t.skey[1].reserve(n1 * 8, fn) ||
+        t.perm_out.reserve(n1 * 4, fn) || t.slot_node[0].reserve(n1 * 4, fn) || t.slot_node[1].reserve(n1 * 4, fn) ||
+        t.oct.reserve(n1, fn) || t.rank.reserve(n1 * 4, fn) ||
         t.meta.reserve(M_WORDS * 4, fn) || t.root_gate.reserve(8, fn) || t.rec0.reserve((size_t)nodes_max * sizeof(WalkRec0), fn) ||
         t.rec1.reserve((size_t)nodes_max * 16, fn) || t.rec2.reserve((size_t)nodes_max * sizeof(WalkRec2), fn) ||
         t.perm[0].reserve(n1 * 4, fn) || t.perm[1].reserve(n1 * 4, fn) || t.spm4[0].reserve(n1 * 16, fn) ||
         t.spm4[1].reserve(n1 * 16, fn))
         return SFE_FAILURE;
-    if (!t.meta_host) SFE_CUDA(fn, cudaMallocHost(&t.meta_host, sizeof(uint32_t) * M_WORDS * (SFE_MAX_LEVELS + 2)));
+    if (!t.meta_host) SFE_CUDA(fn, cudaMallocHost(&t.meta_host, sizeof(uint32_t) * M_WORDS));
+    if (!t.summary_host) {
+        SFE_CUDA(fn, cudaHostAlloc(&t.summary_host, sizeof(uint32_t) * 4 * (SFE_MAX_LEVELS + 4), cudaHostAllocMapped));
+        memset(t.summary_host, 0, sizeof(uint32_t) * 4 * (SFE_MAX_LEVELS + 4));
+        SFE_CUDA(fn, cudaHostGetDevicePointer(&t.summary_dev, t.summary_host, 0));
+    }
     if (!t.ev_init) {
-        for (int k = 0; k < SFE_MAX_LEVELS + 2; k++) {
-            SFE_CUDA(fn, cudaEventCreateWithFlags(&t.ev_level[k], cudaEventDisableTiming));
+        for (int k = 0; k < SFE_MAX_LEVELS + 3; k++)
             SFE_CUDA(fn, cudaEventCreateWithFlags(&t.ev_perm[k], trace_enabled() ? cudaEventDefault : cudaEventDisableTiming));
-        }
         for (auto& ev : t.ev_side) SFE_CUDA(fn, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         if (trace_enabled()) for (auto& ev : g_trace_ev) SFE_CUDA(fn, cudaEventCreate(&ev));
         t.ev_init = true;
     }
+    t.build_id++;
+    if (t.build_id == 0u) t.build_id = 1u;
 
     TreeDev dv = make_dev(t);
-    const uint32_t pgrid = [&] { uint32_t g = (N + PT_TILE - 1) / PT_TILE; uint32_t cap = (uint32_t)c->sm_count * 8; return g < 1 ? 1u : (g < cap ? g : cap); }();
+    if (t.lookback.reserve(lookback_bytes(dv), fn)) return SFE_FAILURE;
+    dv = make_dev(t);
+    SFE_CUDA(fn, cudaMemsetAsync(t.lookback.p, 0, lookback_bytes(dv), s));
+    const uint32_t pgrid = [&] { uint32_t g = (N + PT_TILE - 1) / PT_TILE; uint32_t cap = (uint32_t)c->sm_count * 6; return g < 1 ? 1u : (g < cap ? g : cap); }();
+    const uint32_t cgrid = [&] { uint32_t g = (nodes_max + CH_THREADS - 1) / CH_THREADS; uint32_t cap = (uint32_t)c->sm_count * 4; return g < 1 ? 1u : (g < cap ? g : cap); }();
     const uint32_t sgrid = [&] { uint32_t g = (N + 255) / 256; uint32_t cap = (uint32_t)c->sm_count * 16; return g < 1 ? 1u : (g < cap ? g : cap); }();
 
     // level 0: in-box compaction + root
@@ -703,24 +832,45 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         CompactOp op{pm4, N, dv};
         if (run_scan(c, op, N, s, fn)) return SFE_FAILURE;
     }
+    root_kernel<<<1, 1, 0, s>>>(dv, depth_max);
+    if (check_launch(fn)) return SFE_FAILURE;
     SFE_CUDA(fn, cudaEventRecord(t.ev_perm[0], s));
 
+    // summary[lv] = {build id, internal nodes of level lv, status, node count}, written by the device into mapped
+    // host memory; the host only spins on it (no stream operation), two levels behind the device
+    auto wait_summary = [&](int lv, uint32_t* internal, uint32_t* status) -> int {
+        volatile uint32_t* h = t.summary_host + 4 * lv;
+        uint64_t spins = 0;
+        while (h[0] != t.build_id) {
+            if ((++spins & 0xFFFFu) == 0u) {
+                cudaError_t q = cudaStreamQuery(s);
+                if (q != cudaErrorNotReady && h[0] != t.build_id) {
+                    if (q == cudaSuccess) set_error(fn, "level %d never reported", lv);
+                    else set_error(fn, "stream failed while building level %d: %s", lv, cudaGetErrorString(q));
+                    return SFE_FAILURE;
+                }
+            }
+        }
+        *internal = h[1]; *status = h[2];
+        return SFE_SUCCESS;
+    };
+
     int levels_run = 0;
-    double host_us[SFE_MAX_LEVELS + 3];
+    double host_us[SFE_MAX_LEVELS + 4];
     const auto host_t0 = std::chrono::steady_clock::now();
     for (int d = 0; d <= depth_max; d++) {
         host_us[d] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count();
+        // level d only exists if level d-1 has internal nodes; the host learns that one level late, so the kernels
+        // of at most one empty level are enqueued (they return at once)
+        if (d >= 2) {
+            uint32_t internal = 0, status = 0;
+            if (wait_summary(d - 1, &internal, &status)) return SFE_FAILURE;
+            if (internal == 0u || status != 0u) break;
+        }
         // make sure perm[d+1] exists (first build at this depth only) and refresh the device view
         if (t.perm[d + 1].cap < n1 * 4 || t.spm4[d + 1].cap < n1 * 16) {
             if (t.perm[d + 1].reserve(n1 * 4, fn) || t.spm4[d + 1].reserve(n1 * 16, fn)) return SFE_FAILURE;
             dv = make_dev(t);
-        }
-        // the host learns level sizes two levels late, which keeps the queue full while it waits
-        if (d >= 2) {
-            SFE_CUDA(fn, cudaEventSynchronize(t.ev_level[d - 2]));
-            const uint32_t* mh = t.meta_host + (size_t)(d - 2) * M_WORDS;
-            const bool more = mh[M_STATUS] == 0 && mh[M_LV_END + d - 1] != mh[M_LV_BEGIN + d - 1];
-            if (!more) break;   // level d-1 is empty (or the build failed): nothing left to split
         }
         levels_run = d + 1;
         // moments of level d on a side stream (needs perm[d]); the root's fold is deferred
@@ -731,27 +881,14 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
             if (launch_moments(c, dv, d, nullptr, false, side, fn)) return SFE_FAILURE;
             if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d + 1], side);
         }
-        // child allocation for level d
-        {
-            AllocOp op{dv, d, depth_max};
-            if (run_scan(c, op, nodes_max, s, fn)) return SFE_FAILURE;
-        }
-        SFE_CUDA(fn, cudaMemcpyAsync(t.meta_host + (size_t)d * M_WORDS, t.meta.p, sizeof(uint32_t) * M_WORDS,
-                                     cudaMemcpyDeviceToHost, s));
-        SFE_CUDA(fn, cudaEventRecord(t.ev_level[d], s));
-        part_aggregate_kernel<<<pgrid, PT_THREADS, 0, s>>>(dv, d);
+        rank_kernel<<<pgrid, PT_THREADS, 0, s>>>(dv, d);
         if (check_launch(fn)) return SFE_FAILURE;
-        part_tilescan_kernel<<<1, TS_THREADS, 0, s>>>(dv, d);
+        children_kernel<<<cgrid, CH_THREADS, 0, s>>>(dv, d, depth_max);
         if (check_launch(fn)) return SFE_FAILURE;
-        part_rank_kernel<<<pgrid, PT_THREADS, 0, s>>>(dv, d);
-        if (check_launch(fn)) return SFE_FAILURE;
-        children_kernel<<<c->sm_count * 2, 128, 0, s>>>(dv, d);
-        if (check_launch(fn)) return SFE_FAILURE;
-        part_scatter_kernel<<<sgrid, 256, 0, s>>>(dv, d);
+        scatter_kernel<<<sgrid, 256, 0, s>>>(dv, d);
         if (check_launch(fn)) return SFE_FAILURE;
         SFE_CUDA(fn, cudaEventRecord(t.ev_perm[d + 1], s));
     }
-    t.final_perm = levels_run;   // perm[levels_run] is the last one written by a scatter
     if (trace_enabled()) {   // SFE_TRACE=1: where does the build spend its time (device time per level vs host enqueue time)
         host_us[levels_run] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count();
         cudaStreamSynchronize(s);
@@ -782,8 +919,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         cudaEventElapsedTime(&b, t.ev_perm[0], g_trace_ev[1]);
         fprintf(stderr, "[sfe trace] finalize: start %8.1f us  end %8.1f us (relative to the end of the compaction)\n", a * 1e3, b * 1e3);
     }
-    SFE_CUDA(fn, cudaMemcpyAsync(t.meta_host + (size_t)(SFE_MAX_LEVELS + 1) * M_WORDS, t.meta.p, sizeof(uint32_t) * M_WORDS,
-                                 cudaMemcpyDeviceToHost, s));
+    SFE_CUDA(fn, cudaMemcpyAsync(t.meta_host, t.meta.p, sizeof(uint32_t) * M_WORDS, cudaMemcpyDeviceToHost, s));
     t.pm4_of_build = pm4;
     SFE_CUDA(fn, cudaMemsetAsync(t.root_gate.p, 0, 8, s));
     t.valid = true;
@@ -842,8 +978,8 @@ int tree_status(Ctx* c, cudaStream_t s) {
     if (!t.valid && !t.meta_host) { set_error(fn, "no tree has been built"); return SFE_FAILURE; }
     if (!t.status_fetched) {
         SFE_CUDA(fn, cudaStreamSynchronize(s));
-        const uint32_t* mh = t.meta_host + (size_t)(SFE_MAX_LEVELS + 1) * M_WORDS;
-        t.num_nodes = mh[M_COUNT]; t.num_inbox = mh[M_NUM_INBOX]; t.depth = mh[M_DEPTH]; t.status = (int)mh[M_STATUS];
+        const uint32_t* mh = t.meta_host;
+        t.num_nodes = mh[M_COUNT]; t.num_inbox = mh[M_NUM_INBOX]; t.depth = mh[M_DEPTH]; t.status = (int)mh[M_STATUS]; t.final_perm = (int)mh[M_FINAL];
         t.status_fetched = true;
     }
     if (t.status == 1) { t.valid = false; set_error(fn, "Exceeded maximum number of tree nodes!"); return SFE_FAILURE; }   // tree.c:181
@@ -879,7 +1015,14 @@ extern "C" int sfe_tree_keys_download(uint64_t* keys, uint32_t* perm, uint32_t N
     if (!t.valid || t.N != N) { set_error(fn, "no valid tree for N=%u", N); return SFE_FAILURE; }
     if (tree_status(c, c->stream)) return SFE_FAILURE;
     if (num_inbox) *num_inbox = t.num_inbox;
-    if (keys) SFE_CUDA(fn, cudaMemcpyAsync(keys, t.keys.p, (size_t)N * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (keys) {
+        if (t.keys.reserve((size_t)(N ? N : 1) * 8, fn)) return SFE_FAILURE;
+        if (N) {
+            keys_gather_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(tree_dev(c), N);
+            if (check_launch(fn)) return SFE_FAILURE;
+        }
+        SFE_CUDA(fn, cudaMemcpyAsync(keys, t.keys.p, (size_t)N * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
     if (perm) {
         SFE_CUDA(fn, cudaMemcpyAsync(perm, t.perm[t.final_perm].p, (size_t)t.num_inbox * 4, cudaMemcpyDeviceToHost, c->stream));
         SFE_CUDA(fn, cudaMemcpyAsync(perm + t.num_inbox, t.perm_out.p, (size_t)(N - t.num_inbox) * 4, cudaMemcpyDeviceToHost, c->stream));

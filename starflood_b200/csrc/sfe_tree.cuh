@@ -12,9 +12,10 @@ enum : int {
     M_STATUS = 1,      // 0 ok, 1 node overflow (tree.c:180-183), 2 depth overflow (tree.c:186-189)
     M_NUM_INBOX = 2,   // particles inside the root box
     M_DEPTH = 3,       // deepest level that holds nodes
-    M_LV_BEGIN = 4,                        // [SFE_MAX_LEVELS + 2] first node id of each level
-    M_LV_END = M_LV_BEGIN + SFE_MAX_LEVELS + 2,   // [SFE_MAX_LEVELS + 2] one past the last node id of each level
-    M_WORDS = M_LV_END + SFE_MAX_LEVELS + 2
+    M_FINAL = 4,       // level whose slot arrays (perm[], spm4[]) hold the final (key, index)-sorted order
+    M_LV_BEGIN = 5,                        // [SFE_MAX_LEVELS + 3] first node id of each level
+    M_LV_END = M_LV_BEGIN + SFE_MAX_LEVELS + 3,   // [SFE_MAX_LEVELS + 3] one past the last node id of each level
+    M_WORDS = M_LV_END + SFE_MAX_LEVELS + 3
 };
 
 // walk records --------------------------------------------------------------------------------------
@@ -43,17 +44,24 @@ struct TreeDev {
     uint32_t* next;
     uint32_t* child_base;
     uint32_t* counts;
-    uint64_t* keys;
-    uint32_t* perm[SFE_MAX_LEVELS + 2];
-    float4* spm4[SFE_MAX_LEVELS + 2];   // slot-ordered copy of pm4 per level
+    uint64_t* keys;               // 48-bit path keys by particle index (filled on demand by sfe_tree_keys_download)
+    uint64_t* skey[2];            // path key of every slot, ping-pong between levels (level d lives in skey[d & 1])
+    uint32_t* perm[SFE_MAX_LEVELS + 3];
+    float4* spm4[SFE_MAX_LEVELS + 3];   // slot-ordered copy of pm4 per level
     uint32_t* perm0;
     uint32_t* perm_out;
     uint32_t* slot_node[2];
     uint32_t* slot_node0;
     uint8_t* oct;
     uint32_t* rank;
-    uint32_t* tile_agg;
     uint32_t* meta;
+    float4* nmid;                 // internal nodes: {mid x, y, z (tree.c:159-163), first slot as bits}
+    uint32_t* ticket;             // [2 * levels] tile tickets of rank_kernel / children_kernel
+    uint32_t* tdesc;              // look-back descriptors of rank_kernel, tdesc_stride words per level
+    unsigned long long* cdesc;    // look-back descriptors of children_kernel, cdesc_stride entries per level
+    uint32_t tdesc_stride, cdesc_stride;
+    volatile uint32_t* summary;   // mapped host memory: {build id, internal nodes, status, node count} per level
+    uint32_t build_id;
     WalkRec0* rec0;
     float4* rec1;      // {com x, y, z, mass}
     WalkRec2* rec2;

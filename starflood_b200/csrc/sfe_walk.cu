@@ -103,14 +103,15 @@ __device__ __forceinline__ bool opens(float w2, float d2, float theta) {
 template <int FLAVOUR>
 __global__ void __launch_bounds__(WALK_THREADS)
 walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restrict__ slots /* null: all */,
-            uint32_t nslots, uint32_t final_perm, float G, float eps2, float theta,
+            uint32_t nslots, float G, float eps2, float theta,
             float* __restrict__ acc, float* __restrict__ pot) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nslots) return;
     const uint32_t M = t.meta[M_NUM_INBOX];
     const uint32_t s = slots ? slots[k] : k;
-    const uint32_t idx = s < M ? t.perm[final_perm][s] : t.perm_out[s - M];
-    const float4 me = s < M ? t.spm4[final_perm][s] : pm4[idx];
+    const uint32_t fin = t.meta[M_FINAL];
+    const uint32_t idx = s < M ? t.perm[fin][s] : t.perm_out[s - M];
+    const float4 me = s < M ? t.spm4[fin][s] : pm4[idx];
     const float x = me.x, y = me.y, z = me.z, mi = me.w;
 
     KahanRef ax = {0.f, 0.f}, ay = {0.f, 0.f}, az = {0.f, 0.f}, ap = {0.f, 0.f};
@@ -194,11 +195,11 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
 
 // slots whose particle index lies in [i0, i0+ni), in slot order (multi-GPU target slices)
 struct SliceOp {
-    TreeDev t; uint32_t N, i0, i1, final_perm; uint32_t* out; uint32_t* count;
+    TreeDev t; uint32_t N, i0, i1; uint32_t* out; uint32_t* count;
     __device__ uint32_t n() const { return N; }
     __device__ uint32_t idx_of(uint32_t s) const {
         const uint32_t M = t.meta[M_NUM_INBOX];
-        return s < M ? t.perm[final_perm][s] : t.perm_out[s - M];
+        return s < M ? t.perm[t.meta[M_FINAL]][s] : t.perm_out[s - M];
     }
     __device__ uint32_t load(uint32_t s) const { const uint32_t i = idx_of(s); return (i >= i0 && i < i1) ? 1u : 0u; }
     __device__ void store(uint32_t s, uint32_t ex) const { const uint32_t i = idx_of(s); if (i >= i0 && i < i1) out[ex] = s; }
@@ -209,7 +210,7 @@ struct SliceOp {
 static int walk_slice_slots(Ctx* c, uint32_t N, uint32_t i0, uint32_t ni, cudaStream_t s, uint32_t** slots_out) {
     Tree& t = c->tree;
     if (t.slice_count.reserve(4, "sfe_bh")) return SFE_FAILURE;
-    SliceOp op{tree_dev(c), N, i0, i0 + ni, (uint32_t)t.final_perm, t.rank.as<uint32_t>(), t.slice_count.as<uint32_t>()};
+    SliceOp op{tree_dev(c), N, i0, i0 + ni, t.rank.as<uint32_t>(), t.slice_count.as<uint32_t>()};
     if (run_scan(c, op, N, s, "sfe_bh")) return SFE_FAILURE;
     *slots_out = t.rank.as<uint32_t>();
     return SFE_SUCCESS;
@@ -229,9 +230,9 @@ int launch_bh(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, f
     if (ni != N && walk_slice_slots(c, N, i0, ni, s, &slots)) return SFE_FAILURE;
     const uint32_t grid = (ni + WALK_THREADS - 1) / WALK_THREADS;
     if (flavour == SFE_WALK_EXACT)
-        walk_kernel<(int)SFE_WALK_EXACT><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, ni, (uint32_t)t.final_perm, G, eps2, theta, acc, pot);
+        walk_kernel<(int)SFE_WALK_EXACT><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, ni, G, eps2, theta, acc, pot);
     else
-        walk_kernel<(int)SFE_WALK_FAST><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, ni, (uint32_t)t.final_perm, G, eps2, theta, acc, pot);
+        walk_kernel<(int)SFE_WALK_FAST><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, ni, G, eps2, theta, acc, pot);
     return check_launch(fn);
 }
 
