@@ -173,7 +173,7 @@ extern "C" int sfe_shutdown(void) {
     DevBuf* bufs[] = {&c->d_pos, &c->d_mas, &c->d_pm4, &c->d_acc, &c->d_pot, &c->d_rad, &c->d_rho, &c->d_prs,
                       &c->pp_src, &c->pp_partial, &c->sph_src, &c->sph_partial,
                       &t.nodes, &t.seg, &t.next, &t.child_base, &t.counts, &t.keys, &t.perm_out, &t.slot_node[0],
-                      &t.slot_node[1], &t.oct, &t.rank, &t.nmid, &t.lookback, &t.scan_tmp, &t.slice_count, &t.root_gate, &t.meta, &t.rec0, &t.rec1, &t.rec2};
+                      &t.slot_node[1], &t.oct, &t.rank, &t.nmid, &t.lookback, &t.xl_sum, &t.xl_map, &t.scan_tmp, &t.slice_count, &t.root_gate, &t.meta, &t.rec0, &t.rec1, &t.rec2};
     for (DevBuf& b : t.perm) b.release();
     for (DevBuf& b : t.spm4) b.release();
     for (DevBuf& b : t.skey) b.release();

@@ -69,7 +69,8 @@ struct Tree {
     DevBuf oct;          // uint8_t[N]
     DevBuf rank;         // uint32_t[N]            stable rank inside (node, octant)
     DevBuf nmid;         // float4[nodes_max]      split planes of internal nodes
-    DevBuf lookback;     // tickets + look-back descriptors of one build (zeroed per build)
+    DevBuf lookback;     // tickets + look-back descriptors + long-node lists of one build (zeroed per build)
+    DevBuf xl_sum, xl_map;   // scratch of the exact chunked fold
     uint32_t* summary_host = nullptr;  // mapped pinned: per-level summaries written by the device
     uint32_t* summary_dev = nullptr;
     uint32_t build_id = 0;

@@ -58,12 +58,11 @@ struct CompactOp {
         t.meta[M_FINAL] = 0u;
         t.meta[M_LV_BEGIN + 0] = 0u;
         t.meta[M_LV_END + 0] = 1u;
-        sfe_node_t root;
-        root.parent = 0u; root.bodies = M;
-        for (int k = 0; k < 8; k++) root.branch[k] = 0u;
-        for (int k = 0; k < 6; k++) root.bounds[k] = t.bounds[k];
-        for (int k = 0; k < 4; k++) root.params[k] = 0.f;
-        t.nodes[0] = root;
+        WalkRec2 root;                       // root cell (tree.c:113-115)
+        for (int k = 0; k < 3; k++) { root.lo[k] = t.bounds[k]; root.hi[k] = t.bounds[3 + k]; }
+        root.parent = 0u; root.pad = 0u;
+        t.rec2[0] = root;
+        t.rec1[0] = make_float4(0.f, 0.f, 0.f, 0.f);
         t.seg[0] = make_uint2(0u, M);
         t.next[0] = NODE_END;
     }
@@ -89,6 +88,7 @@ constexpr int PT_TILE = PT_THREADS * PT_ITEMS;
 constexpr uint32_t DESC_WORDS = 20u;   // tile descriptor of the segmented look-back: [0] status, [1] has_head, [2..9] agg, [10..17] incl
 constexpr uint32_t ST_NONE = 0u, ST_AGG = 1u, ST_INCL = 2u;
 constexpr int CH_THREADS = 256;
+constexpr int XL_DEPTH_MAX = 6;          // deeper levels never use the chunked exact fold (their long nodes go through moments_long)
 
 struct Cnt8 {                // eight 16-bit counters (a tile holds 2048 slots)
     uint32_t w[4];
@@ -357,10 +357,10 @@ __global__ void root_kernel(TreeDev t, int depth_max) {
     t.child_base[0] = internal ? 1u : NODE_END;
     const float* b = t.bounds;
     t.nmid[0] = make_float4(__fmul_rn(0.5f, __fadd_rn(b[0], b[3])), __fmul_rn(0.5f, __fadd_rn(b[1], b[4])),
-                            __fmul_rn(0.5f, __fadd_rn(b[2], b[5])), __uint_as_float(0u));
+                            __fmul_rn(0.5f, __fadd_rn(b[2], b[5])), 0.f);
+    if (M > t.xl_min) { t.xl_count[0] = 1u; t.xl_nodes[0] = 0u; }
     open_level(t, 0, internal ? 1u : 0u, depth_max);
     if (t.meta[M_STATUS] != 0u) t.child_base[0] = NODE_END;
-    else if (internal) for (int k = 0; k < 8; k++) t.nodes[0].branch[k] = 1u + k;
 }
 
 __global__ void __launch_bounds__(CH_THREADS) children_kernel(TreeDev t, int d, int depth_max) {
@@ -426,44 +426,40 @@ __global__ void __launch_bounds__(CH_THREADS) children_kernel(TreeDev t, int d, 
         }
         __syncthreads();
         if (base != NODE_END) {
-            const sfe_node_t* nd = &t.nodes[n];
-            float lo[3], hi[3], mid[3];
+            const float4 b0 = *reinterpret_cast<const float4*>(&t.rec2[n]);          // lo.x lo.y lo.z hi.x
+            const float4 b1 = *(reinterpret_cast<const float4*>(&t.rec2[n]) + 1);    // hi.y hi.z parent -
+            const float lo[3] = {b0.x, b0.y, b0.z}, hi[3] = {b0.w, b1.x, b1.y};
+            float mid[3];
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                lo[k] = nd->bounds[k]; hi[k] = nd->bounds[3 + k];
-                mid[k] = __fmul_rn(0.5f, __fadd_rn(lo[k], hi[k]));
-            }
+            for (int k = 0; k < 3; k++) mid[k] = __fmul_rn(0.5f, __fadd_rn(lo[k], hi[k]));   // tree.c:159-163
             uint32_t start = t.seg[n].x;
             const uint32_t nxt = t.next[n];
             uint32_t r = s_prefix + ex;                  // rank of this node's first internal child within level d+1
 #pragma unroll
             for (uint32_t o = 0; o < 8; o++) {
                 const uint32_t c = base + o, cn = cnt[o];
-                sfe_node_t ch;
-                ch.parent = n; ch.bodies = cn;
-#pragma unroll
-                for (int k = 0; k < 8; k++) ch.branch[k] = 0u;
                 float clo[3], chi[3];
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
                     clo[k] = (o >> k) & 1u ? mid[k] : lo[k];          // tree.c:219-226
                     chi[k] = (o >> k) & 1u ? hi[k] : mid[k];
-                    ch.bounds[k] = clo[k]; ch.bounds[3 + k] = chi[k];
                 }
-#pragma unroll
-                for (int k = 0; k < 4; k++) ch.params[k] = 0.f;
+                float4* cell = reinterpret_cast<float4*>(&t.rec2[c]);
+                cell[0] = make_float4(clo[0], clo[1], clo[2], chi[0]);
+                cell[1] = make_float4(chi[1], chi[2], __uint_as_float(n), 0.f);
+                t.rec1[c] = make_float4(0.f, 0.f, 0.f, 0.f);          // moments of empty nodes stay zero (tree.c:302-310)
                 if (cn > 8u) {
-                    const uint32_t cb = child_level_end + 8u * r; r++;
-                    t.child_base[c] = cb;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) ch.branch[k] = cb + k;
+                    t.child_base[c] = child_level_end + 8u * r; r++;
                     t.nmid[c] = make_float4(__fmul_rn(0.5f, __fadd_rn(clo[0], chi[0])), __fmul_rn(0.5f, __fadd_rn(clo[1], chi[1])),
-                                            __fmul_rn(0.5f, __fadd_rn(clo[2], chi[2])), __uint_as_float(start));
+                                            __fmul_rn(0.5f, __fadd_rn(clo[2], chi[2])), 0.f);
                 } else {
                     t.child_base[c] = NODE_END;
                 }
-                t.nodes[c] = ch;
                 t.seg[c] = make_uint2(start, start + cn);
+                if (d + 1 <= XL_DEPTH_MAX && cn > t.xl_min) {     // very long fold: chunked exact evaluation (moments_xl)
+                    const uint32_t k = atomicAdd(&t.xl_count[d + 1], 1u);
+                    if (k < t.xl_max) t.xl_nodes[(size_t)(d + 1) * t.xl_max + k] = c;
+                }
                 // depth-first successor when c is not opened: the next NON-EMPTY sibling, else the parent's successor.
                 // The reference only steps back to the parent at an empty node (gravity.c:324-328), so leaving empty
                 // nodes out of the walk links changes neither the visit order nor the sums.
@@ -543,6 +539,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// which kernel folds a node with cn members at level d
+__device__ __forceinline__ bool xl_owns(const TreeDev& t, int d, uint32_t cn) { return d <= XL_DEPTH_MAX && cn > t.xl_min; }
+__device__ __forceinline__ bool ml_owns(const TreeDev& t, int d, uint32_t cn) { return cn > ML_MIN && !xl_owns(t, d, cn); }
+
 __global__ void __launch_bounds__(ML_THREADS) moments_long_kernel(TreeDev t, int d,
                                                                   uint32_t* __restrict__ gate /* {needed, done} or null */) {
     extern __shared__ __align__(16) unsigned char ml_smem[];
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(ML_THREADS) moments_long_kernel(TreeDev t, int
         for (int i = 0; i < 8; i++) {
             const uint2 sg = base + i < e ? t.seg[base + i] : make_uint2(0u, 0u);
             const uint32_t cn = sg.y - sg.x;
-            maxcnt = max(maxcnt, cn > ML_MIN ? cn : 0u);
+            maxcnt = max(maxcnt, ml_owns(t, d, cn) ? cn : 0u);
         }
         if (maxcnt == 0u) continue;
         const uint32_t nbatch = (maxcnt + ML_B - 1) / ML_B;
@@ -579,17 +579,17 @@ __global__ void __launch_bounds__(ML_THREADS) moments_long_kernel(TreeDev t, int
             __syncthreads();                                       // group done: buffers may be reused
             const uint32_t q = lane >> 2, c = lane & 3u;
             const uint2 msg = base + q < e ? t.seg[base + q] : make_uint2(0u, 0u);
-            const uint32_t mycount = (msg.y - msg.x) > ML_MIN ? (msg.y - msg.x) : 0u;
+            const uint32_t mycount = ml_owns(t, d, msg.y - msg.x) ? (msg.y - msg.x) : 0u;
             const float mass = __shfl_sync(0xFFFFFFFFu, sum, lane | 3u);
             if (mycount) {
                 const float inv = 0.f < mass ? __fdiv_rn(1.0f, mass) : 1.0f;   // tree.c:303-304
-                t.nodes[base + q].params[c] = c < 3u ? __fmul_rn(sum, inv) : sum;
+                reinterpret_cast<float*>(&t.rec1[base + q])[c] = c < 3u ? __fmul_rn(sum, inv) : sum;
             }
         } else {
             // ---------------------------------------------------------------- producers: one node per warp
             const uint32_t node = warp - 1u;
             const uint2 sg = base + node < e ? t.seg[base + node] : make_uint2(0u, 0u);
-            const uint32_t cnt = (sg.y - sg.x) > ML_MIN ? (sg.y - sg.x) : 0u;
+            const uint32_t cnt = ml_owns(t, d, sg.y - sg.x) ? (sg.y - sg.x) : 0u;
             const float4* __restrict__ src = spm4 + sg.x;
             auto issue = [&](uint32_t k) {       // raw batch k -> ring slot k % ML_R
                 const uint32_t j0 = k * ML_B;
@@ -665,8 +665,210 @@ __global__ void __launch_bounds__(256) moments_short_kernel(TreeDev t, int d, ui
         const float mass = __shfl_sync(0xFFFFFFFFu, sum, (threadIdx.x & 31u) | 3u);
         if (cnt) {
             const float inv = 0.f < mass ? __fdiv_rn(1.0f, mass) : 1.0f;   // tree.c:303-304
-            t.nodes[n].params[c] = c < 3u ? __fmul_rn(sum, inv) : sum;
+            reinterpret_cast<float*>(&t.rec1[n])[c] = c < 3u ? __fmul_rn(sum, inv) : sum;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------- exact chunked fold of very long nodes
+// The left fold s <- RN(s + p_j) is serial, but while s stays inside one binade [2^23, 2^24) * u every addition is an
+// integer step on k = s / u:  k <- RNE(k + p_j / u) = k + floor(t_j) + [frac(t_j) > 1/2] (+1 on an exact tie when
+// k + floor(t_j) is odd).  As a function of k such a step only depends on the PARITY of k, steps of that kind are
+// closed under composition, and composition is associative - so a whole chunk of XL_CHUNK members collapses, in
+// parallel, into a map k -> k + a[k & 1], together with the extremes of the running value inside the chunk.
+//   xl_sums / xl_prefix   approximate value of the fold at every chunk boundary (double sums of the rounded products),
+//                         good enough to GUESS the binade, i.e. u, of each chunk;
+//   xl_maps               per chunk and component: the parity map and the prefix extremes for the guessed u;
+//   xl_chain              the only serial part: one step per CHUNK.  The map is used only if the actual s is a
+//                         multiple of u strictly inside the binade and the extremes keep every intermediate value
+//                         inside it; otherwise (binade crossings, the first chunks, wrong guesses) that chunk is folded
+//                         member by member.  The result is the reference's bit pattern either way.
+constexpr int XL_CHUNK = 1024;
+constexpr long long XL_INF = 1ll << 62;
+struct XlMap { long long a0, a1, mn0, mx0, mn1, mx1, e2, usable; };   // 64 B
+
+__device__ __forceinline__ XlMap xl_combine(const XlMap& A, const XlMap& B) {   // A first, then B
+    XlMap C;
+    const bool p0 = (A.a0 & 1ll) != 0;            // parity after A when entering even
+    const bool p1 = ((1ll + A.a1) & 1ll) != 0;    // parity after A when entering odd
+    C.a0 = A.a0 + (p0 ? B.a1 : B.a0);
+    C.a1 = A.a1 + (p1 ? B.a1 : B.a0);
+    C.mn0 = min(A.mn0, A.a0 + (p0 ? B.mn1 : B.mn0));
+    C.mx0 = max(A.mx0, A.a0 + (p0 ? B.mx1 : B.mx0));
+    C.mn1 = min(A.mn1, A.a1 + (p1 ? B.mn1 : B.mn0));
+    C.mx1 = max(A.mx1, A.a1 + (p1 ? B.mx1 : B.mx0));
+    C.e2 = A.e2; C.usable = A.usable;
+    return C;
+}
+__device__ __forceinline__ long long shfl_down_ll(long long v, int off) {
+    const int lo = __shfl_down_sync(0xFFFFFFFFu, (int)(v & 0xFFFFFFFFll), off);
+    const int hi = __shfl_down_sync(0xFFFFFFFFu, (int)(v >> 32), off);
+    return ((long long)hi << 32) | (unsigned int)lo;
+}
+__device__ __forceinline__ float xl_term(float4 p, uint32_t q) {   // the q-th summand of tree.c:166-169
+    return q == 0u ? __fmul_rn(p.w, p.x) : q == 1u ? __fmul_rn(p.w, p.y) : q == 2u ? __fmul_rn(p.w, p.z) : p.w;
+}
+struct XlNode { uint32_t n, first, cnt, nchunks, slot0; };
+__device__ __forceinline__ bool xl_node(const TreeDev& t, int d, uint32_t k, XlNode* out) {
+    if (k >= t.xl_count[d]) return false;
+    out->n = t.xl_nodes[(size_t)d * t.xl_max + k];
+    const uint2 sg = t.seg[out->n];
+    out->first = sg.x; out->cnt = sg.y - sg.x;
+    out->nchunks = (out->cnt + XL_CHUNK - 1) / XL_CHUNK;
+    // disjoint chunk-slot ranges with one spare slot per node for the grand total, independent of the (arbitrary) list
+    // order: a long node has more than xl_min members, so the next one starts at least one xl_min block later
+    out->slot0 = sg.x / XL_CHUNK + 3u * (sg.x / t.xl_min);
+    return true;
+}
+
+__global__ void __launch_bounds__(256) xl_sums_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
+    if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
+    XlNode nd;
+    if (!xl_node(t, d, blockIdx.y, &nd)) return;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const float4* __restrict__ src = t.spm4[d] + nd.first;
+    double* __restrict__ sums = t.xl_sum + ((size_t)area * t.xl_slots + nd.slot0) * 4u;
+    for (uint32_t c = blockIdx.x * 8u + warp; c < nd.nchunks; c += gridDim.x * 8u) {
+        double a[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+        for (uint32_t i = 0; i < XL_CHUNK / 32; i++) {
+            const uint32_t j = c * XL_CHUNK + i * 32u + lane;
+            if (j < nd.cnt) {
+                const float4 p = src[j];
+                a[0] += (double)__fmul_rn(p.w, p.x); a[1] += (double)__fmul_rn(p.w, p.y);
+                a[2] += (double)__fmul_rn(p.w, p.z); a[3] += (double)p.w;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int sh = 16; sh >= 1; sh >>= 1) a[q] += __shfl_xor_sync(0xFFFFFFFFu, a[q], sh);
+        if (lane < 4u) sums[(size_t)c * 4u + lane] = a[lane];
+    }
+}
+
+// exclusive prefix over the chunks of every long node (in place; slot nchunks receives the total)
+__global__ void __launch_bounds__(32) xl_prefix_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
+    if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
+    XlNode nd;
+    if (!xl_node(t, d, blockIdx.x, &nd)) return;
+    if (threadIdx.x >= 4u) return;
+    double* __restrict__ sums = t.xl_sum + ((size_t)area * t.xl_slots + nd.slot0) * 4u + threadIdx.x;
+    double run = 0.0;
+    for (uint32_t c = 0; c < nd.nchunks; c++) { const double v = sums[(size_t)c * 4u]; sums[(size_t)c * 4u] = run; run += v; }
+    sums[(size_t)nd.nchunks * 4u] = run;
+}
+
+__global__ void __launch_bounds__(256) xl_maps_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
+    if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
+    XlNode nd;
+    if (!xl_node(t, d, blockIdx.y, &nd)) return;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const float4* __restrict__ src = t.spm4[d] + nd.first;
+    const double* __restrict__ pre = t.xl_sum + ((size_t)area * t.xl_slots + nd.slot0) * 4u;
+    XlMap* __restrict__ maps = reinterpret_cast<XlMap*>(t.xl_map) + ((size_t)area * t.xl_slots + nd.slot0) * 4u;
+    for (uint32_t c = blockIdx.x * 8u + warp; c < nd.nchunks; c += gridDim.x * 8u) {
+        // the lane's 32 consecutive members, kept in registers for the four components
+        float4 mem[32];
+        const uint32_t j0 = c * XL_CHUNK + lane * 32u;
+#pragma unroll
+        for (int i = 0; i < 32; i++) mem[i] = j0 + i < nd.cnt ? src[j0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t q = 0; q < 4u; q++) {
+            // binade guess from the approximate fold value at both ends of the chunk
+            const float fs = (float)pre[(size_t)c * 4u + q], fe = (float)pre[(size_t)(c + 1u) * 4u + q];
+            const uint32_t es = (__float_as_uint(fs) >> 23) & 0xFFu, ee = (__float_as_uint(fe) >> 23) & 0xFFu;
+            const bool usable = es == ee && es > 40u && es < 250u && ((__float_as_uint(fs) ^ __float_as_uint(fe)) >> 31) == 0u;
+            XlMap m;
+            m.a0 = m.a1 = 0; m.mn0 = m.mn1 = XL_INF; m.mx0 = m.mx1 = -XL_INF;
+            m.e2 = (long long)es - 127 - 23; m.usable = usable ? 1 : 0;
+            if (usable) {                                            // warp-uniform
+                const double inv_u = __longlong_as_double((long long)(1023 - m.e2) << 52);
+                long long S0 = 0, S1 = 0;
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    if (j0 + i < nd.cnt) {
+                        const double tt = (double)xl_term(mem[i], q) * inv_u;   // exact: scaling by a power of two
+                        const double fl = floor(tt);
+                        const double fr = tt - fl;                               // exact
+                        const long long fll = (long long)fl;
+                        const long long bi = fll + (fr > 0.5 ? 1 : 0);
+                        const bool tie = fr == 0.5;
+                        S0 += bi + ((tie && ((S0 + fll) & 1ll)) ? 1 : 0);        // entering even: k + S0 + floor odd -> round up
+                        S1 += bi + ((tie && ((1ll + S1 + fll) & 1ll)) ? 1 : 0);  // entering odd
+                        m.mn0 = min(m.mn0, S0); m.mx0 = max(m.mx0, S0);
+                        m.mn1 = min(m.mn1, S1); m.mx1 = max(m.mx1, S1);
+                    }
+                }
+                m.a0 = S0; m.a1 = S1;
+                // ordered reduction: lane i absorbs lane i + off
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    XlMap o;
+                    o.a0 = shfl_down_ll(m.a0, off); o.a1 = shfl_down_ll(m.a1, off);
+                    o.mn0 = shfl_down_ll(m.mn0, off); o.mx0 = shfl_down_ll(m.mx0, off);
+                    o.mn1 = shfl_down_ll(m.mn1, off); o.mx1 = shfl_down_ll(m.mx1, off);
+                    o.e2 = m.e2; o.usable = m.usable;
+                    if ((lane & (2u * off - 1u)) == 0u) m = xl_combine(m, o);
+                }
+            }
+            if (lane == 0u) maps[(size_t)c * 4u + q] = m;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
+    __shared__ __align__(16) float buf[4][XL_CHUNK];
+    __shared__ float s_mass;
+    if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
+    XlNode nd;
+    if (!xl_node(t, d, blockIdx.x, &nd)) return;
+    const uint32_t lane = threadIdx.x & 31u, q = threadIdx.x >> 5;   // one warp per component
+    const float4* __restrict__ src = t.spm4[d] + nd.first;
+    const XlMap* __restrict__ maps = reinterpret_cast<const XlMap*>(t.xl_map) + ((size_t)area * t.xl_slots + nd.slot0) * 4u;
+    float s = 0.f;
+    for (uint32_t c = 0; c < nd.nchunks; c++) {
+        const XlMap m = maps[(size_t)c * 4u + q];
+        bool ok = m.usable != 0;
+        long long k = 0;
+        double u = 0.0;
+        if (ok) {
+            u = __longlong_as_double((long long)(1023 + m.e2) << 52);
+            const double kd = (double)s * __longlong_as_double((long long)(1023 - m.e2) << 52);   // exact
+            k = (long long)kd;
+            const long long par = k & 1ll;
+            const long long lo = k + (par ? m.mn1 : m.mn0), hi = k + (par ? m.mx1 : m.mx0);
+            const long long B0 = (1ll << 23) + 1, B1 = (1ll << 24) - 1;
+            ok = (double)k == kd &&
+                 ((k >= B0 && k <= B1 && lo >= B0 && hi <= B1) || (k <= -B0 && k >= -B1 && hi <= -B0 && lo >= -B1));
+            if (ok) { k += par ? m.a1 : m.a0; s = (float)((double)k * u); }
+        }
+        if (!ok) {
+            // member-by-member fold of this chunk (tree.c:166-169): the warp stages the summands, lane 0 adds them up
+            const uint32_t j0 = c * XL_CHUNK;
+#pragma unroll 4
+            for (uint32_t i = 0; i < XL_CHUNK / 32; i++) {
+                const uint32_t j = j0 + i * 32u + lane;
+                buf[q][i * 32u + lane] = j < nd.cnt ? xl_term(src[j], q) : 0.f;    // pads are +0: s + 0 == s
+            }
+            __syncwarp();
+            if (lane == 0u) {
+                const float4* row = reinterpret_cast<const float4*>(&buf[q][0]);
+#pragma unroll 8
+                for (int v4 = 0; v4 < XL_CHUNK / 4; v4++) {
+                    const float4 v = row[v4];
+                    s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
+                }
+            }
+            s = __shfl_sync(0xFFFFFFFFu, s, 0);
+            __syncwarp();
+        }
+    }
+    if (threadIdx.x == 96u) s_mass = s;
+    __syncthreads();
+    if (lane == 0u) {
+        const float mass = s_mass;
+        const float inv = 0.f < mass ? __fdiv_rn(1.0f, mass) : 1.0f;   // tree.c:303-304
+        reinterpret_cast<float*>(&t.rec1[nd.n])[q] = q < 3u ? __fmul_rn(s, inv) : s;
     }
 }
 
@@ -675,6 +877,18 @@ static int launch_moments(Ctx* c, const TreeDev& dv, int d, uint32_t* gate, bool
     if (!attr_set) {
         SFE_CUDA(fn, cudaFuncSetAttribute(moments_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ML_SMEM));
         attr_set = true;
+    }
+    if (d <= XL_DEPTH_MAX) {
+        const uint32_t area = (uint32_t)(d % SFE_SIDE_STREAMS);   // one scratch area per side stream; the deferred root uses area 0 after the join
+        const dim3 g2(16, dv.xl_max);
+        xl_sums_kernel<<<g2, 256, 0, s>>>(dv, d, area, gate);
+        if (check_launch(fn)) return SFE_FAILURE;
+        xl_prefix_kernel<<<dv.xl_max, 32, 0, s>>>(dv, d, area, gate);
+        if (check_launch(fn)) return SFE_FAILURE;
+        xl_maps_kernel<<<g2, 256, 0, s>>>(dv, d, area, gate);
+        if (check_launch(fn)) return SFE_FAILURE;
+        xl_chain_kernel<<<dv.xl_max, 128, 0, s>>>(dv, d, area, gate);
+        if (check_launch(fn)) return SFE_FAILURE;
     }
     moments_long_kernel<<<single ? 1 : c->sm_count * 2, ML_THREADS, ML_SMEM, s>>>(dv, d, gate);
     if (check_launch(fn)) return SFE_FAILURE;
@@ -686,19 +900,15 @@ static int launch_moments(Ctx* c, const TreeDev& dv, int d, uint32_t* gate, bool
 __global__ void finalize_kernel(TreeDev t, uint32_t* __restrict__ gate /* null: all nodes; else root only, gated */) {
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
     const uint32_t count = gate ? 1u : t.meta[M_COUNT];
-    const uint32_t* __restrict__ perm_final = t.perm[t.meta[M_FINAL]];
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < count; n += gridDim.x * blockDim.x) {
-        sfe_node_t nd = t.nodes[n];
-        if (!gate && nd.bodies <= 8u) {
-            // leaf: branch[] lists the members in arrival (= ascending index) order (tree.c:172-175); a leaf's slot
-            // range does not move once the leaf exists, so the final order serves every level
-            const uint32_t sx = t.seg[n].x;
-            for (uint32_t b = 0; b < 8u; b++) { nd.branch[b] = b < nd.bodies ? perm_final[sx + b] : 0u; t.nodes[n].branch[b] = nd.branch[b]; }
-        }
-        const float* b = nd.bounds;
+        const float4 b0 = *reinterpret_cast<const float4*>(&t.rec2[n]);          // lo.x lo.y lo.z hi.x
+        const float4 b1 = *(reinterpret_cast<const float4*>(&t.rec2[n]) + 1);    // hi.y hi.z parent -
+        const float b[6] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y};
+        const uint2 sg = t.seg[n];
+        const uint32_t bodies = sg.y - sg.x;
         WalkRec0 r0;
         const float ex = __fsub_rn(b[3], b[0]), ey = __fsub_rn(b[4], b[1]), ez = __fsub_rn(b[5], b[2]);
-        const uint32_t kind = nd.bodies == 0u ? KIND_EMPTY : nd.bodies == 1u ? KIND_SINGLE : nd.bodies <= 8u ? KIND_LEAF : KIND_INTERNAL;
+        const uint32_t kind = bodies == 0u ? KIND_EMPTY : bodies == 1u ? KIND_SINGLE : bodies <= 8u ? KIND_LEAF : KIND_INTERNAL;
         // squared-distance filters in front of the exact inside-the-box test: generous by a few ulps of the
         // coordinates, because the centre / COM are themselves rounded
         const float slack = 4e-6f * (fabsf(b[0]) + fabsf(b[1]) + fabsf(b[2]) + fabsf(b[3]) + fabsf(b[4]) + fabsf(b[5]));
@@ -712,9 +922,11 @@ __global__ void finalize_kernel(TreeDev t, uint32_t* __restrict__ gate /* null: 
             r0.a[3] = __fmul_rn(w, w);
             // conservative squared radius about the geometric centre outside of which a point cannot be inside the box
             r0.rin2 = (0.5f * diag + slack) * (0.5f * diag + slack) * 1.0001f + 1e-30f;
-            for (uint32_t o = 8u; o > 0u; o--) if (t.counts[(size_t)n * 8u + o - 1u] > 0u) child = nd.branch[o - 1u];
+            const uint32_t base = t.child_base[n];
+            for (uint32_t o = 8u; o > 0u; o--) if (t.counts[(size_t)n * 8u + o - 1u] > 0u) child = base + o - 1u;
         } else {
-            r0.a[0] = nd.params[0]; r0.a[1] = nd.params[1]; r0.a[2] = nd.params[2]; r0.a[3] = nd.params[3];
+            const float4 cm = t.rec1[n];
+            r0.a[0] = cm.x; r0.a[1] = cm.y; r0.a[2] = cm.z; r0.a[3] = cm.w;
             // the COM lies inside the box, so does a target that must be self-subtracted: at most one diagonal apart
             r0.rin2 = (diag + slack) * (diag + slack) * 1.0001f + 1e-30f;
         }
@@ -722,11 +934,30 @@ __global__ void finalize_kernel(TreeDev t, uint32_t* __restrict__ gate /* null: 
         r0.child_kind = (kind << 30) | child;
         r0.pad = 0.f;
         t.rec0[n] = r0;
-        t.rec1[n] = make_float4(nd.params[0], nd.params[1], nd.params[2], nd.params[3]);
-        WalkRec2 r2;
-        r2.lo[0] = b[0]; r2.lo[1] = b[1]; r2.lo[2] = b[2]; r2.hi[0] = b[3]; r2.hi[1] = b[4]; r2.hi[2] = b[5];
-        r2.pad[0] = r2.pad[1] = 0.f;
-        t.rec2[n] = r2;
+    }
+}
+
+// the reference-layout node table (tree.h:18-24) for sfe_tree_download(): assembled from the engine's own records
+__global__ void table_kernel(TreeDev t) {
+    const uint32_t count = t.meta[M_COUNT];
+    const uint32_t* __restrict__ perm_final = t.perm[t.meta[M_FINAL]];
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < count; n += gridDim.x * blockDim.x) {
+        const WalkRec2 cell = t.rec2[n];
+        const float4 cm = t.rec1[n];
+        const uint2 sg = t.seg[n];
+        sfe_node_t nd;
+        nd.parent = cell.parent;
+        nd.bodies = sg.y - sg.x;
+        const uint32_t base = t.child_base[n];
+        for (uint32_t k = 0; k < 8u; k++) {
+            // internal: the eight children; leaf: its members in arrival (= ascending index) order (tree.c:172-175) -
+            // a leaf's slot range does not move once the leaf exists, so the final order serves every level
+            if (nd.bodies > 8u) nd.branch[k] = base + k;
+            else nd.branch[k] = k < nd.bodies ? perm_final[sg.x + k] : 0u;
+        }
+        for (int k = 0; k < 3; k++) { nd.bounds[k] = cell.lo[k]; nd.bounds[3 + k] = cell.hi[k]; }
+        nd.params[0] = cm.x; nd.params[1] = cm.y; nd.params[2] = cm.z; nd.params[3] = cm.w;
+        t.nodes[n] = nd;
     }
 }
 
@@ -738,6 +969,12 @@ static bool trace_enabled() {
 }
 
 static cudaEvent_t g_trace_ev[2 * (SFE_MAX_LEVELS + 3)];
+
+static uint32_t xl_min_members() {   // SFE_XL_MIN lowers the threshold so that small test trees exercise the chunked fold
+    static uint32_t v = 0;
+    if (v == 0) { const char* e = getenv("SFE_XL_MIN"); v = e ? (uint32_t)atoi(e) : 8192u; if (v < 64u) v = 64u; }
+    return v;
+}
 
 static TreeDev make_dev(Tree& t) {
     TreeDev d;
@@ -761,13 +998,23 @@ static TreeDev make_dev(Tree& t) {
     d.rank = t.rank.as<uint32_t>();
     d.meta = t.meta.as<uint32_t>();
     d.nmid = t.nmid.as<float4>();
-    // one zero-initialised block per build: [tickets | rank_kernel descriptors | children_kernel descriptors]
+    // one zero-initialised block per build: [tickets | long-node counters and lists | rank_kernel descriptors |
+    // children_kernel descriptors]
     const uint32_t levels = SFE_MAX_LEVELS + 2;
-    d.tdesc_stride = (uint32_t)(((size_t)(t.N ? t.N : 1) + PT_TILE - 1) / PT_TILE + 1) * DESC_WORDS;
+    const size_t n1 = t.N ? t.N : 1;
+    d.xl_min = xl_min_members();
+    d.xl_max = (uint32_t)(n1 / d.xl_min) + 2u;
+    d.xl_slots = (uint32_t)(n1 / 1024u) + 3u * d.xl_max + 8u;
+    d.tdesc_stride = (uint32_t)((n1 + PT_TILE - 1) / PT_TILE + 1) * DESC_WORDS;
     d.cdesc_stride = (t.nodes_max + CH_THREADS - 1) / CH_THREADS + 1;
-    d.ticket = t.lookback.as<uint32_t>();
-    d.tdesc = d.ticket + 2 * levels;
-    d.cdesc = reinterpret_cast<unsigned long long*>(t.lookback.as<char>() + (((size_t)(2 * levels) + (size_t)levels * d.tdesc_stride) * 4 + 7) / 8 * 8);
+    uint32_t* w = t.lookback.as<uint32_t>();
+    d.ticket = w;                 w += 2 * levels;
+    d.xl_count = w;               w += levels;
+    d.xl_nodes = w;               w += (size_t)(XL_DEPTH_MAX + 1) * d.xl_max;
+    d.tdesc = w;                  w += (size_t)levels * d.tdesc_stride;
+    d.cdesc = reinterpret_cast<unsigned long long*>(t.lookback.as<char>() + ((size_t)(w - t.lookback.as<uint32_t>()) * 4 + 7) / 8 * 8);
+    d.xl_sum = t.xl_sum.as<double>();
+    d.xl_map = t.xl_map.as<long long>();
     d.summary = t.summary_dev;
     d.build_id = t.build_id;
     d.rec0 = t.rec0.as<WalkRec0>();
@@ -778,7 +1025,8 @@ static TreeDev make_dev(Tree& t) {
 
 static size_t lookback_bytes(const TreeDev& d) {
     const size_t levels = SFE_MAX_LEVELS + 2;
-    return ((2 * levels + levels * d.tdesc_stride) * 4 + 7) / 8 * 8 + levels * (size_t)d.cdesc_stride * 8;
+    const size_t words = 2 * levels + levels + (size_t)(XL_DEPTH_MAX + 1) * d.xl_max + levels * d.tdesc_stride;
+    return (words * 4 + 7) / 8 * 8 + levels * (size_t)d.cdesc_stride * 8;
 }
 
 TreeDev tree_dev(Ctx* c) { return make_dev(c->tree); }
@@ -793,7 +1041,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     t.N = N; t.nodes_max = nodes_max; t.depth_max = depth_max;
     for (int k = 0; k < 6; k++) t.bounds[k] = bounds[k];
     const size_t n1 = N ? N : 1;
-    if (t.nodes.reserve((size_t)nodes_max * sizeof(sfe_node_t), fn) || t.seg.reserve((size_t)nodes_max * 8, fn) ||
+    if (t.seg.reserve((size_t)nodes_max * 8, fn) ||
         t.next.reserve((size_t)nodes_max * 4, fn) || t.child_base.reserve((size_t)nodes_max * 4, fn) ||
         t.counts.reserve((size_t)nodes_max * 32, fn) || t.nmid.reserve((size_t)nodes_max * 16, fn) || t.skey[0].reserve(n1 * 8, fn) || t.skey[1].reserve(n1 * 8, fn) ||
         t.perm_out.reserve(n1 * 4, fn) || t.slot_node[0].reserve(n1 * 4, fn) || t.slot_node[1].reserve(n1 * 4, fn) ||
@@ -820,7 +1068,9 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     if (t.build_id == 0u) t.build_id = 1u;
 
     TreeDev dv = make_dev(t);
-    if (t.lookback.reserve(lookback_bytes(dv), fn)) return SFE_FAILURE;
+    if (t.lookback.reserve(lookback_bytes(dv), fn) || t.xl_sum.reserve((size_t)SFE_SIDE_STREAMS * dv.xl_slots * 4 * 8, fn) ||
+        t.xl_map.reserve((size_t)SFE_SIDE_STREAMS * dv.xl_slots * 4 * 64, fn))
+        return SFE_FAILURE;
     dv = make_dev(t);
     SFE_CUDA(fn, cudaMemsetAsync(t.lookback.p, 0, lookback_bytes(dv), s));
     const uint32_t pgrid = [&] { uint32_t g = (N + PT_TILE - 1) / PT_TILE; uint32_t cap = (uint32_t)c->sm_count * 6; return g < 1 ? 1u : (g < cap ? g : cap); }();
@@ -1002,6 +1252,9 @@ extern "C" int sfe_tree_download(sfe_node_t* nodes, uint32_t max_nodes, uint32_t
     if (num_nodes) *num_nodes = t.num_nodes;
     if (!nodes) return SFE_SUCCESS;
     if (max_nodes < t.num_nodes) { set_error(fn, "buffer holds %u nodes, tree has %u", max_nodes, t.num_nodes); return SFE_FAILURE; }
+    if (t.nodes.reserve((size_t)t.num_nodes * sizeof(sfe_node_t), fn)) return SFE_FAILURE;
+    table_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(tree_dev(c));
+    if (check_launch(fn)) return SFE_FAILURE;
     SFE_CUDA(fn, cudaMemcpyAsync(nodes, t.nodes.p, (size_t)t.num_nodes * sizeof(sfe_node_t), cudaMemcpyDeviceToHost, c->stream));
     SFE_CUDA(fn, cudaStreamSynchronize(c->stream));
     return SFE_SUCCESS;

@@ -31,15 +31,17 @@ struct __align__(32) WalkRec0 {   // 32 B = one L1 sector, fetched with ONE 256-
                                   // is surely outside the box: filter in front of the exact bounds test (gravity.c:473-476)
     float pad;
 };
-struct __align__(16) WalkRec2 {   // 32 B: bounds, only for the self-subtraction test (gravity.c:473-476)
-    float lo[3], hi[3], pad[2];
+struct __align__(16) WalkRec2 {   // 32 B: the cell itself - bounds (gravity.c:473-476 self-subtraction test, tree.c:219-226) + parent
+    float lo[3], hi[3];
+    uint32_t parent;
+    uint32_t pad;
 };
 static_assert(sizeof(WalkRec0) == 32 && sizeof(WalkRec2) == 32, "walk records are 32 bytes");
 
 struct TreeDev {
     float bounds[6];
     uint32_t nodes_max;
-    sfe_node_t* nodes;
+    sfe_node_t* nodes;            // reference-layout table (tree.h:18-24), materialised on demand by sfe_tree_download()
     uint2* seg;
     uint32_t* next;
     uint32_t* child_base;
@@ -60,6 +62,13 @@ struct TreeDev {
     uint32_t* tdesc;              // look-back descriptors of rank_kernel, tdesc_stride words per level
     unsigned long long* cdesc;    // look-back descriptors of children_kernel, cdesc_stride entries per level
     uint32_t tdesc_stride, cdesc_stride;
+    // exact chunked fold of very long nodes (moments_xl_*): per-level work lists and one scratch area per side stream
+    uint32_t* xl_count;           // [levels] number of nodes with more than XL_MIN members
+    uint32_t* xl_nodes;           // [levels][xl_max]
+    uint32_t xl_max, xl_slots;    // list capacity per level, chunk slots per scratch area
+    uint32_t xl_min;              // nodes with more members than this use the chunked exact fold
+    double* xl_sum;               // [SFE_SIDE_STREAMS][xl_slots][4] chunk sums, then exclusive prefixes, of the rounded products
+    long long* xl_map;            // [SFE_SIDE_STREAMS][xl_slots][4][8] {a0, a1, min0, max0, min1, max1, exponent, usable}
     volatile uint32_t* summary;   // mapped host memory: {build id, internal nodes, status, node count} per level
     uint32_t build_id;
     WalkRec0* rec0;
