@@ -95,7 +95,7 @@ struct Ctx {
     // device copies of the host arrays
     DevBuf d_pos, d_mas, d_pm4, d_acc, d_pot, d_rad, d_rho, d_prs;
     // PP / SPH scratch
-    DevBuf pp_src, pp_partial, sph_src, sph_partial;
+    DevBuf pp_src, pp_partial, pp_flag, sph_src, sph_partial;
     // pinned bounce buffer for unregistered host memory
     void* bounce = nullptr; size_t bounce_cap = 0;
     Tree tree;

@@ -51,17 +51,32 @@ __global__ void pp_pad_kernel(const float4* __restrict__ pm4, float4* __restrict
     if (j < npad) src[j] = j < N ? pm4[j] : make_float4(PP_PAD_POS, PP_PAD_POS, PP_PAD_POS, 0.0f);
 }
 
+// Equal-mass detection: flag = 1 as soon as one source's mass differs (bitwise) from source 0's.  Runs on the
+// stream ahead of the pair kernels, which read the flag on the device (no host round trip).
+__global__ void pp_mass_scan_kernel(const float4* __restrict__ pm4, uint32_t N, uint32_t* __restrict__ flag) {
+    const uint32_t m0 = __float_as_uint(pm4[0].w);
+    bool differs = false;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x)
+        differs |= __float_as_uint(pm4[j].w) != m0;
+    if (__syncthreads_or(differs) && threadIdx.x == 0) atomicOr(flag, 1u);
+}
+
 // combine the j-splits in a fixed order (double accumulation) and apply the reference's prefactors
 // acc = ((-G) * m_i) * S, pot = (-G) * Phi   (gravity.c:808-811)
 __global__ void pp_finish_kernel(const float4* __restrict__ partial, const float4* __restrict__ pm4,
                                  uint32_t i0, uint32_t ni, uint32_t splits, float G,
-                                 float* __restrict__ acc, float* __restrict__ pot) {
+                                 float* __restrict__ acc, float* __restrict__ pot,
+                                 const uint32_t* __restrict__ mixed_masses) {
     uint32_t il = blockIdx.x * blockDim.x + threadIdx.x;
     if (il >= ni) return;
     double sx = 0, sy = 0, sz = 0, sp = 0;
     for (uint32_t s = 0; s < splits; s++) {
         float4 v = partial[(size_t)s * ni + il];
         sx += v.x; sy += v.y; sz += v.z; sp += v.w;
+    }
+    if (*mixed_masses == 0u) {   // equal-mass specialisation: the common m_j was left out of the sums
+        const double mj = (double)pm4[0].w;
+        sx *= mj; sy *= mj; sz *= mj; sp *= mj;
     }
     const uint32_t i = i0 + il;
     const float gm = __fmul_rn(-G, pm4[i].w);
@@ -77,11 +92,13 @@ int launch_pp(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, f
     const char* fn = "sfe_dev_pp";
     if (ni == 0 || N == 0) return SFE_SUCCESS;
     if ((uint64_t)i0 + ni > N) { set_error(fn, "target slice [%u,%u) exceeds N=%u", i0, i0 + ni, N); return SFE_FAILURE; }
-    auto kernel = pp_kernel_tp<PP_T, PP_THREADS, PP_MINB, PP_TILE, PP_UNROLL>;
+    auto kernel = pp_kernel_tp<PP_T, PP_THREADS, PP_MINB, PP_TILE, PP_UNROLL, 0, false>;   // general masses
+    auto kernel_um = pp_kernel_tp<PP_T, PP_THREADS, PP_MINB, PP_TILE, PP_UNROLL, 0, true>;  // all m_j equal
     constexpr size_t smem = pp_tp_smem_bytes<PP_T, PP_THREADS, PP_TILE>();
     static int occ = 0;
     if (occ == 0) {
         SFE_CUDA(fn, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SFE_CUDA(fn, cudaFuncSetAttribute(kernel_um, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SFE_CUDA(fn, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, PP_THREADS, smem));
         if (occ < 1) occ = 1;
     }
@@ -118,10 +135,19 @@ int launch_pp(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, f
     splits = (tiles + tps - 1) / tps;
     if (c->pp_partial.reserve((size_t)splits * ni * sizeof(float4), fn)) return SFE_FAILURE;
 
-    dim3 grid(iblocks, splits);
-    kernel<<<grid, PP_THREADS, smem, s>>>(src, pm4, N, i0, ni, tiles, tps, eps2, c->pp_partial.as<float4>());
+    // equal-mass detection on the device; both specialisations are enqueued and the flag picks one
+    if (c->pp_flag.reserve(sizeof(uint32_t), fn)) return SFE_FAILURE;
+    uint32_t* flag = c->pp_flag.as<uint32_t>();
+    SFE_CUDA(fn, cudaMemsetAsync(flag, 0, sizeof(uint32_t), s));
+    pp_mass_scan_kernel<<<std::min<uint32_t>((N + 255) / 256, 4u * (uint32_t)c->sm_count), 256, 0, s>>>(pm4, N, flag);
     if (check_launch(fn)) return SFE_FAILURE;
-    pp_finish_kernel<<<(ni + 255) / 256, 256, 0, s>>>(c->pp_partial.as<float4>(), pm4, i0, ni, splits, G, acc, pot);
+
+    dim3 grid(iblocks, splits);
+    kernel_um<<<grid, PP_THREADS, smem, s>>>(src, pm4, N, i0, ni, tiles, tps, eps2, c->pp_partial.as<float4>(), flag);
+    if (check_launch(fn)) return SFE_FAILURE;
+    kernel<<<grid, PP_THREADS, smem, s>>>(src, pm4, N, i0, ni, tiles, tps, eps2, c->pp_partial.as<float4>(), flag);
+    if (check_launch(fn)) return SFE_FAILURE;
+    pp_finish_kernel<<<(ni + 255) / 256, 256, 0, s>>>(c->pp_partial.as<float4>(), pm4, i0, ni, splits, G, acc, pot, flag);
     return check_launch(fn);
 }
 

@@ -148,12 +148,18 @@ pp_kernel(const float4* __restrict__ pairs,   // pair records, whole tiles
 template <int T, int THREADS, int TILE>
 constexpr size_t pp_tp_smem_bytes() { return (size_t)PP_STAGES * TILE * 16 + (size_t)T * 16 * THREADS * 4 + PP_STAGES * 8; }
 
-template <int T, int THREADS, int MINBLOCKS, int TILE, int UNROLL>
+// ACC: 0 = accumulate with FFMA2 (three fresh 64-bit operands), 1 = two scalar FFMA per accumulate (three 32-bit
+// operands each run at full rate, the packed form is limited by register-file operand bandwidth).
+// UM: every source has the same mass (checked by the launcher): the mass factor moves out of the sums.
+template <int T, int THREADS, int MINBLOCKS, int TILE, int UNROLL, int ACC = 0, bool UM = false>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 pp_kernel_tp(const float4* __restrict__ src,     // sources {x,y,z,m}, padded to whole tiles
              const float4* __restrict__ pm4,     // targets are read from here
              uint32_t N, uint32_t i0, uint32_t ni, uint32_t tiles_total, uint32_t tiles_per_split, float eps2,
-             float4* __restrict__ partial /* [gridDim.y][ni] */) {
+             float4* __restrict__ partial /* [gridDim.y][ni] */,
+             const uint32_t* __restrict__ mixed_masses = nullptr /* device flag written by pp_mass_scan_kernel */) {
+    // the launcher enqueues both specialisations; the one that does not match the flag retires immediately
+    if (mixed_masses != nullptr && (*mixed_masses != 0u) == UM) return;
     constexpr int TILE_BYTES = TILE * 16;
     extern __shared__ __align__(128) unsigned char pp_smem[];   // pp_tp_smem_bytes<T, THREADS, TILE>()
     float4 (*tile)[TILE] = reinterpret_cast<float4 (*)[TILE]>(pp_smem);                                 // [PP_STAGES][TILE]
@@ -216,12 +222,18 @@ pp_kernel_tp(const float4* __restrict__ src,     // sources {x,y,z,m}, padded to
                 float2 inv;
                 inv.x = rsqrt_approx(r2.x);
                 inv.y = rsqrt_approx(r2.y);
-                const float2 u = __fmul2_rn(inv, mj);     // m_j / r          (pot_j, gravity.c:761)
+                const float2 u = UM ? inv : __fmul2_rn(inv, mj);     // m_j / r          (pot_j, gravity.c:761)
                 const float2 i2 = __fmul2_rn(inv, inv);   // 1 / r^2
                 const float2 w = __fmul2_rn(u, i2);       // m_j / r^3
-                ax[k] = __ffma2_rn(w, dx, ax[k]);
-                ay[k] = __ffma2_rn(w, dy, ay[k]);
-                az[k] = __ffma2_rn(w, dz, az[k]);
+                if (ACC == 0) {
+                    ax[k] = __ffma2_rn(w, dx, ax[k]);
+                    ay[k] = __ffma2_rn(w, dy, ay[k]);
+                    az[k] = __ffma2_rn(w, dz, az[k]);
+                } else {
+                    ax[k].x = __fmaf_rn(w.x, dx.x, ax[k].x); ax[k].y = __fmaf_rn(w.y, dx.y, ax[k].y);
+                    ay[k].x = __fmaf_rn(w.x, dy.x, ay[k].x); ay[k].y = __fmaf_rn(w.y, dy.y, ay[k].y);
+                    az[k].x = __fmaf_rn(w.x, dz.x, az[k].x); az[k].y = __fmaf_rn(w.y, dz.y, az[k].y);
+                }
                 ap[k] = __fadd2_rn(ap[k], u);
             }
         }

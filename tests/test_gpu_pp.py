@@ -54,6 +54,26 @@ def test_unequal_masses_and_clustering(engine):
     assert rel_rms(sim.acc, acc) <= TOL and rel_rms(sim.pot, pot) <= TOL
 
 
+def test_equal_mass_specialisation_switch(engine):
+    """The launcher runs an equal-mass specialisation (common m_j factored out of the sums) when every source has
+    the same mass, selected by a device-side flag: one differing mass anywhere must select the general kernel,
+    and both must agree with the oracle."""
+    N = 5000
+    pos, vel, mas = sfo.initcond(N)
+    assert (mas == mas[0]).all()
+    a = run_pp(engine, pos, mas)
+    acc, pot = sfo.pp(pos, mas)
+    assert rel_rms(a.acc, acc) <= TOL and rel_rms(a.pot, pot) <= TOL
+    for where in (0, N // 2, N - 1):
+        m2 = mas.copy(); m2[where] *= np.float32(3.0)
+        b = run_pp(engine, pos, m2)
+        acc2, pot2 = sfo.pp(pos, m2)
+        assert rel_rms(b.acc, acc2) <= TOL and rel_rms(b.pot, pot2) <= TOL
+    # and back: the flag is re-evaluated on every call
+    c = run_pp(engine, pos, mas)
+    assert np.array_equal(a.acc, c.acc) and np.array_equal(a.pot, c.pot)
+
+
 def test_slice_writes_only_its_targets(engine):
     N = 5000
     pos, vel, mas = sfo.initcond(N)

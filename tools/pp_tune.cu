@@ -79,7 +79,7 @@ __global__ void pad_kernel(const float4* __restrict__ pm4, float4* __restrict__ 
     if (j < npad) src[j] = j < N ? pm4[j] : make_float4(PP_PAD_POS, PP_PAD_POS, PP_PAD_POS, 0.f);
 }
 
-template <int T, int THREADS, int MINB, int TILE, int UNR>
+template <int T, int THREADS, int MINB, int TILE, int UNR, int ACC = 0, bool UM = false>
 void run_tp(const char* name, const float4* pm4, float4* srcbuf, float4* partial, uint32_t N) {
     const uint32_t tiles = (N + TILE - 1) / TILE, npad = tiles * TILE;
     pad_kernel<<<(npad + 255) / 256, 256>>>(pm4, srcbuf, N, npad);
@@ -87,8 +87,8 @@ void run_tp(const char* name, const float4* pm4, float4* srcbuf, float4* partial
     const uint32_t iblocks = (N + per_cta - 1) / per_cta;
     int occ = 0;
     const size_t smem = pp_tp_smem_bytes<T, THREADS, TILE>();
-    cudaFuncSetAttribute(pp_kernel_tp<T, THREADS, MINB, TILE, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_kernel_tp<T, THREADS, MINB, TILE, UNR>, THREADS, smem);
+    cudaFuncSetAttribute(pp_kernel_tp<T, THREADS, MINB, TILE, UNR, ACC, UM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_kernel_tp<T, THREADS, MINB, TILE, UNR, ACC, UM>, THREADS, smem);
     const uint32_t wave = (uint32_t)(occ * g_sms);
     uint32_t best = 1; double best_eff = 0;
     for (uint32_t sp = 1; sp <= 64 && sp <= tiles; sp++) {
@@ -100,12 +100,12 @@ void run_tp(const char* name, const float4* pm4, float4* srcbuf, float4* partial
     }
     uint32_t tps = (tiles + best - 1) / best, splits = (tiles + tps - 1) / tps;
     dim3 grid(iblocks, splits);
-    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, pp_kernel_tp<T, THREADS, MINB, TILE, UNR>);
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, pp_kernel_tp<T, THREADS, MINB, TILE, UNR, ACC, UM>);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best_ms = 1e30f;
     for (int r = 0; r < 4; r++) {
         cudaEventRecord(e0);
-        pp_kernel_tp<T, THREADS, MINB, TILE, UNR><<<grid, THREADS, smem>>>(srcbuf, pm4, N, 0, N, tiles, tps, 1e-6f, partial);
+        pp_kernel_tp<T, THREADS, MINB, TILE, UNR, ACC, UM><<<grid, THREADS, smem>>>(srcbuf, pm4, N, 0, N, tiles, tps, 1e-6f, partial);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (r > 0 && ms < best_ms) best_ms = ms;
@@ -144,33 +144,17 @@ int main(int argc, char** argv) {
     cudaMalloc(&partial, (size_t)N * 64 * 16);
     cudaMemcpy(pm4, h.data(), (size_t)N * 16, cudaMemcpyHostToDevice);
     printf("N = %u, %s, %d SMs; nominal FP32 peak %.2f TFLOP/s\n", N, p.name, g_sms, 2.0 * 128 * g_sms * 1.965e9 / 1e12);
-    //   T  THR MINB TILE SMEMTOT UNROLL
     run<4, 256, 2, 512, false, 4>("T4 256x2 tile512 reg-tot u4 (r01)", pm4, pairs, partial, N);
-    run<4, 256, 2, 1024, false, 4>("T4 256x2 tile1024 reg-tot u4", pm4, pairs, partial, N);
-    run<4, 128, 5, 512, true, 4>("T4 128x5 tile512 smem-tot u4", pm4, pairs, partial, N);
-    run<4, 128, 5, 512, true, 2>("T4 128x5 tile512 smem-tot u2", pm4, pairs, partial, N);
-    run<4, 128, 4, 512, true, 4>("T4 128x4 tile512 smem-tot u4", pm4, pairs, partial, N);
-    run<4, 128, 4, 512, false, 4>("T4 128x4 tile512 reg-tot u4", pm4, pairs, partial, N);
-    run<4, 192, 3, 512, true, 4>("T4 192x3 tile512 smem-tot u4", pm4, pairs, partial, N);
-    run<4, 64, 10, 512, true, 4>("T4 64x10 tile512 smem-tot u4", pm4, pairs, partial, N);
-    run<2, 256, 3, 512, false, 4>("T2 256x3 tile512 reg-tot u4", pm4, pairs, partial, N);
-    run<2, 256, 4, 512, true, 4>("T2 256x4 tile512 smem-tot u4", pm4, pairs, partial, N);
-    run<2, 256, 4, 512, true, 2>("T2 256x4 tile512 smem-tot u2", pm4, pairs, partial, N);
-    run<2, 128, 8, 512, true, 4>("T2 128x8 tile512 smem-tot u4", pm4, pairs, partial, N);
-    run<3, 256, 2, 512, false, 4>("T3 256x2 tile512 reg-tot u4", pm4, pairs, partial, N);
-    run<3, 128, 6, 512, true, 4>("T3 128x6 tile512 smem-tot u4", pm4, pairs, partial, N);
-    run<6, 128, 3, 512, true, 2>("T6 128x3 tile512 smem-tot u2", pm4, pairs, partial, N);
-    //      T(pairs) THR MINB TILE UNROLL
-    run_tp<2, 128, 6, 512, 4>("TP T2 128x6 tile512 u4", pm4, pairs, partial, N);
-    run_tp<2, 256, 3, 512, 4>("TP T2 256x3 tile512 u4", pm4, pairs, partial, N);
-    run_tp<3, 128, 5, 512, 4>("TP T3 128x5 tile512 u4", pm4, pairs, partial, N);
-    run_tp<4, 128, 4, 512, 4>("TP T4 128x4 tile512 u4", pm4, pairs, partial, N);
-    run_tp<4, 128, 4, 512, 2>("TP T4 128x4 tile512 u2", pm4, pairs, partial, N);
-    run_tp<4, 128, 3, 512, 4>("TP T4 128x3 tile512 u4", pm4, pairs, partial, N);
-    run_tp<4, 64, 8, 512, 4>("TP T4 64x8 tile512 u4", pm4, pairs, partial, N);
-    run_tp<4, 256, 2, 512, 4>("TP T4 256x2 tile512 u4", pm4, pairs, partial, N);
-    run_tp<6, 128, 2, 512, 2>("TP T6 128x2 tile512 u2", pm4, pairs, partial, N);
-    run_tp<6, 64, 5, 512, 2>("TP T6 64x5 tile512 u2", pm4, pairs, partial, N);
-    run_tp<8, 64, 4, 512, 2>("TP T8 64x4 tile512 u2", pm4, pairs, partial, N);
+    //      T(pairs) THR MINB TILE UNROLL ACC UM
+    run_tp<6, 128, 2, 512, 2>("TP T6 128x2 u2 packed (current)", pm4, pairs, partial, N);
+    run_tp<6, 128, 2, 512, 2, 1>("TP T6 128x2 u2 scalar-acc", pm4, pairs, partial, N);
+    run_tp<4, 128, 3, 512, 4, 1>("TP T4 128x3 u4 scalar-acc", pm4, pairs, partial, N);
+    run_tp<4, 128, 4, 512, 4, 1>("TP T4 128x4 u4 scalar-acc", pm4, pairs, partial, N);
+    run_tp<4, 256, 2, 512, 4, 1>("TP T4 256x2 u4 scalar-acc", pm4, pairs, partial, N);
+    run_tp<3, 128, 5, 512, 4, 1>("TP T3 128x5 u4 scalar-acc", pm4, pairs, partial, N);
+    run_tp<8, 64, 4, 512, 2, 1>("TP T8 64x4 u2 scalar-acc", pm4, pairs, partial, N);
+    run_tp<6, 128, 2, 512, 2, 0, true>("TP T6 128x2 u2 packed UM", pm4, pairs, partial, N);
+    run_tp<6, 128, 2, 512, 2, 1, true>("TP T6 128x2 u2 scalar-acc UM", pm4, pairs, partial, N);
+    run_tp<4, 128, 4, 512, 4, 1, true>("TP T4 128x4 u4 scalar-acc UM", pm4, pairs, partial, N);
     return 0;
 }
