@@ -171,7 +171,9 @@ extern "C" int sfe_shutdown(void) {
     g_registered.clear();
     Tree& t = c->tree;
     DevBuf* bufs[] = {&c->d_pos, &c->d_mas, &c->d_pm4, &c->d_acc, &c->d_pot, &c->d_rad, &c->d_rho, &c->d_prs,
-                      &c->pp_src, &c->pp_partial, &c->sph_src, &c->sph_partial,
+                      &c->pp_src, &c->pp_partial, &c->pp_flag, &c->sph_src, &c->sph_partial,
+                      &c->sph_cells.desc, &c->sph_cells.count, &c->sph_cells.start, &c->sph_cells.key[0], &c->sph_cells.key[1],
+                      &c->sph_cells.val[0], &c->sph_cells.val[1], &c->sph_cells.hist, &c->sph_cells.rec, &c->sph_cells.tlist,
                       &t.nodes, &t.seg, &t.next, &t.child_base, &t.counts, &t.keys, &t.perm_out, &t.slot_node[0],
                       &t.slot_node[1], &t.oct, &t.rank, &t.nmid, &t.lookback, &t.xl_sum, &t.xl_map, &t.scan_tmp, &t.slice_count, &t.root_gate, &t.meta, &t.rec0, &t.rec1, &t.rec2};
     for (DevBuf& b : t.perm) b.release();
@@ -322,7 +324,7 @@ extern "C" int sfe_sph(const float* pos, const float* mas, const float* rad, flo
     if (launch_sph_density(c, pm4, c->d_rad.as<float>(), N, 0, N, c->d_rho.as<float>(), c->stream)) return SFE_FAILURE;
     if (launch_sph_eos(c->d_rho.as<float>(), c->d_prs.as<float>(), N, eos_k, eos_n, c->stream)) return SFE_FAILURE;
     if (launch_sph_force(c, pm4, c->d_rad.as<float>(), c->d_rho.as<float>(), c->d_prs.as<float>(), N, 0, N, cutoff2,
-                         c->d_acc.as<float>(), c->stream))
+                         c->d_acc.as<float>(), c->stream, /*reuse_cells=*/true))   // same snapshot as the density pass
         return SFE_FAILURE;
     t_mark(c, 3);
     if (d2h(fn, rho, c->d_rho.p, (size_t)N * 4, c->stream)) return SFE_FAILURE;

@@ -84,6 +84,19 @@ struct Tree {
     bool ev_init = false;
 };
 
+// ---------------------------------------------------------------------------- SPH cell list (sfe_sph_cells.cu)
+struct CellGrid {                 // device-resident descriptor, written by cl_grid_kernel
+    uint32_t bmin[3], bmax[3];    // bounding box (order-preserving uint encoding of the floats)
+    uint32_t hmin, hmax;          // smoothing-length range (same encoding)
+    float origin[3], inv_s, rr;   // cell (0,0,0) corner, 1 / cell size, (R / s)^2 with R = 4 h_max
+    uint32_t n[3], ncells, cpr;   // grid dimensions, reach in cells
+    uint32_t use_cells, uniform_h;
+};
+struct SphCells {
+    DevBuf desc, count, start, key[2], val[2], hist, rec, tlist;
+    bool maybe = false;           // host-side: the cell kernels were enqueued for the current snapshot
+};
+
 // ---------------------------------------------------------------------------- context
 struct Ctx {
     int device = -1;
@@ -96,6 +109,7 @@ struct Ctx {
     DevBuf d_pos, d_mas, d_pm4, d_acc, d_pot, d_rad, d_rho, d_prs;
     // PP / SPH scratch
     DevBuf pp_src, pp_partial, pp_flag, sph_src, sph_partial;
+    SphCells sph_cells;
     // pinned bounce buffer for unregistered host memory
     void* bounce = nullptr; size_t bounce_cap = 0;
     Tree tree;
@@ -124,7 +138,12 @@ int launch_sph_density(Ctx* c, const float4* pm4, const float* rad, uint32_t N, 
                        float* rho, cudaStream_t s);
 int launch_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float eos_n, cudaStream_t s);
 int launch_sph_force(Ctx* c, const float4* pm4, const float* rad, const float* rho, const float* prs,
-                     uint32_t N, uint32_t i0, uint32_t ni, float cutoff2, float* acc, cudaStream_t s);
+                     uint32_t N, uint32_t i0, uint32_t ni, float cutoff2, float* acc, cudaStream_t s,
+                     bool reuse_cells = false);
+// SPH neighbour search (sfe_sph_cells.cu): grid + sort for one snapshot, then one gated pass per mode
+int cells_prepare(Ctx* c, const float4* pm4, const float* rad, uint32_t N, bool force_all_pairs, cudaStream_t s, const char* fn);
+int cells_run(Ctx* c, int mode, const float4* pm4, const float* rad, const float* rho, const float* prs, uint32_t N,
+              uint32_t i0, uint32_t ni, float cutoff2, float* out, cudaStream_t s, const char* fn);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- mbarrier / bulk-copy PTX

@@ -16,6 +16,7 @@
 // Staging is the same TMA bulk-copy / mbarrier double buffer as the PP kernel; sources are 32-byte
 // records {x,y,z,q0 | k,q1,-,-}.
 #include "sfe_internal.cuh"
+#include <stdlib.h>
 
 namespace sfe {
 
@@ -82,7 +83,8 @@ sph_pair_kernel(const float4* __restrict__ rec, const float4* __restrict__ pm4, 
                 const float* __restrict__ rho, const float* __restrict__ prs,
                 const uint32_t* __restrict__ h_bits_minmax,
                 uint32_t i0, uint32_t ni, uint32_t tiles_total, uint32_t tiles_per_split, float cutoff2,
-                float4* __restrict__ partial) {
+                float4* __restrict__ partial, const CellGrid* __restrict__ gate) {
+    if (gate != nullptr && gate->use_cells) return;   // the cell-list kernels (sfe_sph_cells.cu) took this snapshot
     __shared__ __align__(128) float4 tile[SPH_STAGES][SPH_TILE * 2];
     __shared__ __align__(8) uint64_t full[SPH_STAGES];
     const uint32_t tid = threadIdx.x;
@@ -192,7 +194,8 @@ sph_pair_kernel(const float4* __restrict__ rec, const float4* __restrict__ pm4, 
 }
 
 __global__ void sph_density_finish(const float4* __restrict__ partial, uint32_t i0, uint32_t ni, uint32_t splits,
-                                   float* __restrict__ rho) {
+                                   float* __restrict__ rho, const CellGrid* __restrict__ gate) {
+    if (gate != nullptr && gate->use_cells) return;
     uint32_t il = blockIdx.x * blockDim.x + threadIdx.x;
     if (il >= ni) return;
     double s = 0;
@@ -201,7 +204,8 @@ __global__ void sph_density_finish(const float4* __restrict__ partial, uint32_t 
 }
 
 __global__ void sph_force_finish(const float4* __restrict__ partial, const float4* __restrict__ pm4, uint32_t i0,
-                                 uint32_t ni, uint32_t splits, float* __restrict__ acc) {
+                                 uint32_t ni, uint32_t splits, float* __restrict__ acc, const CellGrid* __restrict__ gate) {
+    if (gate != nullptr && gate->use_cells) return;
     uint32_t il = blockIdx.x * blockDim.x + threadIdx.x;
     if (il >= ni) return;
     double sx = 0, sy = 0, sz = 0;
@@ -239,9 +243,17 @@ static void split_plan(const Ctx* c, uint32_t iblocks, uint32_t tiles, uint32_t*
 }
 
 static int sph_run(Ctx* c, int mode, const float4* pm4, const float* rad, const float* rho, const float* prs,
-                   uint32_t N, uint32_t i0, uint32_t ni, float cutoff2, float* out, cudaStream_t s, const char* fn) {
+                   uint32_t N, uint32_t i0, uint32_t ni, float cutoff2, float* out, cudaStream_t s, const char* fn,
+                   bool reuse_cells) {
     if (N == 0 || ni == 0) return SFE_SUCCESS;
     if ((uint64_t)i0 + ni > N) { set_error(fn, "target slice [%u,%u) exceeds N=%u", i0, i0 + ni, N); return SFE_FAILURE; }
+    // neighbour search first: grid descriptor + sort (skipped when the force pass follows the density pass of
+    // the same snapshot inside sfe_sph), then the cell-list pass.  Whether it applies is decided on the device;
+    // the all-pairs kernels below are enqueued behind the same flag and retire at once when it does.
+    static const bool all_pairs_only = getenv("SFE_SPH_ALL_PAIRS") != nullptr;   // test / measurement hook
+    if (!reuse_cells && cells_prepare(c, pm4, rad, N, all_pairs_only, s, fn)) return SFE_FAILURE;
+    if (cells_run(c, mode, pm4, rad, rho, prs, N, i0, ni, cutoff2, out, s, fn)) return SFE_FAILURE;
+    const CellGrid* gate = c->sph_cells.maybe ? c->sph_cells.desc.as<CellGrid>() : nullptr;
     const uint32_t tiles = (N + SPH_TILE - 1) / SPH_TILE, npad = tiles * SPH_TILE;
     if (c->sph_src.reserve((size_t)npad * 32 + 64, fn)) return SFE_FAILURE;
     // the last 8 bytes of sph_src hold the (min, max) bit patterns of h, refreshed by every pass
@@ -257,21 +269,21 @@ static int sph_run(Ctx* c, int mode, const float4* pm4, const float* rad, const 
     dim3 grid(iblocks, splits);
     if (mode == 0) {
         sph_pair_kernel<0><<<grid, SPH_THREADS, 0, s>>>(c->sph_src.as<float4>(), pm4, rad, rho, prs, mm, i0, ni, tiles, tps,
-                                                        cutoff2, c->sph_partial.as<float4>());
+                                                        cutoff2, c->sph_partial.as<float4>(), gate);
         if (check_launch(fn)) return SFE_FAILURE;
-        sph_density_finish<<<(ni + 255) / 256, 256, 0, s>>>(c->sph_partial.as<float4>(), i0, ni, splits, out);
+        sph_density_finish<<<(ni + 255) / 256, 256, 0, s>>>(c->sph_partial.as<float4>(), i0, ni, splits, out, gate);
     } else {
         sph_pair_kernel<1><<<grid, SPH_THREADS, 0, s>>>(c->sph_src.as<float4>(), pm4, rad, rho, prs, mm, i0, ni, tiles, tps,
-                                                        cutoff2, c->sph_partial.as<float4>());
+                                                        cutoff2, c->sph_partial.as<float4>(), gate);
         if (check_launch(fn)) return SFE_FAILURE;
-        sph_force_finish<<<(ni + 255) / 256, 256, 0, s>>>(c->sph_partial.as<float4>(), pm4, i0, ni, splits, out);
+        sph_force_finish<<<(ni + 255) / 256, 256, 0, s>>>(c->sph_partial.as<float4>(), pm4, i0, ni, splits, out, gate);
     }
     return check_launch(fn);
 }
 
 int launch_sph_density(Ctx* c, const float4* pm4, const float* rad, uint32_t N, uint32_t i0, uint32_t ni,
                        float* rho, cudaStream_t s) {
-    return sph_run(c, 0, pm4, rad, nullptr, nullptr, N, i0, ni, 0.f, rho, s, "sfe_dev_sph_density");
+    return sph_run(c, 0, pm4, rad, nullptr, nullptr, N, i0, ni, 0.f, rho, s, "sfe_dev_sph_density", false);
 }
 
 int launch_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float eos_n, cudaStream_t s) {
@@ -282,8 +294,8 @@ int launch_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float 
 }
 
 int launch_sph_force(Ctx* c, const float4* pm4, const float* rad, const float* rho, const float* prs,
-                     uint32_t N, uint32_t i0, uint32_t ni, float cutoff2, float* acc, cudaStream_t s) {
-    return sph_run(c, 1, pm4, rad, rho, prs, N, i0, ni, cutoff2, acc, s, "sfe_dev_sph_force");
+                     uint32_t N, uint32_t i0, uint32_t ni, float cutoff2, float* acc, cudaStream_t s, bool reuse_cells) {
+    return sph_run(c, 1, pm4, rad, rho, prs, N, i0, ni, cutoff2, acc, s, "sfe_dev_sph_force", reuse_cells);
 }
 
 }  // namespace sfe
