@@ -127,6 +127,64 @@ int sfe_dev_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float
 int sfe_dev_sph_force(const void* pm4, const float* rad, const float* rho, const float* prs, uint32_t N,
                       uint32_t i0, uint32_t ni, float cutoff2, float* acc, void* stream);
 
+
+/* ---------------------------------------------------------------- resident leapfrog
+ * The O(N) parts of sim_step() (simulation.c:348-519) and the root box of sim_solv() (simulation.c:245-301) as
+ * device kernels, so that the state stays in HBM between steps.  vel / pos / ken / pen are bit-identical to the
+ * reference's loops (no FMA contraction); the three double sums (mean radius, T, V) are exactly rounded sums where the
+ * reference runs a serial Kahan fold (<= 2 ulp of double apart). */
+/* kick_0 + drift (simulation.c:381-395) for the particles [i0, i0+ni): vel += 0.5 dt acc; pos += dt vel.
+ * pm4 / vel / acc are indexed by global particle number. */
+int sfe_dev_kick_drift(void* pm4, float* vel, const float* acc, uint32_t i0, uint32_t ni, float dt, void* stream);
+/* Root box of sim_solv() (simulation.c:245-301): mean |pos| over all N particles, pcg4d(step_number) jitter.
+ * `bounds` is HOST memory; the call returns when the device has published the box (it does not drain the stream). */
+int sfe_dev_root_box(const void* pm4, uint32_t N, uint32_t step_number, float bounds[6], void* stream);
+/* kick_1 (when do_kick != 0) + ken / pen + their sums (simulation.c:423-504) for [i0, i0+ni);
+ * tv (device memory) receives {T, V} = {sum ken, sum pen} of the slice. */
+int sfe_dev_kick_energy(const void* pm4, float* vel, const float* acc, const float* pot, float* ken, float* pen,
+                        uint32_t i0, uint32_t ni, float dt, int do_kick, double* tv, void* stream);
+
+/* Blocks of sim.mem (enum sim_conf, simulation.h:17-51) for sfe_sim_download(). */
+#define SFE_SIM_POS (1u << 0)
+#define SFE_SIM_VEL (1u << 1)
+#define SFE_SIM_ACC (1u << 2)
+#define SFE_SIM_MAS (1u << 3)
+#define SFE_SIM_POT (1u << 4)
+#define SFE_SIM_KEN (1u << 5)
+#define SFE_SIM_PEN (1u << 6)
+#define SFE_SIM_RAD (1u << 7)
+#define SFE_SIM_RHO (1u << 8)
+#define SFE_SIM_PRS (1u << 9)
+#define SFE_SIM_ALL 0x3FFu
+/* Solver selection = the reference's compile-time switches ENABLE_TREE / ENABLE_SPH (config.h:35,190). */
+#define SFE_SOLVER_TREE 1u
+#define SFE_SOLVER_SPH  2u
+typedef struct {
+    float    dt;          /* TIMESTEP_SIZE (config.h:170) */
+    float    grav_g;      /* G (config.h:178) */
+    float    eps2;        /* (real)(EPSILON*EPSILON) (gravity.c:754) */
+    float    theta;       /* TREE_THETA (config.h:44) */
+    int32_t  depth_max;   /* TREE_DEPTH_MAX (config.h:38) */
+    uint32_t nodes_max;   /* TREE_NODES_MAX (config.h:41) */
+    uint32_t flavour;     /* SFE_WALK_EXACT / SFE_WALK_FAST */
+    uint32_t solver;      /* SFE_SOLVER_TREE | SFE_SOLVER_SPH; 0 = PP gravity only */
+    float    eos_k, eos_n, cutoff2;   /* sph.c:148-149,231 */
+} sfe_sim_params_t;
+/* Copy a whole RAW-layout state block real[N*dof] (sim.mem, simulation.c:33-53; dof = SIM_DOF = 13 or 16) into HBM. */
+int sfe_sim_upload(const float* mem, uint32_t N, uint32_t dof);
+/* Copy the selected blocks back into a RAW-layout block (e.g. before sim_save_raw(), simulation_io.c:81-149). */
+int sfe_sim_download(float* mem, uint32_t N, uint32_t dof, uint32_t blocks);
+/* sim_solv() (simulation.c:231-345) on the resident state: root box + tree build + walk, or PP; then SPH. */
+int sfe_sim_solv(const sfe_sim_params_t* p, uint32_t step_number);
+/* sim_step() (simulation.c:348-519) on the resident state; energy = {E_tot, V, T} as written to statistics.csv
+ * (simulation.c:499-503).  sfe_sim_run() does nsteps of them back to back (energy[3*nsteps]) with step numbers
+ * first_step, first_step+1, ... (the reference's main loop sets sim.step_number before each step, main.c:451). */
+int sfe_sim_step(const sfe_sim_params_t* p, uint32_t step_number, double energy[3]);
+int sfe_sim_run(const sfe_sim_params_t* p, uint32_t first_step, uint32_t nsteps, double* energy);
+/* The root box of the last tree solve (what sim_solv() would have put into sim.tree.bounds). */
+int sfe_sim_last_box(float bounds[6]);
+int sfe_sim_release(void);
+
 #ifdef __cplusplus
 }
 #endif

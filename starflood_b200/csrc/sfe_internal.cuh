@@ -97,6 +97,20 @@ struct SphCells {
     bool maybe = false;           // host-side: the cell kernels were enqueued for the current snapshot
 };
 
+// ---------------------------------------------------------------------------- resident simulation state (sfe_sim.cu)
+constexpr int SFE_SIM_TV_RING = 64;   // steps whose energies may be in flight before sfe_sim_run() synchronises
+struct SimState {
+    uint32_t N = 0, dof = 0;
+    bool loaded = false, scratch_ready = false;
+    DevBuf pm4, vel, acc, pot, ken, pen, rad, rho, prs;   // the blocks of sim.mem (simulation.h:17-51); pos + mas live in pm4
+    DevBuf stage;                                         // pos3 / mas staging for upload and download
+    DevBuf partial, ticket, box_dev, tv_dev;              // reduction scratch, device copy of the root box, {T, V}
+    void* box_host = nullptr; void* box_host_dev = nullptr;   // mapped: the root box as the device publishes it
+    double* tv_host = nullptr;                            // pinned ring of {T, V}
+    uint32_t box_seq = 0;
+    float last_box[6] = {0, 0, 0, 0, 0, 0};
+};
+
 // ---------------------------------------------------------------------------- context
 struct Ctx {
     int device = -1;
@@ -113,6 +127,7 @@ struct Ctx {
     // pinned bounce buffer for unregistered host memory
     void* bounce = nullptr; size_t bounce_cap = 0;
     Tree tree;
+    SimState sim;
     sfe_timings_t timings;
     uint32_t launches = 0;
     uint64_t total_launches = 0;
@@ -140,6 +155,12 @@ int launch_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float 
 int launch_sph_force(Ctx* c, const float4* pm4, const float* rad, const float* rho, const float* prs,
                      uint32_t N, uint32_t i0, uint32_t ni, float cutoff2, float* acc, cudaStream_t s,
                      bool reuse_cells = false);
+// resident leapfrog (sfe_sim.cu)
+int launch_kick_drift(Ctx* c, float4* pm4, float* vel, const float* acc, uint32_t i0, uint32_t ni, float dt, cudaStream_t s);
+int launch_root_box(Ctx* c, const float4* pm4, uint32_t N, uint32_t step_number, float bounds[6], cudaStream_t s);
+int launch_kick_energy(Ctx* c, const float4* pm4, float* vel, const float* acc, const float* pot, float* ken, float* pen,
+                       uint32_t i0, uint32_t ni, float dt, int do_kick, double* tv_dev, cudaStream_t s);
+void sim_release(Ctx* c);
 // SPH neighbour search (sfe_sph_cells.cu): grid + sort for one snapshot, then one gated pass per mode
 int cells_prepare(Ctx* c, const float4* pm4, const float* rad, uint32_t N, bool force_all_pairs, cudaStream_t s, const char* fn);
 int cells_run(Ctx* c, int mode, const float4* pm4, const float* rad, const float* rho, const float* prs, uint32_t N,

@@ -34,8 +34,15 @@ EOS_K = 0.100
 EOS_N = 1.000
 SPH_CUTOFF2 = 1.000 * 1.000
 
+TIMESTEP_SIZE = 1.0     # config.h:170
+
 WALK_EXACT = 0
 WALK_FAST = 1
+SOLVER_TREE = 1         # ENABLE_TREE (config.h:35)
+SOLVER_SPH = 2          # ENABLE_SPH (config.h:190)
+SIM_BLOCKS = {"pos": 1 << 0, "vel": 1 << 1, "acc": 1 << 2, "mas": 1 << 3, "pot": 1 << 4, "ken": 1 << 5, "pen": 1 << 6,
+              "rad": 1 << 7, "rho": 1 << 8, "prs": 1 << 9}
+SIM_ALL = 0x3FF
 
 NODE_DTYPE = np.dtype([
     ("parent", "<u4"), ("bodies", "<u4"), ("branch", "<u4", (8,)),
@@ -47,6 +54,13 @@ class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("build_ms", C.c_float), ("solve_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("total_ms", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("launches", C.c_uint32)]
+
+
+class SimParams(C.Structure):
+    """sfe_sim_params_t: the compile-time configuration of the reference (config.h) as run-time values."""
+    _fields_ = [("dt", C.c_float), ("grav_g", C.c_float), ("eps2", C.c_float), ("theta", C.c_float),
+                ("depth_max", C.c_int32), ("nodes_max", C.c_uint32), ("flavour", C.c_uint32), ("solver", C.c_uint32),
+                ("eos_k", C.c_float), ("eos_n", C.c_float), ("cutoff2", C.c_float)]
 
 
 class EngineError(RuntimeError):
@@ -82,6 +96,16 @@ SIGNATURES = {
     "sfe_dev_sph_density": ([_P, _P, _u32, _u32, _u32, _P, _P], C.c_int),
     "sfe_dev_sph_eos": ([_P, _P, _u32, _f, _f, _P], C.c_int),
     "sfe_dev_sph_force": ([_P, _P, _P, _P, _u32, _u32, _u32, _f, _P, _P], C.c_int),
+    "sfe_dev_kick_drift": ([_P, _P, _P, _u32, _u32, _f, _P], C.c_int),
+    "sfe_dev_root_box": ([_P, _u32, _u32, _P, _P], C.c_int),
+    "sfe_dev_kick_energy": ([_P, _P, _P, _P, _P, _P, _u32, _u32, _f, C.c_int, _P, _P], C.c_int),
+    "sfe_sim_upload": ([_P, _u32, _u32], C.c_int),
+    "sfe_sim_download": ([_P, _u32, _u32, _u32], C.c_int),
+    "sfe_sim_solv": ([_P, _u32], C.c_int),
+    "sfe_sim_step": ([_P, _u32, _P], C.c_int),
+    "sfe_sim_run": ([_P, _u32, _u32, _P], C.c_int),
+    "sfe_sim_last_box": ([_P], C.c_int),
+    "sfe_sim_release": ([], C.c_int),
 }
 
 _lib = None
@@ -182,6 +206,7 @@ class Sim:
     acc = property(lambda s: s.find("acc")); mas = property(lambda s: s.find("mas"))
     pot = property(lambda s: s.find("pot")); rad = property(lambda s: s.find("rad"))
     rho = property(lambda s: s.find("rho")); prs = property(lambda s: s.find("prs"))
+    ken = property(lambda s: s.find("ken")); pen = property(lambda s: s.find("pen"))
 
 
 # ---------------------------------------------------------------------------------- reference interface
@@ -293,3 +318,44 @@ def sim_solv(sim, tree=True, sph=False, flavour=WALK_EXACT):
     if sph:
         rc = solve_sph(sim)
     return rc
+
+
+# ---------------------------------------------------------------------------------- resident leapfrog
+def sim_params(tree=True, sph=False, flavour=WALK_EXACT, dt=TIMESTEP_SIZE, nodes_max=TREE_NODES_MAX, theta=TREE_THETA,
+               depth_max=TREE_DEPTH_MAX):
+    return SimParams(dt, G, EPS2, theta, depth_max, nodes_max, flavour,
+                     (SOLVER_TREE if tree else 0) | (SOLVER_SPH if sph else 0), EOS_K, EOS_N, SPH_CUTOFF2)
+
+
+def sim_upload(sim):
+    """Make the whole state block resident in HBM (sim.mem, simulation.c:33-53)."""
+    return lib().sfe_sim_upload(_ptr(sim.mem), sim.N, sim.dof)
+
+
+def sim_download(sim, blocks=SIM_ALL):
+    """Copy blocks of the resident state back into sim.mem (names from Sim.OFFSETS or a bit mask)."""
+    if not isinstance(blocks, int):
+        m = 0
+        for b in blocks:
+            m |= SIM_BLOCKS[b]
+        blocks = m
+    return lib().sfe_sim_download(_ptr(sim.mem), sim.N, sim.dof, blocks)
+
+
+def sim_solv_resident(sim, params):
+    """sim_solv() (simulation.c:231-345) on the resident state, root box included."""
+    return lib().sfe_sim_solv(C.byref(params), sim.step_number)
+
+
+def sim_step(sim, params, nsteps=1):
+    """sim_step() (simulation.c:348-519) nsteps times on the resident state, numbered sim.step_number, +1, ...
+    Returns (rc, energy[nsteps, 3]) with the columns of statistics.csv: E_tot, V, T (simulation.c:499-503)."""
+    en = np.zeros((nsteps, 3), np.float64)
+    rc = lib().sfe_sim_run(C.byref(params), sim.step_number, nsteps, _ptr(en))
+    return rc, en
+
+
+def sim_last_box():
+    b = np.zeros(6, np.float32)
+    _check(lib().sfe_sim_last_box(_ptr(b)), "sfe_sim_last_box")
+    return b
