@@ -185,6 +185,39 @@ int sfe_sim_run(const sfe_sim_params_t* p, uint32_t first_step, uint32_t nsteps,
 int sfe_sim_last_box(float bounds[6]);
 int sfe_sim_release(void);
 
+/* ---------------------------------------------------------------- peer exchange, one process per GPU
+ * The exchange step of the multi-GPU partition - "all-gather of {x,y,z,m} after each drift", and of rho between the
+ * two SPH passes - done by the engine's own kernels over NVLink peer memory instead of a library collective: every
+ * rank owns a WINDOW of device memory that all other ranks map through CUDA IPC, a producer kernel stores its slice
+ * straight into every rank's window, and a one-warp kernel exchanges arrival flags (release/acquire at system scope).
+ * No counterpart in the reference (it is single-node OpenMP).  The host only has to carry the 64-byte handles between
+ * the processes once (any transport: torch.distributed, MPI, a file).
+ *
+ *   rank r:  sfe_peer_create(r, world, bytes, handle_r)   ->  exchange handles  ->  sfe_peer_open(handles[world])
+ *
+ * Exchanges are collective: every rank must enqueue the same sequence of them.  A region written by exchange k may
+ * be overwritten by exchange k+2 at the earliest (ping-pong the regions), because a rank can run at most one
+ * exchange ahead of its slowest peer.  A peer that never arrives makes the wait kernel give up after
+ * $SFE_PEER_TIMEOUT_MS (default 10000) and the next host-synchronous entry point fail. */
+#define SFE_PEER_MAX 16
+#define SFE_PEER_HANDLE_BYTES 64
+int sfe_peer_create(uint32_t rank, uint32_t world, uint64_t bytes, void* handle /* out: SFE_PEER_HANDLE_BYTES */);
+int sfe_peer_open(const void* handles /* world x SFE_PEER_HANDLE_BYTES, indexed by rank */);
+void* sfe_peer_window(void);   /* device pointer of this rank's window (NULL before sfe_peer_create) */
+/* Store [offset, offset+bytes) of this rank's window into the same range of every peer's window, then exchange
+ * arrival flags; work enqueued on `stream` after this call sees every rank's range.  bytes may differ per rank. */
+int sfe_dev_peer_put(uint64_t offset, uint64_t bytes, void* stream);
+/* Flags only (a barrier on the device, no host involvement). */
+int sfe_dev_peer_barrier(void* stream);
+int sfe_peer_close(void);
+/* Window size that sfe_sim_upload() needs when the resident leapfrog runs on `world` ranks: two {x,y,z,m} arrays
+ * (ping-pong between steps) and, for SIM_DOF = 16, rho.  With an open window of at least this size the sfe_sim_*
+ * entry points partition the particles by target slice [rank*N/world, (rank+1)*N/world): kick_0 + drift stores the
+ * moved slice into every rank's next {x,y,z,m} array (the drift and its all-gather are ONE kernel), every rank builds
+ * the full tree and evaluates its slice, {T, V} are combined in rank order.  sfe_sim_download() then returns pos /
+ * mas / rho / prs in full and the other blocks for the rank's slice only. */
+uint64_t sfe_sim_peer_bytes(uint32_t N, uint32_t dof);
+
 #ifdef __cplusplus
 }
 #endif

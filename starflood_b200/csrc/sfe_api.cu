@@ -170,6 +170,7 @@ extern "C" int sfe_shutdown(void) {
     for (auto& kv : g_registered) cudaHostUnregister(kv.first);
     g_registered.clear();
     sim_release(c);
+    peer_release(c);
     Tree& t = c->tree;
     DevBuf* bufs[] = {&c->d_pos, &c->d_mas, &c->d_pm4, &c->d_acc, &c->d_pot, &c->d_rad, &c->d_rho, &c->d_prs,
                       &c->pp_src, &c->pp_partial, &c->pp_flag, &c->sph_src, &c->sph_partial,

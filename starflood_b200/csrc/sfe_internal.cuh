@@ -109,6 +109,32 @@ struct SimState {
     double* tv_host = nullptr;                            // pinned ring of {T, V}
     uint32_t box_seq = 0;
     float last_box[6] = {0, 0, 0, 0, 0, 0};
+    // multi-rank mode (an open peer window with world > 1, sfe_peer.cu): the {x,y,z,m} arrays ping-pong inside the window
+    bool peer_mode = false;
+    uint32_t i0 = 0, ni = 0;              // target slice of this rank ([0, N) otherwise)
+    int cur = 0;                          // which of the two window arrays holds the current positions
+    uint64_t pm4_off[2] = {0, 0}, rho_off = 0;   // window offsets
+    uint32_t tv_parity = 0;               // which {T, V} slot set of the control page the next step uses
+};
+
+// ---------------------------------------------------------------------------- peer exchange window (sfe_peer.cu)
+constexpr uint32_t SFE_PEER_CTRL_BYTES = 4096;   // control page behind the payload: arrival flags, error word, {T, V} slots
+struct PeerPtrs { char* base[SFE_PEER_MAX]; uint32_t world, rank; };   // kernel argument: every rank's window
+struct PeerCtrl {                          // the control page behind the payload
+    uint32_t flag[SFE_PEER_MAX];           // flag[r]: last epoch that rank r has completed (written by rank r)
+    uint32_t pad[16];
+    double tv[2][SFE_PEER_MAX][4];         // {T.hi, T.lo, V.hi, V.lo} of every rank's slice, ping-pong by step parity
+};
+static_assert(sizeof(PeerCtrl) <= SFE_PEER_CTRL_BYTES, "control page too small");
+struct PeerState {
+    bool created = false, open = false;
+    uint32_t rank = 0, world = 1;
+    uint64_t bytes = 0;                 // payload bytes (the control page follows at this offset)
+    void* local = nullptr;              // cudaMalloc'ed window of this rank
+    void* base[SFE_PEER_MAX] = {};      // every rank's window as mapped into this process (base[rank] == local)
+    uint32_t epoch = 0;                 // exchanges enqueued so far (all ranks enqueue the same sequence)
+    uint32_t* err_host = nullptr;       // mapped pinned: set by a wait kernel that timed out
+    uint32_t* err_dev = nullptr;
 };
 
 // ---------------------------------------------------------------------------- context
@@ -128,6 +154,7 @@ struct Ctx {
     void* bounce = nullptr; size_t bounce_cap = 0;
     Tree tree;
     SimState sim;
+    PeerState peer;
     sfe_timings_t timings;
     uint32_t launches = 0;
     uint64_t total_launches = 0;
@@ -161,6 +188,12 @@ int launch_root_box(Ctx* c, const float4* pm4, uint32_t N, uint32_t step_number,
 int launch_kick_energy(Ctx* c, const float4* pm4, float* vel, const float* acc, const float* pot, float* ken, float* pen,
                        uint32_t i0, uint32_t ni, float dt, int do_kick, double* tv_dev, cudaStream_t s);
 void sim_release(Ctx* c);
+// peer exchange (sfe_peer.cu)
+PeerPtrs peer_ptrs(const Ctx* c);
+int launch_peer_barrier(Ctx* c, cudaStream_t s, const char* fn);          // signal every peer, wait for every peer
+int launch_peer_put(Ctx* c, uint64_t offset, uint64_t bytes, cudaStream_t s, const char* fn);
+int peer_status(Ctx* c, const char* fn);                                   // raises a timed-out exchange
+void peer_release(Ctx* c);
 // SPH neighbour search (sfe_sph_cells.cu): grid + sort for one snapshot, then one gated pass per mode
 int cells_prepare(Ctx* c, const float4* pm4, const float* rad, uint32_t N, bool force_all_pairs, cudaStream_t s, const char* fn);
 int cells_run(Ctx* c, int mode, const float4* pm4, const float* rad, const float* rho, const float* prs, uint32_t N,

@@ -22,6 +22,7 @@ constexpr int SIM_THREADS = 256;
 constexpr int SIM_MAX_BLOCKS = 1024;   // partial sums per reduction
 
 struct __align__(16) dd { double hi, lo; };
+struct TvPeers { double* slot[SFE_PEER_MAX]; uint32_t world; };   // world == 0: single rank, {T, V} go to tv[] directly
 
 __device__ __forceinline__ dd dd_add(dd a, dd b) {
     // error-free sum of the high parts (Knuth two-sum), low parts added in, renormalised (fast two-sum)
@@ -112,6 +113,29 @@ __global__ void __launch_bounds__(SIM_THREADS) kick_drift_kernel(float4* __restr
     }
 }
 
+// The same for a rank's target slice in multi-rank mode, fused with the all-gather that SURVEY 8(e) puts after each drift:
+// the moved {x,y,z,m} record goes straight into the NEXT array of every rank's window (16-byte stores over NVLink peer
+// pointers), so no separate collective runs; the arrival flags follow in peer_barrier_kernel (sfe_peer.cu).
+__global__ void __launch_bounds__(SIM_THREADS) kick_drift_put_kernel(PeerPtrs pp, uint64_t off_cur, uint64_t off_nxt,
+                                                                     float* __restrict__ vel, const float* __restrict__ acc,
+                                                                     uint32_t i0, uint32_t ni, float dt) {
+    const float hdt = __fmul_rn(0.5f, dt);
+    const float4* __restrict__ cur = reinterpret_cast<const float4*>(pp.base[pp.rank] + off_cur);
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ni; t += gridDim.x * blockDim.x) {
+        const uint32_t i = i0 + t;
+        const float4 p = cur[i];
+        float v[3], q[3] = {p.x, p.y, p.z};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            v[k] = __fadd_rn(vel[3u * i + k], __fmul_rn(hdt, acc[3u * i + k]));
+            q[k] = __fadd_rn(q[k], __fmul_rn(dt, v[k]));
+            vel[3u * i + k] = v[k];
+        }
+        const float4 out = make_float4(q[0], q[1], q[2], p.w);
+        for (uint32_t r = 0; r < pp.world; r++) reinterpret_cast<float4*>(pp.base[r] + off_nxt)[i] = out;
+    }
+}
+
 // ---------------------------------------------------------------- root box (simulation.c:245-301)
 __device__ __forceinline__ void pcg4d_dev(uint32_t (&v)[4]) {   // rng.h:13-40
 #pragma unroll
@@ -161,7 +185,7 @@ __global__ void __launch_bounds__(SIM_THREADS) kick_energy_kernel(const float4* 
                                                                   float* __restrict__ ken, float* __restrict__ pen,
                                                                   uint32_t i0, uint32_t ni, float dt, int do_kick,
                                                                   dd* __restrict__ partial, uint32_t* __restrict__ ticket,
-                                                                  double* __restrict__ tv) {
+                                                                  double* __restrict__ tv, TvPeers tp) {
     const float hdt = __fmul_rn(0.5f, dt);
     dd s[2] = {{0.0, 0.0}, {0.0, 0.0}};
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ni; t += gridDim.x * blockDim.x) {
@@ -181,7 +205,22 @@ __global__ void __launch_bounds__(SIM_THREADS) kick_energy_kernel(const float4* 
         s[1] = dd_add(s[1], (double)pe);
     }
     if (!grid_sum<2>(s, partial, ticket)) return;
-    tv[0] = s[0].hi; tv[1] = s[1].hi;
+    if (tp.world == 0u) { tv[0] = s[0].hi; tv[1] = s[1].hi; return; }
+    // multi-rank: the slice's double-double sums go into slot [rank] of every rank's control page; tv_fold_kernel adds
+    // the slots in rank order after the barrier
+    for (uint32_t r = 0; r < tp.world; r++) {
+        double* d = tp.slot[r];
+        d[0] = s[0].hi; d[1] = s[0].lo; d[2] = s[1].hi; d[3] = s[1].lo;
+    }
+}
+
+__global__ void tv_fold_kernel(const double* __restrict__ slots /* [world][4] */, uint32_t world, double* __restrict__ tv) {
+    dd T{0.0, 0.0}, V{0.0, 0.0};
+    for (uint32_t r = 0; r < world; r++) {
+        T = dd_add(T, dd{__ldcg(&slots[4u * r]), __ldcg(&slots[4u * r + 1u])});
+        V = dd_add(V, dd{__ldcg(&slots[4u * r + 2u]), __ldcg(&slots[4u * r + 3u])});
+    }
+    tv[0] = T.hi; tv[1] = V.hi;
 }
 
 __global__ void unpack_pos_kernel(const float4* __restrict__ pm4, float* __restrict__ pos, float* __restrict__ mas, uint32_t n) {
@@ -251,9 +290,51 @@ int launch_kick_energy(Ctx* c, const float4* pm4, float* vel, const float* acc, 
     if (sim_scratch(c, fn, s)) return SFE_FAILURE;
     SimState& st = c->sim;
     if (ni == 0) { SFE_CUDA(fn, cudaMemsetAsync(tv_dev, 0, 2 * sizeof(double), s)); return SFE_SUCCESS; }
+    TvPeers tp; tp.world = 0u;
     kick_energy_kernel<<<sim_grid(c, ni), SIM_THREADS, 0, s>>>(pm4, vel, acc, pot, ken, pen, i0, ni, dt, do_kick,
-                                                              st.partial.as<dd>(), st.ticket.as<uint32_t>() + 1, tv_dev);
+                                                              st.partial.as<dd>(), st.ticket.as<uint32_t>() + 1, tv_dev, tp);
     return check_launch(fn);
+}
+
+// Multi-rank kick_1 + energies: the slice's sums are stored into every rank's control page, the ranks exchange arrival
+// flags, and each of them folds the slots in rank order (the same {T, V} everywhere).  An empty slice still takes part.
+static int launch_kick_energy_peers(Ctx* c, const float4* pm4, float dt, cudaStream_t s, const char* fn) {
+    SimState& st = c->sim;
+    PeerState& pr = c->peer;
+    const uint32_t parity = st.tv_parity; st.tv_parity ^= 1u;
+    TvPeers tp; tp.world = pr.world;
+    for (uint32_t r = 0; r < pr.world; r++)
+        tp.slot[r] = reinterpret_cast<PeerCtrl*>((char*)pr.base[r] + pr.bytes)->tv[parity][pr.rank];
+    kick_energy_kernel<<<sim_grid(c, st.ni), SIM_THREADS, 0, s>>>(pm4, st.vel.as<float>(), st.acc.as<float>(), st.pot.as<float>(),
+                                                                 st.ken.as<float>(), st.pen.as<float>(), st.i0, st.ni, dt, 1,
+                                                                 st.partial.as<dd>(), st.ticket.as<uint32_t>() + 1,
+                                                                 st.tv_dev.as<double>(), tp);
+    if (check_launch(fn)) return SFE_FAILURE;
+    if (launch_peer_barrier(c, s, fn)) return SFE_FAILURE;
+    tv_fold_kernel<<<1, 1, 0, s>>>(&reinterpret_cast<PeerCtrl*>((char*)pr.local + pr.bytes)->tv[parity][0][0], pr.world,
+                                   st.tv_dev.as<double>());
+    return check_launch(fn);
+}
+
+static int launch_kick_drift_peers(Ctx* c, float dt, cudaStream_t s, const char* fn) {
+    SimState& st = c->sim;
+    if (st.ni) {
+        kick_drift_put_kernel<<<sim_grid(c, st.ni), SIM_THREADS, 0, s>>>(peer_ptrs(c), st.pm4_off[st.cur], st.pm4_off[st.cur ^ 1],
+                                                                        st.vel.as<float>(), st.acc.as<float>(), st.i0, st.ni, dt);
+        if (check_launch(fn)) return SFE_FAILURE;
+    }
+    if (launch_peer_barrier(c, s, fn)) return SFE_FAILURE;
+    st.cur ^= 1;
+    return SFE_SUCCESS;
+}
+
+static float4* sim_pm4(Ctx* c) {
+    SimState& st = c->sim;
+    return st.peer_mode ? reinterpret_cast<float4*>((char*)c->peer.local + st.pm4_off[st.cur]) : st.pm4.as<float4>();
+}
+static float* sim_rho(Ctx* c) {
+    SimState& st = c->sim;
+    return st.peer_mode ? reinterpret_cast<float*>((char*)c->peer.local + st.rho_off) : st.rho.as<float>();
 }
 
 int launch_unpack(const float4* pm4, float* pos, float* mas, uint32_t n, cudaStream_t s) {
@@ -314,20 +395,36 @@ extern "C" int sfe_sim_upload(const float* mem, uint32_t N, uint32_t dof) {
     cudaStream_t s = c->stream;
     const size_t n = N;
     if (sim_scratch(c, fn, s)) return SFE_FAILURE;
-    if (st.pm4.reserve(n * 16, fn) || st.vel.reserve(n * 12, fn) || st.acc.reserve(n * 12, fn) || st.pot.reserve(n * 4, fn) ||
+    // multi-rank mode: an open peer window with more than one rank; the particles are partitioned by target slice
+    const PeerState& pr = c->peer;
+    st.peer_mode = pr.open && pr.world > 1u;
+    st.i0 = 0u; st.ni = N; st.cur = 0; st.tv_parity = 0u;
+    if (st.peer_mode) {
+        if (pr.bytes < sfe_sim_peer_bytes(N, dof)) {
+            set_error(fn, "the peer window holds %llu bytes; N=%u SIM_DOF=%u needs sfe_sim_peer_bytes() = %llu",
+                      (unsigned long long)pr.bytes, N, dof, (unsigned long long)sfe_sim_peer_bytes(N, dof));
+            st.peer_mode = false; st.loaded = false;
+            return SFE_FAILURE;
+        }
+        const uint64_t n64 = ((uint64_t)N + 63u) & ~(uint64_t)63u;
+        st.pm4_off[0] = 0u; st.pm4_off[1] = 16u * n64; st.rho_off = 32u * n64;
+        st.i0 = (uint32_t)(((uint64_t)N * pr.rank) / pr.world);
+        st.ni = (uint32_t)(((uint64_t)N * (pr.rank + 1u)) / pr.world) - st.i0;
+    }
+    if ((!st.peer_mode && st.pm4.reserve(n * 16, fn)) || st.vel.reserve(n * 12, fn) || st.acc.reserve(n * 12, fn) || st.pot.reserve(n * 4, fn) ||
         st.ken.reserve(n * 4, fn) || st.pen.reserve(n * 4, fn) || st.stage.reserve(n * 16, fn))
         return SFE_FAILURE;
-    if (dof == 16u && (st.rad.reserve(n * 4, fn) || st.rho.reserve(n * 4, fn) || st.prs.reserve(n * 4, fn))) return SFE_FAILURE;
+    if (dof == 16u && (st.rad.reserve(n * 4, fn) || (!st.peer_mode && st.rho.reserve(n * 4, fn)) || st.prs.reserve(n * 4, fn))) return SFE_FAILURE;
     st.loaded = false;
     // RAW layout: block p starts at mem + N*p (simulation.c:52); pos/mas go through the staging buffer into pm4
     float* stage = st.stage.as<float>();
     if (h2d(fn, stage, mem, n * 12, s) || h2d(fn, stage + 3 * n, mem + 9 * n, n * 4, s)) return SFE_FAILURE;
-    if (launch_pack_pm4(stage, stage + 3 * n, st.pm4.as<float4>(), N, s)) return SFE_FAILURE;
+    if (launch_pack_pm4(stage, stage + 3 * n, sim_pm4(c), N, s)) return SFE_FAILURE;
     if (h2d(fn, st.vel.p, mem + 3 * n, n * 12, s) || h2d(fn, st.acc.p, mem + 6 * n, n * 12, s) ||
         h2d(fn, st.pot.p, mem + 10 * n, n * 4, s) || h2d(fn, st.ken.p, mem + 11 * n, n * 4, s) ||
         h2d(fn, st.pen.p, mem + 12 * n, n * 4, s))
         return SFE_FAILURE;
-    if (dof == 16u && (h2d(fn, st.rad.p, mem + 13 * n, n * 4, s) || h2d(fn, st.rho.p, mem + 14 * n, n * 4, s) ||
+    if (dof == 16u && (h2d(fn, st.rad.p, mem + 13 * n, n * 4, s) || h2d(fn, sim_rho(c), mem + 14 * n, n * 4, s) ||
                        h2d(fn, st.prs.p, mem + 15 * n, n * 4, s)))
         return SFE_FAILURE;
     SFE_CUDA(fn, cudaStreamSynchronize(s));
@@ -346,19 +443,21 @@ extern "C" int sfe_sim_download(float* mem, uint32_t N, uint32_t dof, uint32_t b
     const size_t n = N;
     if (blocks & (SFE_SIM_POS | SFE_SIM_MAS)) {
         float* stage = st.stage.as<float>();
-        if (launch_unpack(st.pm4.as<float4>(), (blocks & SFE_SIM_POS) ? stage : nullptr, (blocks & SFE_SIM_MAS) ? stage + 3 * n : nullptr, N, s))
+        if (launch_unpack(sim_pm4(c), (blocks & SFE_SIM_POS) ? stage : nullptr, (blocks & SFE_SIM_MAS) ? stage + 3 * n : nullptr, N, s))
             return SFE_FAILURE;
         if ((blocks & SFE_SIM_POS) && d2h(fn, mem, stage, n * 12, s)) return SFE_FAILURE;
         if ((blocks & SFE_SIM_MAS) && d2h(fn, mem + 9 * n, stage + 3 * n, n * 4, s)) return SFE_FAILURE;
     }
-    if ((blocks & SFE_SIM_VEL) && d2h(fn, mem + 3 * n, st.vel.p, n * 12, s)) return SFE_FAILURE;
-    if ((blocks & SFE_SIM_ACC) && d2h(fn, mem + 6 * n, st.acc.p, n * 12, s)) return SFE_FAILURE;
-    if ((blocks & SFE_SIM_POT) && d2h(fn, mem + 10 * n, st.pot.p, n * 4, s)) return SFE_FAILURE;
-    if ((blocks & SFE_SIM_KEN) && d2h(fn, mem + 11 * n, st.ken.p, n * 4, s)) return SFE_FAILURE;
-    if ((blocks & SFE_SIM_PEN) && d2h(fn, mem + 12 * n, st.pen.p, n * 4, s)) return SFE_FAILURE;
+    // per-particle blocks that only the owning rank maintains: the slice [i0, i0+ni) (everything on a single rank)
+    const size_t a = st.i0, m = st.ni;
+    if ((blocks & SFE_SIM_VEL) && d2h(fn, mem + 3 * n + 3 * a, st.vel.as<float>() + 3 * a, m * 12, s)) return SFE_FAILURE;
+    if ((blocks & SFE_SIM_ACC) && d2h(fn, mem + 6 * n + 3 * a, st.acc.as<float>() + 3 * a, m * 12, s)) return SFE_FAILURE;
+    if ((blocks & SFE_SIM_POT) && d2h(fn, mem + 10 * n + a, st.pot.as<float>() + a, m * 4, s)) return SFE_FAILURE;
+    if ((blocks & SFE_SIM_KEN) && d2h(fn, mem + 11 * n + a, st.ken.as<float>() + a, m * 4, s)) return SFE_FAILURE;
+    if ((blocks & SFE_SIM_PEN) && d2h(fn, mem + 12 * n + a, st.pen.as<float>() + a, m * 4, s)) return SFE_FAILURE;
     if (dof == 16u) {
         if ((blocks & SFE_SIM_RAD) && d2h(fn, mem + 13 * n, st.rad.p, n * 4, s)) return SFE_FAILURE;
-        if ((blocks & SFE_SIM_RHO) && d2h(fn, mem + 14 * n, st.rho.p, n * 4, s)) return SFE_FAILURE;
+        if ((blocks & SFE_SIM_RHO) && d2h(fn, mem + 14 * n, sim_rho(c), n * 4, s)) return SFE_FAILURE;
         if ((blocks & SFE_SIM_PRS) && d2h(fn, mem + 15 * n, st.prs.p, n * 4, s)) return SFE_FAILURE;
     }
     SFE_CUDA(fn, cudaStreamSynchronize(s));
@@ -369,7 +468,8 @@ extern "C" int sfe_sim_download(float* mem, uint32_t N, uint32_t dof, uint32_t b
 static int sim_solv_enqueue(Ctx* c, const sfe_sim_params_t* p, uint32_t step_number, const char* fn) {
     SimState& st = c->sim;
     cudaStream_t s = c->stream;
-    const float4* pm4 = st.pm4.as<float4>();
+    const float4* pm4 = sim_pm4(c);
+    const uint32_t i0 = st.i0, ni = st.ni;
     if (p->solver & SFE_SOLVER_TREE) {
         float box[6];
         if (launch_root_box(c, pm4, st.N, step_number, box, s)) return SFE_FAILURE;
@@ -378,16 +478,19 @@ static int sim_solv_enqueue(Ctx* c, const sfe_sim_params_t* p, uint32_t step_num
         // engine raises the failure instead (a truncated tree has no defined contents here)
         if (launch_tree_build(c, box, pm4, st.N, p->depth_max, p->nodes_max, s)) return SFE_FAILURE;
         if (tree_status(c, s)) return SFE_FAILURE;
-        if (launch_bh(c, pm4, st.N, 0, st.N, st.acc.as<float>(), st.pot.as<float>(), p->grav_g, p->eps2, p->theta, p->flavour, s))
+        if (launch_bh(c, pm4, st.N, i0, ni, st.acc.as<float>(), st.pot.as<float>(), p->grav_g, p->eps2, p->theta, p->flavour, s))
             return SFE_FAILURE;
     } else {
-        if (launch_pp(c, pm4, st.N, 0, st.N, st.acc.as<float>(), st.pot.as<float>(), p->grav_g, p->eps2, s)) return SFE_FAILURE;
+        if (launch_pp(c, pm4, st.N, i0, ni, st.acc.as<float>(), st.pot.as<float>(), p->grav_g, p->eps2, s)) return SFE_FAILURE;
     }
     if (p->solver & SFE_SOLVER_SPH) {
         if (st.dof < 16u) { set_error(fn, "SFE_SOLVER_SPH needs a SIM_DOF=16 state"); return SFE_FAILURE; }
-        if (launch_sph_density(c, pm4, st.rad.as<float>(), st.N, 0, st.N, st.rho.as<float>(), s)) return SFE_FAILURE;
-        if (launch_sph_eos(st.rho.as<float>(), st.prs.as<float>(), st.N, p->eos_k, p->eos_n, s)) return SFE_FAILURE;
-        if (launch_sph_force(c, pm4, st.rad.as<float>(), st.rho.as<float>(), st.prs.as<float>(), st.N, 0, st.N, p->cutoff2,
+        float* rho = sim_rho(c);
+        if (launch_sph_density(c, pm4, st.rad.as<float>(), st.N, i0, ni, rho, s)) return SFE_FAILURE;
+        // second exchange of SURVEY 8(e): every rank needs rho of ALL sources for the force pass (P is recomputed locally)
+        if (st.peer_mode && launch_peer_put(c, st.rho_off + 4u * (uint64_t)i0, 4u * (uint64_t)ni, s, fn)) return SFE_FAILURE;
+        if (launch_sph_eos(rho, st.prs.as<float>(), st.N, p->eos_k, p->eos_n, s)) return SFE_FAILURE;
+        if (launch_sph_force(c, pm4, st.rad.as<float>(), rho, st.prs.as<float>(), st.N, i0, ni, p->cutoff2,
                              st.acc.as<float>(), s, /*reuse_cells=*/true))
             return SFE_FAILURE;
     }
@@ -396,6 +499,7 @@ static int sim_solv_enqueue(Ctx* c, const sfe_sim_params_t* p, uint32_t step_num
 
 static int sim_finish(Ctx* c, const sfe_sim_params_t* p, const char* fn) {
     SFE_CUDA(fn, cudaStreamSynchronize(c->stream));
+    if (c->sim.peer_mode && peer_status(c, fn)) return SFE_FAILURE;
     if ((p->solver & SFE_SOLVER_TREE) && tree_status(c, c->stream)) return SFE_FAILURE;
     return SFE_SUCCESS;
 }
@@ -418,6 +522,7 @@ extern "C" int sfe_sim_run(const sfe_sim_params_t* p, uint32_t first_step, uint3
     uint32_t pending = 0;   // steps whose {T, V} sit in the pinned ring and have not been handed out yet
     auto flush = [&](uint32_t upto) -> int {
         SFE_CUDA(fn, cudaStreamSynchronize(s));
+        if (st.peer_mode && peer_status(c, fn)) return SFE_FAILURE;
         if ((p->solver & SFE_SOLVER_TREE) && tree_status(c, s)) return SFE_FAILURE;
         for (; pending < upto; pending++) {
             const double T = st.tv_host[2 * (pending % SFE_SIM_TV_RING)], V = st.tv_host[2 * (pending % SFE_SIM_TV_RING) + 1];
@@ -427,11 +532,17 @@ extern "C" int sfe_sim_run(const sfe_sim_params_t* p, uint32_t first_step, uint3
     };
     for (uint32_t k = 0; k < nsteps; k++) {
         if (k - pending == SFE_SIM_TV_RING && flush(k)) return SFE_FAILURE;
-        if (launch_kick_drift(c, st.pm4.as<float4>(), st.vel.as<float>(), st.acc.as<float>(), 0, st.N, p->dt, s)) return SFE_FAILURE;
-        if (sim_solv_enqueue(c, p, first_step + k, fn)) return SFE_FAILURE;
-        if (launch_kick_energy(c, st.pm4.as<float4>(), st.vel.as<float>(), st.acc.as<float>(), st.pot.as<float>(), st.ken.as<float>(),
-                               st.pen.as<float>(), 0, st.N, p->dt, 1, st.tv_dev.as<double>(), s))
-            return SFE_FAILURE;
+        if (st.peer_mode) {
+            if (launch_kick_drift_peers(c, p->dt, s, fn)) return SFE_FAILURE;
+            if (sim_solv_enqueue(c, p, first_step + k, fn)) return SFE_FAILURE;
+            if (launch_kick_energy_peers(c, sim_pm4(c), p->dt, s, fn)) return SFE_FAILURE;
+        } else {
+            if (launch_kick_drift(c, st.pm4.as<float4>(), st.vel.as<float>(), st.acc.as<float>(), 0, st.N, p->dt, s)) return SFE_FAILURE;
+            if (sim_solv_enqueue(c, p, first_step + k, fn)) return SFE_FAILURE;
+            if (launch_kick_energy(c, st.pm4.as<float4>(), st.vel.as<float>(), st.acc.as<float>(), st.pot.as<float>(), st.ken.as<float>(),
+                                   st.pen.as<float>(), 0, st.N, p->dt, 1, st.tv_dev.as<double>(), s))
+                return SFE_FAILURE;
+        }
         SFE_CUDA(fn, cudaMemcpyAsync(st.tv_host + 2 * (k % SFE_SIM_TV_RING), st.tv_dev.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     return flush(nsteps);

@@ -106,6 +106,13 @@ SIGNATURES = {
     "sfe_sim_run": ([_P, _u32, _u32, _P], C.c_int),
     "sfe_sim_last_box": ([_P], C.c_int),
     "sfe_sim_release": ([], C.c_int),
+    "sfe_peer_create": ([_u32, _u32, C.c_uint64, _P], C.c_int),
+    "sfe_peer_open": ([_P], C.c_int),
+    "sfe_peer_window": ([], _P),
+    "sfe_dev_peer_put": ([C.c_uint64, C.c_uint64, _P], C.c_int),
+    "sfe_dev_peer_barrier": ([_P], C.c_int),
+    "sfe_peer_close": ([], C.c_int),
+    "sfe_sim_peer_bytes": ([_u32, _u32], C.c_uint64),
 }
 
 _lib = None
@@ -359,3 +366,29 @@ def sim_last_box():
     b = np.zeros(6, np.float32)
     _check(lib().sfe_sim_last_box(_ptr(b)), "sfe_sim_last_box")
     return b
+
+
+# ---------------------------------------------------------------------------------- peer exchange
+PEER_HANDLE_BYTES = 64
+
+
+def peer_setup(rank, world, nbytes, allgather):
+    """Create this rank's exchange window, swap the IPC handles and map every peer's window (sfe_peer_create /
+    sfe_peer_open).  `allgather(bytes) -> list of bytes indexed by rank` is the host-side transport, e.g.
+    torch.distributed.all_gather_object; it is only used here, once.  Returns the window's device pointer."""
+    h = C.create_string_buffer(PEER_HANDLE_BYTES)
+    _check(lib().sfe_peer_create(rank, world, nbytes, h), "sfe_peer_create")
+    handles = allgather(h.raw)
+    if len(handles) != world or any(len(x) != PEER_HANDLE_BYTES for x in handles):
+        raise EngineError("peer_setup: the transport returned %d handles for %d ranks" % (len(handles), world))
+    _check(lib().sfe_peer_open(b"".join(handles)), "sfe_peer_open")
+    return lib().sfe_peer_window()
+
+
+def peer_close():
+    return lib().sfe_peer_close()
+
+
+def sim_slice(N, rank, world):
+    """Target slice of a rank: [rank*N/world, (rank+1)*N/world)."""
+    return (N * rank) // world, (N * (rank + 1)) // world
