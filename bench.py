@@ -54,6 +54,10 @@ def parse():
     ap.add_argument("--flavour", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-pp", action="store_true", help="skip the PP leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sph", action="store_true", help="skip the C3 (PP + SPH) legs")
+    ap.add_argument("--no-resident", action="store_true", help="skip the device-resident leapfrog legs")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: all-gather of {x,y,z,m} by the engine's peer-memory kernels (sfe_dev_peer_put) or by NCCL")
     return ap.parse_args()
 
 
@@ -189,6 +193,100 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------ secondary legs
+C3_N = 262144
+
+
+def sph_leg(e, L, torch, dev, stream):
+    """C3 snapshot: N = 262144 gas sphere, h = 0.1.  Times density + EOS + pressure force (the solve_sph()
+    replacement) with the snapshot resident, and reports it against SURVEY 8(d)'s byte model with the cutoff the cell
+    list uses (R = 4 h): B = 20 B n_rho + 24 B n_F + 64 B per particle, n = mean number of sources within R."""
+    from starflood_b200 import ics
+    N = C3_N
+    pos, vel, mas = ics.uniform_ball(N, outflow=0.0)
+    rad = np.full(N, 0.1, np.float32)
+    pm = np.empty((N, 4), np.float32); pm[:, :3] = pos.reshape(-1, 3); pm[:, 3] = mas
+    d_pm4 = torch.from_numpy(pm).to(dev).reshape(-1)
+    d_rad = torch.from_numpy(rad).to(dev)
+    rho = torch.zeros(N, dtype=torch.float32, device=dev); prs = torch.zeros_like(rho)
+    acc = torch.zeros(3 * N, dtype=torch.float32, device=dev)
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)
+    sptr = stream.cuda_stream
+
+    def solve():
+        rc = L.sfe_dev_sph_density(d_pm4.data_ptr(), d_rad.data_ptr(), N, 0, N, rho.data_ptr(), sptr)
+        rc |= L.sfe_dev_sph_eos(rho.data_ptr(), prs.data_ptr(), N, e.EOS_K, e.EOS_N, sptr)
+        rc |= L.sfe_dev_sph_force(d_pm4.data_ptr(), d_rad.data_ptr(), rho.data_ptr(), prs.data_ptr(), N, 0, N, e.SPH_CUTOFF2,
+                                  acc.data_ptr(), sptr)
+        if rc != 0:
+            raise SystemExit("bench.py: SPH call failed: " + e.last_error())
+    for _ in range(3):
+        solve()
+    torch.cuda.synchronize()
+    reps, tot = 10, 0.0
+    for _ in range(reps):
+        flush.fill_(1)                                  # 160 MiB > L2: the snapshot is read from HBM again
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream); solve(); b.record(stream)
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    ms = tot / reps
+    # mean number of sources within R = 4 h of a target, on a sample (input analysis, outside every timed region)
+    from scipy.spatial import cKDTree
+    P = pos.reshape(-1, 3).astype(np.float64)
+    sample = P[np.random.default_rng(1).choice(N, 2048, replace=False)]
+    nn = float(np.mean(cKDTree(P).query_ball_point(sample, 0.4, return_length=True)))
+    hbm, hbm_src = measured_peaks()
+    bytes_alg = (20.0 * nn + 24.0 * nn + 64.0) * N
+    ach = bytes_alg / (ms * 1e-3) / 1e9
+    return {"workload": "C3 snapshot: SPH density + EOS + pressure force, N=%d, h=0.1 (solve_sph replacement), device resident" % N,
+            "ms_per_solve": ms, "particle_solves_per_s": N / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": hbm_src,
+                         "model": "SURVEY 8(d): (20 B + 24 B) x n + 64 B per particle, n = %.0f sources within R = 4 h = 0.4 "
+                                  "(sampled); source tiles are shared through shared memory, so DRAM traffic is far below this" % nn,
+                         "algorithmic_bytes_per_solve": bytes_alg},
+            "l2": "160 MiB flush buffer written between repetitions"}
+
+
+def resident_leg(e, L, torch, dist, world, rank, N, tree, with_sph, flavour, allgather_bytes, barrier, max_over_ranks, use_peer):
+    """Whole sim_step()s (kick, drift, root box, build + walk | PP, [SPH], kick, energies) on the HBM-resident state
+    through sfe_sim_run(); with more than one rank the drift kernel stores straight into every rank's window."""
+    from starflood_b200 import ics
+    pos, vel, mas = ics.uniform_ball(N, outflow=4.0e-3 if tree else 0.0)
+    sim = e.Sim(N, sph=with_sph)
+    sim.pos[:] = pos; sim.vel[:] = vel; sim.mas[:] = mas
+    if with_sph:
+        sim.rad[:] = 0.1
+    if world > 1:
+        if not use_peer:
+            return None                              # the resident leapfrog's exchange is the engine's own
+        e.peer_setup(rank, world, int(L.sfe_sim_peer_bytes(N, sim.dof)), allgather_bytes)
+    prm = e.sim_params(tree=tree, sph=with_sph, flavour=flavour, nodes_max=max(N, 1024))
+    if e.sim_upload(sim) != 0 or e.sim_solv_resident(sim, prm) != 0:
+        raise SystemExit("bench.py: resident leg failed: " + e.last_error())
+    steps = 20 if tree else 5
+    sim.step_number = 0
+    rc, _ = e.sim_step(sim, prm, nsteps=3)
+    barrier()
+    l0 = L.sfe_launch_count()
+    t0 = time.perf_counter()
+    sim.step_number = 3
+    rc2, E = e.sim_step(sim, prm, nsteps=steps)
+    barrier()
+    ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / steps)
+    if rc != 0 or rc2 != 0:
+        raise SystemExit("bench.py: resident leg failed: " + e.last_error())
+    launches = int(L.sfe_launch_count() - l0)
+    L.sfe_sim_release()
+    if world > 1:
+        e.peer_close(dist.barrier)
+    return {"workload": ("Barnes-Hut" if tree else "PP + SPH") + " leapfrog N=%d, %d sim_step()s through sfe_sim_run()" % (N, steps),
+            "ms_per_step": ms, "particle_steps_per_s": N / (ms * 1e-3), "gpu_launches": launches,
+            "energy_last": [float(x) for x in E[-1]],
+            "timing": "host clock around the synchronous call, barrier on both sides, max over ranks",
+            "l2": "the state evolves in place (a real trajectory); its working set is what the workload has"}
+
+
 # ------------------------------------------------------------------------------------------ engine arm
 def run_engine(args):
     import torch
@@ -220,8 +318,27 @@ def run_engine(args):
     snaps = snapshots(N, ring)
     nodes_max = max(N, 1024)
 
+    def allgather_bytes(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+
+    class Window:
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
     # device-resident state: per snapshot the rank's slice of pm4 records; full pm4 + outputs shared
-    pm4_full = torch.empty(N * 4, dtype=torch.float32, device=dev)
+    use_peer = world > 1 and args.exchange == "peer"
+    if use_peer:
+        # two {x,y,z,m} arrays inside the exchange window, alternated between steps (sfengine.h: a range written by
+        # exchange k may be rewritten by exchange k+2 at the earliest)
+        wptr = e.peer_setup(rank, world, 2 * 16 * N, allgather_bytes)
+        wt = torch.as_tensor(Window(wptr, 2 * 16 * N), device=dev)
+        pm4_regions = [wt[:4 * N], wt[4 * N:]]
+        pm4_full = pm4_regions[0]
+    else:
+        pm4_full = torch.empty(N * 4, dtype=torch.float32, device=dev)
+    xstate = {"n": 0}
     acc = torch.zeros(3 * N, dtype=torch.float32, device=dev)
     pot = torch.zeros(N, dtype=torch.float32, device=dev)
     slices, boxes = [], []
@@ -233,17 +350,25 @@ def run_engine(args):
     import ctypes as C
 
     def gather(k):
+        """Returns the tensor that holds all N records of snapshot k on this rank."""
+        if use_peer:
+            reg = xstate["n"] & 1; xstate["n"] += 1
+            pm4_regions[reg][4 * i0:4 * i1].copy_(slices[k])
+            if L.sfe_dev_peer_put(16 * (N * reg + i0), 16 * ni, sptr) != 0:
+                raise SystemExit("bench.py: peer exchange failed: " + e.last_error())
+            return pm4_regions[reg]
         if world > 1:
             dist.all_gather_into_tensor(pm4_full, slices[k])
         else:
             pm4_full.copy_(slices[k])      # at N=1 the "gather" is a device copy of the resident snapshot
+        return pm4_full
 
     def step_dev(k, ev=None):
-        gather(k)
-        rc = L.sfe_dev_tree_build(boxes[k].ctypes.data, pm4_full.data_ptr(), N, e.TREE_DEPTH_MAX, nodes_max, sptr)
+        pm4 = gather(k)
+        rc = L.sfe_dev_tree_build(boxes[k].ctypes.data, pm4.data_ptr(), N, e.TREE_DEPTH_MAX, nodes_max, sptr)
         if ev is not None:
             ev[0].record(stream)
-        rc |= L.sfe_dev_bh(pm4_full.data_ptr(), N, i0, ni, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, THETA, flavour, sptr)
+        rc |= L.sfe_dev_bh(pm4.data_ptr(), N, i0, ni, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, THETA, flavour, sptr)
         if ev is not None:
             ev[1].record(stream)
         if rc != 0:
@@ -343,15 +468,15 @@ def run_engine(args):
     # ---- PP leg: interactions/s at the same N, target-sliced the same way
     pp = None
     if not args.no_pp:
-        gather(0)
+        pm4 = gather(0)
         reps = 2 if N >= (1 << 19) else 5
-        L.sfe_dev_pp(pm4_full.data_ptr(), N, i0, ni, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, sptr)
+        L.sfe_dev_pp(pm4.data_ptr(), N, i0, ni, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, sptr)
         barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record(stream)
         for r in range(reps):
-            gather(r % ring)
-            L.sfe_dev_pp(pm4_full.data_ptr(), N, i0, ni, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, sptr)
+            pm4 = gather(r % ring)
+            L.sfe_dev_pp(pm4.data_ptr(), N, i0, ni, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, sptr)
         p1.record(stream)
         barrier()
         pp_ms = max_over_ranks(p0.elapsed_time(p1)) / reps
@@ -363,6 +488,26 @@ def run_engine(args):
               "fp32_peak_tflops": info["fp32_peak_tflops"] * world,
               "peak_note": "2*128 lanes*%d SMs*%.0f MHz per GPU (cudaDevAttrClockRate)" % (info["sm_count"], info["clock_khz"] / 1e3),
               "frac": tf / (info["fp32_peak_tflops"] * world)}
+
+    # ---- C3 SPH kernels alone (single rank): density + EOS + pressure force on a resident snapshot
+    sph = None
+    if not args.no_sph and world == 1:
+        sph = sph_leg(e, L, torch, dev, stream)
+
+    # ---- device-resident leapfrog: whole sim_step()s with the state in HBM, through sfe_sim_run()
+    resident = None
+    if not args.no_resident:
+        barrier()
+        if use_peer:
+            del wt, pm4_regions, pm4_full
+            e.peer_close(dist.barrier)
+        resident = {}
+        legs = [("C2", N, True, False)]
+        if not args.no_sph:
+            legs.append(("C3", 262144, False, True))
+        for name, n_leg, tree, with_sph in legs:
+            resident[name] = resident_leg(e, L, torch, dist, world, rank, n_leg, tree, with_sph, flavour, allgather_bytes,
+                                          barrier, max_over_ranks, world > 1 and args.exchange == "peer")
 
     if rank != 0:
         if world > 1:
@@ -404,7 +549,9 @@ def run_engine(args):
         "config": {"workload": "C2: Barnes-Hut gravity N=%d uniform sphere (reference initcond), theta=0.5 monopole, "
                                "tree_build + solve_gravity_part_tree per step" % N,
                    "N": N, "theta": THETA, "depth_max": 16, "walk": args.flavour,
-                   "partition": "target slices, tree per GPU, all-gather of {x,y,z,m}" if world > 1 else "single GPU",
+                   "partition": ("target slices, tree per GPU, all-gather of {x,y,z,m} by %s" %
+                                 ("the engine's peer-memory put + flag kernels (NVLink, sfe_dev_peer_put)" if use_peer else "NCCL"))
+                                if world > 1 else "single GPU",
                    "l2": "ring of %d distinct snapshots (%d MiB of inputs > L2) rotated between steps" % (ring, ring * 16 * N >> 20),
                    "tree_nodes": int(st[0].value), "tree_depth": int(st[2].value)},
         "e2e": {"value": N / (e2e_ms * 1e-3), "unit": "particle-steps/s", "ms_per_step": e2e_ms,
@@ -416,6 +563,8 @@ def run_engine(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "pp": pp,
+        "sph": sph,
+        "resident": resident,
     }
     print(json.dumps(line))
     if world > 1:

@@ -209,13 +209,20 @@ void* sfe_peer_window(void);   /* device pointer of this rank's window (NULL bef
 int sfe_dev_peer_put(uint64_t offset, uint64_t bytes, void* stream);
 /* Flags only (a barrier on the device, no host involvement). */
 int sfe_dev_peer_barrier(void* stream);
+/* Tear-down, in two phases so that no window is freed while a peer still maps it: every rank unmaps its peers'
+ * windows (sfe_peer_detach), the HOSTS synchronise by their own means, then every rank frees its window
+ * (sfe_peer_close; it detaches first when that has not happened yet).  A resident state that lives in the window
+ * is released with it. */
+int sfe_peer_detach(void);
 int sfe_peer_close(void);
 /* Window size that sfe_sim_upload() needs when the resident leapfrog runs on `world` ranks: two {x,y,z,m} arrays
  * (ping-pong between steps) and, for SIM_DOF = 16, rho.  With an open window of at least this size the sfe_sim_*
  * entry points partition the particles by target slice [rank*N/world, (rank+1)*N/world): kick_0 + drift stores the
  * moved slice into every rank's next {x,y,z,m} array (the drift and its all-gather are ONE kernel), every rank builds
  * the full tree and evaluates its slice, {T, V} are combined in rank order.  sfe_sim_download() then returns pos /
- * mas / rho / prs in full and the other blocks for the rank's slice only. */
+ * mas / rho / prs in full and the other blocks for the rank's slice only.  In this mode sfe_sim_upload(), sfe_sim_solv()
+ * and sfe_sim_run() are collective (every rank calls them with the same arguments; upload ends with an exchange of
+ * flags so that no rank stores into a window its owner is still filling). */
 uint64_t sfe_sim_peer_bytes(uint32_t N, uint32_t dof);
 
 #ifdef __cplusplus

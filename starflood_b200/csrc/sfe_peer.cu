@@ -121,11 +121,16 @@ int peer_status(Ctx* c, const char* fn) {
     return SFE_SUCCESS;
 }
 
-void peer_release(Ctx* c) {
-    PeerState& p = c->peer;
+static void peer_detach(PeerState& p) {
     if (p.open)
         for (uint32_t r = 0; r < p.world; r++)
-            if (r != p.rank && p.base[r]) cudaIpcCloseMemHandle(p.base[r]);
+            if (r != p.rank && p.base[r]) { cudaIpcCloseMemHandle(p.base[r]); p.base[r] = nullptr; }
+    p.open = false;
+}
+
+void peer_release(Ctx* c) {
+    PeerState& p = c->peer;
+    peer_detach(p);
     if (p.local) cudaFree(p.local);
     if (p.err_host) cudaFreeHost(p.err_host);
     p = PeerState();
@@ -194,6 +199,16 @@ extern "C" int sfe_dev_peer_put(uint64_t offset, uint64_t bytes, void* stream) {
 extern "C" int sfe_dev_peer_barrier(void* stream) {
     if (ensure_init("sfe_dev_peer_barrier")) return SFE_FAILURE;
     return launch_peer_barrier(ctx(), (cudaStream_t)stream, "sfe_dev_peer_barrier");
+}
+
+extern "C" int sfe_peer_detach(void) {
+    Ctx* c = ctx();
+    if (!c) return SFE_SUCCESS;
+    cudaDeviceSynchronize();
+    if (c->sim.loaded && c->sim.peer_mode) sim_release(c);
+    const int rc = peer_status(c, "sfe_peer_detach");
+    peer_detach(c->peer);
+    return rc;
 }
 
 extern "C" int sfe_peer_close(void) {

@@ -427,7 +427,11 @@ extern "C" int sfe_sim_upload(const float* mem, uint32_t N, uint32_t dof) {
     if (dof == 16u && (h2d(fn, st.rad.p, mem + 13 * n, n * 4, s) || h2d(fn, sim_rho(c), mem + 14 * n, n * 4, s) ||
                        h2d(fn, st.prs.p, mem + 15 * n, n * 4, s)))
         return SFE_FAILURE;
+    // multi-rank: nobody may store into a window (the first rho exchange, the first drift) before its owner has finished
+    // filling it, and nobody may refill a window that a slower peer still reads: one exchange of flags
+    if (st.peer_mode && launch_peer_barrier(c, s, fn)) return SFE_FAILURE;
     SFE_CUDA(fn, cudaStreamSynchronize(s));
+    if (st.peer_mode && peer_status(c, fn)) return SFE_FAILURE;
     st.N = N; st.dof = dof; st.loaded = true;
     return SFE_SUCCESS;
 }

@@ -111,6 +111,7 @@ SIGNATURES = {
     "sfe_peer_window": ([], _P),
     "sfe_dev_peer_put": ([C.c_uint64, C.c_uint64, _P], C.c_int),
     "sfe_dev_peer_barrier": ([_P], C.c_int),
+    "sfe_peer_detach": ([], C.c_int),
     "sfe_peer_close": ([], C.c_int),
     "sfe_sim_peer_bytes": ([_u32, _u32], C.c_uint64),
 }
@@ -385,8 +386,13 @@ def peer_setup(rank, world, nbytes, allgather):
     return lib().sfe_peer_window()
 
 
-def peer_close():
-    return lib().sfe_peer_close()
+def peer_close(barrier=None):
+    """Unmap the peers' windows, let the hosts meet (`barrier()`, e.g. torch.distributed.barrier), free this rank's
+    window: no window disappears while a peer still maps it."""
+    rc = lib().sfe_peer_detach()
+    if barrier is not None:
+        barrier()
+    return rc | lib().sfe_peer_close()
 
 
 def sim_slice(N, rank, world):

@@ -64,7 +64,7 @@ def main():
     # a range outside the window is refused
     assert L.sfe_dev_peer_put(2 * half - 8, 64, s) == e.STARFLOOD_FAILURE
     del win
-    assert e.peer_close() == 0, e.last_error()
+    assert e.peer_close(dist.barrier) == 0, e.last_error()
 
     # ---- 2. Barnes-Hut leapfrog on `world` ranks against the oracle-driven run (bit for bit on the rank's slice)
     N, steps = 6000, 5
@@ -92,7 +92,7 @@ def main():
     allE = allgather(E.tobytes())
     assert all(x == allE[0] for x in allE), "every rank must report the same energies"
     assert L.sfe_sim_release() == 0
-    assert e.peer_close() == 0, e.last_error()
+    assert e.peer_close(dist.barrier) == 0, e.last_error()
 
     # ---- 3. PP + SPH on `world` ranks against the single-rank resident path.  A slice splits the source loop differently
     # from the full evaluation (same gate as tests/test_gpu_device_api.py: 1e-6 per solve), so this leg is held to the
@@ -124,7 +124,7 @@ def main():
     # the window is too small for a bigger state: refused, and the engine falls back to nothing
     big = e.Sim(2 * N, sph=True); big.mas[:] = 1.0
     assert e.sim_upload(big) == e.STARFLOOD_FAILURE and "sfe_sim_peer_bytes" in e.last_error()
-    assert e.peer_close() == 0, e.last_error()
+    assert e.peer_close(dist.barrier) == 0, e.last_error()
     dist.barrier()
     dist.destroy_process_group()
     print("PEER_OK", rank, flush=True)
