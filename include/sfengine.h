@@ -181,6 +181,15 @@ int sfe_sim_solv(const sfe_sim_params_t* p, uint32_t step_number);
  * first_step, first_step+1, ... (the reference's main loop sets sim.step_number before each step, main.c:451). */
 int sfe_sim_step(const sfe_sim_params_t* p, uint32_t step_number, double energy[3]);
 int sfe_sim_run(const sfe_sim_params_t* p, uint32_t first_step, uint32_t nsteps, double* energy);
+/* sim_save_raw() (simulation_io.c:81-149) fed from the resident state: the same file - the whole
+ * block real[N*SIM_DOF] - written WITHOUT stopping the leapfrog.  The call takes a device-side copy of the state on
+ * the engine's stream (so the next step may start at once), a copy stream brings it to pinned host memory and a
+ * writer thread puts it on disk.  Two snapshots may be in flight; a third call waits for the oldest.  In multi-rank
+ * mode every rank writes the rows of its own target slice into the same file (all ranks must name the same path on a
+ * file system they share, and call this collectively).  Errors of the writer (open / write / close) surface in
+ * sfe_sim_save_wait(), which returns when every requested snapshot is on disk. */
+int sfe_sim_save_raw_async(const char* filename);
+int sfe_sim_save_wait(void);
 /* The root box of the last tree solve (what sim_solv() would have put into sim.tree.bounds). */
 int sfe_sim_last_box(float bounds[6]);
 int sfe_sim_release(void);

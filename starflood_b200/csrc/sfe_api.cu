@@ -169,6 +169,7 @@ extern "C" int sfe_shutdown(void) {
     cudaDeviceSynchronize();
     for (auto& kv : g_registered) cudaHostUnregister(kv.first);
     g_registered.clear();
+    saver_release();
     sim_release(c);
     peer_release(c);
     Tree& t = c->tree;

@@ -194,6 +194,7 @@ int launch_peer_barrier(Ctx* c, cudaStream_t s, const char* fn);          // sig
 int launch_peer_put(Ctx* c, uint64_t offset, uint64_t bytes, cudaStream_t s, const char* fn);
 int peer_status(Ctx* c, const char* fn);                                   // raises a timed-out exchange
 void peer_release(Ctx* c);
+void saver_release();        // sfe_save.cu: drains pending snapshots, stops the writer thread
 // SPH neighbour search (sfe_sph_cells.cu): grid + sort for one snapshot, then one gated pass per mode
 int cells_prepare(Ctx* c, const float4* pm4, const float* rad, uint32_t N, bool force_all_pairs, cudaStream_t s, const char* fn);
 int cells_run(Ctx* c, int mode, const float4* pm4, const float* rad, const float* rho, const float* prs, uint32_t N,

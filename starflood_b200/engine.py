@@ -106,6 +106,8 @@ SIGNATURES = {
     "sfe_sim_run": ([_P, _u32, _u32, _P], C.c_int),
     "sfe_sim_last_box": ([_P], C.c_int),
     "sfe_sim_release": ([], C.c_int),
+    "sfe_sim_save_raw_async": ([C.c_char_p], C.c_int),
+    "sfe_sim_save_wait": ([], C.c_int),
     "sfe_peer_create": ([_u32, _u32, C.c_uint64, _P], C.c_int),
     "sfe_peer_open": ([_P], C.c_int),
     "sfe_peer_window": ([], _P),
@@ -361,6 +363,15 @@ def sim_step(sim, params, nsteps=1):
     en = np.zeros((nsteps, 3), np.float64)
     rc = lib().sfe_sim_run(C.byref(params), sim.step_number, nsteps, _ptr(en))
     return rc, en
+
+
+def sim_save_raw_async(filename):
+    """sim_save_raw() (simulation_io.c:81-149) from the resident state, overlapped with the following steps."""
+    return lib().sfe_sim_save_raw_async(os.fsencode(filename))
+
+
+def sim_save_wait():
+    return lib().sfe_sim_save_wait()
 
 
 def sim_last_box():

@@ -91,6 +91,16 @@ def main():
     assert np.all(np.abs(E - Eo) <= 1e-15 * np.abs(Eo).max()), (rank, E - Eo)
     allE = allgather(E.tobytes())
     assert all(x == allE[0] for x in allE), "every rank must report the same energies"
+    # RAW snapshot: every rank writes the rows of its slice into ONE file; together they are the block
+    import tempfile
+    path = allgather(os.path.join(tempfile.gettempdir(), "sfe_peer_%d_%d.raw" % (port, os.getpid())))[0]
+    assert e.sim_save_raw_async(path) == 0 and e.sim_save_wait() == 0, e.last_error()
+    dist.barrier()
+    want = np.concatenate([p, v, a, mas, po, ken, pen]).astype(np.float32)
+    assert np.fromfile(path, np.float32).tobytes() == want.tobytes(), (rank, "snapshot file")
+    dist.barrier()
+    if rank == 0:
+        os.remove(path)
     assert L.sfe_sim_release() == 0
     assert e.peer_close(dist.barrier) == 0, e.last_error()
 
@@ -127,6 +137,7 @@ def main():
     assert e.peer_close(dist.barrier) == 0, e.last_error()
     dist.barrier()
     dist.destroy_process_group()
+    e.shutdown()
     print("PEER_OK", rank, flush=True)
 
 

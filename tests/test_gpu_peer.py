@@ -20,7 +20,7 @@ def free_port():
         return s.getsockname()[1]
 
 
-def run_world(world, timeout=420):
+def run_world(world, timeout=150):
     port = free_port()
     env = dict(os.environ, SFE_PEER_TIMEOUT_MS="60000")
     procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "peer_worker.py"), str(r), str(world), str(port)],

@@ -191,6 +191,54 @@ def test_resident_pp_sph_run_matches_host_path(engine):
     assert abs(E[-1, 2] - T) <= 1e-15 * abs(T) and abs(E[-1, 1] - V) <= 1e-15 * abs(V)
 
 
+def test_async_raw_snapshots_are_the_state_block(engine, tmp_path):
+    """sfe_sim_save_raw_async() writes sim_save_raw()'s file (real[N*SIM_DOF], simulation_io.c:126-133)
+    from the resident state while the leapfrog goes on.  Every file must equal the state block that a second,
+    step-by-step run downloads at the same step."""
+    N, steps = 20000, 5
+    for sph in (False, True):
+        if sph:
+            pos, vel, mas, rad = sfo.initcond(N, outflow=0.0, sph=True)
+        else:
+            pos, vel, mas = sfo.initcond(N)
+        prm = engine.sim_params(tree=not sph, sph=sph, nodes_max=2 * N)
+
+        def fresh():
+            sim = engine.Sim(N, sph=sph); sim.pos[:] = pos; sim.vel[:] = vel; sim.mas[:] = mas
+            if sph:
+                sim.rad[:] = rad
+            assert engine.sim_upload(sim) == 0 and engine.sim_solv_resident(sim, prm) == 0, engine.last_error()
+            return sim
+        sim = fresh()
+        names = [str(tmp_path / ("sph%d_step_%04d.raw" % (sph, k))) for k in range(steps + 1)]
+        assert engine.sim_save_raw_async(names[0]) == 0, engine.last_error()
+        for k in range(steps):                       # no waiting between steps: up to two snapshots are in flight
+            sim.step_number = k
+            assert engine.sim_step(sim, prm)[0] == 0, engine.last_error()
+            assert engine.sim_save_raw_async(names[k + 1]) == 0, engine.last_error()
+        assert engine.sim_save_wait() == 0, engine.last_error()
+        ref = fresh()
+        for k in range(steps + 1):
+            if k:
+                ref.step_number = k - 1
+                assert engine.sim_step(ref, prm)[0] == 0
+            assert engine.sim_download(ref) == 0
+            data = np.fromfile(names[k], np.float32)
+            assert data.size == N * ref.dof and data.tobytes() == ref.mem.tobytes(), (sph, k)
+        # overwriting an existing, longer file leaves exactly the block
+        with open(names[0], "ab") as f:
+            f.write(b"x" * 1000)
+        assert engine.sim_save_raw_async(names[0]) == 0 and engine.sim_save_wait() == 0
+        assert np.fromfile(names[0], np.float32).tobytes() == ref.mem.tobytes()
+    # writer errors surface in sfe_sim_save_wait(), once
+    assert engine.sim_save_raw_async(str(tmp_path / "no_such_dir" / "x.raw")) == 0
+    assert engine.sim_save_wait() == engine.STARFLOOD_FAILURE and "open" in engine.last_error()
+    assert engine.sim_save_wait() == 0
+    assert engine.lib().sfe_sim_save_raw_async(None) == engine.STARFLOOD_FAILURE
+    engine.lib().sfe_sim_release()
+    assert engine.sim_save_raw_async(str(tmp_path / "y.raw")) == engine.STARFLOOD_FAILURE      # nothing resident
+
+
 def test_resident_errors(engine):
     L = engine.lib()
     engine.lib().sfe_sim_release()
