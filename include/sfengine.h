@@ -104,6 +104,14 @@ int sfe_tree_keys_download(uint64_t* keys, uint32_t* perm, uint32_t N, uint32_t*
  * used and returns the number of mismatching bit patterns per function (must be {0, 0, 0}). */
 int sfe_selftest_exact_math(uint64_t mismatches[3]);
 
+/* The SOLVER_VIS part of solve_gravity_part_tree() (gravity.h:14-18 with SOLVER_VIS defined, the reference's default;
+ * gravity.c:16-111, :380-445, :550-574): the debug overlay of particle `idx` (SOLVER_VIS = 3) - the
+ * outline of every internal cell its walk looks at, coloured by depth, and a segment to every monopole it evaluates -
+ * added (`+=`) to the host RGBA float buffer render_buffer[4*sizex*sizey] through the row-major 4x4 matrix mvp
+ * (visualization.c's matMVP).  Uses the tree and the particle records of the last sfe_tree_build(); bit-identical to the
+ * reference's drawing.  idx >= N draws nothing, like the reference. */
+int sfe_bh_overlay(uint32_t idx, float theta, const float mvp[16], float* render_buffer, uint32_t sizex, uint32_t sizey);
+
 /* Replaces solve_sph() (sph.h:6, sph.c:14-283): density (all pairs, no cutoff), EOS
  * P = (eos_k rho)^(1/eos_n + 1), pressure force added to acc (read-modify-write) for r^2 <= cutoff2. */
 int sfe_sph(const float* pos, const float* mas, const float* rad, float* rho, float* prs, float* acc,

@@ -17,7 +17,10 @@
 #   tree      ENABLE_TREE on, TREE_NODES_MAX=2^20  -> tree_build + solve_gravity_part_tree
 #   tree_big  ENABLE_TREE on, TREE_NODES_MAX=2^23  (N up to 2^24)
 #   pp_sph    ENABLE_TREE off, ENABLE_SPH on       -> + solve_sph
-# In all variants: ENABLE_VIS / SOLVER_VIS / VIS_FILENAME off (no rasteriser dependency),
+#   tree_vis  like tree with SOLVER_VIS 3 left ON  -> solve_gravity_part_tree(sim, render_buffer, sizex, sizey)
+#             draws its debug overlay (gravity.c:16-111,380-445,550-574).  The only symbol that needs is matMVP, which
+#             lives in visualization.c (not compiled here): a one-line definition is generated in the scratch directory.
+# In all other variants: ENABLE_VIS / SOLVER_VIS / VIS_FILENAME off (no rasteriser dependency),
 # CSV logs and timing prints off, Kahan flags ON (shipped default), fp32.
 #
 # Flags: the reference Makefile's performance set is -O3 -march=native -fopenmp -std=c99
@@ -39,7 +42,7 @@ SCRATCH="$(mktemp -d /tmp/sfref.XXXXXX)"
 trap 'rm -rf "$SCRATCH"' EXIT
 
 build_variant() {
-  local name="$1" tree="$2" sph="$3" nodes="$4"
+  local name="$1" tree="$2" sph="$3" nodes="$4" vis="${5:-0}"
   local d="$SCRATCH/$name"
   mkdir -p "$d"
   cp "$REF"/src/*.c "$REF"/src/*.h "$d"/
@@ -59,8 +62,14 @@ build_variant() {
     "$cfg"
   if [ "$tree" = 0 ]; then sed -i -E 's|^#define ENABLE_TREE$|//#define ENABLE_TREE|' "$cfg"; fi
   if [ "$sph" = 1 ]; then sed -i -E 's|^//#define ENABLE_SPH$|#define ENABLE_SPH|' "$cfg"; fi
+  local extra=""
+  if [ "$vis" = 1 ]; then
+    sed -i -E 's|^//#define SOLVER_VIS 3$|#define SOLVER_VIS 3|' "$cfg"
+    printf '#include "types.h"\nreal matMVP[16];\n' > "$d/sfref_matmvp.c"
+    extra="sfref_matmvp.c"
+  fi
   ( cd "$d" && "$CC" -shared -fPIC -fopenmp -O3 -march=x86-64-v3 -std=c99 -w \
-      simulation.c gravity.c tree.c sph.c initcond.c log.c grid.c \
+      simulation.c gravity.c tree.c sph.c initcond.c log.c grid.c $extra \
       -o "$OUT/libsfref_$name.so" -lm )
   echo "built $OUT/libsfref_$name.so"
 }
@@ -69,3 +78,4 @@ build_variant pp       0 0 262144
 build_variant tree     1 0 1048576
 build_variant tree_big 1 0 8388608
 build_variant pp_sph   0 1 262144
+build_variant tree_vis 1 0 1048576 1

@@ -422,6 +422,85 @@ void sfo_bh_walk(const sfo_node_t* nodes, uint32_t N, const float* pos, const fl
     }
 }
 
+/* ------------------------------------------------------------------ gravity.c:16-111 (SOLVER_VIS rasteriser)
+ * One 3-D segment: both ends through the row-major 4x4 matrix (w ignored, no perspective divide), pixel
+ * coordinates as gravity.c:61-65, then the all-octant error-term line walk of gravity.c:79-107 with `+=` into the
+ * RGBA float buffer for pixels with 0 < x < sizex and 0 < y < sizey. */
+static void overlay_segment(float* rb, uint32_t sx_, uint32_t sy_, const float* mvp, const float rgba[4],
+                            const float a[3], const float b[3]) {
+    int px[2], py[2];
+    for (int e = 0; e < 2; e++) {
+        const float* q = e ? b : a;
+        float h[2];
+        for (int r = 0; r < 2; r++)
+            h[r] = (mvp[4*r+0] * q[0]) + (mvp[4*r+1] * q[1]) + (mvp[4*r+2] * q[2]) + (mvp[4*r+3] * 1.0f);
+        px[e] = (int)(-0.5f + 0.5f * (float)sy_ * h[0] + 0.5f * (float)sx_);
+        py[e] = (int)(-0.5f + 0.5f * (float)sy_ * h[1] + 0.5f * (float)sy_);
+    }
+    const int dx = abs(px[1] - px[0]), dy = -abs(py[1] - py[0]);
+    const int stepx = px[0] < px[1] ? 1 : -1, stepy = py[0] < py[1] ? 1 : -1;
+    int x = px[0], y = py[0], err = dx + dy;
+    for (;;) {
+        if (0 < x && x < (int)sx_ && 0 < y && y < (int)sy_)
+            for (int c = 0; c < 4; c++) rb[4u * (uint32_t)((int)sx_ * y + x) + c] += rgba[c];
+        const int e2 = 2 * err;
+        if (e2 >= dy) { if (x == px[1]) break; err += dy; x += stepx; }
+        if (e2 <= dx) { if (y == py[1]) break; err += dx; y += stepy; }
+    }
+}
+
+/* gravity.c:380-445 (cell outline of every internal node when it is first looked at, colour by depth) and
+ * gravity.c:550-574 (one segment from the particle to every monopole it evaluates), for particle `idx` only. */
+void sfo_bh_overlay(const sfo_node_t* nodes, uint32_t N, const float* pos, const float* mas, float theta, int depth_max,
+                    uint32_t idx, const float* mvp, float* rb, uint32_t sizex, uint32_t sizey) {
+    if (idx >= N) return;
+    const float ri[3] = {pos[3u*idx+0], pos[3u*idx+1], pos[3u*idx+2]};
+    const float mi = mas[idx];
+    int path[64];
+    for (int d = 0; d < depth_max && d < 64; d++) path[d] = -1;
+    uint32_t cur = 0;
+    int depth = 0;
+    while (depth >= 0) {
+        const sfo_node_t* n = &nodes[cur];
+        const float* b = n->bounds;
+        if (n->bodies == 0u) { cur = n->parent; depth--; continue; }
+        if (n->bodies > 8u) {
+            const int o = path[depth];
+            if (o >= 7) { path[depth] = -1; cur = n->parent; depth--; continue; }
+            if (o >= 0) { path[depth] = o + 1; cur = n->branch[o + 1]; depth++; continue; }
+            const float off[3] = {0.5f * (b[0] + b[3]) - ri[0], 0.5f * (b[1] + b[4]) - ri[1], 0.5f * (b[2] + b[5]) - ri[2]};
+            const float d2 = (off[0]*off[0]) + (off[1]*off[1]) + (off[2]*off[2]);
+            const float w = (float)(1.0 / 3.0) * ((b[3] - b[0]) + (b[4] - b[1]) + (b[5] - b[2]));
+            const float ratio = 0.0f < d2 ? (w * w) / d2 : 0.0f;
+            const float f = 1.0f / (float)(depth + 1);
+            const float rgba[4] = {f * (0 == depth % 3 ? 0.8f : 0.1f), f * (1 == depth % 3 ? 0.8f : 0.1f),
+                                   f * (2 == depth % 3 ? 0.8f : 0.1f), 1.0f};
+            for (int ax = 0; ax < 3; ax++) {                 /* four edges along each axis, gravity.c:390-442 */
+                const int u = ax == 0 ? 1 : 0, v = ax == 2 ? 1 : 2;
+                for (int q = 0; q < 4; q++) {
+                    float p0[3], p1[3];
+                    p0[u] = p1[u] = (q & 1) ? b[3 + u] : b[u];
+                    p0[v] = p1[v] = (q & 2) ? b[3 + v] : b[v];
+                    p0[ax] = b[ax]; p1[ax] = b[3 + ax];
+                    overlay_segment(rb, sizex, sizey, mvp, rgba, p0, p1);
+                }
+            }
+            if (theta <= ratio) { path[depth] = 0; cur = n->branch[0]; depth++; continue; }
+        }
+        float rj[3] = {n->params[0], n->params[1], n->params[2]};
+        float mj = n->params[3];
+        if (b[0] <= ri[0] && ri[0] <= b[3] && b[1] <= ri[1] && ri[1] <= b[4] && b[2] <= ri[2] && ri[2] <= b[5] && 1u < n->bodies) {
+            for (int k = 0; k < 3; k++) rj[k] *= mj;
+            for (int k = 0; k < 3; k++) rj[k] -= mi * ri[k];
+            mj -= mi;
+            for (int k = 0; k < 3; k++) rj[k] *= 0.0f < mj ? 1.0f / mj : 1.0f;
+        }
+        const float magenta[4] = {0.8f, 0.1f, 0.8f, 1.0f};
+        overlay_segment(rb, sizex, sizey, mvp, magenta, ri, rj);
+        cur = n->parent; depth--;
+    }
+}
+
 /* ------------------------------------------------------------------ sph.c:32-145 */
 void sfo_sph_density(uint32_t N, const float* pos, const float* mas, const float* rad,
                      uint32_t i0, uint32_t i1, float* rho) {

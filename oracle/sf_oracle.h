@@ -88,6 +88,11 @@ void sfo_bh_walk(const sfo_node_t* nodes, uint32_t N, const float* pos, const fl
                  float G, float eps2, float theta, int depth_max,
                  uint32_t i0, uint32_t i1, float* acc, float* pot, sfo_walk_stats_t* stats);
 
+/* gravity.c:16-111,380-445,550-574 : the SOLVER_VIS debug overlay of particle `idx` - cell outlines and interaction
+ * segments rasterised with `+=` into an RGBA float buffer through the row-major 4x4 matrix mvp (matMVP) */
+void sfo_bh_overlay(const sfo_node_t* nodes, uint32_t N, const float* pos, const float* mas, float theta, int depth_max,
+                    uint32_t idx, const float* mvp, float* rb, uint32_t sizex, uint32_t sizey);
+
 /* sph.c:32-145 density, :147-159 EOS, :169-277 pressure force (acc +=) for targets [i0,i1) */
 void sfo_sph_density(uint32_t N, const float* pos, const float* mas, const float* rad,
                      uint32_t i0, uint32_t i1, float* rho);

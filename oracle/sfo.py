@@ -156,6 +156,18 @@ def bh_walk(nodes, pos, mas, i0=0, i1=None, G_=G, eps2=EPS2, theta=THETA, depth_
     return acc, pot, st
 
 
+def bh_overlay(nodes, pos, mas, idx, mvp, rb, sizex, sizey, theta=THETA, depth_max=DEPTH_MAX):
+    """SOLVER_VIS overlay of particle idx added into rb (float32[sizey*sizex*4]); gravity.c:16-111,380-445,550-574."""
+    L = lib()
+    L.sfo_bh_overlay.argtypes = [C.c_void_p, C.c_uint32, _f32p, _f32p, C.c_float, C.c_int, C.c_uint32, _f32p, _f32p,
+                                 C.c_uint32, C.c_uint32]
+    L.sfo_bh_overlay.restype = None
+    nodes = np.ascontiguousarray(nodes)
+    L.sfo_bh_overlay(nodes.ctypes.data, len(mas), pos, mas, theta, depth_max, idx, np.ascontiguousarray(mvp, np.float32), rb,
+                     sizex, sizey)
+    return rb
+
+
 def sph_density(pos, mas, rad, i0=0, i1=None):
     N = len(mas); i1 = N if i1 is None else i1
     rho = np.zeros(N, np.float32)
@@ -199,7 +211,7 @@ class RefSimFlat(C.Structure):       # simulation.h:53-67 without ENABLE_TREE
     _fields_ = [("step_number", C.c_uint), ("N", C.c_uint), ("mem", C.c_void_p)]
 
 
-REF_NODES_MAX = {"tree": 1048576, "tree_big": 8388608}
+REF_NODES_MAX = {"tree": 1048576, "tree_big": 8388608, "tree_vis": 1048576}
 
 
 def ref_available(variant="pp"):
@@ -258,6 +270,16 @@ class RefSim:
         self.sim.step_number = step_number
         with quiet_stdout():
             self.lib.sim_step(C.byref(self.sim))
+
+    def solv_vis(self, step_number, mvp, rb, sizex, sizey):
+        """sim_solv() of the SOLVER_VIS build (variant tree_vis): simulation.c:231-232 takes the render buffer."""
+        assert self.variant == "tree_vis"
+        m = (C.c_float * 16).in_dll(self.lib, "matMVP")
+        m[:] = [float(x) for x in np.asarray(mvp, np.float32).ravel()]
+        self.sim.step_number = step_number
+        self.lib.sim_solv.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint]
+        with quiet_stdout():
+            self.lib.sim_solv(C.byref(self.sim), rb.ctypes.data, sizex, sizey)
 
     def nodes(self):
         """The reference's node table after the last tree_build (num_nodes is never stored, tree.c:77;

@@ -72,6 +72,8 @@ static bool is_pinned(const void* p) {
 static int ensure_bounce(const char* fn, size_t bytes) {
     Ctx* c = g_ctx;
     if (bytes <= c->bounce_cap) return SFE_SUCCESS;
+    c->ov_lines.release(); c->ov_rows.release();
+    if (c->ov_info) cudaFreeHost(c->ov_info);
     if (c->bounce) cudaFreeHost(c->bounce);
     c->bounce = nullptr; c->bounce_cap = 0;
     SFE_CUDA(fn, cudaMallocHost(&c->bounce, bytes));
@@ -191,6 +193,8 @@ extern "C" int sfe_shutdown(void) {
     }
     t.valid = false;
     for (DevBuf* b : bufs) b->release();
+    c->ov_lines.release(); c->ov_rows.release();
+    if (c->ov_info) cudaFreeHost(c->ov_info);
     if (c->bounce) cudaFreeHost(c->bounce);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);

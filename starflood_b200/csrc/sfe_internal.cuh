@@ -155,6 +155,9 @@ struct Ctx {
     Tree tree;
     SimState sim;
     PeerState peer;
+    // SOLVER_VIS overlay (sfe_overlay.cu): segment list, resident rows of the render buffer, mapped result block
+    DevBuf ov_lines, ov_rows;
+    void* ov_info = nullptr; void* ov_info_dev = nullptr;
     sfe_timings_t timings;
     uint32_t launches = 0;
     uint64_t total_launches = 0;

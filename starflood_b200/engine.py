@@ -88,6 +88,7 @@ SIGNATURES = {
     "sfe_tree_keys_download": ([_P, _P, _u32, C.POINTER(_u32)], C.c_int),
     "sfe_selftest_exact_math": ([C.POINTER(C.c_uint64)], C.c_int),
     "sfe_sph": ([_P, _P, _P, _P, _P, _P, _u32, _f, _f, _f], C.c_int),
+    "sfe_bh_overlay": ([_u32, _f, _P, _P, _u32, _u32], C.c_int),
     "sfe_dev_pack_pm4": ([_P, _P, _P, _u32, _P], C.c_int),
     "sfe_dev_pp": ([_P, _u32, _u32, _u32, _P, _P, _f, _f, _P], C.c_int),
     "sfe_dev_tree_build": ([_P, _P, _u32, C.c_int, _u32, _P], C.c_int),
@@ -276,6 +277,19 @@ def solve_gravity_part_tree(sim, flavour=WALK_EXACT, i0=0, ni=None, theta=TREE_T
     ni = sim.N - i0 if ni is None else ni
     return lib().sfe_bh_slice(_ptr(sim.pos), _ptr(sim.mas), _ptr(sim.acc), _ptr(sim.pot), sim.N, i0, ni,
                               G, EPS2, theta, flavour)
+
+
+SOLVER_VIS = 3   # config.h:32
+
+
+def solve_gravity_part_tree_vis(sim, mvp, render_buffer, sizex, sizey, flavour=WALK_EXACT, idx=SOLVER_VIS, theta=TREE_THETA):
+    """solve_gravity_part_tree(sim, render_buffer, sizex, sizey) of a SOLVER_VIS build (gravity.h:14-18): the walk, then
+    the debug overlay of particle idx through the matrix the reference keeps in matMVP (visualization.c:251)."""
+    rc = solve_gravity_part_tree(sim, flavour, theta=theta)
+    if rc != 0:
+        return rc
+    m = np.ascontiguousarray(mvp, np.float32)
+    return lib().sfe_bh_overlay(idx, theta, _ptr(m), _ptr(render_buffer), sizex, sizey)
 
 
 def solve_sph(sim):

@@ -7,7 +7,11 @@
 # (tests/test_gpu_dropin.py).  Reference sources are copied to a scratch dir under /tmp only; config.h is
 # sed-edited there (the reference has no run-time configuration).
 #
-# usage: build_dropin.sh <pp|tree|pp_sph> <N> <steps> [TREE_NODES_MAX]
+# Variant tree_vis keeps the reference's default ENABLE_VIS + SOLVER_VIS 3 (config.h:29,32): every step vis_draw()
+# renders the particles, sim_step() adds the tree walk's debug overlay of particle #3 (gravity.c:380-445,550-574; in the
+# drop-in: sfe_bh_overlay) and main.c saves the frame - as PFM (float RGB) here, so that frames compare bit for bit.
+#
+# usage: build_dropin.sh <pp|tree|pp_sph|tree_vis> <N> <steps> [TREE_NODES_MAX]
 set -euo pipefail
 VARIANT=${1:?variant}; N=${2:?N}; STEPS=${3:?steps}; NODES=${4:-1048576}
 REF=${SF_REFERENCE:-/root/reference}
@@ -33,6 +37,9 @@ sed -i -E \
 case "$VARIANT" in
   pp)     sed -i -E 's|^#define ENABLE_TREE$|//#define ENABLE_TREE|' "$S/config.h" ;;
   tree)   ;;
+  tree_vis) sed -i -E -e 's|^//#define ENABLE_VIS$|#define ENABLE_VIS|' -e 's|^//#define SOLVER_VIS 3$|#define SOLVER_VIS 3|' \
+                -e 's|^//#define VIS_FILENAME |#define VIS_FILENAME |' -e 's|^#define ENABLE_OFFLOAD_VIS$|//#define ENABLE_OFFLOAD_VIS|' \
+                -e 's|^#define SPATIAL_SAMPLES .*|#define SPATIAL_SAMPLES 4|' "$S/config.h" ;;
   pp_sph) sed -i -E -e 's|^#define ENABLE_TREE$|//#define ENABLE_TREE|' -e 's|^//#define ENABLE_SPH$|#define ENABLE_SPH|' "$S/config.h" ;;
   *) echo "unknown variant $VARIANT" >&2; exit 1 ;;
 esac

@@ -53,6 +53,25 @@ def test_tree_dropin_is_bit_identical(tmp_path):
     assert e_ref and e_ref == e_b200
 
 
+def test_tree_vis_dropin_default_feature_set(tmp_path):
+    """The reference's DEFAULT feature set (ENABLE_VIS + SOLVER_VIS 3, config.h:29,32) builds and runs as a drop-in:
+    vis_draw() renders the particles, solve_gravity_part_tree() gets the render buffer (the shim draws the overlay with
+    sfe_bh_overlay) and main.c writes the frame.  RAW snapshots and PFM frames (float RGB) of both binaries are
+    identical byte for byte.  (The frames do not prove the overlay: main.c serialises vis.binary_buffer, which
+    vis_draw() filled BEFORE sim_step() drew into render_buffer - the render buffer itself is compared against the
+    reference in tests/test_gpu_overlay.py.)"""
+    need("starflood_tree_vis")
+    N, steps = 16384, 3
+    a, b = tmp_path / "ref", tmp_path / "b200"
+    a.mkdir(); b.mkdir()
+    run("starflood_tree_vis_ref", str(a)); run("starflood_tree_vis_b200", str(b))
+    for s in range(steps + 1):
+        assert np.array_equal(snap(str(a), s, N, 13)["raw"], snap(str(b), s, N, 13)["raw"]), "snapshot %d differs" % s
+        fa = open(os.path.join(str(a), "out", "vis", "step_%04u.pfm" % s), "rb").read()
+        fb = open(os.path.join(str(b), "out", "vis", "step_%04u.pfm" % s), "rb").read()
+        assert len(fa) > 1000000 and fa == fb, "frame %d differs" % s
+
+
 def test_pp_dropin(tmp_path):
     need("starflood_pp")
     N, steps = 8192, 5

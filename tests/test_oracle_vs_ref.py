@@ -59,3 +59,25 @@ def test_walk_statistics_match_survey():
     acc, pot, st = sfo.bh_walk(nodes[:n], pos, mas)
     assert abs(st.iterations / N - 795.2) < 0.1 and abs(st.evals / N - 274.2) < 0.1
     assert abs(st.opened / N - 49.6) < 0.1 and abs(st.empty / N - 74.2) < 0.1
+
+
+@pytest.mark.skipif(not sfo.ref_available("tree_vis"), reason="reference SOLVER_VIS library not built")
+def test_overlay_restatement_equals_reference_drawing():
+    """sfo_bh_overlay() against the unmodified reference compiled WITH SOLVER_VIS 3 (config.h:32): the
+    render buffer after sim_solv(sim, render_buffer, sizex, sizey) is reproduced bit for bit."""
+    N, sx, sy = 20000, 640, 360
+    a, b, sc = 0.7, 0.4, 0.3
+    ca, sa, cb, sb = np.cos(a), np.sin(a), np.cos(b), np.sin(b)
+    R = np.array([[ca, 0, sa, 0], [0, 1, 0, 0], [-sa, 0, ca, 0], [0, 0, 0, 1]]) @ \
+        np.array([[1, 0, 0, 0], [0, cb, -sb, 0], [0, sb, cb, 0], [0, 0, 0, 1]])
+    M = (np.diag([sc, sc, sc, 1.0]) @ R).astype(np.float32).ravel()
+    M[3] = 0.05; M[7] = -0.02
+    r = sfo.RefSim("tree_vis", N); r.initcond()
+    for step in (0, 5):
+        rb = np.full(sx * sy * 4, 0.25, np.float32)
+        r.solv_vis(step, M, rb, sx, sy)
+        box = sfo.root_box(r.pos.copy(), step)
+        rc, nodes, n, *_ = sfo.tree_build_sorted(box, r.pos.copy(), r.mas.copy(), 2 * N)
+        ob = sfo.bh_overlay(nodes[:n], r.pos.copy(), r.mas.copy(), 3, M, np.full(sx * sy * 4, 0.25, np.float32), sx, sy)
+        assert (rb != 0.25).sum() > 1000 and np.array_equal(rb, ob)
+    r.close()
