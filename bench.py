@@ -332,15 +332,20 @@ def run_engine(args):
     if use_peer:
         # two {x,y,z,m} arrays inside the exchange window, alternated between steps (sfengine.h: a range written by
         # exchange k may be rewritten by exchange k+2 at the earliest)
-        wptr = e.peer_setup(rank, world, 2 * 16 * N, allgather_bytes)
-        wt = torch.as_tensor(Window(wptr, 2 * 16 * N), device=dev)
-        pm4_regions = [wt[:4 * N], wt[4 * N:]]
+        # ... and acc / pot: the routed walk (sfe_dev_bh_peer) stores every result into its owner's window
+        wptr = e.peer_setup(rank, world, 3 * 16 * N, allgather_bytes)
+        wt = torch.as_tensor(Window(wptr, 3 * 16 * N), device=dev)
+        pm4_regions = [wt[:4 * N], wt[4 * N:8 * N]]
         pm4_full = pm4_regions[0]
+        acc_w, pot_w = wt[8 * N:11 * N], wt[11 * N:12 * N]
     else:
         pm4_full = torch.empty(N * 4, dtype=torch.float32, device=dev)
     xstate = {"n": 0}
-    acc = torch.zeros(3 * N, dtype=torch.float32, device=dev)
-    pot = torch.zeros(N, dtype=torch.float32, device=dev)
+    if use_peer:
+        acc, pot = acc_w, pot_w
+    else:
+        acc = torch.zeros(3 * N, dtype=torch.float32, device=dev)
+        pot = torch.zeros(N, dtype=torch.float32, device=dev)
     slices, boxes = [], []
     for sim, box in snaps:
         pm = np.empty((N, 4), np.float32)
@@ -368,7 +373,11 @@ def run_engine(args):
         rc = L.sfe_dev_tree_build(boxes[k].ctypes.data, pm4.data_ptr(), N, e.TREE_DEPTH_MAX, nodes_max, sptr)
         if ev is not None:
             ev[0].record(stream)
-        rc |= L.sfe_dev_bh(pm4.data_ptr(), N, i0, ni, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, THETA, flavour, sptr)
+        if use_peer:
+            # every rank walks a Morton-contiguous slot range and delivers acc / pot to the owners of the particles
+            rc |= L.sfe_dev_bh_peer(pm4.data_ptr(), N, 16 * 2 * N, 16 * 2 * N + 12 * N, e.G, e.EPS2, THETA, flavour, sptr)
+        else:
+            rc |= L.sfe_dev_bh(pm4.data_ptr(), N, i0, ni, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, THETA, flavour, sptr)
         if ev is not None:
             ev[1].record(stream)
         if rc != 0:
@@ -499,7 +508,7 @@ def run_engine(args):
     if not args.no_resident:
         barrier()
         if use_peer:
-            del wt, pm4_regions, pm4_full
+            del wt, pm4_regions, pm4_full, acc_w, pot_w, acc, pot
             e.peer_close(dist.barrier)
         resident = {}
         legs = [("C2", N, True, False)]
@@ -549,15 +558,16 @@ def run_engine(args):
         "config": {"workload": "C2: Barnes-Hut gravity N=%d uniform sphere (reference initcond), theta=0.5 monopole, "
                                "tree_build + solve_gravity_part_tree per step" % N,
                    "N": N, "theta": THETA, "depth_max": 16, "walk": args.flavour,
-                   "partition": ("target slices, tree per GPU, all-gather of {x,y,z,m} by %s" %
-                                 ("the engine's peer-memory put + flag kernels (NVLink, sfe_dev_peer_put)" if use_peer else "NCCL"))
+                   "partition": ("tree per GPU; " + ("all-gather of {x,y,z,m} by the engine's peer-memory put + flag kernels "
+                                 "(NVLink, sfe_dev_peer_put), walk by Morton slot range with results stored into the owner's window "
+                                 "(sfe_dev_bh_peer)" if use_peer else "target index slices, all-gather of {x,y,z,m} by NCCL"))
                                 if world > 1 else "single GPU",
                    "l2": "ring of %d distinct snapshots (%d MiB of inputs > L2) rotated between steps" % (ring, ring * 16 * N >> 20),
                    "tree_nodes": int(st[0].value), "tree_depth": int(st[2].value)},
         "e2e": {"value": N / (e2e_ms * 1e-3), "unit": "particle-steps/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
                 "api": "sfe_tree_build + sfe_bh on pinned host arrays" if world == 1 else
-                       "pinned slice H2D + all_gather + sfe_dev_tree_build + sfe_dev_bh + slice D2H"},
+                       "pinned slice H2D + exchange + sfe_dev_tree_build + walk + slice D2H"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,

@@ -224,6 +224,15 @@ void* sfe_peer_window(void);   /* device pointer of this rank's window (NULL bef
 /* Store [offset, offset+bytes) of this rank's window into the same range of every peer's window, then exchange
  * arrival flags; work enqueued on `stream` after this call sees every rank's range.  bytes may differ per rank. */
 int sfe_dev_peer_put(uint64_t offset, uint64_t bytes, void* stream);
+/* Barnes-Hut walk on `world` ranks, collective.  Every rank has built the same tree from the same {x,y,z,m} array
+ * (sfe_dev_tree_build).  Rank r walks the SLOTS [r*N/world, (r+1)*N/world) of the Morton-sorted order - spatial
+ * neighbours, so its warps are as coherent as on one GPU, which a slice of particle indices is not - and stores acc / pot
+ * of every particle it evaluated straight into the window of the rank that owns that particle's INDEX slice
+ * [q*N/world, (q+1)*N/world), at acc_off + 12*i and pot_off + 4*i (byte offsets into the window, the same on all
+ * ranks); the flag exchange follows.  On return of the stream every rank finds acc / pot of its own index slice in
+ * its window; rows of other ranks' particles are not written. */
+int sfe_dev_bh_peer(const void* pm4, uint32_t N, uint64_t acc_off, uint64_t pot_off, float grav_g, float eps2,
+                    float theta, uint32_t flavour, void* stream);
 /* Flags only (a barrier on the device, no host involvement). */
 int sfe_dev_peer_barrier(void* stream);
 /* Tear-down, in two phases so that no window is freed while a peer still maps it: every rank unmaps its peers'
@@ -233,7 +242,7 @@ int sfe_dev_peer_barrier(void* stream);
 int sfe_peer_detach(void);
 int sfe_peer_close(void);
 /* Window size that sfe_sim_upload() needs when the resident leapfrog runs on `world` ranks: two {x,y,z,m} arrays
- * (ping-pong between steps) and, for SIM_DOF = 16, rho.  With an open window of at least this size the sfe_sim_*
+ * (ping-pong between steps), acc and pot (the routed walk delivers them to the owner) and, for SIM_DOF = 16, rho.  With an open window of at least this size the sfe_sim_*
  * entry points partition the particles by target slice [rank*N/world, (rank+1)*N/world): kick_0 + drift stores the
  * moved slice into every rank's next {x,y,z,m} array (the drift and its all-gather are ONE kernel), every rank builds
  * the full tree and evaluates its slice, {T, V} are combined in rank order.  sfe_sim_download() then returns pos /

@@ -113,7 +113,7 @@ struct SimState {
     bool peer_mode = false;
     uint32_t i0 = 0, ni = 0;              // target slice of this rank ([0, N) otherwise)
     int cur = 0;                          // which of the two window arrays holds the current positions
-    uint64_t pm4_off[2] = {0, 0}, rho_off = 0;   // window offsets
+    uint64_t pm4_off[2] = {0, 0}, rho_off = 0, acc_off = 0, pot_off = 0;   // window offsets
     uint32_t tv_parity = 0;               // which {T, V} slot set of the control page the next step uses
 };
 
@@ -179,6 +179,8 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
 int tree_status(Ctx* c, cudaStream_t s);
 int launch_bh(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, float* acc, float* pot,
               float G, float eps2, float theta, uint32_t flavour, cudaStream_t s);
+int launch_bh_routed(Ctx* c, const float4* pm4, uint32_t N, uint64_t acc_off, uint64_t pot_off,
+                     float G, float eps2, float theta, uint32_t flavour, cudaStream_t s);
 int launch_sph_density(Ctx* c, const float4* pm4, const float* rad, uint32_t N, uint32_t i0, uint32_t ni,
                        float* rho, cudaStream_t s);
 int launch_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float eos_n, cudaStream_t s);

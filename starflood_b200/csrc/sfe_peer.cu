@@ -223,5 +223,5 @@ extern "C" int sfe_peer_close(void) {
 
 extern "C" uint64_t sfe_sim_peer_bytes(uint32_t N, uint32_t dof) {
     const uint64_t n = ((uint64_t)N + 63u) & ~(uint64_t)63u;   // keeps every array 256-byte aligned
-    return 2u * 16u * n + (dof == 16u ? 4u * n : 0u);
+    return 2u * 16u * n + 16u * n + (dof == 16u ? 4u * n : 0u);   // {x,y,z,m} x 2, acc + pot, rho
 }

@@ -196,10 +196,12 @@ extern "C" int sfe_sim_save_raw_async(const char* filename) {
         float* d = (float*)sv.dev[slot];
         const float4* pm4 = st.peer_mode ? reinterpret_cast<const float4*>((const char*)c->peer.local + st.pm4_off[st.cur]) : st.pm4.as<float4>();
         const float* rho = st.peer_mode ? reinterpret_cast<const float*>((const char*)c->peer.local + st.rho_off) : st.rho.as<float>();
+        const float* acc = st.peer_mode ? reinterpret_cast<const float*>((const char*)c->peer.local + st.acc_off) : st.acc.as<float>();
+        const float* pot = st.peer_mode ? reinterpret_cast<const float*>((const char*)c->peer.local + st.pot_off) : st.pot.as<float>();
         // slot layout = the blocks in file order, each restricted to the rank's rows (enum sim_conf, simulation.h:17-51)
         struct Blk { uint32_t off, w; const float* src; };
-        const Blk blk[10] = {{0, 3, nullptr}, {3, 3, st.vel.as<float>()}, {6, 3, st.acc.as<float>()}, {9, 1, nullptr},
-                             {10, 1, st.pot.as<float>()}, {11, 1, st.ken.as<float>()}, {12, 1, st.pen.as<float>()},
+        const Blk blk[10] = {{0, 3, nullptr}, {3, 3, st.vel.as<float>()}, {6, 3, acc}, {9, 1, nullptr},
+                             {10, 1, pot}, {11, 1, st.ken.as<float>()}, {12, 1, st.pen.as<float>()},
                              {13, 1, st.rad.as<float>()}, {14, 1, rho}, {15, 1, st.prs.as<float>()}};
         const int nblk = st.dof == 16u ? 10 : 7;
         job.path = filename; job.slot = slot; job.nseg = nblk;

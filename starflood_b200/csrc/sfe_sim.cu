@@ -305,7 +305,9 @@ static int launch_kick_energy_peers(Ctx* c, const float4* pm4, float dt, cudaStr
     TvPeers tp; tp.world = pr.world;
     for (uint32_t r = 0; r < pr.world; r++)
         tp.slot[r] = reinterpret_cast<PeerCtrl*>((char*)pr.base[r] + pr.bytes)->tv[parity][pr.rank];
-    kick_energy_kernel<<<sim_grid(c, st.ni), SIM_THREADS, 0, s>>>(pm4, st.vel.as<float>(), st.acc.as<float>(), st.pot.as<float>(),
+    const float* acc = reinterpret_cast<const float*>((const char*)pr.local + st.acc_off);
+    const float* pot = reinterpret_cast<const float*>((const char*)pr.local + st.pot_off);
+    kick_energy_kernel<<<sim_grid(c, st.ni), SIM_THREADS, 0, s>>>(pm4, st.vel.as<float>(), acc, pot,
                                                                  st.ken.as<float>(), st.pen.as<float>(), st.i0, st.ni, dt, 1,
                                                                  st.partial.as<dd>(), st.ticket.as<uint32_t>() + 1,
                                                                  st.tv_dev.as<double>(), tp);
@@ -319,8 +321,9 @@ static int launch_kick_energy_peers(Ctx* c, const float4* pm4, float dt, cudaStr
 static int launch_kick_drift_peers(Ctx* c, float dt, cudaStream_t s, const char* fn) {
     SimState& st = c->sim;
     if (st.ni) {
+        const float* acc = reinterpret_cast<const float*>((const char*)c->peer.local + st.acc_off);
         kick_drift_put_kernel<<<sim_grid(c, st.ni), SIM_THREADS, 0, s>>>(peer_ptrs(c), st.pm4_off[st.cur], st.pm4_off[st.cur ^ 1],
-                                                                        st.vel.as<float>(), st.acc.as<float>(), st.i0, st.ni, dt);
+                                                                        st.vel.as<float>(), acc, st.i0, st.ni, dt);
         if (check_launch(fn)) return SFE_FAILURE;
     }
     if (launch_peer_barrier(c, s, fn)) return SFE_FAILURE;
@@ -331,6 +334,14 @@ static int launch_kick_drift_peers(Ctx* c, float dt, cudaStream_t s, const char*
 static float4* sim_pm4(Ctx* c) {
     SimState& st = c->sim;
     return st.peer_mode ? reinterpret_cast<float4*>((char*)c->peer.local + st.pm4_off[st.cur]) : st.pm4.as<float4>();
+}
+static float* sim_acc(Ctx* c) {
+    SimState& st = c->sim;
+    return st.peer_mode ? reinterpret_cast<float*>((char*)c->peer.local + st.acc_off) : st.acc.as<float>();
+}
+static float* sim_pot(Ctx* c) {
+    SimState& st = c->sim;
+    return st.peer_mode ? reinterpret_cast<float*>((char*)c->peer.local + st.pot_off) : st.pot.as<float>();
 }
 static float* sim_rho(Ctx* c) {
     SimState& st = c->sim;
@@ -407,11 +418,11 @@ extern "C" int sfe_sim_upload(const float* mem, uint32_t N, uint32_t dof) {
             return SFE_FAILURE;
         }
         const uint64_t n64 = ((uint64_t)N + 63u) & ~(uint64_t)63u;
-        st.pm4_off[0] = 0u; st.pm4_off[1] = 16u * n64; st.rho_off = 32u * n64;
+        st.pm4_off[0] = 0u; st.pm4_off[1] = 16u * n64; st.acc_off = 32u * n64; st.pot_off = 44u * n64; st.rho_off = 48u * n64;
         st.i0 = (uint32_t)(((uint64_t)N * pr.rank) / pr.world);
         st.ni = (uint32_t)(((uint64_t)N * (pr.rank + 1u)) / pr.world) - st.i0;
     }
-    if ((!st.peer_mode && st.pm4.reserve(n * 16, fn)) || st.vel.reserve(n * 12, fn) || st.acc.reserve(n * 12, fn) || st.pot.reserve(n * 4, fn) ||
+    if ((!st.peer_mode && (st.pm4.reserve(n * 16, fn) || st.acc.reserve(n * 12, fn) || st.pot.reserve(n * 4, fn))) || st.vel.reserve(n * 12, fn) ||
         st.ken.reserve(n * 4, fn) || st.pen.reserve(n * 4, fn) || st.stage.reserve(n * 16, fn))
         return SFE_FAILURE;
     if (dof == 16u && (st.rad.reserve(n * 4, fn) || (!st.peer_mode && st.rho.reserve(n * 4, fn)) || st.prs.reserve(n * 4, fn))) return SFE_FAILURE;
@@ -420,8 +431,8 @@ extern "C" int sfe_sim_upload(const float* mem, uint32_t N, uint32_t dof) {
     float* stage = st.stage.as<float>();
     if (h2d(fn, stage, mem, n * 12, s) || h2d(fn, stage + 3 * n, mem + 9 * n, n * 4, s)) return SFE_FAILURE;
     if (launch_pack_pm4(stage, stage + 3 * n, sim_pm4(c), N, s)) return SFE_FAILURE;
-    if (h2d(fn, st.vel.p, mem + 3 * n, n * 12, s) || h2d(fn, st.acc.p, mem + 6 * n, n * 12, s) ||
-        h2d(fn, st.pot.p, mem + 10 * n, n * 4, s) || h2d(fn, st.ken.p, mem + 11 * n, n * 4, s) ||
+    if (h2d(fn, st.vel.p, mem + 3 * n, n * 12, s) || h2d(fn, sim_acc(c), mem + 6 * n, n * 12, s) ||
+        h2d(fn, sim_pot(c), mem + 10 * n, n * 4, s) || h2d(fn, st.ken.p, mem + 11 * n, n * 4, s) ||
         h2d(fn, st.pen.p, mem + 12 * n, n * 4, s))
         return SFE_FAILURE;
     if (dof == 16u && (h2d(fn, st.rad.p, mem + 13 * n, n * 4, s) || h2d(fn, sim_rho(c), mem + 14 * n, n * 4, s) ||
@@ -455,8 +466,8 @@ extern "C" int sfe_sim_download(float* mem, uint32_t N, uint32_t dof, uint32_t b
     // per-particle blocks that only the owning rank maintains: the slice [i0, i0+ni) (everything on a single rank)
     const size_t a = st.i0, m = st.ni;
     if ((blocks & SFE_SIM_VEL) && d2h(fn, mem + 3 * n + 3 * a, st.vel.as<float>() + 3 * a, m * 12, s)) return SFE_FAILURE;
-    if ((blocks & SFE_SIM_ACC) && d2h(fn, mem + 6 * n + 3 * a, st.acc.as<float>() + 3 * a, m * 12, s)) return SFE_FAILURE;
-    if ((blocks & SFE_SIM_POT) && d2h(fn, mem + 10 * n + a, st.pot.as<float>() + a, m * 4, s)) return SFE_FAILURE;
+    if ((blocks & SFE_SIM_ACC) && d2h(fn, mem + 6 * n + 3 * a, sim_acc(c) + 3 * a, m * 12, s)) return SFE_FAILURE;
+    if ((blocks & SFE_SIM_POT) && d2h(fn, mem + 10 * n + a, sim_pot(c) + a, m * 4, s)) return SFE_FAILURE;
     if ((blocks & SFE_SIM_KEN) && d2h(fn, mem + 11 * n + a, st.ken.as<float>() + a, m * 4, s)) return SFE_FAILURE;
     if ((blocks & SFE_SIM_PEN) && d2h(fn, mem + 12 * n + a, st.pen.as<float>() + a, m * 4, s)) return SFE_FAILURE;
     if (dof == 16u) {
@@ -482,10 +493,13 @@ static int sim_solv_enqueue(Ctx* c, const sfe_sim_params_t* p, uint32_t step_num
         // engine raises the failure instead (a truncated tree has no defined contents here)
         if (launch_tree_build(c, box, pm4, st.N, p->depth_max, p->nodes_max, s)) return SFE_FAILURE;
         if (tree_status(c, s)) return SFE_FAILURE;
-        if (launch_bh(c, pm4, st.N, i0, ni, st.acc.as<float>(), st.pot.as<float>(), p->grav_g, p->eps2, p->theta, p->flavour, s))
+        if (st.peer_mode) {
+            // every rank walks a slot range of the (identical) tree and delivers acc / pot to the particles' owners
+            if (launch_bh_routed(c, pm4, st.N, st.acc_off, st.pot_off, p->grav_g, p->eps2, p->theta, p->flavour, s)) return SFE_FAILURE;
+        } else if (launch_bh(c, pm4, st.N, i0, ni, sim_acc(c), sim_pot(c), p->grav_g, p->eps2, p->theta, p->flavour, s))
             return SFE_FAILURE;
     } else {
-        if (launch_pp(c, pm4, st.N, i0, ni, st.acc.as<float>(), st.pot.as<float>(), p->grav_g, p->eps2, s)) return SFE_FAILURE;
+        if (launch_pp(c, pm4, st.N, i0, ni, sim_acc(c), sim_pot(c), p->grav_g, p->eps2, s)) return SFE_FAILURE;
     }
     if (p->solver & SFE_SOLVER_SPH) {
         if (st.dof < 16u) { set_error(fn, "SFE_SOLVER_SPH needs a SIM_DOF=16 state"); return SFE_FAILURE; }
@@ -495,7 +509,7 @@ static int sim_solv_enqueue(Ctx* c, const sfe_sim_params_t* p, uint32_t step_num
         if (st.peer_mode && launch_peer_put(c, st.rho_off + 4u * (uint64_t)i0, 4u * (uint64_t)ni, s, fn)) return SFE_FAILURE;
         if (launch_sph_eos(rho, st.prs.as<float>(), st.N, p->eos_k, p->eos_n, s)) return SFE_FAILURE;
         if (launch_sph_force(c, pm4, st.rad.as<float>(), rho, st.prs.as<float>(), st.N, i0, ni, p->cutoff2,
-                             st.acc.as<float>(), s, /*reuse_cells=*/true))
+                             sim_acc(c), s, /*reuse_cells=*/true))
             return SFE_FAILURE;
     }
     return SFE_SUCCESS;

@@ -100,15 +100,21 @@ __device__ __forceinline__ bool opens(float w2, float d2, float theta) {
     return theta <= __fdiv_rn(w2, d2);
 }
 
-template <int FLAVOUR>
+// Multi-rank routing: a rank walks a contiguous range of SLOTS - neighbours in Morton order, so its warps stay
+// as coherent as on one GPU, which a slice of particle INDICES is not (indices are random in space) - and delivers every
+// result straight into the window of the rank that OWNS the particle (index slice [r*N/world, (r+1)*N/world)), with
+// plain stores over NVLink peer pointers; the arrival flags follow in peer_barrier_kernel.
+struct WalkRoute { char* base[SFE_PEER_MAX]; uint64_t acc_off, pot_off; uint32_t world, N; };
+
+template <int FLAVOUR, bool ROUTED>
 __global__ void __launch_bounds__(WALK_THREADS)
-walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restrict__ slots /* null: all */,
-            uint32_t nslots, float G, float eps2, float theta,
-            float* __restrict__ acc, float* __restrict__ pot) {
+walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restrict__ slots /* null: the range from s0 */,
+            uint32_t s0, uint32_t nslots, float G, float eps2, float theta,
+            float* __restrict__ acc, float* __restrict__ pot, WalkRoute route) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nslots) return;
     const uint32_t M = t.meta[M_NUM_INBOX];
-    const uint32_t s = slots ? slots[k] : k;
+    const uint32_t s = slots ? slots[k] : s0 + k;
     const uint32_t fin = t.meta[M_FINAL];
     const uint32_t idx = s < M ? t.perm[fin][s] : t.perm_out[s - M];
     const float4 me = s < M ? t.spm4[fin][s] : pm4[idx];
@@ -187,6 +193,14 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
     }
     if (FLAVOUR == (int)SFE_WALK_EXACT) { fx = ax.s; fy = ay.s; fz = az.s; fp = ap.s; }
     const float gm = __fmul_rn(-G, mi);                                            // gravity.c:656-659
+    if (ROUTED) {
+        // owner r of particle idx: (N*r)/world <= idx < (N*(r+1))/world
+        uint32_t r = (uint32_t)(((uint64_t)idx * route.world) / route.N);
+        while (idx < (uint32_t)(((uint64_t)route.N * r) / route.world)) r--;
+        while (idx >= (uint32_t)(((uint64_t)route.N * (r + 1u)) / route.world)) r++;
+        acc = reinterpret_cast<float*>(route.base[r] + route.acc_off);
+        pot = reinterpret_cast<float*>(route.base[r] + route.pot_off);
+    }
     acc[3u * idx + 0u] = __fmul_rn(gm, fx);
     acc[3u * idx + 1u] = __fmul_rn(gm, fy);
     acc[3u * idx + 2u] = __fmul_rn(gm, fz);
@@ -229,14 +243,57 @@ int launch_bh(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, f
     uint32_t* slots = nullptr;
     if (ni != N && walk_slice_slots(c, N, i0, ni, s, &slots)) return SFE_FAILURE;
     const uint32_t grid = (ni + WALK_THREADS - 1) / WALK_THREADS;
+    WalkRoute none; none.world = 0u; none.N = N; none.acc_off = none.pot_off = 0u;
     if (flavour == SFE_WALK_EXACT)
-        walk_kernel<(int)SFE_WALK_EXACT><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, ni, G, eps2, theta, acc, pot);
+        walk_kernel<(int)SFE_WALK_EXACT, false><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, 0u, ni, G, eps2, theta, acc, pot, none);
     else
-        walk_kernel<(int)SFE_WALK_FAST><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, ni, G, eps2, theta, acc, pot);
+        walk_kernel<(int)SFE_WALK_FAST, false><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, 0u, ni, G, eps2, theta, acc, pot, none);
     return check_launch(fn);
 }
 
+// Collective over the open peer window: this rank walks the slots [rank*N/world, (rank+1)*N/world) of the (identical)
+// tree every rank has built and stores acc / pot of each particle into its owner's window at acc_off + 12*i, pot_off + 4*i;
+// after the flag exchange every rank holds acc / pot of its own index slice.
+int launch_bh_routed(Ctx* c, const float4* pm4, uint32_t N, uint64_t acc_off, uint64_t pot_off,
+                     float G, float eps2, float theta, uint32_t flavour, cudaStream_t s) {
+    const char* fn = "sfe_dev_bh_peer";
+    Tree& t = c->tree;
+    PeerState& pr = c->peer;
+    if (!pr.open) { set_error(fn, "the peer window is not open: call sfe_peer_create() and sfe_peer_open() first"); return SFE_FAILURE; }
+    if (!t.valid || t.N != N) { set_error(fn, "no tree for N=%u: call sfe_tree_build() first", N); return SFE_FAILURE; }
+    if (flavour != SFE_WALK_EXACT && flavour != SFE_WALK_FAST) { set_error(fn, "unknown walk flavour %u", flavour); return SFE_FAILURE; }
+    if ((acc_off & 3u) || (pot_off & 3u) || acc_off + 12ull * N > pr.bytes || pot_off + 4ull * N > pr.bytes) {
+        set_error(fn, "acc / pot ranges [%llu,+%llu) [%llu,+%llu) do not fit the %llu-byte window", (unsigned long long)acc_off,
+                  12ull * N, (unsigned long long)pot_off, 4ull * N, (unsigned long long)pr.bytes);
+        return SFE_FAILURE;
+    }
+    if (N) {
+        if (tree_root_moments(c, pm4, 0, N, theta, false, s)) return SFE_FAILURE;   // same gate on every rank
+        const uint32_t s0 = (uint32_t)(((uint64_t)N * pr.rank) / pr.world);
+        const uint32_t ns = (uint32_t)(((uint64_t)N * (pr.rank + 1u)) / pr.world) - s0;
+        if (ns) {
+            WalkRoute rt;
+            for (uint32_t r = 0; r < SFE_PEER_MAX; r++) rt.base[r] = (char*)pr.base[r];
+            rt.acc_off = acc_off; rt.pot_off = pot_off; rt.world = pr.world; rt.N = N;
+            const uint32_t grid = (ns + WALK_THREADS - 1) / WALK_THREADS;
+            TreeDev dv = tree_dev(c);
+            if (flavour == SFE_WALK_EXACT)
+                walk_kernel<(int)SFE_WALK_EXACT, true><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, nullptr, s0, ns, G, eps2, theta, nullptr, nullptr, rt);
+            else
+                walk_kernel<(int)SFE_WALK_FAST, true><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, nullptr, s0, ns, G, eps2, theta, nullptr, nullptr, rt);
+            if (check_launch(fn)) return SFE_FAILURE;
+        }
+    }
+    return launch_peer_barrier(c, s, fn);
+}
+
 }  // namespace sfe
+
+extern "C" int sfe_dev_bh_peer(const void* pm4, uint32_t N, uint64_t acc_off, uint64_t pot_off, float grav_g, float eps2,
+                               float theta, uint32_t flavour, void* stream) {
+    if (sfe::ensure_init("sfe_dev_bh_peer")) return SFE_FAILURE;
+    return sfe::launch_bh_routed(sfe::ctx(), (const float4*)pm4, N, acc_off, pot_off, grav_g, eps2, theta, flavour, (cudaStream_t)stream);
+}
 
 extern "C" int sfe_selftest_exact_math(uint64_t mismatches[3]) {
     using namespace sfe;

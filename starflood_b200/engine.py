@@ -114,6 +114,7 @@ SIGNATURES = {
     "sfe_peer_window": ([], _P),
     "sfe_dev_peer_put": ([C.c_uint64, C.c_uint64, _P], C.c_int),
     "sfe_dev_peer_barrier": ([_P], C.c_int),
+    "sfe_dev_bh_peer": ([_P, _u32, C.c_uint64, C.c_uint64, _f, _f, _f, _u32, _P], C.c_int),
     "sfe_peer_detach": ([], C.c_int),
     "sfe_peer_close": ([], C.c_int),
     "sfe_sim_peer_bytes": ([_u32, _u32], C.c_uint64),

@@ -66,6 +66,33 @@ def main():
     del win
     assert e.peer_close(dist.barrier) == 0, e.last_error()
 
+    # ---- 1b. routed walk (sfe_dev_bh_peer): slot ranges walked, results delivered to the owners of the particle indices
+    N = 30011
+    pos, vel, mas = sfo.initcond(N)
+    pos[3 * 5:3 * 5 + 3] = [30.0, -20.0, 25.0]                       # one particle outside the root box
+    box = sfo.root_box(pos, 0)
+    ptr = e.peer_setup(rank, world, 32 * N, allgather)
+    win = torch.as_tensor(_Window(ptr, 32 * N), device="cuda").view(torch.float32)
+    pm = np.empty((N, 4), np.float32); pm[:, :3] = pos.reshape(-1, 3); pm[:, 3] = mas
+    win[:4 * N] = torch.from_numpy(pm.ravel()).cuda()
+    win[4 * N:] = -7.0
+    ref = e.Sim(N); ref.pos[:] = pos; ref.mas[:] = mas
+    e.tree_init(ref.tree, 2 * N); ref.tree.bounds[:] = box
+    for flavour in (e.WALK_EXACT, e.WALK_FAST):
+        assert e.tree_build(ref.tree, N, ref.pos, ref.mas) == 0 and e.solve_gravity_part_tree(ref, flavour) == 0
+        assert L.sfe_dev_tree_build(box.ctypes.data, win.data_ptr(), N, e.TREE_DEPTH_MAX, 2 * N, s) == 0, e.last_error()
+        assert L.sfe_dev_bh_peer(win.data_ptr(), N, 16 * N, 28 * N, e.G, e.EPS2, e.TREE_THETA, flavour, s) == 0, e.last_error()
+        got = win[4 * N:].cpu().numpy()
+        i0, i1 = e.sim_slice(N, rank, world)
+        assert np.array_equal(got[3 * i0:3 * i1], ref.acc[3 * i0:3 * i1]) and np.array_equal(got[3 * N + i0:3 * N + i1], ref.pot[i0:i1])
+        rest = np.concatenate([got[:3 * i0], got[3 * i1:3 * N + i0], got[3 * N + i1:]])
+        assert np.all(rest == -7.0), "rows of other ranks' particles must not be written"
+        assert L.sfe_dev_peer_barrier(s) == 0                         # nobody rewrites a window that is still being read
+        torch.cuda.synchronize()
+    assert L.sfe_dev_bh_peer(win.data_ptr(), N, 24 * N, 28 * N, e.G, e.EPS2, e.TREE_THETA, e.WALK_EXACT, s) == e.STARFLOOD_FAILURE
+    del win
+    assert e.peer_close(dist.barrier) == 0, e.last_error()
+
     # ---- 2. Barnes-Hut leapfrog on `world` ranks against the oracle-driven run (bit for bit on the rank's slice)
     N, steps = 6000, 5
     pos, vel, mas = sfo.initcond(N)

@@ -75,4 +75,4 @@ def test_single_rank_window_and_errors(engine):
     assert rc == 0 and engine.sim_download(sim) == 0
     assert np.isfinite(sim.mem).all() and not np.array_equal(sim.pos, pos)
     assert L.sfe_sim_release() == 0 and L.sfe_peer_close() == 0
-    assert L.sfe_sim_peer_bytes(1000, 13) == 2 * 16 * 1024 and L.sfe_sim_peer_bytes(1000, 16) == 36 * 1024
+    assert L.sfe_sim_peer_bytes(1000, 13) == 48 * 1024 and L.sfe_sim_peer_bytes(1000, 16) == 52 * 1024
