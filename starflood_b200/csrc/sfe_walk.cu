@@ -107,7 +107,7 @@ __device__ __forceinline__ bool opens(float w2, float d2, float theta) {
 struct WalkRoute { char* base[SFE_PEER_MAX]; uint64_t acc_off, pot_off; uint32_t world, N; };
 
 template <int FLAVOUR, bool ROUTED>
-__global__ void __launch_bounds__(WALK_THREADS)
+__global__ void __launch_bounds__(WALK_THREADS, 16)
 walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restrict__ slots /* null: the range from s0 */,
             uint32_t s0, uint32_t nslots, float G, float eps2, float theta,
             float* __restrict__ acc, float* __restrict__ pot, WalkRoute route) {
