@@ -181,12 +181,15 @@ int launch_bh(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, f
               float G, float eps2, float theta, uint32_t flavour, cudaStream_t s);
 int launch_bh_routed(Ctx* c, const float4* pm4, uint32_t N, uint64_t acc_off, uint64_t pot_off,
                      float G, float eps2, float theta, uint32_t flavour, cudaStream_t s);
+// Multi-rank routing of the cell-list pass (sfe_sph_cells.cu): the rank evaluates the targets of a contiguous range of
+// SORTED slots (dense in space) and stores rho into every rank's window / adds the pressure force into the owner's acc.
+struct SphRoute { char* base[SFE_PEER_MAX]; uint64_t off; uint32_t world, rank; };
 int launch_sph_density(Ctx* c, const float4* pm4, const float* rad, uint32_t N, uint32_t i0, uint32_t ni,
-                       float* rho, cudaStream_t s);
+                       float* rho, cudaStream_t s, const SphRoute* route = nullptr);
 int launch_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float eos_n, cudaStream_t s);
 int launch_sph_force(Ctx* c, const float4* pm4, const float* rad, const float* rho, const float* prs,
                      uint32_t N, uint32_t i0, uint32_t ni, float cutoff2, float* acc, cudaStream_t s,
-                     bool reuse_cells = false);
+                     bool reuse_cells = false, const SphRoute* route = nullptr);
 // resident leapfrog (sfe_sim.cu)
 int launch_kick_drift(Ctx* c, float4* pm4, float* vel, const float* acc, uint32_t i0, uint32_t ni, float dt, cudaStream_t s);
 int launch_root_box(Ctx* c, const float4* pm4, uint32_t N, uint32_t step_number, float bounds[6], cudaStream_t s);
@@ -203,7 +206,7 @@ void saver_release();        // sfe_save.cu: drains pending snapshots, stops the
 // SPH neighbour search (sfe_sph_cells.cu): grid + sort for one snapshot, then one gated pass per mode
 int cells_prepare(Ctx* c, const float4* pm4, const float* rad, uint32_t N, bool force_all_pairs, cudaStream_t s, const char* fn);
 int cells_run(Ctx* c, int mode, const float4* pm4, const float* rad, const float* rho, const float* prs, uint32_t N,
-              uint32_t i0, uint32_t ni, float cutoff2, float* out, cudaStream_t s, const char* fn);
+              uint32_t i0, uint32_t ni, float cutoff2, float* out, cudaStream_t s, const char* fn, const SphRoute* route = nullptr);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- mbarrier / bulk-copy PTX

@@ -504,13 +504,32 @@ static int sim_solv_enqueue(Ctx* c, const sfe_sim_params_t* p, uint32_t step_num
     if (p->solver & SFE_SOLVER_SPH) {
         if (st.dof < 16u) { set_error(fn, "SFE_SOLVER_SPH needs a SIM_DOF=16 state"); return SFE_FAILURE; }
         float* rho = sim_rho(c);
-        if (launch_sph_density(c, pm4, st.rad.as<float>(), st.N, i0, ni, rho, s)) return SFE_FAILURE;
-        // second exchange of SURVEY 8(e): every rank needs rho of ALL sources for the force pass (P is recomputed locally)
-        if (st.peer_mode && launch_peer_put(c, st.rho_off + 4u * (uint64_t)i0, 4u * (uint64_t)ni, s, fn)) return SFE_FAILURE;
-        if (launch_sph_eos(rho, st.prs.as<float>(), st.N, p->eos_k, p->eos_n, s)) return SFE_FAILURE;
-        if (launch_sph_force(c, pm4, st.rad.as<float>(), rho, st.prs.as<float>(), st.N, i0, ni, p->cutoff2,
-                             sim_acc(c), s, /*reuse_cells=*/true))
-            return SFE_FAILURE;
+        if (st.peer_mode) {
+            // Second exchange of SURVEY 8(e).  Cell-list pass: every rank evaluates a dense range of the cell-sorted
+            // targets and stores rho into EVERY rank's window (the force pass needs rho of all sources), then adds the
+            // pressure force into the owner's acc over NVLink.  All-pairs pass (small N; the choice is made on the device,
+            // the same on every rank): the index slice, locally, and the slice is put to the peers - a no-op re-send when
+            // the cell pass ran.
+            SphRoute rt;
+            for (uint32_t r = 0; r < SFE_PEER_MAX; r++) rt.base[r] = (char*)c->peer.base[r];
+            rt.world = c->peer.world; rt.rank = c->peer.rank;
+            rt.off = st.rho_off;
+            if (launch_sph_density(c, pm4, st.rad.as<float>(), st.N, i0, ni, rho, s, &rt)) return SFE_FAILURE;
+            if (launch_peer_barrier(c, s, fn)) return SFE_FAILURE;
+            if (launch_peer_put(c, st.rho_off + 4u * (uint64_t)i0, 4u * (uint64_t)ni, s, fn)) return SFE_FAILURE;
+            if (launch_sph_eos(rho, st.prs.as<float>(), st.N, p->eos_k, p->eos_n, s)) return SFE_FAILURE;
+            rt.off = st.acc_off;
+            if (launch_sph_force(c, pm4, st.rad.as<float>(), rho, st.prs.as<float>(), st.N, i0, ni, p->cutoff2, sim_acc(c), s,
+                                 /*reuse_cells=*/true, &rt))
+                return SFE_FAILURE;
+            if (launch_peer_barrier(c, s, fn)) return SFE_FAILURE;
+        } else {
+            if (launch_sph_density(c, pm4, st.rad.as<float>(), st.N, i0, ni, rho, s)) return SFE_FAILURE;
+            if (launch_sph_eos(rho, st.prs.as<float>(), st.N, p->eos_k, p->eos_n, s)) return SFE_FAILURE;
+            if (launch_sph_force(c, pm4, st.rad.as<float>(), rho, st.prs.as<float>(), st.N, i0, ni, p->cutoff2, sim_acc(c), s,
+                                 /*reuse_cells=*/true))
+                return SFE_FAILURE;
+        }
     }
     return SFE_SUCCESS;
 }

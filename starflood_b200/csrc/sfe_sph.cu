@@ -244,15 +244,16 @@ static void split_plan(const Ctx* c, uint32_t iblocks, uint32_t tiles, uint32_t*
 
 static int sph_run(Ctx* c, int mode, const float4* pm4, const float* rad, const float* rho, const float* prs,
                    uint32_t N, uint32_t i0, uint32_t ni, float cutoff2, float* out, cudaStream_t s, const char* fn,
-                   bool reuse_cells) {
-    if (N == 0 || ni == 0) return SFE_SUCCESS;
+                   bool reuse_cells, const SphRoute* route) {
+    if (N == 0 || (ni == 0 && !route)) return SFE_SUCCESS;
     if ((uint64_t)i0 + ni > N) { set_error(fn, "target slice [%u,%u) exceeds N=%u", i0, i0 + ni, N); return SFE_FAILURE; }
     // neighbour search first: grid descriptor + sort (skipped when the force pass follows the density pass of
     // the same snapshot inside sfe_sph), then the cell-list pass.  Whether it applies is decided on the device;
     // the all-pairs kernels below are enqueued behind the same flag and retire at once when it does.
     static const bool all_pairs_only = getenv("SFE_SPH_ALL_PAIRS") != nullptr;   // test / measurement hook
     if (!reuse_cells && cells_prepare(c, pm4, rad, N, all_pairs_only, s, fn)) return SFE_FAILURE;
-    if (cells_run(c, mode, pm4, rad, rho, prs, N, i0, ni, cutoff2, out, s, fn)) return SFE_FAILURE;
+    if (cells_run(c, mode, pm4, rad, rho, prs, N, i0, ni, cutoff2, out, s, fn, route)) return SFE_FAILURE;
+    if (ni == 0) return SFE_SUCCESS;   // (a routed rank with an empty index slice still took part in the cell pass)
     const CellGrid* gate = c->sph_cells.maybe ? c->sph_cells.desc.as<CellGrid>() : nullptr;
     const uint32_t tiles = (N + SPH_TILE - 1) / SPH_TILE, npad = tiles * SPH_TILE;
     if (c->sph_src.reserve((size_t)npad * 32 + 64, fn)) return SFE_FAILURE;
@@ -282,8 +283,8 @@ static int sph_run(Ctx* c, int mode, const float4* pm4, const float* rad, const 
 }
 
 int launch_sph_density(Ctx* c, const float4* pm4, const float* rad, uint32_t N, uint32_t i0, uint32_t ni,
-                       float* rho, cudaStream_t s) {
-    return sph_run(c, 0, pm4, rad, nullptr, nullptr, N, i0, ni, 0.f, rho, s, "sfe_dev_sph_density", false);
+                       float* rho, cudaStream_t s, const SphRoute* route) {
+    return sph_run(c, 0, pm4, rad, nullptr, nullptr, N, i0, ni, 0.f, rho, s, "sfe_dev_sph_density", false, route);
 }
 
 int launch_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float eos_n, cudaStream_t s) {
@@ -294,8 +295,9 @@ int launch_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float 
 }
 
 int launch_sph_force(Ctx* c, const float4* pm4, const float* rad, const float* rho, const float* prs,
-                     uint32_t N, uint32_t i0, uint32_t ni, float cutoff2, float* acc, cudaStream_t s, bool reuse_cells) {
-    return sph_run(c, 1, pm4, rad, rho, prs, N, i0, ni, cutoff2, acc, s, "sfe_dev_sph_force", reuse_cells);
+                     uint32_t N, uint32_t i0, uint32_t ni, float cutoff2, float* acc, cudaStream_t s, bool reuse_cells,
+                     const SphRoute* route) {
+    return sph_run(c, 1, pm4, rad, rho, prs, N, i0, ni, cutoff2, acc, s, "sfe_dev_sph_force", reuse_cells, route);
 }
 
 }  // namespace sfe

@@ -292,8 +292,8 @@ struct TargetScanOp {
 template <int MODE>
 __global__ void __launch_bounds__(CL_THREADS)
 cl_pair_kernel(const CellGrid* __restrict__ g, const uint32_t* __restrict__ start, const uint32_t* __restrict__ key,
-               const float4* __restrict__ rec, const uint32_t* __restrict__ tlist, uint32_t nt,
-               const float4* __restrict__ pm4, float cutoff2, float* __restrict__ out) {
+               const float4* __restrict__ rec, const uint32_t* __restrict__ tlist, uint32_t slot0, uint32_t nt,
+               const float4* __restrict__ pm4, float cutoff2, float* __restrict__ out, SphRoute route, uint32_t N) {
     if (!g->use_cells) return;
     __shared__ __align__(128) float4 tile[CL_STAGES][CL_CHUNK * 2];
     __shared__ __align__(8) uint64_t full[CL_STAGES];
@@ -326,13 +326,13 @@ cl_pair_kernel(const CellGrid* __restrict__ g, const uint32_t* __restrict__ star
     const uint32_t tcount = min(2u * CL_THREADS, nt - g0);
     const uint32_t ia = 2u * tid, ib = ia + 1u;
     const bool va = ia < tcount, vb = ib < tcount;
-    const uint32_t sa = va ? (tlist ? tlist[g0 + ia] : g0 + ia) : 0u, sb = vb ? (tlist ? tlist[g0 + ib] : g0 + ib) : 0u;
+    const uint32_t sa = va ? (tlist ? tlist[g0 + ia] : slot0 + g0 + ia) : 0u, sb = vb ? (tlist ? tlist[g0 + ib] : slot0 + g0 + ib) : 0u;
     float4 Aa = make_float4(0.f, 0.f, 0.f, 0.f), Ba = make_float4(-1.f, 0.f, 0.f, 0.f), Ab = Aa, Bb = Ba;
     uint32_t ca = 0xFFFFFFFFu, cb = 0xFFFFFFFFu;
     if (va) { Aa = rec[2u * sa]; Ba = rec[2u * sa + 1u]; ca = key[sa]; }
     if (vb) { Ab = rec[2u * sb]; Bb = rec[2u * sb + 1u]; cb = key[sb]; }
     const uint32_t rowa = va ? ca / nx_ : 0xFFFFFFFFu, rowb = vb ? cb / nx_ : 0xFFFFFFFFu;
-    const uint32_t slot_first = tlist ? tlist[g0] : g0, slot_last = tlist ? tlist[g0 + tcount - 1u] : g0 + tcount - 1u;
+    const uint32_t slot_first = tlist ? tlist[g0] : slot0 + g0, slot_last = tlist ? tlist[g0 + tcount - 1u] : slot0 + g0 + tcount - 1u;
     const uint32_t row_first = key[slot_first] / nx_, row_last = key[slot_last] / nx_;
 
     const float2 ki = make_float2(Ba.x, Bb.x);
@@ -422,8 +422,17 @@ cl_pair_kernel(const CellGrid* __restrict__ g, const uint32_t* __restrict__ star
         if (!(l == 0 ? va : vb)) continue;
         const uint32_t i = __float_as_uint(l == 0 ? Ba.w : Bb.w);
         if (MODE == 0) {
-            out[i] = (float)((double)(tot[l][0].s - tot[l][0].c) + (double)(tot[l][1].s - tot[l][1].c));
+            const float v = (float)((double)(tot[l][0].s - tot[l][0].c) + (double)(tot[l][1].s - tot[l][1].c));
+            if (route.world) {   // every rank needs rho of every source for the force pass: store it everywhere
+                for (uint32_t r = 0; r < route.world; r++) reinterpret_cast<float*>(route.base[r] + route.off)[i] = v;
+            } else out[i] = v;
         } else {
+            if (route.world) {   // the pressure force goes into the acc array of the rank that owns particle i
+                uint32_t r = (uint32_t)(((uint64_t)i * route.world) / N);
+                while (i < (uint32_t)(((uint64_t)N * r) / route.world)) r--;
+                while (i >= (uint32_t)(((uint64_t)N * (r + 1u)) / route.world)) r++;
+                out = reinterpret_cast<float*>(route.base[r] + route.off);
+            }
             // sums were taken with d' = -(r_i - r_j): acc += -m_i * S  (sph.c:274-276)  =>  acc += m_i * S'
             const float m = pm4[i].w;
             out[3u * i + 0u] = __fadd_rn(out[3u * i + 0u], __fmul_rn(m, tot[l][0].s - tot[l][0].c));
@@ -473,23 +482,30 @@ int cells_prepare(Ctx* c, const float4* pm4, const float* rad, uint32_t N, bool 
 }
 
 int cells_run(Ctx* c, int mode, const float4* pm4, const float* rad, const float* rho, const float* prs, uint32_t N,
-              uint32_t i0, uint32_t ni, float cutoff2, float* out, cudaStream_t s, const char* fn) {
+              uint32_t i0, uint32_t ni, float cutoff2, float* out, cudaStream_t s, const char* fn, const SphRoute* route) {
     SphCells& k = c->sph_cells;
     if (!k.maybe) return SFE_SUCCESS;
     const CellGrid* g = k.desc.as<CellGrid>();
     cl_rec_kernel<<<(N + 255) / 256, 256, 0, s>>>(pm4, rad, rho, prs, mode, k.val[0].as<uint32_t>(), N, g, k.rec.as<float4>());
     if (check_launch(fn)) return SFE_FAILURE;
     const uint32_t* tlist = nullptr;
-    if (!(i0 == 0 && ni == N)) {   // owned targets of the slice, in cell order
+    SphRoute rt; rt.world = 0u; rt.rank = 0u; rt.off = 0u;
+    uint32_t slot0 = 0u;
+    if (route) {                   // multi-rank: a dense range of sorted slots, results routed to the owners
+        rt = *route;
+        slot0 = (uint32_t)(((uint64_t)N * rt.rank) / rt.world);
+        ni = (uint32_t)(((uint64_t)N * (rt.rank + 1u)) / rt.world) - slot0;
+        if (ni == 0u) return SFE_SUCCESS;
+    } else if (!(i0 == 0 && ni == N)) {   // owned targets of the slice, in cell order
         if (k.tlist.reserve((size_t)ni * 4, fn)) return SFE_FAILURE;
         if (run_scan(c, TargetScanOp{k.rec.as<float4>(), k.tlist.as<uint32_t>(), N, i0, ni, g}, N, s, fn)) return SFE_FAILURE;
         tlist = k.tlist.as<uint32_t>();
     }
     const uint32_t grid = (ni + 2u * CL_THREADS - 1u) / (2u * CL_THREADS);
     if (mode == 0)
-        cl_pair_kernel<0><<<grid, CL_THREADS, 0, s>>>(g, k.start.as<uint32_t>(), k.key[0].as<uint32_t>(), k.rec.as<float4>(), tlist, ni, pm4, cutoff2, out);
+        cl_pair_kernel<0><<<grid, CL_THREADS, 0, s>>>(g, k.start.as<uint32_t>(), k.key[0].as<uint32_t>(), k.rec.as<float4>(), tlist, slot0, ni, pm4, cutoff2, out, rt, N);
     else
-        cl_pair_kernel<1><<<grid, CL_THREADS, 0, s>>>(g, k.start.as<uint32_t>(), k.key[0].as<uint32_t>(), k.rec.as<float4>(), tlist, ni, pm4, cutoff2, out);
+        cl_pair_kernel<1><<<grid, CL_THREADS, 0, s>>>(g, k.start.as<uint32_t>(), k.key[0].as<uint32_t>(), k.rec.as<float4>(), tlist, slot0, ni, pm4, cutoff2, out, rt, N);
     return check_launch(fn);
 }
 

@@ -158,6 +158,30 @@ def main():
     assert np.all(np.abs(E - Er) <= 1e-6 * np.abs(Er).max()), (rank, E - Er)
     allE = allgather(E.tobytes()); allpos = allgather(sim.pos.tobytes())
     assert all(x == allE[0] for x in allE) and all(x == allpos[0] for x in allpos), "the ranks must agree bit for bit"
+    # the same at a size where the SPH sums run over the cell list: every rank evaluates a dense range of the cell-sorted
+    # targets, rho is stored into every rank's window and the pressure force into the owner's acc (routed over NVLink)
+    assert L.sfe_sim_release() == 0 and e.peer_close(dist.barrier) == 0
+    N, steps = 40000, 2
+    pos, vel, mas, rad = sfo.initcond(N, outflow=0.0, sph=True)
+    ref = e.Sim(N, sph=True); ref.pos[:] = pos; ref.vel[:] = vel; ref.mas[:] = mas; ref.rad[:] = rad
+    assert e.sim_upload(ref) == 0 and e.sim_solv_resident(ref, prm) == 0, e.last_error()
+    rc, Er = e.sim_step(ref, prm, nsteps=steps)
+    assert rc == 0 and e.sim_download(ref) == 0, e.last_error()
+    L.sfe_sim_release()
+    e.peer_setup(rank, world, int(L.sfe_sim_peer_bytes(N, 16)), allgather)
+    sim = e.Sim(N, sph=True); sim.pos[:] = pos; sim.vel[:] = vel; sim.mas[:] = mas; sim.rad[:] = rad
+    assert e.sim_upload(sim) == 0 and e.sim_solv_resident(sim, prm) == 0, e.last_error()
+    rc, E = e.sim_step(sim, prm, nsteps=steps)
+    assert rc == 0 and e.sim_download(sim) == 0, e.last_error()
+    i0, i1 = e.sim_slice(N, rank, world)
+    for name in ("pos", "rho", "prs"):
+        assert rel_rms(sim.find(name), ref.find(name)) <= 1e-5, (rank, name, rel_rms(sim.find(name), ref.find(name)))
+    for name, w in (("vel", 3), ("acc", 3), ("pot", 1)):
+        d = rel_rms(sim.find(name)[w * i0:w * i1], ref.find(name)[w * i0:w * i1])
+        assert d <= 1e-5, (rank, name, d)
+    assert np.all(np.abs(E - Er) <= 1e-6 * np.abs(Er).max()), (rank, E - Er)
+    allpos = allgather(sim.pos.tobytes()); allrho = allgather(sim.rho.tobytes())
+    assert all(x == allpos[0] for x in allpos) and all(x == allrho[0] for x in allrho), "the ranks must agree bit for bit"
     # the window is too small for a bigger state: refused, and the engine falls back to nothing
     big = e.Sim(2 * N, sph=True); big.mas[:] = 1.0
     assert e.sim_upload(big) == e.STARFLOOD_FAILURE and "sfe_sim_peer_bytes" in e.last_error()
