@@ -41,6 +41,17 @@ struct KahanRef {   // gravity.c:771-799: y = F - com; t = sum + y; z = t - sum;
     }
 };
 
+struct KahanRef2 {  // two of them in the lanes of packed fp32x2 instructions (same roundings, lane by lane)
+    float2 s, c;
+    __device__ __forceinline__ void add(float2 x) {
+        const float2 y = __fadd2_rn(x, make_float2(-c.x, -c.y));
+        const float2 t = __fadd2_rn(s, y);
+        const float2 z = __fadd2_rn(t, make_float2(-s.x, -s.y));
+        c = __fadd2_rn(z, make_float2(-y.x, -y.y));
+        s = t;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // Correctly rounded 1/q, sqrt(q) and 1/sqrt-then-reciprocal for the EXACT flavour.  The reference computes
 // inv_r2 = 1/q and inv_r1 = 1/sqrtf(q) with IEEE division and square root (gravity.c:754-759); __fdiv_rn /
@@ -120,7 +131,7 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
     const float4 me = s < M ? t.spm4[fin][s] : pm4[idx];
     const float x = me.x, y = me.y, z = me.z, mi = me.w;
 
-    KahanRef ax = {0.f, 0.f}, ay = {0.f, 0.f}, az = {0.f, 0.f}, ap = {0.f, 0.f};
+    KahanRef2 kxy = {{0.f, 0.f}, {0.f, 0.f}}, kzp = {{0.f, 0.f}, {0.f, 0.f}};   // (acc x, acc y) and (acc z, pot)
     float fx = 0.f, fy = 0.f, fz = 0.f, fp = 0.f;
 
     const WalkRec0* __restrict__ rec0 = t.rec0;
@@ -141,8 +152,10 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
         float rx, ry, rz, mj;
         bool maybe_inside;
         if (kind == KIND_INTERNAL) {
-            const float ox = __fsub_rn(a0, x), oy = __fsub_rn(a1, y), oz = __fsub_rn(a2, z);
-            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ox, ox), __fmul_rn(oy, oy)), __fmul_rn(oz, oz));
+            const float2 oxy = __fadd2_rn(make_float2(a0, a1), make_float2(-x, -y));   // packed: same roundings, fewer issue slots
+            const float2 osq = __fmul2_rn(oxy, oxy);
+            const float oz = __fsub_rn(a2, z);
+            const float d2 = __fadd_rn(__fadd_rn(osq.x, osq.y), __fmul_rn(oz, oz));
             if (opens(a3, d2, theta)) { n = r[5] & 0x3FFFFFFFu; continue; }   // gravity.c:448-453 (first non-empty child)
             const float4 cm = __ldg(&rec1[n]);                                   // accepted: monopole of the cell
             rx = cm.x; ry = cm.y; rz = cm.z; mj = cm.w;
@@ -166,23 +179,41 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
                 rx = __fmul_rn(rx, inv); ry = __fmul_rn(ry, inv); rz = __fmul_rn(rz, inv);
             }
         }
-        const float dx = __fsub_rn(x, rx), dy = __fsub_rn(y, ry), dz = __fsub_rn(z, rz);
-        const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        const float q = __fadd_rn(r2, eps2);
         if (FLAVOUR == (int)SFE_WALK_EXACT) {
+            // Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2 round each lane to nearest like their scalar forms, so every
+            // value below is the bit pattern of the scalar sequence): the EXACT walk is bound by issue slots, and a packed
+            // instruction does two of its independent operations in one.
+            const float2 dxy = __fadd2_rn(make_float2(x, y), make_float2(-rx, -ry));
+            const float2 sq = __fmul2_rn(dxy, dxy);
+            const float dz = __fsub_rn(z, rz);
+            const float r2 = __fadd_rn(__fadd_rn(sq.x, sq.y), __fmul_rn(dz, dz));
+            const float q = __fadd_rn(r2, eps2);
             float inv_r2, inv_r1;
             if (seq_ok && q < SEQ_HI) {      // q >= eps2 >= SEQ_LO here
-                inv_r2 = rcp_rn_seq(q);
-                inv_r1 = rcp_rn_seq(sqrt_rn_seq(q));
+                // rcp_rn_seq(q) and rcp_rn_seq(sqrt_rn_seq(q)) side by side in the two lanes
+                const float sr = sqrt_rn_seq(q);
+                const float2 nqs = make_float2(-q, -sr), one = make_float2(1.0f, 1.0f);
+                float2 r = make_float2(rcp_approx(q), rcp_approx(sr));
+                float2 e = __ffma2_rn(nqs, r, one);
+                r = __ffma2_rn(r, e, r);
+                e = __ffma2_rn(nqs, r, one);
+                r = __ffma2_rn(r, e, r);
+                inv_r2 = r.x; inv_r1 = r.y;
             } else {
                 inv_r2 = __fdiv_rn(1.0f, q);
                 inv_r1 = __fdiv_rn(1.0f, __fsqrt_rn(q));
             }
             const float pj = __fmul_rn(mj, inv_r1);
             const float w = __fmul_rn(pj, inv_r2);
-            ax.add(__fmul_rn(w, dx)); ay.add(__fmul_rn(w, dy)); az.add(__fmul_rn(w, dz));
-            ap.add(pj);
+            // (scalar products on purpose: ptxas contracts a mul.rn.f32x2 that feeds an add.rn.f32x2 into one FFMA2 -
+            // one rounding instead of two - which it never does to the scalar .rn forms; seen in SASS, caught by the golden test)
+            const float2 fxy = make_float2(__fmul_rn(w, dxy.x), __fmul_rn(w, dxy.y));
+            const float2 fzp = make_float2(__fmul_rn(w, dz), pj);
+            kxy.add(fxy); kzp.add(fzp);
         } else {
+            const float dx = __fsub_rn(x, rx), dy = __fsub_rn(y, ry), dz = __fsub_rn(z, rz);
+            const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            const float q = __fadd_rn(r2, eps2);
             const float inv = rsqrt_approx(q);
             const float pj = mj * inv;
             const float w = pj * (inv * inv);
@@ -191,7 +222,7 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
         }
         n = next;
     }
-    if (FLAVOUR == (int)SFE_WALK_EXACT) { fx = ax.s; fy = ay.s; fz = az.s; fp = ap.s; }
+    if (FLAVOUR == (int)SFE_WALK_EXACT) { fx = kxy.s.x; fy = kxy.s.y; fz = kzp.s.x; fp = kzp.s.y; }
     const float gm = __fmul_rn(-G, mi);                                            // gravity.c:656-659
     if (ROUTED) {
         // owner r of particle idx: (N*r)/world <= idx < (N*(r+1))/world
