@@ -61,6 +61,31 @@ def test_no_cpu_fallback_without_gpu():
     assert engine.solve_gravity_part_tree(sim) == engine.STARFLOOD_FAILURE
 
 
+def test_new_entry_points_fail_loudly_without_gpu(tmp_path):
+    """Resident leapfrog, snapshots, overlay and the peer exchange have no CPU path either."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from starflood_b200 import engine
+    L = engine.lib()
+    sim = engine.Sim(32); sim.mas[:] = 1.0
+    prm = engine.sim_params()
+    assert engine.sim_upload(sim) == engine.STARFLOOD_FAILURE and "no CUDA device" in engine.last_error()
+    assert engine.sim_solv_resident(sim, prm) == engine.STARFLOOD_FAILURE
+    assert engine.sim_step(sim, prm)[0] == engine.STARFLOOD_FAILURE
+    assert engine.sim_download(sim) == engine.STARFLOOD_FAILURE
+    assert engine.sim_save_raw_async(str(tmp_path / "x.raw")) == engine.STARFLOOD_FAILURE
+    assert not (tmp_path / "x.raw").exists()
+    h = C.create_string_buffer(64)
+    assert L.sfe_peer_create(0, 1, 1024, h) == engine.STARFLOOD_FAILURE
+    assert L.sfe_dev_peer_put(0, 16, None) == engine.STARFLOOD_FAILURE
+    assert L.sfe_dev_bh_peer(None, 32, 0, 0, 1.0, 1e-6, 0.5, 0, None) == engine.STARFLOOD_FAILURE
+    rb = np.zeros(64, np.float32); m = np.eye(4, dtype=np.float32)
+    assert L.sfe_bh_overlay(3, 0.5, m.ctypes.data, rb.ctypes.data, 4, 4) == engine.STARFLOOD_FAILURE and not rb.any()
+    assert L.sfe_peer_window() is None
+    assert L.sfe_sim_peer_bytes(1000, 13) == 48 * 1024          # pure arithmetic, no device involved
+
+
 def test_product_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "starflood_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -93,6 +93,24 @@ print("rank", rank, "ok")
 '''
 
 
+@pytest.mark.parametrize("N,world", [(1 << 20, 8), (1000, 3), (5, 8), (0, 4), (6000, 16), (30011, 7)])
+def test_sim_slice_is_a_partition_and_names_the_owner(N, world):
+    """rank r owns [r*N/world, (r+1)*N/world).  The routed walk (csrc/sfe_walk.cu) finds the owner of a
+    particle from its index with the same arithmetic; mirrored here."""
+    from starflood_b200 import engine
+    cuts = [engine.sim_slice(N, r, world) for r in range(world)]
+    assert cuts[0][0] == 0 and cuts[-1][1] == N
+    assert all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))
+    assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= 1
+    for i in list(range(min(N, 50))) + list(range(max(N - 50, 0), N)) + ([N // 2, N // 3] if N else []):
+        r = (i * world) // N
+        while i < (N * r) // world:
+            r -= 1
+        while i >= (N * (r + 1)) // world:
+            r += 1
+        assert cuts[r][0] <= i < cuts[r][1]
+
+
 def test_two_rank_gloo_slice_flow(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER % ROOT)
