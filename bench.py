@@ -329,11 +329,24 @@ def run_engine(args):
 
     # device-resident state: per snapshot the rank's slice of pm4 records; full pm4 + outputs shared
     use_peer = world > 1 and args.exchange == "peer"
+    peer_note = None
     if use_peer:
         # two {x,y,z,m} arrays inside the exchange window, alternated between steps (sfengine.h: a range written by
         # exchange k may be rewritten by exchange k+2 at the earliest)
         # ... and acc / pot: the routed walk (sfe_dev_bh_peer) stores every result into its owner's window
-        wptr = e.peer_setup(rank, world, 3 * 16 * N, allgather_bytes)
+        ok = 1
+        try:
+            wptr = e.peer_setup(rank, world, 3 * 16 * N, allgather_bytes)
+        except e.EngineError as err:      # e.g. CUDA IPC not permitted in this container: every rank falls back together
+            ok, peer_note = 0, str(err)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            e.peer_close(dist.barrier)
+            use_peer = False
+            args.exchange = "nccl"
+            peer_note = "peer window unavailable (%s): NCCL all-gather + index slices instead" % (peer_note or "a peer failed")
+    if use_peer:
         wt = torch.as_tensor(Window(wptr, 3 * 16 * N), device=dev)
         pm4_regions = [wt[:4 * N], wt[4 * N:8 * N]]
         pm4_full = pm4_regions[0]
@@ -341,6 +354,7 @@ def run_engine(args):
     else:
         pm4_full = torch.empty(N * 4, dtype=torch.float32, device=dev)
     xstate = {"n": 0}
+    use_peer_at_start = use_peer
     if use_peer:
         acc, pot = acc_w, pot_w
     else:
@@ -532,7 +546,7 @@ def run_engine(args):
             legs.append(("C3", 262144, False, True))
         for name, n_leg, tree, with_sph in legs:
             resident[name] = resident_leg(e, L, torch, dist, world, rank, n_leg, tree, with_sph, flavour, allgather_bytes,
-                                          barrier, max_over_ranks, world > 1 and args.exchange == "peer")
+                                          barrier, max_over_ranks, use_peer_at_start)
 
     if rank != 0:
         if world > 1:
@@ -579,7 +593,8 @@ def run_engine(args):
                                  "(sfe_dev_bh_peer)" if use_peer else "target index slices, all-gather of {x,y,z,m} by NCCL"))
                                 if world > 1 else "single GPU",
                    "l2": "ring of %d distinct snapshots (%d MiB of inputs > L2) rotated between steps" % (ring, ring * 16 * N >> 20),
-                   "tree_nodes": int(st[0].value), "tree_depth": int(st[2].value)},
+                   "tree_nodes": int(st[0].value), "tree_depth": int(st[2].value),
+                   **({"note": peer_note} if peer_note else {})},
         "e2e": {"value": N / (e2e_ms * 1e-3), "unit": "particle-steps/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
                 "api": "sfe_tree_build + sfe_bh on pinned host arrays" if world == 1 else

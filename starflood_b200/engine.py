@@ -404,10 +404,12 @@ def peer_setup(rank, world, nbytes, allgather):
     sfe_peer_open).  `allgather(bytes) -> list of bytes indexed by rank` is the host-side transport, e.g.
     torch.distributed.all_gather_object; it is only used here, once.  Returns the window's device pointer."""
     h = C.create_string_buffer(PEER_HANDLE_BYTES)
-    _check(lib().sfe_peer_create(rank, world, nbytes, h), "sfe_peer_create")
-    handles = allgather(h.raw)
+    rc = lib().sfe_peer_create(rank, world, nbytes, h)
+    why = last_error() if rc != STARFLOOD_SUCCESS else ""
+    handles = allgather(h.raw if rc == STARFLOOD_SUCCESS else b"")       # always take part: the transport is collective
     if len(handles) != world or any(len(x) != PEER_HANDLE_BYTES for x in handles):
-        raise EngineError("peer_setup: the transport returned %d handles for %d ranks" % (len(handles), world))
+        lib().sfe_peer_close()
+        raise EngineError("peer_setup: %s" % (why or "a peer could not create its window"))
     _check(lib().sfe_peer_open(b"".join(handles)), "sfe_peer_open")
     return lib().sfe_peer_window()
 
