@@ -20,6 +20,9 @@
 #   tree_vis  like tree with SOLVER_VIS 3 left ON  -> solve_gravity_part_tree(sim, render_buffer, sizex, sizey)
 #             draws its debug overlay (gravity.c:16-111,380-445,550-574).  The only symbol that needs is matMVP, which
 #             lives in visualization.c (not compiled here): a one-line definition is generated in the scratch directory.
+#   vis       like tree, plus the reference's visualization.c (vis_init / vis_draw / vis_free): the
+#             particle splat of vis_draw() with the shipped SPATIAL_SAMPLES 128, EXPOSURE, ORTHO_SCALE, AUTOSCALING and
+#             the tanh tonemap (VIS_FILE_FORMAT 2); the I/O thread and the OpenMP target pragma are off.
 # In all other variants: ENABLE_VIS / SOLVER_VIS / VIS_FILENAME off (no rasteriser dependency),
 # CSV logs and timing prints off, Kahan flags ON (shipped default), fp32.
 #
@@ -68,6 +71,7 @@ build_variant() {
     printf '#include "types.h"\nreal matMVP[16];\n' > "$d/sfref_matmvp.c"
     extra="sfref_matmvp.c"
   fi
+  if [ "$vis" = 2 ]; then extra="visualization.c"; fi
   ( cd "$d" && "$CC" -shared -fPIC -fopenmp -O3 -march=x86-64-v3 -std=c99 -w \
       simulation.c gravity.c tree.c sph.c initcond.c log.c grid.c $extra \
       -o "$OUT/libsfref_$name.so" -lm )
@@ -79,3 +83,4 @@ build_variant tree     1 0 1048576
 build_variant tree_big 1 0 8388608
 build_variant pp_sph   0 1 262144
 build_variant tree_vis 1 0 1048576 1
+build_variant vis      1 0 1048576 2

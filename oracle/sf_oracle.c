@@ -582,3 +582,106 @@ void sfo_energies(uint32_t N, const float* vel, const float* mas, const float* p
     }
     *T = ts; *V = vs;
 }
+
+/* ================================================================== visualization.c:253-739 (vis_draw)
+ * SURVEY 8(f) row N4, second half: the particle splat.  SHUTTER_SPEED is off in the reference (config.h:215), so
+ * time_offset is 0 and the velocity term of visualization.c:593-606 is `p += 0 * v`. */
+
+/* visualization.c:274-307: mean |pos| in double, serial Kahan */
+double sfo_vis_mean_radius(uint32_t N, const float* pos) {
+    double sum = 0.0, com = 0.0;
+    for (uint32_t i = 0; i < N; i++) {
+        const double x = pos[3u*i+0], y = pos[3u*i+1], z = pos[3u*i+2];
+        const double r1 = sqrt((x*x) + (y*y) + (z*z));
+        const double yy = r1 - com;
+        volatile double t = sum + yy;
+        volatile double zz = t - sum;
+        com = zz - yy;
+        sum = t;
+    }
+    return sum * (1.0 / (double)N);
+}
+
+static void mat4_mul(const float* A, const float* B, float* C) {   /* visualization.c:432-446 (term order 3,2,1,0) */
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++)
+            C[4*i+j] = (A[4*i+3] * B[4*3+j]) + (A[4*i+2] * B[4*2+j]) + (A[4*i+1] * B[4*1+j]) + (A[4*i+0] * B[4*0+j]);
+}
+
+/* visualization.c:327,344-489: model (rotation), view (identity), projection (ortho_scale on the 3x3 part).
+ * ortho_exp2 = ORTHO_SCALE (config.h:209, -1.0), autoscale = AUTOSCALING (config.h:212), dt = TIMESTEP_SIZE. */
+void sfo_vis_matrices(double average_radius, uint32_t step_number, double dt, double ortho_exp2, int autoscale,
+                      float mat_vm[16], float mvp[16]) {
+    const float time = (float)(dt * (double)step_number);
+    float M[16], V[16], P[16], VM[16];
+    for (int i = 0; i < 16; i++) M[i] = V[i] = P[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    float alp = 0.0f, bet = (float)SFO_TAU * 0.1250f, gam = (float)SFO_TAU * 0.0625f;
+    alp += (float)SFO_TAU * 1.000e-4f * time;
+    bet += (float)SFO_TAU * 1.000e-4f * time;
+    gam += (float)SFO_TAU * 1.000e-4f * time;
+    const float ca = cosf(alp), sa = sinf(alp), cb = cosf(bet), sb = sinf(bet), cg = cosf(gam), sg = sinf(gam);
+    const float rot[16] = {
+        ca*cb, ca*sb*sg - sa*cg, ca*sb*cg + sa*sg, 0.0f,
+        sa*cb, sa*sb*sg + ca*cg, sa*sb*cg - ca*sg, 0.0f,
+          -sb,            cb*sg,            cb*cg, 0.0f,
+         0.0f,             0.0f,             0.0f, 1.0f};
+    for (int i = 0; i < 16; i++) M[i] = rot[i];
+    float ortho = (float)exp2(ortho_exp2);
+    if (autoscale) ortho *= (float)(1.0 / average_radius);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) P[4*i+j] *= ortho;
+    mat4_mul(V, M, VM);
+    mat4_mul(P, VM, mvp);
+    if (mat_vm) memcpy(mat_vm, VM, sizeof VM);
+}
+
+/* visualization.c:334-342 (clear) + :503-683 (atomic accumulation rasterisation).  Integer adds commute, so the
+ * buffer does not depend on the thread schedule. */
+void sfo_vis_splat(uint32_t N, const float* pos, const float* pot, uint32_t step_number, const float mvp[16],
+                   uint32_t sizex, uint32_t sizey, uint32_t samples, int32_t* atomic_buffer) {
+    memset(atomic_buffer, 0, sizeof(int32_t) * 4u * (size_t)sizex * sizey);
+    #pragma omp parallel for schedule(dynamic, 256)
+    for (uint32_t idx = 0; idx < N; idx++) {
+        const float x[4] = {pos[3u*idx+0], pos[3u*idx+1], pos[3u*idx+2], 1.0f};
+        float p[4];
+        for (int i = 0; i < 4; i++) p[i] = (mvp[4*i+0]*x[0]) + (mvp[4*i+1]*x[1]) + (mvp[4*i+2]*x[2]) + (mvp[4*i+3]*x[3]);
+        const float phase = 1.000e-1f * pot[idx];
+        const float color[3] = {
+            0.5f * cosf((float)SFO_TAU * phase - (float)(SFO_TAU * (0.0 / 3.0))) + 0.5f,
+            0.5f * cosf((float)SFO_TAU * phase - (float)(SFO_TAU * (1.0 / 3.0))) + 0.5f,
+            0.5f * cosf((float)SFO_TAU * phase - (float)(SFO_TAU * (2.0 / 3.0))) + 0.5f};
+        const int32_t ac[4] = {(int32_t)(100.0f * color[0]), (int32_t)(100.0f * color[1]), (int32_t)(100.0f * color[2]), 1};
+        for (uint32_t samp = 0; samp < samples; samp++) {
+            uint32_t s[4] = {0xB79ABC95u + samp, 0xE0DA3F84u + idx, 0xAB75F07Bu + step_number, 0xCF52CA01u};
+            sfo_pcg4d(s);
+            const float r2 = (float)SFO_INV_U32 * (float)s[2], r3 = (float)SFO_INV_U32 * (float)s[3];
+            const float n0 = sqrtf(-2.0f * logf(r2)) * cosf((float)SFO_TAU * r3);
+            const float n1 = sqrtf(-2.0f * logf(r2)) * sinf((float)SFO_TAU * r3);
+            const float so0 = 0.750f * n0, so1 = 0.750f * n1;
+            const float fx = so0 + -0.5f + 0.5f * (float)sizey * p[0] + 0.5f * (float)sizex;
+            const float fy = so1 + -0.5f + 0.5f * (float)sizey * p[1] + 0.5f * (float)sizey;
+            /* (int) of a NaN / out-of-range float is INT_MIN on x86-64 (cvttss2si) and so fails the bounds test */
+            if (!(fx > -2147483648.0f && fx < 2147483648.0f && fy > -2147483648.0f && fy < 2147483648.0f)) continue;
+            const int cx = (int)fx, cy = (int)fy;
+            if (0 <= cx && cx < (int)sizex && 0 <= cy && cy < (int)sizey) {
+                const uint32_t pix = sizex * (uint32_t)cy + (uint32_t)cx;
+                for (int i = 0; i < 4; i++) {
+                    #pragma omp atomic update
+                    atomic_buffer[4u*pix+i] += ac[i];
+                }
+            }
+        }
+    }
+}
+
+/* visualization.c:691-735: pixel_value_scale = 0.01 / SPATIAL_SAMPLES * exp2(EXPOSURE); tanh tonemap when
+ * VIS_FILE_FORMAT > 0; alpha = 1 */
+void sfo_vis_finish(const int32_t* atomic_buffer, uint32_t sizex, uint32_t sizey, double pixel_value_scale, int tonemap,
+                    float* render_buffer) {
+    for (size_t i = 0; i < (size_t)sizex * sizey; i++) {
+        double px[4];
+        for (int j = 0; j < 4; j++) px[j] = pixel_value_scale * (double)atomic_buffer[4u*i+j];
+        if (tonemap) for (int j = 0; j < 4; j++) px[j] = tanh(px[j]);
+        px[3] = 1.000;
+        for (int j = 0; j < 4; j++) render_buffer[4u*i+j] = (float)px[j];
+    }
+}

@@ -107,6 +107,16 @@ void sfo_drift(uint32_t N, float* pos, const float* vel, float dt);
 void sfo_energies(uint32_t N, const float* vel, const float* mas, const float* pot,
                   float* ken, float* pen, double* T, double* V);
 
+/* visualization.c:253-739 (vis_draw), SURVEY 8(f) row N4: mean radius, MVP matrices, particle splat into the integer
+ * accumulation buffer, finishing pass into the float render buffer */
+double sfo_vis_mean_radius(uint32_t N, const float* pos);
+void sfo_vis_matrices(double average_radius, uint32_t step_number, double dt, double ortho_exp2, int autoscale,
+                      float mat_vm[16], float mvp[16]);
+void sfo_vis_splat(uint32_t N, const float* pos, const float* pot, uint32_t step_number, const float mvp[16],
+                   uint32_t sizex, uint32_t sizey, uint32_t samples, int32_t* atomic_buffer);
+void sfo_vis_finish(const int32_t* atomic_buffer, uint32_t sizex, uint32_t sizey, double pixel_value_scale, int tonemap,
+                    float* render_buffer);
+
 #ifdef __cplusplus
 }
 #endif

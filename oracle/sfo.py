@@ -73,6 +73,12 @@ def lib():
         L.sfo_drift.argtypes = [C.c_uint32, _f32p, _f32p, C.c_float]
         L.sfo_energies.argtypes = [C.c_uint32, _f32p, _f32p, _f32p, _f32p, _f32p,
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+        L.sfo_vis_mean_radius.argtypes = [C.c_uint32, _f32p]
+        L.sfo_vis_mean_radius.restype = C.c_double
+        L.sfo_vis_matrices.argtypes = [C.c_double, C.c_uint32, C.c_double, C.c_double, C.c_int, _f32p, _f32p]
+        L.sfo_vis_splat.argtypes = [C.c_uint32, _f32p, _f32p, C.c_uint32, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _i32p]
+        L.sfo_vis_finish.argtypes = [_i32p, C.c_uint32, C.c_uint32, C.c_double, C.c_int, _f32p]
         _lib = L
     return _lib
 
@@ -168,6 +174,48 @@ def bh_overlay(nodes, pos, mas, idx, mvp, rb, sizex, sizey, theta=THETA, depth_m
     return rb
 
 
+# vis_draw() parameters of the shipped configuration (config.h:170,203-212; VIS_FILE_FORMAT 2 -> tanh tonemap)
+VIS_SAMPLES = 128
+VIS_DT = 1.0
+VIS_ORTHO_EXP2 = -1.0
+VIS_AUTOSCALE = 1
+VIS_EXPOSURE = -1.0
+VIS_TONEMAP = 1
+
+
+def vis_pixel_scale(samples=VIS_SAMPLES, exposure=VIS_EXPOSURE):
+    """visualization.c:691-695"""
+    scale = 0.01 / float(samples)
+    if exposure is not None:
+        scale *= 2.0 ** exposure
+    return scale
+
+
+def vis_mean_radius(pos):
+    """visualization.c:274-307"""
+    return float(lib().sfo_vis_mean_radius(len(pos) // 3, pos))
+
+
+def vis_matrices(average_radius, step_number, dt=VIS_DT, ortho_exp2=VIS_ORTHO_EXP2, autoscale=VIS_AUTOSCALE):
+    """visualization.c:327,344-489 -> (matV * matM, matMVP), row-major 4x4"""
+    vm = np.zeros(16, np.float32); mvp = np.zeros(16, np.float32)
+    lib().sfo_vis_matrices(average_radius, step_number, dt, ortho_exp2, autoscale, vm, mvp)
+    return vm, mvp
+
+
+def vis_draw(pos, pot, step_number, sizex, sizey, samples=VIS_SAMPLES, exposure=VIS_EXPOSURE, tonemap=VIS_TONEMAP,
+             dt=VIS_DT, ortho_exp2=VIS_ORTHO_EXP2, autoscale=VIS_AUTOSCALE):
+    """The whole vis_draw() (visualization.c:253-739) -> (average_radius, matMVP, atomic_buffer, render_buffer)."""
+    N = len(pot)
+    rbar = vis_mean_radius(pos)
+    _, mvp = vis_matrices(rbar, step_number, dt, ortho_exp2, autoscale)
+    ab = np.zeros(4 * sizex * sizey, np.int32)
+    rb = np.zeros(4 * sizex * sizey, np.float32)
+    lib().sfo_vis_splat(N, pos, pot, step_number, mvp, sizex, sizey, samples, ab)
+    lib().sfo_vis_finish(ab, sizex, sizey, vis_pixel_scale(samples, exposure), tonemap, rb)
+    return rbar, mvp, ab, rb
+
+
 def sph_density(pos, mas, rad, i0=0, i1=None):
     N = len(mas); i1 = N if i1 is None else i1
     rho = np.zeros(N, np.float32)
@@ -211,7 +259,12 @@ class RefSimFlat(C.Structure):       # simulation.h:53-67 without ENABLE_TREE
     _fields_ = [("step_number", C.c_uint), ("N", C.c_uint), ("mem", C.c_void_p)]
 
 
-REF_NODES_MAX = {"tree": 1048576, "tree_big": 8388608, "tree_vis": 1048576}
+REF_NODES_MAX = {"tree": 1048576, "tree_big": 8388608, "tree_vis": 1048576, "vis": 1048576}
+
+
+class RefVis(C.Structure):           # visualization.h:19-28
+    _fields_ = [("sizex", C.c_uint), ("sizey", C.c_uint), ("mem", C.c_void_p), ("atomic_buffer", C.c_void_p),
+                ("render_buffer", C.c_void_p), ("binary_buffer", C.c_void_p)]
 
 
 def ref_available(variant="pp"):
@@ -236,7 +289,7 @@ class RefSim:
     def __init__(self, variant, N):
         self.variant = variant
         self.lib = C.CDLL(os.path.join(REF_DIR, "libsfref_%s.so" % variant))
-        self.has_tree = variant.startswith("tree")
+        self.has_tree = variant.startswith("tree") or variant == "vis"
         self.dof = 16 if variant.endswith("sph") else 13
         self.N = N
         self.mem = np.zeros(N * self.dof, np.float32)
@@ -280,6 +333,27 @@ class RefSim:
         self.lib.sim_solv.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint]
         with quiet_stdout():
             self.lib.sim_solv(C.byref(self.sim), rb.ctypes.data, sizex, sizey)
+
+    def vis_draw(self, step_number, sizex, sizey):
+        """The reference's own vis_init() + vis_draw() + vis_free() (variant vis, visualization.c:37-739) on the
+        current state -> (matMVP, atomic_buffer, render_buffer) copies."""
+        assert self.variant == "vis"
+        vis = RefVis()
+        L = self.lib
+        L.vis_init.argtypes = [C.POINTER(RefVis), C.c_uint, C.c_uint]
+        L.vis_draw.argtypes = [C.POINTER(RefVis), C.c_void_p]
+        L.vis_free.argtypes = [C.POINTER(RefVis)]
+        self.sim.step_number = step_number
+        with quiet_stdout():
+            assert L.vis_init(C.byref(vis), sizex, sizey) == 0
+            assert L.vis_draw(C.byref(vis), C.byref(self.sim)) == 0
+        n = 4 * sizex * sizey
+        ab = np.frombuffer((C.c_int32 * n).from_address(vis.atomic_buffer), np.int32).copy()
+        rb = np.frombuffer((C.c_float * n).from_address(vis.render_buffer), np.float32).copy()
+        mvp = np.array((C.c_float * 16).in_dll(L, "matMVP")[:], np.float32)
+        with quiet_stdout():
+            L.vis_free(C.byref(vis))
+        return mvp, ab, rb
 
     def nodes(self):
         """The reference's node table after the last tree_build (num_nodes is never stored, tree.c:77;
