@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sph", action="store_true", help="skip the C3 (PP + SPH) legs")
     ap.add_argument("--no-resident", action="store_true", help="skip the device-resident leapfrog legs")
+    ap.add_argument("--no-vis", action="store_true", help="skip the vis_draw() leg")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: all-gather of {x,y,z,m} by the engine's peer-memory kernels (sfe_dev_peer_put) or by NCCL")
     return ap.parse_args()
@@ -246,6 +247,74 @@ def sph_leg(e, L, torch, dev, stream):
                                   "(sampled); source tiles are shared through shared memory, so DRAM traffic is far below this" % nn,
                          "algorithmic_bytes_per_solve": bytes_alg},
             "l2": "160 MiB flush buffer written between repetitions"}
+
+
+def vis_leg(e, L, torch, dev, stream, N, pm4, pot, with_cpu):
+    """vis_draw() replacement (visualization.c:253-739) on the C2 state: N particles x SPATIAL_SAMPLES 128
+    samples into the reference's default 1080 x 1080 image (main.c:81).  `ms_per_frame` = mean radius + matrix + clear +
+    splat + finishing pass with the state resident in HBM; `e2e` = sfe_vis_draw() on pinned host arrays (pos + pot up,
+    render buffer down); `cpu_reference` = the unmodified reference's vis_draw() on the host cores."""
+    import ctypes as C
+    sx = sy = 1080
+    npix = sx * sy
+    vm = e.vis_model_view(0)
+    ortho, auto, samples, scale, tonemap = e._vis_args()
+    ab = torch.zeros(4 * npix, dtype=torch.int32, device=dev)
+    rb = torch.zeros(4 * npix, dtype=torch.float32, device=dev)
+    info = torch.zeros(32, dtype=torch.float64, device=dev)
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)
+    sptr = stream.cuda_stream
+
+    def frame():
+        if L.sfe_dev_vis_draw(pm4.data_ptr(), pot.data_ptr(), N, 0, vm.ctypes.data, ortho, auto, sx, sy, samples, scale, tonemap,
+                              ab.data_ptr(), rb.data_ptr(), info.data_ptr(), sptr) != 0:
+            raise SystemExit("bench.py: sfe_dev_vis_draw failed: " + e.last_error())
+    for _ in range(3):
+        frame()
+    torch.cuda.synchronize()
+    reps, tot = 10, 0.0
+    for _ in range(reps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream); frame(); b.record(stream)
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    ms = tot / reps
+    landed = int(ab[3::4].sum().item())
+    # through the host entry point (what the vis shim calls), pinned host arrays
+    host_pm = pm4.reshape(-1, 4).cpu().numpy()
+    sim = e.Sim(N, pinned=True)
+    sim.pos[:] = host_pm[:, :3].reshape(-1); sim.mas[:] = host_pm[:, 3]; sim.pot[:] = pot.cpu().numpy()
+    vis = e.Vis(); e.vis_init(vis, sx, sy)
+    vis.atomic_buffer = None                              # like the shim: the accumulation buffer stays on the device
+    e._check(L.sfe_host_register(vis.render_buffer.ctypes.data, vis.render_buffer.nbytes), "sfe_host_register")
+    for _ in range(2):
+        e._check(e.vis_draw(vis, sim), "sfe_vis_draw")
+    t0 = time.perf_counter()
+    for _ in range(5):
+        e._check(e.vis_draw(vis, sim), "sfe_vis_draw")
+    e2e_ms = (time.perf_counter() - t0) / 5 * 1e3
+    L.sfe_host_unregister(vis.render_buffer.ctypes.data)
+    out = {"workload": "vis_draw(): N=%d particles x %d samples into %d x %d (reference defaults), on the C2 state" % (N, samples, sx, sy),
+           "ms_per_frame": ms, "samples_per_s": float(N) * samples / (ms * 1e-3), "samples_landed": landed,
+           "e2e": {"ms_per_frame": e2e_ms, "h2d_bytes": 16 * N, "d2h_bytes": 16 * npix, "api": "sfe_vis_draw on pinned host arrays"},
+           "parity": "integer accumulation buffer bit-identical to the reference (tests/test_gpu_vis.py)",
+           "l2": "160 MiB flush buffer written between repetitions"}
+    if with_cpu:
+        from oracle import sfo
+        if sfo.ref_available("vis"):
+            r = sfo.RefSim("vis", N)
+            r.pos[:] = sim.pos; r.mas[:] = sim.mas; r.pot[:] = sim.pot
+            cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count()))
+            r.vis_draw(0, sx, sy)
+            t = []
+            for _ in range(2):
+                t0 = time.perf_counter(); r.vis_draw(0, sx, sy); t.append(time.perf_counter() - t0)
+            r.close()
+            out["cpu_reference"] = {"ms_per_frame": 1e3 * min(t), "cores": cores, "kind": "reference",
+                                    "sample": "2 full vis_init()+vis_draw() calls of the unmodified visualization.c at the same N "
+                                              "and image size (best), OpenMP"}
+    return out
 
 
 def resident_leg(e, L, torch, dist, world, rank, N, tree, with_sph, flavour, allgather_bytes, barrier, max_over_ranks, use_peer):
@@ -533,6 +602,11 @@ def run_engine(args):
     if not args.no_sph and world == 1:
         sph = sph_leg(e, L, torch, dev, stream)
 
+    # ---- vis_draw() replacement on the same state (single rank)
+    vis = None
+    if not args.no_vis and world == 1:
+        vis = vis_leg(e, L, torch, dev, stream, N, gather(0), pot, not args.no_cpu)
+
     # ---- device-resident leapfrog: whole sim_step()s with the state in HBM, through sfe_sim_run()
     resident = None
     if not args.no_resident:
@@ -607,6 +681,7 @@ def run_engine(args):
                      "unit": "particle-steps/s"},
         "pp": pp,
         "sph": sph,
+        "vis": vis,
         "resident": resident,
     }
     print(json.dumps(line))

@@ -112,6 +112,21 @@ int sfe_selftest_exact_math(uint64_t mismatches[3]);
  * reference's drawing.  idx >= N draws nothing, like the reference. */
 int sfe_bh_overlay(uint32_t idx, float theta, const float mvp[16], float* render_buffer, uint32_t sizex, uint32_t sizey);
 
+/* Replaces vis_draw() (visualization.h:40, visualization.c:253-739): mean radius (:274-307), model-
+ * view-projection matrix (:418-489), clear (:334-342), the particle splat - SPATIAL_SAMPLES Gaussian-jittered samples per
+ * particle added to the integer accumulation buffer (:503-683) - and the finishing pass into the float RGBA render buffer
+ * (:691-735).  The caller passes what visualization.c derives from config.h: mat_vm = matV * matM (row-major 4x4, :344-446),
+ * ortho_scale = (real)exp2(ORTHO_SCALE), autoscale = AUTOSCALING defined, samples = SPATIAL_SAMPLES, pixel_value_scale =
+ * 0.01 / SPATIAL_SAMPLES * exp2(EXPOSURE), tonemap = (0 < VIS_FILE_FORMAT).  Out: render_buffer[4*sizex*sizey] (host),
+ * atomic_buffer[4*sizex*sizey] (host, may be NULL: nothing but vis_draw() itself reads it), average_radius (the value the
+ * reference prints, may be NULL) and mvp[16] = the matMVP the reference leaves behind for the SOLVER_VIS overlay (may be
+ * NULL).  The accumulation buffer is bit-identical to the reference's (integer adds commute; logf / sinf / cosf follow the
+ * host C library bit for bit, csrc/sfe_libm.cuh); SHUTTER_SPEED (config.h:215, off) is not supported. */
+int sfe_vis_draw(const float* pos, const float* pot, uint32_t N, uint32_t step_number, const float mat_vm[16],
+                 float ortho_scale, int autoscale, uint32_t sizex, uint32_t sizey, uint32_t samples,
+                 double pixel_value_scale, int tonemap, int32_t* atomic_buffer, float* render_buffer,
+                 double* average_radius, float mvp[16]);
+
 /* Replaces solve_sph() (sph.h:6, sph.c:14-283): density (all pairs, no cutoff), EOS
  * P = (eos_k rho)^(1/eos_n + 1), pressure force added to acc (read-modify-write) for r^2 <= cutoff2. */
 int sfe_sph(const float* pos, const float* mas, const float* rad, float* rho, float* prs, float* acc,
@@ -120,6 +135,12 @@ int sfe_sph(const float* pos, const float* mas, const float* rad, float* rho, fl
 /* ---------------------------------------------------------------- device entry points */
 /* Particle records on the device are float4 {x, y, z, m} ("pm4"): the 16-byte unit that the
  * ncclAllGather of SURVEY 8(e) moves.  All pointers below are device pointers. */
+/* sfe_vis_draw() on device buffers: pm4 {x,y,z,*}[N], pot[N]; atomic_buffer / render_buffer 16-byte aligned device arrays of
+ * 4*sizex*sizey elements; info = device block of 16 floats (matMVP) followed by one double (average radius), 8-byte aligned. */
+int sfe_dev_vis_draw(const void* pm4, const float* pot, uint32_t N, uint32_t step_number, const float mat_vm[16],
+                     float ortho_scale, int autoscale, uint32_t sizex, uint32_t sizey, uint32_t samples,
+                     double pixel_value_scale, int tonemap, int32_t* atomic_buffer, float* render_buffer, void* info,
+                     void* stream);
 int sfe_dev_pack_pm4(const float* pos, const float* mas, void* pm4, uint32_t n, void* stream);
 int sfe_dev_pp(const void* pm4, uint32_t N, uint32_t i0, uint32_t ni, float* acc, float* pot,
                float grav_g, float eps2, void* stream);
@@ -199,6 +220,10 @@ int sfe_sim_run(const sfe_sim_params_t* p, uint32_t first_step, uint32_t nsteps,
 int sfe_sim_save_raw_async(const char* filename);
 int sfe_sim_save_wait(void);
 /* The root box of the last tree solve (what sim_solv() would have put into sim.tree.bounds). */
+/* vis_draw() of the resident state (single-rank mode): same as sfe_vis_draw() without the upload of pos / pot. */
+int sfe_sim_vis_draw(uint32_t step_number, const float mat_vm[16], float ortho_scale, int autoscale, uint32_t sizex,
+                     uint32_t sizey, uint32_t samples, double pixel_value_scale, int tonemap, int32_t* atomic_buffer,
+                     float* render_buffer, double* average_radius, float mvp[16]);
 int sfe_sim_last_box(float bounds[6]);
 int sfe_sim_release(void);
 

@@ -194,6 +194,7 @@ extern "C" int sfe_shutdown(void) {
     t.valid = false;
     for (DevBuf* b : bufs) b->release();
     c->ov_lines.release(); c->ov_rows.release();
+    c->vis_atomic.release(); c->vis_render.release(); c->vis_info.release(); c->vis_pm4.release();
     if (c->ov_info) cudaFreeHost(c->ov_info);
     if (c->bounce) cudaFreeHost(c->bounce);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);

@@ -157,6 +157,8 @@ struct Ctx {
     PeerState peer;
     // SOLVER_VIS overlay (sfe_overlay.cu): segment list, resident rows of the render buffer, mapped result block
     DevBuf ov_lines, ov_rows;
+    // vis_draw() replacement (sfe_vis.cu): integer accumulation buffer, float render buffer, {MVP, mean radius} block
+    DevBuf vis_atomic, vis_render, vis_info, vis_pm4;
     void* ov_info = nullptr; void* ov_info_dev = nullptr;
     sfe_timings_t timings;
     uint32_t launches = 0;
@@ -195,6 +197,8 @@ int launch_kick_drift(Ctx* c, float4* pm4, float* vel, const float* acc, uint32_
 int launch_root_box(Ctx* c, const float4* pm4, uint32_t N, uint32_t step_number, float bounds[6], cudaStream_t s);
 int launch_kick_energy(Ctx* c, const float4* pm4, float* vel, const float* acc, const float* pot, float* ken, float* pen,
                        uint32_t i0, uint32_t ni, float dt, int do_kick, double* tv_dev, cudaStream_t s);
+int launch_mean_radius(Ctx* c, const float4* pm4, uint32_t N, const double** rbar_dev, cudaStream_t s);
+int sim_resident_views(Ctx* c, const float4** pm4, const float** pot, uint32_t* N, const char* fn);
 void sim_release(Ctx* c);
 // peer exchange (sfe_peer.cu)
 PeerPtrs peer_ptrs(const Ctx* c);

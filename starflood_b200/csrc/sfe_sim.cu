@@ -284,6 +284,29 @@ int launch_root_box(Ctx* c, const float4* pm4, uint32_t N, uint32_t step_number,
     return SFE_SUCCESS;
 }
 
+// Mean |pos| left in device memory (visualization.c:274-307 computes the same double Kahan mean as simulation.c:245-277):
+// the root-box kernel without the host hand-over.  *rbar_dev stays valid until the next root box / mean radius.
+int launch_mean_radius(Ctx* c, const float4* pm4, uint32_t N, const double** rbar_dev, cudaStream_t s) {
+    const char* fn = "sfe_vis_draw";
+    if (N == 0) { set_error(fn, "N must be at least 1 (the reference divides by N, visualization.c:304)"); return SFE_FAILURE; }
+    if (sim_scratch(c, fn, s)) return SFE_FAILURE;
+    SimState& st = c->sim;
+    const uint32_t seq = ++st.box_seq ? st.box_seq : ++st.box_seq;
+    root_box_kernel<<<sim_grid(c, N), SIM_THREADS, 0, s>>>(pm4, N, 0u, st.partial.as<dd>(), st.ticket.as<uint32_t>(),
+                                                           st.box_dev.as<BoxOut>(), (volatile BoxOut*)st.box_host_dev, seq);
+    *rbar_dev = &st.box_dev.as<BoxOut>()->rbar;
+    return check_launch(fn);
+}
+
+// the resident state's particle records and potentials (single-rank mode), for the splat of sfe_sim_vis_draw()
+int sim_resident_views(Ctx* c, const float4** pm4, const float** pot, uint32_t* N, const char* fn) {
+    SimState& st = c->sim;
+    if (!st.loaded) { set_error(fn, "no resident state: call sfe_sim_upload() first"); return SFE_FAILURE; }
+    if (st.peer_mode) { set_error(fn, "not available in multi-rank mode (every rank holds the potentials of its slice only)"); return SFE_FAILURE; }
+    *pm4 = st.pm4.as<float4>(); *pot = st.pot.as<float>(); *N = st.N;
+    return SFE_SUCCESS;
+}
+
 int launch_kick_energy(Ctx* c, const float4* pm4, float* vel, const float* acc, const float* pot, float* ken, float* pen,
                        uint32_t i0, uint32_t ni, float dt, int do_kick, double* tv_dev, cudaStream_t s) {
     const char* fn = "sfe_dev_kick_energy";

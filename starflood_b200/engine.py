@@ -35,6 +35,12 @@ EOS_N = 1.000
 SPH_CUTOFF2 = 1.000 * 1.000
 
 TIMESTEP_SIZE = 1.0     # config.h:170
+# vis_draw() (config.h:108,203-212): tanh tonemap for VIS_FILE_FORMAT > 0, SHUTTER_SPEED off
+SPATIAL_SAMPLES = 128
+EXPOSURE = -1.000
+ORTHO_SCALE = -1.000
+AUTOSCALING = True
+VIS_FILE_FORMAT = 2
 
 WALK_EXACT = 0
 WALK_FAST = 1
@@ -89,6 +95,9 @@ SIGNATURES = {
     "sfe_selftest_exact_math": ([C.POINTER(C.c_uint64)], C.c_int),
     "sfe_sph": ([_P, _P, _P, _P, _P, _P, _u32, _f, _f, _f], C.c_int),
     "sfe_bh_overlay": ([_u32, _f, _P, _P, _u32, _u32], C.c_int),
+    "sfe_vis_draw": ([_P, _P, _u32, _u32, _P, _f, C.c_int, _u32, _u32, _u32, C.c_double, C.c_int, _P, _P, _P, _P], C.c_int),
+    "sfe_sim_vis_draw": ([_u32, _P, _f, C.c_int, _u32, _u32, _u32, C.c_double, C.c_int, _P, _P, _P, _P], C.c_int),
+    "sfe_dev_vis_draw": ([_P, _P, _u32, _u32, _P, _f, C.c_int, _u32, _u32, _u32, C.c_double, C.c_int, _P, _P, _P, _P], C.c_int),
     "sfe_dev_pack_pm4": ([_P, _P, _P, _u32, _P], C.c_int),
     "sfe_dev_pp": ([_P, _u32, _u32, _u32, _P, _P, _f, _f, _P], C.c_int),
     "sfe_dev_tree_build": ([_P, _P, _u32, C.c_int, _u32, _P], C.c_int),
@@ -291,6 +300,98 @@ def solve_gravity_part_tree_vis(sim, mvp, render_buffer, sizex, sizey, flavour=W
         return rc
     m = np.ascontiguousarray(mvp, np.float32)
     return lib().sfe_bh_overlay(idx, theta, _ptr(m), _ptr(render_buffer), sizex, sizey)
+
+
+class Vis:
+    """vis_t (visualization.h:19-28): the integer accumulation buffer and the float RGBA render buffer."""
+    def __init__(self):
+        self.sizex = self.sizey = 0
+        self.atomic_buffer = self.render_buffer = None
+        self.average_radius = float("nan")
+        self.matMVP = np.zeros(16, np.float32)     # visualization.c:251
+
+
+def vis_init(vis, sizex, sizey):
+    """visualization.h:31 / visualization.c:37-192 (host allocation only)."""
+    vis.sizex, vis.sizey = int(sizex), int(sizey)
+    vis.atomic_buffer = np.zeros(4 * vis.sizex * vis.sizey, np.int32)
+    vis.render_buffer = np.zeros(4 * vis.sizex * vis.sizey, np.float32)
+    return STARFLOOD_SUCCESS
+
+
+def vis_free(vis):
+    """visualization.h:34"""
+    vis.sizex = vis.sizey = 0
+    vis.atomic_buffer = vis.render_buffer = None
+    return STARFLOOD_SUCCESS
+
+
+_libm = None
+
+
+def _f32_libm(name, x):
+    """cosf / sinf of the host C library (numpy's float32 ufuncs are a different implementation)."""
+    global _libm
+    if _libm is None:
+        _libm = C.CDLL("libm.so.6")
+        for f in ("cosf", "sinf"):
+            getattr(_libm, f).argtypes = [C.c_float]; getattr(_libm, f).restype = C.c_float
+    return np.float32(getattr(_libm, name)(float(x)))
+
+
+def vis_model_view(step_number, dt=TIMESTEP_SIZE):
+    """matV * matM of vis_draw() (visualization.c:327,344-446): the model matrix is a slowly turning rotation, the view
+    matrix the identity.  Same fp32 operations in the same order as the reference's C."""
+    f = np.float32
+    TAU = f(6.2831853071795864769)
+    time = f(float(dt) * float(step_number))
+    alp = f(0.0); bet = TAU * f(0.1250); gam = TAU * f(0.0625)
+    alp = alp + TAU * f(1.000e-4) * time; bet = bet + TAU * f(1.000e-4) * time; gam = gam + TAU * f(1.000e-4) * time
+    ca, sa = _f32_libm("cosf", alp), _f32_libm("sinf", alp)
+    cb, sb = _f32_libm("cosf", bet), _f32_libm("sinf", bet)
+    cg, sg = _f32_libm("cosf", gam), _f32_libm("sinf", gam)
+    M = np.array([ca * cb, ca * sb * sg - sa * cg, ca * sb * cg + sa * sg, 0,
+                  sa * cb, sa * sb * sg + ca * cg, sa * sb * cg - ca * sg, 0,
+                  -sb, cb * sg, cb * cg, 0,
+                  0, 0, 0, 1], np.float32)
+    V = np.eye(4, dtype=np.float32).ravel()
+    VM = np.zeros(16, np.float32)
+    for i in range(4):
+        for j in range(4):
+            VM[4 * i + j] = (V[4 * i + 3] * M[12 + j]) + (V[4 * i + 2] * M[8 + j]) + (V[4 * i + 1] * M[4 + j]) + (V[4 * i] * M[j])
+    return VM
+
+
+def _vis_args():
+    scale = 0.01 / float(SPATIAL_SAMPLES)
+    if EXPOSURE is not None:
+        scale *= 2.0 ** EXPOSURE
+    ortho = np.float32(2.0 ** ORTHO_SCALE) if ORTHO_SCALE is not None else np.float32(1.0)
+    return ortho, 1 if AUTOSCALING else 0, SPATIAL_SAMPLES, scale, 1 if VIS_FILE_FORMAT > 0 else 0
+
+
+def vis_draw(vis, sim):
+    """visualization.h:40 / visualization.c:253-739: renders sim into vis.atomic_buffer / vis.render_buffer and leaves
+    matMVP behind like the reference does."""
+    vm = vis_model_view(sim.step_number)
+    ortho, auto, samples, scale, tonemap = _vis_args()
+    rbar = C.c_double()
+    rc = lib().sfe_vis_draw(_ptr(sim.pos), _ptr(sim.pot), sim.N, sim.step_number, _ptr(vm), ortho, auto, vis.sizex, vis.sizey,
+                            samples, scale, tonemap, _ptr(vis.atomic_buffer), _ptr(vis.render_buffer), C.addressof(rbar),
+                            _ptr(vis.matMVP))
+    vis.average_radius = rbar.value
+    return rc
+
+
+def sim_vis_draw(vis, step_number):
+    """vis_draw() of the HBM-resident state (sfe_sim_upload / sfe_sim_run): no particle upload."""
+    vm = vis_model_view(step_number)
+    ortho, auto, samples, scale, tonemap = _vis_args()
+    rbar = C.c_double()
+    rc = lib().sfe_sim_vis_draw(step_number, _ptr(vm), ortho, auto, vis.sizex, vis.sizey, samples, scale, tonemap,
+                                _ptr(vis.atomic_buffer), _ptr(vis.render_buffer), C.addressof(rbar), _ptr(vis.matMVP))
+    vis.average_radius = rbar.value
+    return rc
 
 
 def solve_sph(sim):

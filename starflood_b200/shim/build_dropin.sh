@@ -9,7 +9,8 @@
 #
 # Variant tree_vis keeps the reference's default ENABLE_VIS + SOLVER_VIS 3 (config.h:29,32): every step vis_draw()
 # renders the particles, sim_step() adds the tree walk's debug overlay of particle #3 (gravity.c:380-445,550-574; in the
-# drop-in: sfe_bh_overlay) and main.c saves the frame - as PFM (float RGB) here, so that frames compare bit for bit.
+# drop-in: sfe_bh_overlay) and main.c saves the frame - as PFM (float RGB) here, so that frames compare bit for bit.  In the
+# drop-in vis_draw() itself is vis_shim.c -> sfe_vis_draw (the particle splat with the shipped SPATIAL_SAMPLES 128).
 #
 # usage: build_dropin.sh <pp|tree|pp_sph|tree_vis> <N> <steps> [TREE_NODES_MAX]
 set -euo pipefail
@@ -38,14 +39,17 @@ case "$VARIANT" in
   pp)     sed -i -E 's|^#define ENABLE_TREE$|//#define ENABLE_TREE|' "$S/config.h" ;;
   tree)   ;;
   tree_vis) sed -i -E -e 's|^//#define ENABLE_VIS$|#define ENABLE_VIS|' -e 's|^//#define SOLVER_VIS 3$|#define SOLVER_VIS 3|' \
-                -e 's|^//#define VIS_FILENAME |#define VIS_FILENAME |' -e 's|^#define ENABLE_OFFLOAD_VIS$|//#define ENABLE_OFFLOAD_VIS|' \
-                -e 's|^#define SPATIAL_SAMPLES .*|#define SPATIAL_SAMPLES 4|' "$S/config.h" ;;
+                -e 's|^//#define VIS_FILENAME |#define VIS_FILENAME |' -e 's|^#define ENABLE_OFFLOAD_VIS$|//#define ENABLE_OFFLOAD_VIS|' "$S/config.h" ;;
   pp_sph) sed -i -E -e 's|^#define ENABLE_TREE$|//#define ENABLE_TREE|' -e 's|^//#define ENABLE_SPH$|#define ENABLE_SPH|' "$S/config.h" ;;
   *) echo "unknown variant $VARIANT" >&2; exit 1 ;;
 esac
 FLAGS="-fopenmp -O3 -march=x86-64-v3 -std=c99 -w"
 HOST="main.c simulation.c simulation_io.c initcond.c log.c grid.c visualization.c visualization_io.c"
 ( cd "$S" && $CC $FLAGS $HOST gravity.c tree.c sph.c -o "$OUT/starflood_${VARIANT}_ref" -lm -lpthread )
-( cd "$S" && $CC $FLAGS -I"$S" -I"$ROOT/include" -I"$HERE" $HOST "$HERE/gravity_shim.c" "$HERE/tree_shim.c" "$HERE/sph_shim.c" \
+# drop-in: visualization.c keeps vis_init() / vis_free() / the matrix globals, its vis_draw() is renamed out of the way and
+# vis_shim.c provides the one main.c calls (-> sfe_vis_draw)
+HOST_B200="main.c simulation.c simulation_io.c initcond.c log.c grid.c visualization_io.c"
+( cd "$S" && $CC $FLAGS -Dvis_draw=vis_draw_reference -c visualization.c -o visualization_novisdraw.o )
+( cd "$S" && $CC $FLAGS -I"$S" -I"$ROOT/include" -I"$HERE" $HOST_B200 visualization_novisdraw.o "$HERE/gravity_shim.c" "$HERE/tree_shim.c" "$HERE/sph_shim.c" "$HERE/vis_shim.c" \
     -o "$OUT/starflood_${VARIANT}_b200" -L"$ROOT/starflood_b200" -lsfengine -Wl,-rpath,'$ORIGIN/../..' -lm -lpthread )
 echo "built $OUT/starflood_${VARIANT}_ref and $OUT/starflood_${VARIANT}_b200 (N=$N, steps=$STEPS)"

@@ -13,6 +13,8 @@ Fixtures (little-endian, numpy .npz, compressed):
   bh_n4096.npz      root box of sim_solv(step 0), tree_build() node table (canonical numbering), BH acc, pot
   sph_n1024.npz     PP + solve_sph(): rad, rho, prs, acc (gravity + pressure), pot
   energy_pp_n512.npz  40 sim_step()s: per-step kinetic / potential totals recomputed from the ken / pen arrays
+  vis_n4096.npz     vis_init() + vis_draw() of the reference's visualization.c (variant vis) on the BH state at step 5,
+                    48 x 96 pixels (narrower than the projected ball): matMVP, integer accumulation buffer, render buffer
   pcg4d.npz         rng.h pcg4d on a few seeds (through initcond: first positions) - covered by pp_n1024
 """
 import os
@@ -56,6 +58,12 @@ def main():
         r.step(s)
         T.append(float(np.sum(r.ken.astype(np.float64)))); V.append(float(np.sum(r.pen.astype(np.float64))))
     np.savez_compressed(os.path.join(OUT, "energy_pp_n512.npz"), T=np.array(T), V=np.array(V), pos=r.pos, vel=r.vel)
+    # ---- vis_draw (visualization.c:253-739)
+    r = sfo.RefSim("vis", 4096); r.initcond(); r.solv(0)
+    mvp, ab, rb = r.vis_draw(5, 48, 96)
+    np.savez_compressed(os.path.join(OUT, "vis_n4096.npz"), pos=r.pos, pot=r.pot, step=5, sizex=48, sizey=96, mvp=mvp,
+                        atomic=ab, render=rb)
+    r.close()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")

@@ -121,3 +121,26 @@ def test_two_rank_gloo_slice_flow(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_device_libm_restatement_matches_host_libm():
+    """csrc/sfe_libm.cuh (the logf / sinf / cosf the splat kernel evaluates, glibc's algorithms in IEEE double operations)
+    against the host C library: tools/libm_probe.cpp compares bit patterns over every `stride`-th float of the ranges
+    vis_draw() can produce (stride 1 = exhaustive, 4.4e9 values, 0 mismatches, run by hand; a prime stride here)."""
+    exe = os.path.join(ROOT, "tools", "libm_probe")
+    src = os.path.join(ROOT, "tools", "libm_probe.cpp")
+    hdr = os.path.join(ROOT, "starflood_b200", "csrc", "sfe_libm.cuh")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fopenmp", src, "-o", exe])
+    import json
+    out = json.loads(subprocess.check_output([exe, "211"]).decode())
+    for f in ("logf", "cosf", "sinf"):
+        assert out[f]["checked"] > 10_000_000 and out[f]["mismatches"] == 0, out
+        assert out[f]["correctly_rounded_differs"] > 0      # why a correctly rounded routine would not do
+
+
+@pytest.mark.parametrize("step", [0, 5, 4000])
+def test_vis_model_view_matches_oracle(step):
+    """engine.vis_model_view() (host side of vis_draw(), visualization.c:344-446) equals the oracle's matrices."""
+    vm, mvp = sfo.vis_matrices(0.75, step)
+    assert np.array_equal(engine.vis_model_view(step), vm)

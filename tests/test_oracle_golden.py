@@ -125,3 +125,16 @@ def test_tie_rule_matters():
     rc, nodes, cnt = sfo.tree_build_insert(b, pos, mas, 512)
     canon, nc = sfo.tree_canonicalise(nodes[:cnt])
     assert canon[:nc].tobytes() == snodes[:scnt].tobytes()
+
+
+def test_vis_draw_bit_exact():
+    """vis_draw() (visualization.c:253-739): matMVP, the integer accumulation buffer and the render buffer of the
+    reference's own run (tests/golden/vis_n4096.npz; the image is narrower than the projected ball, so samples are
+    dropped at the border)."""
+    g = load("vis_n4096.npz")
+    sx, sy, step = int(g["sizex"]), int(g["sizey"]), int(g["step"])
+    rbar, mvp, ab, rb = sfo.vis_draw(np.ascontiguousarray(g["pos"]), np.ascontiguousarray(g["pot"]), step, sx, sy)
+    assert np.array_equal(mvp, g["mvp"])
+    assert np.array_equal(ab, g["atomic"])
+    assert np.array_equal(rb, g["render"])
+    assert 0 < int(ab[3::4].sum()) < 128 * len(g["pot"])

@@ -81,3 +81,20 @@ def test_overlay_restatement_equals_reference_drawing():
         ob = sfo.bh_overlay(nodes[:n], r.pos.copy(), r.mas.copy(), 3, M, np.full(sx * sy * 4, 0.25, np.float32), sx, sy)
         assert (rb != 0.25).sum() > 1000 and np.array_equal(rb, ob)
     r.close()
+
+
+@pytest.mark.skipif(not sfo.ref_available("vis"), reason="reference visualization library not built")
+@pytest.mark.parametrize("N,sx,sy,step", [(4096, 256, 256, 0), (20000, 320, 200, 7), (3000, 33, 17, 123), (9, 64, 64, 1),
+                                          (30000, 60, 240, 4000), (65536, 1080, 1080, 2)])
+def test_vis_draw_restatement_equals_reference(N, sx, sy, step):
+    """The oracle's vis_draw() (mean radius, matrices, splat, finishing pass) against the unmodified reference's
+    vis_init() + vis_draw() (visualization.c:37-739, oracle/_ref/libsfref_vis.so): matMVP, the integer accumulation
+    buffer and the float render buffer bit for bit - images wider, narrower and much smaller than the projected ball."""
+    r = sfo.RefSim("vis", N); r.initcond(); r.solv(0)
+    mvp, ab, rb = r.vis_draw(step, sx, sy)
+    rbar, mvp2, ab2, rb2 = sfo.vis_draw(r.pos.copy(), r.pot.copy(), step, sx, sy)
+    r.close()
+    assert np.array_equal(mvp, mvp2)
+    assert np.array_equal(ab, ab2)
+    assert np.array_equal(rb, rb2)
+    assert ab[3::4].sum() > 0
