@@ -84,19 +84,20 @@ SFE_LM_HD float logf_glibc_normal(float x) {
 }
 
 // ---------------------------------------------------------------------------- sinf / cosf
-SFE_LM_HD double sincos_poly(double x, double x2, bool flip, int n) {
+// the two polynomials of s_sincosf.h: sinf_poly(x, x2, p, n) evaluates the sine one for even n, the cosine one for odd n
+SFE_LM_HD double sin_poly(double x, double x2) {
+    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    const double x3 = SFE_LM_MUL(x, x2);
+    const double t1 = SFE_LM_FMA(x2, s3, s2);                   // s2 + x2 * s3
+    const double x7 = SFE_LM_MUL(x3, x2);
+    const double s = SFE_LM_FMA(x3, s1, x);                     // x + x3 * s1
+    return SFE_LM_FMA(x7, t1, s);                               // s + x7 * s1'
+}
+SFE_LM_HD double cos_poly(double x2, bool flip) {
     // __sincosf_table[flip]: the second entry negates the cosine coefficients
     const double sg = flip ? -1.0 : 1.0;
     const double c0 = sg * 0x1p0, c1 = sg * -0x1.ffffffd0c621cp-2, c2 = sg * 0x1.55553e1068f19p-5,
                  c3 = sg * -0x1.6c087e89a359dp-10, c4 = sg * 0x1.99343027bf8c3p-16;
-    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
-    if ((n & 1) == 0) {
-        const double x3 = SFE_LM_MUL(x, x2);
-        const double t1 = SFE_LM_FMA(x2, s3, s2);               // s2 + x2 * s3
-        const double x7 = SFE_LM_MUL(x3, x2);
-        const double s = SFE_LM_FMA(x3, s1, x);                 // x + x3 * s1
-        return SFE_LM_FMA(x7, t1, s);                           // s + x7 * s1'
-    }
     const double x4 = SFE_LM_MUL(x2, x2);
     const double q2 = SFE_LM_FMA(x2, c4, c3);                   // c3 + x2 * c4
     const double q1 = SFE_LM_FMA(x2, c1, c0);                   // c0 + x2 * c1
@@ -107,20 +108,26 @@ SFE_LM_HD double sincos_poly(double x, double x2, bool flip, int n) {
 
 SFE_LM_HD uint32_t abstop12(float x) { return (as_u32(x) >> 20) & 0x7ffu; }
 
-// want_cos = 0: sinf, 1: cosf.  Valid for |y| < 120 (the caller handles the rest).
-SFE_LM_HD float sincosf_glibc_fast(float y, int want_cos) {
+// sinf(y) and cosf(y) together, valid for |y| < 120 (the caller handles the rest).  glibc's sinf and cosf reduce the
+// argument the same way and then call sinf_poly with n and n ^ 1: the SAME two polynomial values, swapped by the quadrant.
+// Evaluating each once gives both results with the bits of the separate calls and without a data-dependent branch.
+SFE_LM_HD void sincosf_glibc_fast(float y, float* sn, float* cs) {
     const double HPI_INV = 0x1.45f306dc9c883p+23, HPI = 0x1.921fb54442d18p+0;
     double x = (double)y;
     if (abstop12(y) < 0x3f4u) {                                  // |y| < pi/4 (abstop12(0x1.921FB6p-1f))
+        if (abstop12(y) < 0x398u) { *sn = y; *cs = 1.0f; return; }   // |y| < 2^-12
         const double x2 = SFE_LM_MUL(x, x);
-        if (abstop12(y) < 0x398u) return want_cos ? 1.0f : y;    // |y| < 2^-12
-        return (float)sincos_poly(x, x2, false, want_cos);
+        *sn = (float)sin_poly(x, x2); *cs = (float)cos_poly(x2, false);
+        return;
     }
     const double r = SFE_LM_MUL(x, HPI_INV);
     const int n = ((int32_t)r + 0x800000) >> 24;
     x = SFE_LM_FMA(-(double)n, HPI, x);                          // x - n * hpi
     const double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;   // sign[n & 3] = {1, -1, -1, 1}
-    return (float)sincos_poly(SFE_LM_MUL(x, s), SFE_LM_MUL(x, x), (n & 2) != 0, n ^ want_cos);
+    const double x2 = SFE_LM_MUL(x, x);
+    const float a = (float)sin_poly(SFE_LM_MUL(x, s), x2), b = (float)cos_poly(x2, (n & 2) != 0);
+    *sn = (n & 1) ? b : a;                                       // sinf: sinf_poly(x * s, x * x, p, n)
+    *cs = (n & 1) ? a : b;                                       // cosf: sinf_poly(x * s, x * x, p, n ^ 1)
 }
 
 // ---------------------------------------------------------------------------- entry points with the fall-backs
@@ -151,15 +158,13 @@ SFE_LM_HD float logf_glibc(float x) {
     return logf_glibc_normal(x);
 }
 
-SFE_LM_HD float cosf_glibc(float y) {
-    if (abstop12(y) < 0x42fu) return sincosf_glibc_fast(y, 1);   // |y| < 120
-    // Fall-back (not bit-pinned): glibc reduces large arguments with a 192-bit 4/pi table; here the double-precision
-    // routine is rounded once.  Differs from glibc in ~1 % of such arguments by one ulp.
-    return (float)cos((double)y);
+// Fall-back for |y| >= 120 (not bit-pinned): glibc reduces large arguments with a 192-bit 4/pi table; here the
+// double-precision routine is rounded once, which differs from glibc in ~1 % of such arguments by one ulp.
+SFE_LM_HD void sincosf_glibc(float y, float* sn, float* cs) {
+    if (abstop12(y) < 0x42fu) { sincosf_glibc_fast(y, sn, cs); return; }   // |y| < 120
+    *sn = (float)sin((double)y); *cs = (float)cos((double)y);
 }
-SFE_LM_HD float sinf_glibc(float y) {
-    if (abstop12(y) < 0x42fu) return sincosf_glibc_fast(y, 0);
-    return (float)sin((double)y);
-}
+SFE_LM_HD float cosf_glibc(float y) { float s, c; sincosf_glibc(y, &s, &c); return c; }
+SFE_LM_HD float sinf_glibc(float y) { float s, c; sincosf_glibc(y, &s, &c); return s; }
 
 }  // namespace sfe_libm

@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(VIS_THREADS) vis_splat_kernel(const float4* __
                 // Box-Muller (visualization.c:583-586)
                 const float rad = __fsqrt_rn(__fmul_rn(-2.0f, sfe_libm::logf_glibc(r2)));
                 const float ang = __fmul_rn(TAUF, r3);
-                const float n0 = __fmul_rn(rad, sfe_libm::cosf_glibc(ang)), n1 = __fmul_rn(rad, sfe_libm::sinf_glibc(ang));
+                float sn, cs;
+                sfe_libm::sincosf_glibc(ang, &sn, &cs);          // cosf(ang), sinf(ang) of the host libm, evaluated together
+                const float n0 = __fmul_rn(rad, cs), n1 = __fmul_rn(rad, sn);
                 // coord = (int)(samp_offset + -0.5 + 0.5*sizey*p + 0.5*size)  (visualization.c:660-663), left to right
                 const float fx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(0.750f, n0), -0.5f), tx), ox);
                 const float fy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(0.750f, n1), -0.5f), ty), oy);
