@@ -177,15 +177,19 @@ __device__ __forceinline__ void tile_segmented_scan(const uint8_t* oct, const bo
 // per-slot byte staged in shared memory between the coalesced load phase and the thread-contiguous scan phase
 constexpr uint32_t SB_ACTIVE = 0x08u, SB_HEAD = 0x10u, SB_LAST = 0x20u;
 
-// Warp-parallel decoupled look-back of the segmented scan: lane l inspects tile (tile-1-l) of the current window;
-// the nearest tile that either already knows its inclusive prefix or starts the open range ends the search.
-__device__ __forceinline__ void rank_lookback(const uint32_t* __restrict__ desc_base, uint32_t tile, uint32_t carry[8]) {
-    const uint32_t lane = threadIdx.x & 31u;
+// Block-parallel decoupled look-back of the segmented scan: thread k inspects tile (tile-1-k) of the current window of
+// PT_THREADS tiles (warp w its 32 nearest-but-32w); the nearest tile that either already knows its inclusive prefix or
+// starts the open range ends the search.  A 2^20-slot level has 512 tiles, so two windows always suffice where a
+// one-warp look-back walked up to sixteen windows of 32 one after the other (the 26 us of the old rank_kernel).
+// Called by ALL threads of the CTA; every thread returns the same carry.
+__device__ __forceinline__ void rank_lookback(const uint32_t* __restrict__ desc_base, uint32_t tile, uint32_t carry[8],
+                                              uint32_t (*s_lb)[9] /* [PT_THREADS / 32][9] */) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 0; o < 8; o++) carry[o] = 0u;
     int base = (int)tile - 1;
     for (;;) {
-        const int j = base - (int)lane;
+        const int j = base - (int)threadIdx.x;
         const bool valid = j >= 0;
         const uint32_t* dj = desc_base + (size_t)(valid ? j : 0) * DESC_WORDS;
         uint32_t st;
@@ -206,10 +210,22 @@ __device__ __forceinline__ void rank_lookback(const uint32_t* __restrict__ desc_
         for (int o = 0; o < 8; o++) {
 #pragma unroll
             for (int sh = 16; sh >= 1; sh >>= 1) v[o] += __shfl_xor_sync(0xFFFFFFFFu, v[o], sh);
-            carry[o] += v[o];
         }
-        if (ballot) return;
-        base -= 32;
+        if (lane == 0u) {
+#pragma unroll
+            for (int o = 0; o < 8; o++) s_lb[warp][o] = v[o];
+            s_lb[warp][8] = ballot ? 1u : 0u;
+        }
+        __syncthreads();
+        bool done = false;
+        for (uint32_t w = 0; w < (uint32_t)(PT_THREADS / 32) && !done; w++) {    // nearest warp first
+#pragma unroll
+            for (int o = 0; o < 8; o++) carry[o] += s_lb[w][o];
+            done = s_lb[w][8] != 0u;
+        }
+        __syncthreads();                                                         // s_lb is reused by the next window
+        if (done) return;
+        base -= PT_THREADS;
     }
 }
 
@@ -217,6 +233,7 @@ __global__ void __launch_bounds__(PT_THREADS) rank_kernel(TreeDev t, int d) {
     __shared__ uint32_t sm[48];
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_carry[8];
+    __shared__ uint32_t s_lb[PT_THREADS / 32][9];
     __shared__ __align__(16) uint8_t s_byte[PT_TILE];
     __shared__ __align__(16) uint32_t s_rank[PT_TILE];
     if (level_idle(t, d)) return;
@@ -267,11 +284,11 @@ __global__ void __launch_bounds__(PT_THREADS) rank_kernel(TreeDev t, int d) {
         if (threadIdx.x == 8) desc[1] = ts.tile_has_head ? 1u : 0u;
         __threadfence();
         __syncthreads();
-        if (threadIdx.x < 32) {
+        {
             uint32_t carry[8];
-            if (tile > 0u) {
+            if (tile > 0u) {                                       // uniform across the CTA
                 if (threadIdx.x == 0) atomicExch(&desc[0], ST_AGG);
-                rank_lookback(desc_base, tile, carry);
+                rank_lookback(desc_base, tile, carry, s_lb);
             } else {
 #pragma unroll
                 for (int o = 0; o < 8; o++) carry[o] = 0u;
@@ -366,6 +383,7 @@ __global__ void root_kernel(TreeDev t, int depth_max) {
 __global__ void __launch_bounds__(CH_THREADS) children_kernel(TreeDev t, int d, int depth_max) {
     __shared__ uint32_t sm[33];
     __shared__ uint32_t s_tile, s_prefix;
+    __shared__ uint32_t s_cl[CH_THREADS / 32][2];
     if (level_idle(t, d)) {
         // nothing splits at level d: level d+1 does not exist
         if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -395,15 +413,17 @@ __global__ void __launch_bounds__(CH_THREADS) children_kernel(TreeDev t, int d, 
         }
         uint32_t tile_total;
         const uint32_t ex = block_excl_scan(ki, &tile_total, sm);
-        // warp-parallel decoupled look-back over the tiles of this level: status in the high word, value in the low
-        if (threadIdx.x < 32) {
-            const uint32_t lane = threadIdx.x;
+        // block-parallel decoupled look-back over the tiles of this level (status in the high word, value in the low):
+        // thread k inspects tile (tile-1-k); a deep level has more than a thousand tiles of CH_THREADS nodes, which a
+        // one-warp look-back walked in windows of 32 one after the other
+        {
+            const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
             uint32_t prefix = 0u;
-            if (tile > 0u) {
-                if (lane == 0) atomicExch(&cdesc[tile], ((unsigned long long)ST_AGG << 32) | tile_total);
+            if (tile > 0u) {                                       // uniform across the CTA
+                if (threadIdx.x == 0) atomicExch(&cdesc[tile], ((unsigned long long)ST_AGG << 32) | tile_total);
                 int jb = (int)tile - 1;
                 for (;;) {
-                    const int j = jb - (int)lane;
+                    const int j = jb - (int)threadIdx.x;
                     const bool valid = j >= 0;
                     unsigned long long v;
                     do { v = valid ? *reinterpret_cast<volatile unsigned long long*>(&cdesc[j]) : ((unsigned long long)ST_INCL << 32); }
@@ -413,12 +433,16 @@ __global__ void __launch_bounds__(CH_THREADS) children_kernel(TreeDev t, int d, 
                     uint32_t x = lane <= first ? (uint32_t)v : 0u;
 #pragma unroll
                     for (int sh = 16; sh >= 1; sh >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, sh);
-                    prefix += x;
-                    if (ballot) break;
-                    jb -= 32;
+                    if (lane == 0u) { s_cl[warp][0] = x; s_cl[warp][1] = ballot ? 1u : 0u; }
+                    __syncthreads();
+                    bool done = false;
+                    for (uint32_t w = 0; w < (uint32_t)(CH_THREADS / 32) && !done; w++) { prefix += s_cl[w][0]; done = s_cl[w][1] != 0u; }
+                    __syncthreads();
+                    if (done) break;
+                    jb -= CH_THREADS;
                 }
             }
-            if (lane == 0) {
+            if (threadIdx.x == 0) {
                 atomicExch(&cdesc[tile], ((unsigned long long)ST_INCL << 32) | (prefix + tile_total));
                 s_prefix = prefix;
                 if (tile == ntiles - 1u) open_level(t, d + 1, prefix + tile_total, depth_max);   // level d+1 has this many internal nodes
