@@ -632,17 +632,28 @@ def run_engine(args):
     walk_bytes = (32.0 * V_C2 + 32.0) * ni            # 32 B per node visit + 32 B particle I/O
     step_bytes = (32.0 * V_C2 + 32.0 + 16.0 + 24.0 * 8 + 32.0 * 0.382) * N
     achieved = walk_bytes / (walk_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, winst = None, None
     prof = os.path.join(ROOT, "profiles", "walk_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get(args.flavour, {}).get("dram_bytes_per_launch")
+            rec = json.load(open(prof)).get(args.flavour, {})
+            traffic = rec.get("dram_bytes_per_launch")
+            winst = rec.get("warp_instructions_per_launch")
         except Exception:
             traffic = None
     roofline = {"kernel": "walk_kernel (sfe_dev_bh)", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                 "frac": achieved / hbm, "traffic": traffic, "peak_source": hbm_src,
                 "algorithmic_bytes_per_launch": walk_bytes, "launch_ms": walk_ms,
                 "model": "32 B x V(=%.1f node visits/particle, oracle-counted) + 32 B particle I/O, x %d targets" % (V_C2, ni),
+                # the bound the walk actually runs into (DRAM traffic is 0.3 % of the algorithmic bytes: the node table is
+                # L1/L2 resident): warp instructions of one full-N launch (ncu capture under profiles/) per second against
+                # 4 issue slots per SM per clock
+                "issue": ({"warp_instructions_per_launch": winst * (ni / float(N)),
+                           "achieved": winst * (ni / float(N)) / (walk_ms * 1e-3),
+                           "peak": 4.0 * e.device_info()["sm_count"] * e.device_info()["clock_khz"] * 1e3,
+                           "unit": "warp-instructions/s",
+                           "frac": winst * (ni / float(N)) / (walk_ms * 1e-3) / (4.0 * e.device_info()["sm_count"] * e.device_info()["clock_khz"] * 1e3)}
+                          if winst and N == N_DEFAULT else None),
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
                                "frac": step_bytes / (ms_step * 1e-3) / 1e9 / hbm,
                                "model": "SURVEY 8(d) B = 32 V + 32 + B_build = 16710 B per particle-step"}}
