@@ -35,6 +35,29 @@
 
 namespace sfe_libm {
 
+// The double constants of the three routines.  On the device they are read as constant-bank operands of DFMA / DMUL
+// (a 64-bit literal costs two UMOV instructions per use instead); the host build uses the literals directly.
+#define SFE_LM_LN2     0x1.62e42fefa39efp-1
+#define SFE_LM_A0      -0x1.00ea348b88334p-2
+#define SFE_LM_A1      0x1.5575b0be00b6ap-2
+#define SFE_LM_A2      -0x1.ffffef20a4123p-2
+#define SFE_LM_S1      -0x1.555545995a603p-3
+#define SFE_LM_S2      0x1.1107605230bc4p-7
+#define SFE_LM_S3      -0x1.994eb3774cf24p-13
+#define SFE_LM_C1      -0x1.ffffffd0c621cp-2
+#define SFE_LM_C2      0x1.55553e1068f19p-5
+#define SFE_LM_C3      -0x1.6c087e89a359dp-10
+#define SFE_LM_C4      0x1.99343027bf8c3p-16
+#define SFE_LM_HPI_INV 0x1.45f306dc9c883p+23
+#define SFE_LM_HPI     0x1.921fb54442d18p+0
+#if defined(__CUDACC__)
+static __constant__ double KTAB[13] = {SFE_LM_LN2, SFE_LM_A0, SFE_LM_A1, SFE_LM_A2, SFE_LM_S1, SFE_LM_S2, SFE_LM_S3,
+                                       SFE_LM_C1, SFE_LM_C2, SFE_LM_C3, SFE_LM_C4, SFE_LM_HPI_INV, SFE_LM_HPI};
+#define SFE_LM_K(i, v) KTAB[i]
+#else
+#define SFE_LM_K(i, v) (v)
+#endif
+
 SFE_LM_HD uint32_t as_u32(float x) {
 #if defined(__CUDACC__)
     return __float_as_uint(x);
@@ -64,8 +87,8 @@ SFE_LM_TABLE double LOGF_TAB[32] = {
 
 // Valid for positive normal x (the caller handles the rest).
 SFE_LM_HD float logf_glibc_normal(float x) {
-    const double LN2 = 0x1.62e42fefa39efp-1;
-    const double A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2;
+    const double LN2 = SFE_LM_K(0, SFE_LM_LN2);
+    const double A0 = SFE_LM_K(1, SFE_LM_A0), A1 = SFE_LM_K(2, SFE_LM_A1), A2 = SFE_LM_K(3, SFE_LM_A2);
     const uint32_t ix = as_u32(x);
     if (ix == 0x3f800000u) return 0.0f;
     const uint32_t tmp = ix - 0x3f330000u;
@@ -83,21 +106,40 @@ SFE_LM_HD float logf_glibc_normal(float x) {
     return (float)y;
 }
 
+// logf for normal x below 1 (what a uniform random number in (0, 1) is): the same evaluation without the x == 1 test
+SFE_LM_HD float logf_glibc_below_one(float x) {
+    const double LN2 = SFE_LM_K(0, SFE_LM_LN2);
+    const double A0 = SFE_LM_K(1, SFE_LM_A0), A1 = SFE_LM_K(2, SFE_LM_A1), A2 = SFE_LM_K(3, SFE_LM_A2);
+    const uint32_t ix = as_u32(x);
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> 19) & 15u);
+    const int k = (int32_t)tmp >> 23;
+    const uint32_t iz = ix - (tmp & 0xff800000u);
+    const double z = (double)as_f32(iz);
+    const double r = SFE_LM_FMA(z, LOGF_TAB[2 * i], -1.0);
+    const double y0 = SFE_LM_FMA((double)k, LN2, LOGF_TAB[2 * i + 1]);
+    const double r2 = SFE_LM_MUL(r, r);
+    double y = SFE_LM_FMA(A1, r, A2);
+    y = SFE_LM_FMA(A0, r2, y);
+    y = SFE_LM_FMA(y, r2, SFE_LM_ADD(y0, r));
+    return (float)y;
+}
+
 // ---------------------------------------------------------------------------- sinf / cosf
 // the two polynomials of s_sincosf.h: sinf_poly(x, x2, p, n) evaluates the sine one for even n, the cosine one for odd n
 SFE_LM_HD double sin_poly(double x, double x2) {
-    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    const double s1 = SFE_LM_K(4, SFE_LM_S1), s2 = SFE_LM_K(5, SFE_LM_S2), s3 = SFE_LM_K(6, SFE_LM_S3);
     const double x3 = SFE_LM_MUL(x, x2);
     const double t1 = SFE_LM_FMA(x2, s3, s2);                   // s2 + x2 * s3
     const double x7 = SFE_LM_MUL(x3, x2);
     const double s = SFE_LM_FMA(x3, s1, x);                     // x + x3 * s1
     return SFE_LM_FMA(x7, t1, s);                               // s + x7 * s1'
 }
-SFE_LM_HD double cos_poly(double x2, bool flip) {
-    // __sincosf_table[flip]: the second entry negates the cosine coefficients
-    const double sg = flip ? -1.0 : 1.0;
-    const double c0 = sg * 0x1p0, c1 = sg * -0x1.ffffffd0c621cp-2, c2 = sg * 0x1.55553e1068f19p-5,
-                 c3 = sg * -0x1.6c087e89a359dp-10, c4 = sg * 0x1.99343027bf8c3p-16;
+SFE_LM_HD double cos_poly(double x2) {
+    // __sincosf_table[0]; table[1] (used when n & 2) holds the same coefficients NEGATED, and since IEEE rounding is
+    // symmetric in sign every intermediate of that evaluation is the exact negation of this one: the caller negates
+    const double c0 = 0x1p0, c1 = SFE_LM_K(7, SFE_LM_C1), c2 = SFE_LM_K(8, SFE_LM_C2),
+                 c3 = SFE_LM_K(9, SFE_LM_C3), c4 = SFE_LM_K(10, SFE_LM_C4);
     const double x4 = SFE_LM_MUL(x2, x2);
     const double q2 = SFE_LM_FMA(x2, c4, c3);                   // c3 + x2 * c4
     const double q1 = SFE_LM_FMA(x2, c1, c0);                   // c0 + x2 * c1
@@ -112,20 +154,24 @@ SFE_LM_HD uint32_t abstop12(float x) { return (as_u32(x) >> 20) & 0x7ffu; }
 // argument the same way and then call sinf_poly with n and n ^ 1: the SAME two polynomial values, swapped by the quadrant.
 // Evaluating each once gives both results with the bits of the separate calls and without a data-dependent branch.
 SFE_LM_HD void sincosf_glibc_fast(float y, float* sn, float* cs) {
-    const double HPI_INV = 0x1.45f306dc9c883p+23, HPI = 0x1.921fb54442d18p+0;
+    const double HPI_INV = SFE_LM_K(11, SFE_LM_HPI_INV), HPI = SFE_LM_K(12, SFE_LM_HPI);
     double x = (double)y;
     if (abstop12(y) < 0x3f4u) {                                  // |y| < pi/4 (abstop12(0x1.921FB6p-1f))
         if (abstop12(y) < 0x398u) { *sn = y; *cs = 1.0f; return; }   // |y| < 2^-12
         const double x2 = SFE_LM_MUL(x, x);
-        *sn = (float)sin_poly(x, x2); *cs = (float)cos_poly(x2, false);
+        *sn = (float)sin_poly(x, x2); *cs = (float)cos_poly(x2);
         return;
     }
     const double r = SFE_LM_MUL(x, HPI_INV);
     const int n = ((int32_t)r + 0x800000) >> 24;
     x = SFE_LM_FMA(-(double)n, HPI, x);                          // x - n * hpi
-    const double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;   // sign[n & 3] = {1, -1, -1, 1}
+    // glibc evaluates sinf_poly(x * sign[n & 3], x * x, &table[(n >> 1) & 1], .) with sign = {1, -1, -1, 1}: the sine
+    // polynomial is odd in its first argument and the cosine one linear in the table's sign, both exactly (symmetric
+    // rounding), so the signs are applied to the results instead
     const double x2 = SFE_LM_MUL(x, x);
-    const float a = (float)sin_poly(SFE_LM_MUL(x, s), x2), b = (float)cos_poly(x2, (n & 2) != 0);
+    const float a0 = (float)sin_poly(x, x2), b0 = (float)cos_poly(x2);
+    const float a = (((n + 1) & 2) != 0) ? -a0 : a0;             // sign[n & 3] < 0 for n & 3 in {1, 2}
+    const float b = ((n & 2) != 0) ? -b0 : b0;
     *sn = (n & 1) ? b : a;                                       // sinf: sinf_poly(x * s, x * x, p, n)
     *cs = (n & 1) ? a : b;                                       // cosf: sinf_poly(x * s, x * x, p, n ^ 1)
 }
@@ -144,8 +190,8 @@ SFE_LM_HD float logf_glibc(float x) {
         const int i = (int)((tmp >> 19) & 15u);
         const int k = (int32_t)tmp >> 23;
         const uint32_t iz = jx - (tmp & 0xff800000u);
-        const double LN2 = 0x1.62e42fefa39efp-1;
-        const double A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2;
+        const double LN2 = SFE_LM_K(0, SFE_LM_LN2);
+        const double A0 = SFE_LM_K(1, SFE_LM_A0), A1 = SFE_LM_K(2, SFE_LM_A1), A2 = SFE_LM_K(3, SFE_LM_A2);
         const double z = (double)as_f32(iz);
         const double r = SFE_LM_FMA(z, LOGF_TAB[2 * i], -1.0);
         const double y0 = SFE_LM_FMA((double)k, LN2, LOGF_TAB[2 * i + 1]);

@@ -106,21 +106,25 @@ __global__ void __launch_bounds__(VIS_THREADS) vis_splat_kernel(const float4* __
         for (uint32_t s0 = 0; s0 < samples; s0 += 32u) {
             const uint32_t samp = s0 + lane;
             if (samp < samples) {
+                bool continue_sample = true;
                 uint32_t h[4] = {0xB79ABC95u + samp, 0xE0DA3F84u + idx, 0xAB75F07Bu + step_number, 0xCF52CA01u};
                 pcg4d_vis(h);
                 const float INV = 2.3283062977608182109179324470460414886474609375e-10f;   // (real)INV_PCG32_MAX
                 const float r2 = __fmul_rn(INV, (float)h[2]), r3 = __fmul_rn(INV, (float)h[3]);
-                // Box-Muller (visualization.c:583-586)
-                const float rad = __fsqrt_rn(__fmul_rn(-2.0f, sfe_libm::logf_glibc(r2)));
+                // Box-Muller (visualization.c:583-586).  r2 = 0 gives logf = -inf, an infinite radius and a coordinate that
+                // is +-inf or NaN: the reference drops such a sample at the bounds test, here it is dropped at once; any
+                // other r2 is a normal float below 1 and ang lies in [0, tau], the ranges the branch-light variants cover
+                if (r2 == 0.0f) continue_sample = false;
+                const float rad = __fsqrt_rn(__fmul_rn(-2.0f, sfe_libm::logf_glibc_below_one(continue_sample ? r2 : 0.5f)));
                 const float ang = __fmul_rn(TAUF, r3);
                 float sn, cs;
-                sfe_libm::sincosf_glibc(ang, &sn, &cs);          // cosf(ang), sinf(ang) of the host libm, evaluated together
+                sfe_libm::sincosf_glibc_fast(ang, &sn, &cs);     // cosf(ang), sinf(ang) of the host libm, evaluated together
                 const float n0 = __fmul_rn(rad, cs), n1 = __fmul_rn(rad, sn);
                 // coord = (int)(samp_offset + -0.5 + 0.5*sizey*p + 0.5*size)  (visualization.c:660-663), left to right
                 const float fx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(0.750f, n0), -0.5f), tx), ox);
                 const float fy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(0.750f, n1), -0.5f), ty), oy);
                 // (int) of NaN / out-of-range is INT_MIN on x86-64 and fails the bounds test
-                if (fx > -2147483648.0f && fx < 2147483648.0f && fy > -2147483648.0f && fy < 2147483648.0f) {
+                if (continue_sample && fx > -2147483648.0f && fx < 2147483648.0f && fy > -2147483648.0f && fy < 2147483648.0f) {
                     const int cx = __float2int_rz(fx), cy = __float2int_rz(fy);
                     if (0 <= cx && cx < (int)sizex && 0 <= cy && cy < (int)sizey) {
                         const uint32_t wx = (uint32_t)(cx - wx0), wy = (uint32_t)(cy - wy0);
