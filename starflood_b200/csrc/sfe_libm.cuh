@@ -156,12 +156,11 @@ SFE_LM_HD uint32_t abstop12(float x) { return (as_u32(x) >> 20) & 0x7ffu; }
 SFE_LM_HD void sincosf_glibc_fast(float y, float* sn, float* cs) {
     const double HPI_INV = SFE_LM_K(11, SFE_LM_HPI_INV), HPI = SFE_LM_K(12, SFE_LM_HPI);
     double x = (double)y;
-    if (abstop12(y) < 0x3f4u) {                                  // |y| < pi/4 (abstop12(0x1.921FB6p-1f))
-        if (abstop12(y) < 0x398u) { *sn = y; *cs = 1.0f; return; }   // |y| < 2^-12
-        const double x2 = SFE_LM_MUL(x, x);
-        *sn = (float)sin_poly(x, x2); *cs = (float)cos_poly(x2);
-        return;
-    }
+    // glibc branches three ways: |y| < 2^-12 returns {y, 1}, |y| < pi/4 evaluates the polynomials on y itself, the rest
+    // reduces first.  The reduction of a |y| < pi/4 finds n = 0 and leaves x untouched (fma(-0, hpi, x) = x), and for
+    // |y| < 2^-12 the polynomials round to y and 1 in single precision - except that -0 would come out as +0 - so only
+    // that (rare) range keeps its early return and one path covers the rest with the same bits (tools/libm_probe.cpp).
+    if (abstop12(y) < 0x398u) { *sn = y; *cs = 1.0f; return; }
     const double r = SFE_LM_MUL(x, HPI_INV);
     const int n = ((int32_t)r + 0x800000) >> 24;
     x = SFE_LM_FMA(-(double)n, HPI, x);                          // x - n * hpi
