@@ -22,11 +22,15 @@
 // is the 16 bytes per particle read plus the atomics.
 #include "sfe_internal.cuh"
 #include "sfe_libm.cuh"
+#include <stdlib.h>
 
 namespace sfe {
 
 constexpr int VIS_THREADS = 256;
 constexpr int VIS_WARPS = VIS_THREADS / 32;
+#ifndef SFE_VIS_MINB
+#define SFE_VIS_MINB 5                           // resident CTAs per SM the splat kernel is compiled for (46 registers)
+#endif
 constexpr int VIS_WIN = 8;                       // window edge in pixels (sigma = 0.75 px: +-4 px is 5.3 sigma)
 
 struct VisInfo { float mvp[16]; double rbar; };  // device block, copied back to the host by the entry points
@@ -66,7 +70,7 @@ __device__ __forceinline__ void splat_add(int32_t* __restrict__ ab, uint32_t pix
     atomicAdd(q + 0, n * c0); atomicAdd(q + 1, n * c1); atomicAdd(q + 2, n * c2); atomicAdd(q + 3, n);
 }
 
-__global__ void __launch_bounds__(VIS_THREADS) vis_splat_kernel(const float4* __restrict__ pm4, const float* __restrict__ pot,
+__global__ void __launch_bounds__(VIS_THREADS, SFE_VIS_MINB) vis_splat_kernel(const float4* __restrict__ pm4, const float* __restrict__ pot,
                                                                 uint32_t N, uint32_t step_number,
                                                                 const VisInfo* __restrict__ info, uint32_t sizex, uint32_t sizey,
                                                                 uint32_t samples, int32_t* __restrict__ ab) {
@@ -164,6 +168,12 @@ __global__ void vis_pack_kernel(const float* __restrict__ pos, float4* __restric
     if (i < n) pm4[i] = make_float4(pos[3u * i], pos[3u * i + 1u], pos[3u * i + 2u], 0.f);
 }
 
+static uint32_t vis_ctas_per_sm() {      // grid size of the splat in CTAs per SM; SFE_VIS_CTAS_PER_SM overrides (tuning knob)
+    static uint32_t v = 0;
+    if (!v) { const char* e = getenv("SFE_VIS_CTAS_PER_SM"); v = e && atoi(e) > 0 ? (uint32_t)atoi(e) : 24u; }
+    return v;
+}
+
 // Enqueue the whole frame on stream s: mean radius -> MVP -> clear -> splat -> finish.  ab / rb / info are device buffers.
 static int launch_vis(Ctx* c, const char* fn, const float4* pm4, const float* pot, uint32_t N, uint32_t step_number,
                       const float mat_vm[16], float ortho_scale, int autoscale, uint32_t sizex, uint32_t sizey,
@@ -176,7 +186,7 @@ static int launch_vis(Ctx* c, const char* fn, const float4* pm4, const float* po
     if (check_launch(fn)) return SFE_FAILURE;
     const size_t npix = (size_t)sizex * sizey;
     SFE_CUDA(fn, cudaMemsetAsync(ab, 0, npix * 16, s));                                    // visualization.c:334-342
-    const uint32_t want = (N + VIS_WARPS - 1) / VIS_WARPS, cap = (uint32_t)c->sm_count * 8u;   // 8 CTAs of 256 threads per SM
+    const uint32_t want = (N + VIS_WARPS - 1) / VIS_WARPS, cap = (uint32_t)c->sm_count * vis_ctas_per_sm();
     vis_splat_kernel<<<want < cap ? (want ? want : 1u) : cap, VIS_THREADS, 0, s>>>(pm4, pot, N, step_number, info, sizex, sizey,
                                                                                  samples, ab);
     if (check_launch(fn)) return SFE_FAILURE;
