@@ -178,7 +178,7 @@ extern "C" int sfe_shutdown(void) {
     DevBuf* bufs[] = {&c->d_pos, &c->d_mas, &c->d_pm4, &c->d_acc, &c->d_pot, &c->d_rad, &c->d_rho, &c->d_prs,
                       &c->pp_src, &c->pp_partial, &c->pp_flag, &c->sph_src, &c->sph_partial,
                       &c->sph_cells.desc, &c->sph_cells.count, &c->sph_cells.start, &c->sph_cells.key[0], &c->sph_cells.key[1],
-                      &c->sph_cells.val[0], &c->sph_cells.val[1], &c->sph_cells.hist, &c->sph_cells.rec, &c->sph_cells.tlist,
+                      &c->sph_cells.val[0], &c->sph_cells.val[1], &c->sph_cells.hist, &c->sph_cells.rec, &c->sph_cells.tlist, &c->sph_cells.part, &c->sph_cells.arrive,
                       &t.nodes, &t.seg, &t.next, &t.child_base, &t.counts, &t.keys, &t.perm_out, &t.slot_node[0],
                       &t.slot_node[1], &t.oct, &t.rank, &t.nmid, &t.lookback, &t.xl_sum, &t.xl_map, &t.scan_tmp, &t.slice_count, &t.root_gate, &t.meta, &t.rec0, &t.rec1, &t.rec2};
     for (DevBuf& b : t.perm) b.release();

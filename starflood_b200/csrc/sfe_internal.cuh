@@ -94,6 +94,7 @@ struct CellGrid {                 // device-resident descriptor, written by cl_g
 };
 struct SphCells {
     DevBuf desc, count, start, key[2], val[2], hist, rec, tlist;
+    DevBuf part, arrive;          // j-split of the pair pass: partial sums of both halves of a group, arrival counters
     bool maybe = false;           // host-side: the cell kernels were enqueued for the current snapshot
 };
 
