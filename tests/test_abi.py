@@ -82,6 +82,10 @@ def test_new_entry_points_fail_loudly_without_gpu(tmp_path):
     assert L.sfe_dev_bh_peer(None, 32, 0, 0, 1.0, 1e-6, 0.5, 0, None) == engine.STARFLOOD_FAILURE
     rb = np.zeros(64, np.float32); m = np.eye(4, dtype=np.float32)
     assert L.sfe_bh_overlay(3, 0.5, m.ctypes.data, rb.ctypes.data, 4, 4) == engine.STARFLOOD_FAILURE and not rb.any()
+    vis = engine.Vis(); engine.vis_init(vis, 8, 8)
+    assert engine.vis_draw(vis, sim) == engine.STARFLOOD_FAILURE and "no CUDA device" in engine.last_error()
+    assert engine.sim_vis_draw(vis, 0) == engine.STARFLOOD_FAILURE
+    assert not vis.atomic_buffer.any() and not vis.render_buffer.any()
     assert L.sfe_peer_window() is None
     assert L.sfe_sim_peer_bytes(1000, 13) == 48 * 1024          # pure arithmetic, no device involved
 
