@@ -993,6 +993,7 @@ static bool trace_enabled() {
 }
 
 static cudaEvent_t g_trace_ev[2 * (SFE_MAX_LEVELS + 3)];
+static cudaEvent_t g_trace_k[2 * (SFE_MAX_LEVELS + 3)];   // SFE_TRACE: after rank_kernel / children_kernel of every level
 
 static uint32_t xl_min_members() {   // SFE_XL_MIN lowers the threshold so that small test trees exercise the chunked fold
     static uint32_t v = 0;
@@ -1086,6 +1087,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
             SFE_CUDA(fn, cudaEventCreateWithFlags(&t.ev_perm[k], trace_enabled() ? cudaEventDefault : cudaEventDisableTiming));
         for (auto& ev : t.ev_side) SFE_CUDA(fn, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         if (trace_enabled()) for (auto& ev : g_trace_ev) SFE_CUDA(fn, cudaEventCreate(&ev));
+        if (trace_enabled()) for (auto& ev : g_trace_k) SFE_CUDA(fn, cudaEventCreate(&ev));
         t.ev_init = true;
     }
     t.build_id++;
@@ -1157,8 +1159,10 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         }
         rank_kernel<<<pgrid, PT_THREADS, 0, s>>>(dv, d);
         if (check_launch(fn)) return SFE_FAILURE;
+        if (trace_enabled()) cudaEventRecord(g_trace_k[2 * d], s);
         children_kernel<<<cgrid, CH_THREADS, 0, s>>>(dv, d, depth_max);
         if (check_launch(fn)) return SFE_FAILURE;
+        if (trace_enabled()) cudaEventRecord(g_trace_k[2 * d + 1], s);
         scatter_kernel<<<sgrid, 256, 0, s>>>(dv, d);
         if (check_launch(fn)) return SFE_FAILURE;
         SFE_CUDA(fn, cudaEventRecord(t.ev_perm[d + 1], s));
@@ -1169,7 +1173,11 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         for (int d = 0; d < levels_run; d++) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, t.ev_perm[d], t.ev_perm[d + 1]);
-            fprintf(stderr, "[sfe trace] level %2d: device %8.1f us   host enqueue at %8.1f us (+%.1f)\n", d, ms * 1e3, host_us[d], host_us[d + 1] - host_us[d]);
+            float r = 0.f, ch = 0.f, sc = 0.f;
+            cudaEventElapsedTime(&r, t.ev_perm[d], g_trace_k[2 * d]);
+            cudaEventElapsedTime(&ch, g_trace_k[2 * d], g_trace_k[2 * d + 1]);
+            cudaEventElapsedTime(&sc, g_trace_k[2 * d + 1], t.ev_perm[d + 1]);
+            fprintf(stderr, "[sfe trace] level %2d: device %8.1f us (rank %.1f children %.1f scatter %.1f)   host enqueue at %8.1f us (+%.1f)\n", d, ms * 1e3, r * 1e3, ch * 1e3, sc * 1e3, host_us[d], host_us[d + 1] - host_us[d]);
         }
     }
     // join the side streams, then build the walk records
