@@ -90,14 +90,6 @@ constexpr uint32_t ST_NONE = 0u, ST_AGG = 1u, ST_INCL = 2u;
 constexpr int CH_THREADS = 256;
 constexpr int XL_DEPTH_MAX = 6;          // deeper levels never use the chunked exact fold (their long nodes go through moments_long)
 
-struct Cnt8 {                // eight 16-bit counters (a tile holds 2048 slots)
-    uint32_t w[4];
-    __device__ __forceinline__ void zero() { w[0] = w[1] = w[2] = w[3] = 0u; }
-    __device__ __forceinline__ void add(const Cnt8& o) { w[0] += o.w[0]; w[1] += o.w[1]; w[2] += o.w[2]; w[3] += o.w[3]; }
-    __device__ __forceinline__ void inc(uint32_t o) { w[o >> 1] += 1u << ((o & 1u) * 16u); }
-    __device__ __forceinline__ uint32_t get(uint32_t o) const { return (w[o >> 1] >> ((o & 1u) * 16u)) & 0xFFFFu; }
-};
-
 // Octant of a member with the reference's tie rule; mid = 0.5f*(lo+hi) (tree.c:159-163) comes from nmid[].
 __device__ __forceinline__ uint32_t pick_octant(float4 mid, float4 p, bool resident) {
     if (resident) return (mid.x < p.x ? 1u : 0u) + (mid.y < p.y ? 2u : 0u) + (mid.z < p.z ? 4u : 0u);     // tree.c:244-247
@@ -109,69 +101,6 @@ __device__ __forceinline__ bool level_idle(const TreeDev& t, int d) {   // no in
 }
 
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
-
-// Tile-local segmented scan.  On return, for each of the thread's PT_ITEMS consecutive slots: `before` = counters
-// of the open range at the thread's first slot counted from the last head inside the tile (or from the tile
-// start), `head_before` tells whether such a head exists inside the tile; tile_trailing / tile_has_head are the
-// tile's aggregate (same value in every thread).
-struct TileScan {
-    Cnt8 before; bool head_before;
-    Cnt8 tile_trailing; bool tile_has_head;
-};
-
-__device__ __forceinline__ void tile_segmented_scan(const uint8_t* oct, const bool* head, TileScan* out,
-                                                    uint32_t* sm /* 8 warps * 5 words + 8 */) {
-    // thread-local
-    Cnt8 v; v.zero(); bool f = false;
-#pragma unroll
-    for (int k = 0; k < PT_ITEMS; k++) {
-        if (head[k]) { v.zero(); f = true; }
-        if (oct[k] != 0xFFu) v.inc(oct[k]);
-    }
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // warp inclusive segmented scan of (f, v)
-    Cnt8 iv = v; bool fi = f;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        Cnt8 pv;
-#pragma unroll
-        for (int q = 0; q < 4; q++) pv.w[q] = __shfl_up_sync(0xFFFFFFFFu, iv.w[q], o);
-        const bool pf = __shfl_up_sync(0xFFFFFFFFu, (int)fi, o) != 0;
-        if (lane >= (uint32_t)o) { if (!fi) iv.add(pv); fi = fi || pf; }
-    }
-    // exclusive within warp
-    Cnt8 ev; bool ef;
-#pragma unroll
-    for (int q = 0; q < 4; q++) ev.w[q] = __shfl_up_sync(0xFFFFFFFFu, iv.w[q], 1);
-    ef = __shfl_up_sync(0xFFFFFFFFu, (int)fi, 1) != 0;
-    if (lane == 0) { ev.zero(); ef = false; }
-    if (lane == 31) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) sm[warp * 5 + q] = iv.w[q];
-        sm[warp * 5 + 4] = fi ? 1u : 0u;
-    }
-    __syncthreads();
-    // carry from previous warps (sequential over at most 7 warps; tiny)
-    Cnt8 cw; cw.zero(); bool cf = false;
-    for (uint32_t w = 0; w < warp; w++) {
-        Cnt8 t;
-#pragma unroll
-        for (int q = 0; q < 4; q++) t.w[q] = sm[w * 5 + q];
-        if (sm[w * 5 + 4]) { cw = t; cf = true; } else cw.add(t);
-    }
-    out->before = ev; out->head_before = ef;
-    if (!ef) { out->before.add(cw); out->head_before = cf; }
-    // tile aggregate (same for every thread): fold all warps
-    Cnt8 tt; tt.zero(); bool tf = false;
-    for (uint32_t w = 0; w < (PT_THREADS >> 5); w++) {
-        Cnt8 t;
-#pragma unroll
-        for (int q = 0; q < 4; q++) t.w[q] = sm[w * 5 + q];
-        if (sm[w * 5 + 4]) { tt = t; tf = true; } else tt.add(t);
-    }
-    out->tile_trailing = tt; out->tile_has_head = tf;
-    __syncthreads();
-}
 
 // ---------------------------------------------------------------------------- rank_kernel
 // per-slot byte staged in shared memory between the coalesced load phase and the thread-contiguous scan phase
@@ -229,114 +158,138 @@ __device__ __forceinline__ void rank_lookback(const uint32_t* __restrict__ desc_
     }
 }
 
+// Ballot of "active and octant == (lane & 7)": eight warp votes, every lane keeps the one of its own octant, so that lanes
+// 0..7 between them hold the eight per-octant member masks of a group of 32 slots.
+__device__ __forceinline__ uint32_t octant_ballot(bool act, uint32_t oc, uint32_t lane) {
+    uint32_t bo = 0u;
+#pragma unroll
+    for (uint32_t o = 0; o < 8u; o++) {
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, act && oc == o);
+        if ((lane & 7u) == o) bo = m;
+    }
+    return bo;
+}
+
+// One tile = PT_TILE consecutive slots; warp w owns the PT_GROUPS * 32 consecutive slots [w * 256, (w + 1) * 256) of it
+// and walks them as PT_GROUPS groups of 32 with lane = slot, so every global access is a coalesced 128-byte line and the
+// segmented scan is done with warp votes instead of a scan of eight counters per element:
+//   rank inside the group   popc(match_any(octant) & lanes before me & lanes from the last range head on)
+//   running counts          lane o (and o + 8, ...) carries the count of octant o of the range that is open at the group
+//                           start; a lane fetches the one of its own octant with one shuffle
+//   node totals             at the LAST member of a range lanes 0..7 store the eight totals (one 32-byte store)
+// Carries between the warps of a tile go through shared memory, between tiles through the decoupled look-back.
+// (An earlier version scanned eight 16-bit counters per element through registers, shuffles and shared memory:
+// ~230 thread instructions per slot and the longest of the three kernels of a level.)
+constexpr int PT_WARPS = PT_THREADS / 32;
+constexpr int PT_GROUPS = PT_TILE / PT_THREADS;
+
 __global__ void __launch_bounds__(PT_THREADS) rank_kernel(TreeDev t, int d) {
-    __shared__ uint32_t sm[48];
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_carry[8];
-    __shared__ uint32_t s_lb[PT_THREADS / 32][9];
-    __shared__ __align__(16) uint8_t s_byte[PT_TILE];
-    __shared__ __align__(16) uint32_t s_rank[PT_TILE];
+    __shared__ uint32_t s_lb[PT_WARPS][9];
+    __shared__ uint32_t s_wtr[PT_WARPS][8];      // per warp: counts of the range that is open at the end of its chunk ...
+    __shared__ uint32_t s_whh[PT_WARPS];         // ... counted from the last head inside the chunk, if there is one
     if (level_idle(t, d)) return;
     const uint32_t M = t.meta[M_NUM_INBOX];
     const uint32_t ntiles = (M + PT_TILE - 1) / PT_TILE;
     const float4* __restrict__ spm4 = t.spm4[d];
     const uint32_t* __restrict__ slot_node = t.slot_node[d & 1];
     uint32_t* __restrict__ desc_base = t.tdesc + (size_t)d * t.tdesc_stride;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, myo = lane & 7u;
+    const uint32_t lt = (1u << lane) - 1u, le = lt | (1u << lane);
     for (;;) {
         // tiles are handed out in launch order, so a tile only ever waits for tiles that are already running
         if (threadIdx.x == 0) s_tile = atomicAdd(&t.ticket[2 * d], 1u);
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= ntiles) return;
-        const uint32_t tile0 = tile * PT_TILE;
-        // phase 1, coalesced: octant of every active slot (tie rule) + range head / last-member flags
+        const uint32_t w0 = tile * PT_TILE + warp * (PT_GROUPS * 32) + lane;      // this lane's slot in group 0
+        // phase 1: octant of every active slot (tie rule) + range head / last-member flags
+        uint32_t b[PT_GROUPS], nn[PT_GROUPS], hm[PT_GROUPS];
 #pragma unroll
-        for (int k = 0; k < PT_ITEMS; k++) {
-            const uint32_t i = k * PT_THREADS + threadIdx.x, s = tile0 + i;
-            uint32_t byte = 0u;
+        for (int g = 0; g < PT_GROUPS; g++) {
+            const uint32_t s = w0 + 32u * g;
+            uint32_t byte = 0u, n = NODE_END;
             if (s < M) {
-                const uint32_t n = slot_node[s];
+                n = slot_node[s];
                 if (n != NODE_END) {                       // slot of an internal node (scatter marks the others)
                     const float4 mid = t.nmid[n];
                     const uint2 sg = t.seg[n];
                     byte = pick_octant(mid, spm4[s], s - sg.x < 8u) | SB_ACTIVE | (s == sg.x ? SB_HEAD : 0u) | (s + 1u == sg.y ? SB_LAST : 0u);
                 }
             }
-            s_byte[i] = (uint8_t)byte;
+            b[g] = byte; nn[g] = n;
         }
-        __syncthreads();
-        // phase 2, thread-contiguous: segmented scan of eight counters
-        uint8_t oct[PT_ITEMS]; bool head[PT_ITEMS]; uint8_t raw[PT_ITEMS];
-        {
-            const uint2 w = *reinterpret_cast<const uint2*>(&s_byte[threadIdx.x * PT_ITEMS]);
+        // pass A: counts of the range that is still open at the end of the warp's chunk (from its last head on)
+        int gl = -1;
 #pragma unroll
-            for (int k = 0; k < PT_ITEMS; k++) {
-                raw[k] = (uint8_t)(((k < 4 ? w.x : w.y) >> (8 * (k & 3))) & 0xFFu);
-                oct[k] = (raw[k] & SB_ACTIVE) ? (uint8_t)(raw[k] & 7u) : (uint8_t)0xFFu;
-                head[k] = (raw[k] & SB_HEAD) != 0u;
+        for (int g = 0; g < PT_GROUPS; g++) { hm[g] = __ballot_sync(0xFFFFFFFFu, (b[g] & SB_HEAD) != 0u); if (hm[g]) gl = g; }
+        uint32_t tr = 0u;
+#pragma unroll
+        for (int g = 0; g < PT_GROUPS; g++) {
+            if (g >= gl) {                                 // uniform across the warp
+                const uint32_t bo = octant_ballot((b[g] & SB_ACTIVE) != 0u, b[g] & 7u, lane);
+                tr += __popc(g == gl ? (bo & (0xFFFFFFFFu << (31 - __clz(hm[g])))) : bo);
             }
         }
-        TileScan ts;
-        tile_segmented_scan(oct, head, &ts, sm);
+        if (lane < 8u) s_wtr[warp][lane] = tr;
+        if (lane == 0u) s_whh[warp] = gl >= 0 ? 1u : 0u;
+        __syncthreads();
+        // what the warps before this one leave open (cw, cut at a head: cf), and the same for the whole tile (tt, tf)
+        uint32_t cw = 0u, tt = 0u; bool cf = false, tf = false;
+#pragma unroll
+        for (uint32_t w = 0; w < (uint32_t)PT_WARPS; w++) {
+            const uint32_t v = s_wtr[w][myo]; const bool h = s_whh[w] != 0u;
+            if (w < warp) { if (h) { cw = v; cf = true; } else cw += v; }
+            if (h) { tt = v; tf = true; } else tt += v;
+        }
         // publish the aggregate, fetch the carry of the range that is open at the tile start (decoupled look-back)
         uint32_t* desc = desc_base + (size_t)tile * DESC_WORDS;
-        if (threadIdx.x < 8) desc[2 + threadIdx.x] = ts.tile_trailing.get(threadIdx.x);
-        if (threadIdx.x == 8) desc[1] = ts.tile_has_head ? 1u : 0u;
+        if (threadIdx.x < 8) desc[2 + threadIdx.x] = tt;
+        if (threadIdx.x == 8) desc[1] = tf ? 1u : 0u;
         __threadfence();
         __syncthreads();
-        {
+        uint32_t cm = 0u;                                  // carry into the tile for octant myo
+        if (tile > 0u) {                                   // uniform across the CTA
             uint32_t carry[8];
-            if (tile > 0u) {                                       // uniform across the CTA
-                if (threadIdx.x == 0) atomicExch(&desc[0], ST_AGG);
-                rank_lookback(desc_base, tile, carry, s_lb);
-            } else {
+            if (threadIdx.x == 0) atomicExch(&desc[0], ST_AGG);
+            rank_lookback(desc_base, tile, carry, s_lb);
 #pragma unroll
-                for (int o = 0; o < 8; o++) carry[o] = 0u;
-            }
-            if (threadIdx.x == 0) {
-#pragma unroll
-                for (int o = 0; o < 8; o++) {
-                    s_carry[o] = carry[o];
-                    desc[10 + o] = ts.tile_trailing.get(o) + (ts.tile_has_head ? 0u : carry[o]);
-                }
-                __threadfence();
-                atomicExch(&desc[0], ST_INCL);
-            }
+            for (uint32_t o = 0; o < 8u; o++) if (o == myo) cm = carry[o];
         }
-        __syncthreads();
-        uint32_t run[8];
-#pragma unroll
-        for (uint32_t o = 0; o < 8; o++) run[o] = ts.before.get(o) + (ts.head_before ? 0u : s_carry[o]);
-#pragma unroll
-        for (int k = 0; k < PT_ITEMS; k++) {
-            if (head[k]) {
-#pragma unroll
-                for (uint32_t o = 0; o < 8; o++) run[o] = 0u;
-            }
-            uint32_t r = 0;
-            if (oct[k] != 0xFFu) {
-#pragma unroll
-                for (uint32_t o = 0; o < 8; o++) if (o == oct[k]) { r = run[o]; run[o] = r + 1u; }
-                if (raw[k] & SB_LAST) {                 // last member: the running counts are the node's totals
-                    const uint32_t n = slot_node[tile0 + threadIdx.x * PT_ITEMS + k];
-                    *reinterpret_cast<uint4*>(&t.counts[(size_t)n * 8u]) = make_uint4(run[0], run[1], run[2], run[3]);
-                    *reinterpret_cast<uint4*>(&t.counts[(size_t)n * 8u + 4u]) = make_uint4(run[4], run[5], run[6], run[7]);
-                }
-            }
-            s_rank[threadIdx.x * PT_ITEMS + k] = r;
+        if (threadIdx.x < 32) {
+            if (threadIdx.x < 8) { desc[10 + threadIdx.x] = tt + (tf ? 0u : cm); __threadfence(); }
+            __syncwarp();
+            if (threadIdx.x == 0) { __threadfence(); atomicExch(&desc[0], ST_INCL); }
         }
-        __syncthreads();
-        // phase 3, coalesced: ranks and octants out
+        // pass B: ranks, node totals
+        uint32_t run = cf ? cw : cw + cm;                  // octant myo of the range open at the start of the warp's chunk
 #pragma unroll
-        for (int k = 0; k < PT_ITEMS; k++) {
-            const uint32_t i = k * PT_THREADS + threadIdx.x, s = tile0 + i;
-            if (s < M) {
-                const uint32_t byte = s_byte[i];
-                t.rank[s] = s_rank[i];
-                t.oct[s] = (byte & SB_ACTIVE) ? (uint8_t)(byte & 7u) : (uint8_t)0xFFu;
+        for (int g = 0; g < PT_GROUPS; g++) {
+            const uint32_t s = w0 + 32u * g, byte = b[g], oc = byte & 7u;
+            const bool act = (byte & SB_ACTIVE) != 0u;
+            const uint32_t headmask = hm[g];
+            const uint32_t bo = octant_ballot(act, oc, lane);
+            const uint32_t mm = __match_any_sync(0xFFFFFFFFu, act ? oc : 8u);
+            const uint32_t hb = headmask & le;             // heads at or before this lane
+            const bool in_open = hb == 0u;                 // my range began before this group
+            const uint32_t seg_lo = in_open ? 0u : 31u - (uint32_t)__clz(hb);
+            uint32_t r = __popc(mm & lt & (0xFFFFFFFFu << seg_lo));
+            const uint32_t base = __shfl_sync(0xFFFFFFFFu, run, (int)oc);
+            if (in_open) r += base;
+            if (s < M) { t.rank[s] = act ? r : 0u; t.oct[s] = act ? (uint8_t)oc : (uint8_t)0xFFu; }
+            // last member of a node: the eight totals of its range
+            for (uint32_t m = __ballot_sync(0xFFFFFFFFu, act && (byte & SB_LAST) != 0u); m; m &= m - 1u) {
+                const uint32_t L = (uint32_t)__ffs(m) - 1u, upto = 0xFFFFFFFFu >> (31u - L);
+                const uint32_t hbl = headmask & upto;
+                const uint32_t range = hbl ? (upto & (0xFFFFFFFFu << (31 - __clz(hbl)))) : upto;
+                const uint32_t val = __popc(bo & range) + (hbl ? 0u : run);
+                const uint32_t n = __shfl_sync(0xFFFFFFFFu, nn[g], (int)L);
+                if (lane < 8u) t.counts[(size_t)n * 8u + lane] = val;
             }
+            // the range that is open at the end of the group
+            if (headmask) run = __popc(bo & (0xFFFFFFFFu << (31 - __clz(headmask)))); else run += __popc(bo);
         }
-        __syncthreads();   // shared buffers are reused by the next ticket
+        __syncthreads();   // s_wtr / s_whh / s_lb are reused by the next ticket
     }
 }
 

@@ -124,3 +124,27 @@ def test_vis_draw_equals_the_reference(engine):
     assert np.array_equal(vis.matMVP, mvp)
     assert np.array_equal(vis.atomic_buffer, ab)
     assert ulp_diff(vis.render_buffer, rb).max() <= 1
+
+
+@pytest.mark.parametrize("samples,exposure,fmt", [(5, None, 0), (100, -3.0, 2), (33, 0.5, 1), (1, -1.0, 0)])
+def test_vis_draw_other_configurations(engine, samples, exposure, fmt, monkeypatch):
+    """SPATIAL_SAMPLES that are not a multiple of the warp size, other EXPOSURE values, VIS_FILE_FORMAT 0 (no tonemap: the
+    render buffer is then a double product rounded once and must be bit-identical), AUTOSCALING / ORTHO_SCALE off."""
+    N, sx, sy, step = 6000, 96, 160, 9
+    sim = state(engine, N, step)
+    monkeypatch.setattr(engine, "SPATIAL_SAMPLES", samples)
+    monkeypatch.setattr(engine, "EXPOSURE", exposure)
+    monkeypatch.setattr(engine, "VIS_FILE_FORMAT", fmt)
+    auto = samples != 33
+    monkeypatch.setattr(engine, "AUTOSCALING", auto)
+    monkeypatch.setattr(engine, "ORTHO_SCALE", None if samples == 1 else -1.0)
+    vis = draw(engine, sim, sx, sy)
+    rbar, mvp, ab, rb = sfo.vis_draw(sim.pos.copy(), sim.pot.copy(), step, sx, sy, samples=samples, exposure=exposure,
+                                     tonemap=1 if fmt > 0 else 0, ortho_exp2=0.0 if samples == 1 else -1.0, autoscale=1 if auto else 0)
+    assert np.array_equal(vis.matMVP, mvp)
+    assert np.array_equal(vis.atomic_buffer, ab)
+    assert int(ab[3::4].sum()) > 0
+    if fmt == 0:
+        assert np.array_equal(vis.render_buffer, rb)
+    else:
+        assert ulp_diff(vis.render_buffer, rb).max() <= 1
