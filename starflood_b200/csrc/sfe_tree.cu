@@ -158,22 +158,20 @@ __device__ __forceinline__ void rank_lookback(const uint32_t* __restrict__ desc_
     }
 }
 
-// Ballot of "active and octant == (lane & 7)": eight warp votes, every lane keeps the one of its own octant, so that lanes
-// 0..7 between them hold the eight per-octant member masks of a group of 32 slots.
-__device__ __forceinline__ uint32_t octant_ballot(bool act, uint32_t oc, uint32_t lane) {
-    uint32_t bo = 0u;
-#pragma unroll
-    for (uint32_t o = 0; o < 8u; o++) {
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, act && oc == o);
-        if ((lane & 7u) == o) bo = m;
-    }
-    return bo;
+// Member masks of a group of 32 slots from four warp votes (active, and the three bits of the octant): the lanes that are
+// active in octant (lane & 7) - lanes 0..7 between them hold the eight per-octant masks, and any lane fetches the mask of
+// its own slot's octant from lane `octant` with one shuffle (what match_any would return).
+__device__ __forceinline__ uint32_t octant_mask(bool act, uint32_t oc, uint32_t lane) {
+    const uint32_t ba = __ballot_sync(0xFFFFFFFFu, act);
+    const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, (oc & 1u) != 0u), b1 = __ballot_sync(0xFFFFFFFFu, (oc & 2u) != 0u),
+                   b2 = __ballot_sync(0xFFFFFFFFu, (oc & 4u) != 0u);
+    return ba & ((lane & 1u) ? b0 : ~b0) & ((lane & 2u) ? b1 : ~b1) & ((lane & 4u) ? b2 : ~b2);
 }
 
 // One tile = PT_TILE consecutive slots; warp w owns the PT_GROUPS * 32 consecutive slots [w * 256, (w + 1) * 256) of it
 // and walks them as PT_GROUPS groups of 32 with lane = slot, so every global access is a coalesced 128-byte line and the
 // segmented scan is done with warp votes instead of a scan of eight counters per element:
-//   rank inside the group   popc(match_any(octant) & lanes before me & lanes from the last range head on)
+//   rank inside the group   popc(lanes of my octant & lanes before me & lanes from the last range head on)
 //   running counts          lane o (and o + 8, ...) carries the count of octant o of the range that is open at the group
 //                           start; a lane fetches the one of its own octant with one shuffle
 //   node totals             at the LAST member of a range lanes 0..7 store the eight totals (one 32-byte store)
@@ -183,7 +181,7 @@ __device__ __forceinline__ uint32_t octant_ballot(bool act, uint32_t oc, uint32_
 constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int PT_GROUPS = PT_TILE / PT_THREADS;
 
-__global__ void __launch_bounds__(PT_THREADS) rank_kernel(TreeDev t, int d) {
+__global__ void __launch_bounds__(PT_THREADS, 4) rank_kernel(TreeDev t, int d) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_lb[PT_WARPS][9];
     __shared__ uint32_t s_wtr[PT_WARPS][8];      // per warp: counts of the range that is open at the end of its chunk ...
@@ -204,7 +202,7 @@ __global__ void __launch_bounds__(PT_THREADS) rank_kernel(TreeDev t, int d) {
         if (tile >= ntiles) return;
         const uint32_t w0 = tile * PT_TILE + warp * (PT_GROUPS * 32) + lane;      // this lane's slot in group 0
         // phase 1: octant of every active slot (tie rule) + range head / last-member flags
-        uint32_t b[PT_GROUPS], nn[PT_GROUPS], hm[PT_GROUPS];
+        uint32_t b[PT_GROUPS], nn[PT_GROUPS], hm[PT_GROUPS], bo[PT_GROUPS];
 #pragma unroll
         for (int g = 0; g < PT_GROUPS; g++) {
             const uint32_t s = w0 + 32u * g;
@@ -222,15 +220,15 @@ __global__ void __launch_bounds__(PT_THREADS) rank_kernel(TreeDev t, int d) {
         // pass A: counts of the range that is still open at the end of the warp's chunk (from its last head on)
         int gl = -1;
 #pragma unroll
-        for (int g = 0; g < PT_GROUPS; g++) { hm[g] = __ballot_sync(0xFFFFFFFFu, (b[g] & SB_HEAD) != 0u); if (hm[g]) gl = g; }
+        for (int g = 0; g < PT_GROUPS; g++) {
+            hm[g] = __ballot_sync(0xFFFFFFFFu, (b[g] & SB_HEAD) != 0u);
+            if (hm[g]) gl = g;
+            bo[g] = octant_mask((b[g] & SB_ACTIVE) != 0u, b[g] & 7u, lane);
+        }
         uint32_t tr = 0u;
 #pragma unroll
-        for (int g = 0; g < PT_GROUPS; g++) {
-            if (g >= gl) {                                 // uniform across the warp
-                const uint32_t bo = octant_ballot((b[g] & SB_ACTIVE) != 0u, b[g] & 7u, lane);
-                tr += __popc(g == gl ? (bo & (0xFFFFFFFFu << (31 - __clz(hm[g])))) : bo);
-            }
-        }
+        for (int g = 0; g < PT_GROUPS; g++)
+            if (g >= gl) tr += __popc(g == gl ? (bo[g] & (0xFFFFFFFFu << (31 - __clz(hm[g])))) : bo[g]);   // uniform across the warp
         if (lane < 8u) s_wtr[warp][lane] = tr;
         if (lane == 0u) s_whh[warp] = gl >= 0 ? 1u : 0u;
         __syncthreads();
@@ -268,12 +266,10 @@ __global__ void __launch_bounds__(PT_THREADS) rank_kernel(TreeDev t, int d) {
             const uint32_t s = w0 + 32u * g, byte = b[g], oc = byte & 7u;
             const bool act = (byte & SB_ACTIVE) != 0u;
             const uint32_t headmask = hm[g];
-            const uint32_t bo = octant_ballot(act, oc, lane);
-            const uint32_t mm = __match_any_sync(0xFFFFFFFFu, act ? oc : 8u);
             const uint32_t hb = headmask & le;             // heads at or before this lane
             const bool in_open = hb == 0u;                 // my range began before this group
             const uint32_t seg_lo = in_open ? 0u : 31u - (uint32_t)__clz(hb);
-            uint32_t r = __popc(mm & lt & (0xFFFFFFFFu << seg_lo));
+            uint32_t r = __popc(__shfl_sync(0xFFFFFFFFu, bo[g], (int)oc) & lt & (0xFFFFFFFFu << seg_lo));   // same octant, same range, before me
             const uint32_t base = __shfl_sync(0xFFFFFFFFu, run, (int)oc);
             if (in_open) r += base;
             if (s < M) { t.rank[s] = act ? r : 0u; t.oct[s] = act ? (uint8_t)oc : (uint8_t)0xFFu; }
@@ -282,12 +278,12 @@ __global__ void __launch_bounds__(PT_THREADS) rank_kernel(TreeDev t, int d) {
                 const uint32_t L = (uint32_t)__ffs(m) - 1u, upto = 0xFFFFFFFFu >> (31u - L);
                 const uint32_t hbl = headmask & upto;
                 const uint32_t range = hbl ? (upto & (0xFFFFFFFFu << (31 - __clz(hbl)))) : upto;
-                const uint32_t val = __popc(bo & range) + (hbl ? 0u : run);
+                const uint32_t val = __popc(bo[g] & range) + (hbl ? 0u : run);
                 const uint32_t n = __shfl_sync(0xFFFFFFFFu, nn[g], (int)L);
                 if (lane < 8u) t.counts[(size_t)n * 8u + lane] = val;
             }
             // the range that is open at the end of the group
-            if (headmask) run = __popc(bo & (0xFFFFFFFFu << (31 - __clz(headmask)))); else run += __popc(bo);
+            if (headmask) run = __popc(bo[g] & (0xFFFFFFFFu << (31 - __clz(headmask)))); else run += __popc(bo[g]);
         }
         __syncthreads();   // s_wtr / s_whh / s_lb are reused by the next ticket
     }
