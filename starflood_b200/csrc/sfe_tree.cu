@@ -88,6 +88,7 @@ constexpr int PT_TILE = PT_THREADS * PT_ITEMS;
 constexpr uint32_t DESC_WORDS = 20u;   // tile descriptor of the segmented look-back: [0] status, [1] has_head, [2..9] agg, [10..17] incl
 constexpr uint32_t ST_NONE = 0u, ST_AGG = 1u, ST_INCL = 2u;
 constexpr int CH_THREADS = 256;
+constexpr uint32_t ML_MIN = 64u;         // nodes with more members than this take the pipelined fold kernel (moments_long)
 constexpr int XL_DEPTH_MAX = 6;          // deeper levels never use the chunked exact fold (their long nodes go through moments_long)
 
 // Octant of a member with the reference's tie rule; mid = 0.5f*(lo+hi) (tree.c:159-163) comes from nmid[].
@@ -432,6 +433,8 @@ __global__ void __launch_bounds__(CH_THREADS) children_kernel(TreeDev t, int d, 
                 if (d + 1 <= XL_DEPTH_MAX && cn > t.xl_min) {     // very long fold: chunked exact evaluation (moments_xl)
                     const uint32_t k = atomicAdd(&t.xl_count[d + 1], 1u);
                     if (k < t.xl_max) t.xl_nodes[(size_t)(d + 1) * t.xl_max + k] = c;
+                } else if (cn > ML_MIN) {
+                    t.ml_count[d + 1] = 1u;                       // level d+1 has work for moments_long_kernel (any writer will do)
                 }
                 // depth-first successor when c is not opened: the next NON-EMPTY sibling, else the parent's successor.
                 // The reference only steps back to the parent at an empty node (gravity.c:324-328), so leaving empty
@@ -503,7 +506,6 @@ constexpr int ML_B = 128;                // members per node per batch
 constexpr int ML_R = 4;                  // raw ring depth in batches
 constexpr int ML_BP = ML_B + 4;          // padded row of the product buffer: conflict-free LDS.128 across 32 rows
 constexpr int ML_THREADS = 288;          // warp 0 consumer, warps 1-8 producers (one node each)
-constexpr uint32_t ML_MIN = 64u;         // nodes with more members than this take the pipelined kernel
 constexpr size_t ML_SMEM = (size_t)ML_R * 8 * ML_B * 16 + (size_t)2 * 32 * ML_BP * 4;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -522,6 +524,9 @@ __global__ void __launch_bounds__(ML_THREADS) moments_long_kernel(TreeDev t, int
     float4 (*raw)[8][ML_B] = reinterpret_cast<float4 (*)[8][ML_B]>(ml_smem);                                  // [ML_R][8][ML_B]
     float (*prod)[32][ML_BP] = reinterpret_cast<float (*)[32][ML_BP]>(ml_smem + (size_t)ML_R * 8 * ML_B * 16);  // [2][32][ML_BP]
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
+    // children_kernel(d-1) notes whether level d has a node for this kernel at all: deep levels have hundreds of thousands of
+    // nodes and none that long, and finding that out group by group costs a 100 us of dependent loads (level 7 at C2)
+    if (d > 0 && t.ml_count[d] == 0u) return;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t b = t.meta[M_LV_BEGIN + d], e = t.meta[M_LV_END + d];
     const float4* __restrict__ spm4 = t.spm4[d];
@@ -984,6 +989,7 @@ static TreeDev make_dev(Tree& t) {
     uint32_t* w = t.lookback.as<uint32_t>();
     d.ticket = w;                 w += 2 * levels;
     d.xl_count = w;               w += levels;
+    d.ml_count = w;               w += levels;
     d.xl_nodes = w;               w += (size_t)(XL_DEPTH_MAX + 1) * d.xl_max;
     d.tdesc = w;                  w += (size_t)levels * d.tdesc_stride;
     d.cdesc = reinterpret_cast<unsigned long long*>(t.lookback.as<char>() + ((size_t)(w - t.lookback.as<uint32_t>()) * 4 + 7) / 8 * 8);
@@ -999,7 +1005,7 @@ static TreeDev make_dev(Tree& t) {
 
 static size_t lookback_bytes(const TreeDev& d) {
     const size_t levels = SFE_MAX_LEVELS + 2;
-    const size_t words = 2 * levels + levels + (size_t)(XL_DEPTH_MAX + 1) * d.xl_max + levels * d.tdesc_stride;
+    const size_t words = 2 * levels + levels + levels + (size_t)(XL_DEPTH_MAX + 1) * d.xl_max + levels * d.tdesc_stride;
     return (words * 4 + 7) / 8 * 8 + levels * (size_t)d.cdesc_stride * 8;
 }
 

@@ -64,6 +64,7 @@ struct TreeDev {
     uint32_t tdesc_stride, cdesc_stride;
     // exact chunked fold of very long nodes (moments_xl_*): per-level work lists and one scratch area per side stream
     uint32_t* xl_count;           // [levels] number of nodes with more than XL_MIN members
+    uint32_t* ml_count;           // [levels] non-zero when the level has a node for moments_long_kernel
     uint32_t* xl_nodes;           // [levels][xl_max]
     uint32_t xl_max, xl_slots;    // list capacity per level, chunk slots per scratch area
     uint32_t xl_min;              // nodes with more members than this use the chunked exact fold
