@@ -218,6 +218,25 @@ __global__ void __launch_bounds__(PT_THREADS, 4) rank_kernel(TreeDev t, int d) {
             }
             b[g] = byte; nn[g] = n;
         }
+        // A tile without a single active slot (most tiles of the deep levels): a range consists of active slots only, so
+        // nothing is open at its start or at its end - its inclusive prefix is zero and there is nothing to rank
+        {
+            uint32_t any = 0u;
+#pragma unroll
+            for (int g = 0; g < PT_GROUPS; g++) any |= b[g];
+            if (__syncthreads_or((int)(any & SB_ACTIVE)) == 0) {
+                uint32_t* desc = desc_base + (size_t)tile * DESC_WORDS;
+                if (threadIdx.x < 32) {
+                    if (threadIdx.x < 8) { desc[2 + threadIdx.x] = 0u; desc[10 + threadIdx.x] = 0u; }
+                    if (threadIdx.x == 8) desc[1] = 0u;
+                    __threadfence();
+                    __syncwarp();
+                    if (threadIdx.x == 0) { __threadfence(); atomicExch(&desc[0], ST_INCL); }
+                }
+                __syncthreads();
+                continue;
+            }
+        }
         // pass A: counts of the range that is still open at the end of the warp's chunk (from its last head on)
         int gl = -1;
 #pragma unroll
@@ -273,7 +292,7 @@ __global__ void __launch_bounds__(PT_THREADS, 4) rank_kernel(TreeDev t, int d) {
             uint32_t r = __popc(__shfl_sync(0xFFFFFFFFu, bo[g], (int)oc) & lt & (0xFFFFFFFFu << seg_lo));   // same octant, same range, before me
             const uint32_t base = __shfl_sync(0xFFFFFFFFu, run, (int)oc);
             if (in_open) r += base;
-            if (s < M) { t.rank[s] = act ? r : 0u; t.oct[s] = act ? (uint8_t)oc : (uint8_t)0xFFu; }
+            if (act) { t.rank[s] = r; t.oct[s] = (uint8_t)oc; }      // scatter_kernel reads them for active slots only
             // last member of a node: the eight totals of its range
             for (uint32_t m = __ballot_sync(0xFFFFFFFFu, act && (byte & SB_LAST) != 0u); m; m &= m - 1u) {
                 const uint32_t L = (uint32_t)__ffs(m) - 1u, upto = 0xFFFFFFFFu >> (31u - L);
