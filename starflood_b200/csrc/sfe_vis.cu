@@ -6,8 +6,8 @@
 // each a pcg4d hash, logf, sqrtf, cosf, sinf); once the solver runs in 3 ms it would be 99 % of a step.
 //
 // Parity: integer adds commute, so the accumulation buffer is a pure function of the inputs and is reproduced BIT FOR BIT.
-// That needs the host libm's logf / sinf / cosf bit patterns (a correctly rounded cosf differs from glibc's in ~0.1 % of
-// the arguments, enough to move a sample across a pixel edge now and then): sfe_libm.cuh restates glibc 2.39's
+// That needs the host libm's logf / sinf / cosf bit patterns (a correctly rounded cosf differs from glibc's in ~1 % of
+// the arguments the splat draws, enough to move a sample across a pixel edge now and then): sfe_libm.cuh restates glibc 2.39's
 // algorithms in IEEE double operations and is pinned exhaustively against the host library (tools/libm_probe.cpp).  All
 // fp32 arithmetic is written without contraction (__fmul_rn / __fadd_rn) in the reference's operation order.
 //
@@ -18,8 +18,10 @@
 //                      non-empty bins go to global memory as {count*r, count*g, count*b, count} (every sample of a
 //                      particle carries the same colour): ~20 bins instead of 128 samples, 6x fewer global atomics
 //   vis_finish_kernel  pixel_value_scale * accum, tanh tonemap in double, alpha = 1                      (:691-735)
-// Bound: the splat is FP64/FMA-issue bound (~60 double operations per sample for the three libm calls); global traffic
-// is the 16 bytes per particle read plus the atomics.
+// Bound: instruction issue (ncu: issue slots 75 % busy, 28.5 of 32 lanes active, DRAM 27 MB per frame): per sample a pcg4d
+// hash, ~35 double-precision operations for logf / sinf / cosf and a dozen int<->float<->double conversions; global traffic
+// is the 16 bytes per particle read plus ~20 x 4 atomics per particle.  [B200] N = 2^20, 128 samples, 1080 x 1080:
+// 0.92 ms per frame against 331 ms for the reference on 16 host threads.
 #include "sfe_internal.cuh"
 #include "sfe_libm.cuh"
 #include <stdlib.h>
