@@ -141,17 +141,29 @@ def ref_lib_available():
     return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libsfref_tree.so"))
 
 
+def workload_name(N):
+    """config.workload, the same string on the engine arm and on the reference arm (the driver compares them)."""
+    return ("C2: Barnes-Hut gravity N=%d uniform sphere (reference initcond), theta=0.5 monopole, "
+            "one sim_solv() per step: root box + tree_build + solve_gravity_part_tree" % N)
+
+
 def cpu_reference_steps(N, steps, warmup):
     """The reference's own sim_solv() (root box + tree_build + solve_gravity_part_tree) from oracle/_ref on all
-    host threads; falls back to the oracle port when the reference library did not travel."""
+    host threads; falls back to the oracle port when the reference library did not travel.
+    Returns (kind, threads actually used, host cores, per-step seconds)."""
     from oracle import sfo
-    cores = os.cpu_count()
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    os.environ.setdefault("OMP_PROC_BIND", "true")
+    cores = sfo.host_cores()
+    # README.md:242-248 of the reference: OMP_NUM_THREADS=$(nproc) OMP_PROC_BIND=true.  Set unconditionally - a launcher's
+    # own OMP_NUM_THREADS (torch.distributed.run exports 1) must not win - and, because libgomp may already be loaded
+    # and reads the environment only once, also through the runtime's API; the count reported is the one read back.
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ["OMP_PROC_BIND"] = "true"
     times = []
     if ref_lib_available() and N <= 2 * sfo.REF_NODES_MAX["tree"]:
         kind = "reference"
-        r = sfo.RefSim("tree", N); r.initcond()
+        r = sfo.RefSim("tree", N)
+        threads = sfo.omp_threads(cores)
+        r.initcond()
         for s in range(warmup + steps):
             t0 = time.perf_counter(); r.solv(s); dt = time.perf_counter() - t0
             if s >= warmup:
@@ -159,6 +171,7 @@ def cpu_reference_steps(N, steps, warmup):
         r.close()
     else:
         kind = "port"
+        threads = 1                       # the oracle port is scalar C
         pos, vel, mas = sfo.initcond(N)
         for s in range(warmup + steps):
             t0 = time.perf_counter()
@@ -168,7 +181,17 @@ def cpu_reference_steps(N, steps, warmup):
             dt = time.perf_counter() - t0
             if s >= warmup:
                 times.append(dt)
-    return kind, cores, times
+    return kind, threads, cores, times
+
+
+def host_cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return None
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -176,18 +199,25 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import sfo
     N = args.n
-    kind, cores, times = cpu_reference_steps(N, args.steps, args.warmup)
+    kind, threads, cores, times = cpu_reference_steps(N, args.steps, args.warmup)
     ms = 1e3 * float(np.mean(times))
     value = N / (ms * 1e-3)
-    sample = "%d full sim_solv() steps (root box + tree_build + BH walk) at N=%d, %d OpenMP threads" % (args.steps, N, cores)
+    sample = ("%d full sim_solv() steps (root box + tree_build + BH walk) at N=%d after %d warm-up, %d OpenMP threads "
+              "(omp_get_max_threads) on %d host cores" % (args.steps, N, args.warmup, threads, cores))
     line = {
         "impl": "reference", "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: Barnes-Hut gravity N=%d uniform sphere, theta=0.5 monopole (CPU, OpenMP)" % N,
-                   "N": N, "theta": THETA},
-        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": workload_name(N), "N": N, "theta": THETA, "depth_max": 16,
+                   "arm": "the unmodified reference sim_solv() on the host CPUs (OpenMP), the same IC re-solved with the "
+                          "root box of step_number = 0, 1, 2, ... (the engine arm rotates z-rotated copies of the same IC: "
+                          "statistically the same work)"},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "host_cores": cores,
+                         "cpu_model": host_cpu_model(), "kind": kind, "sample": sample,
+                         "build_flags": sfo.REF_BUILD_FLAGS + " (BASELINE.md section 3 asks for -march=native; the library is "
+                                        "built in the dev container for a different host CPU, hence x86-64-v3)"},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -305,7 +335,7 @@ def vis_leg(e, L, torch, dev, stream, N, pm4, pot, with_cpu):
         if sfo.ref_available("vis"):
             r = sfo.RefSim("vis", N)
             r.pos[:] = sim.pos; r.mas[:] = sim.mas; r.pot[:] = sim.pot
-            cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count()))
+            cores = sfo.omp_threads(sfo.host_cores())
             r.vis_draw(0, sx, sy)
             t = []
             for _ in range(2):
@@ -661,10 +691,13 @@ def run_engine(args):
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only, bounded sample)
     cpu = None
     if world == 1 and not args.no_cpu:
-        kind, cores, times = cpu_reference_steps(N, 4, 1)
+        from oracle import sfo
+        kind, threads, cores, times = cpu_reference_steps(N, 4, 1)
         cms = 1e3 * float(np.median(times))
-        cpu = {"value": N / (cms * 1e-3), "unit": "particle-steps/s", "cores": cores, "kind": kind,
-               "sample": "4 full sim_solv() steps at N=%d after 1 warm-up (%.2f s each, median), %d OpenMP threads" % (N, cms / 1e3, cores)}
+        cpu = {"value": N / (cms * 1e-3), "unit": "particle-steps/s", "cores": threads, "host_cores": cores,
+               "cpu_model": host_cpu_model(), "kind": kind, "build_flags": sfo.REF_BUILD_FLAGS,
+               "sample": "4 full sim_solv() steps at N=%d after 1 warm-up (%.2f s each, median), %d OpenMP threads "
+                         "(omp_get_max_threads) on %d host cores" % (N, cms / 1e3, threads, cores)}
 
     line = {
         "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,

@@ -16,7 +16,10 @@
  *     completely written to HOST memory when the call returns (simulation.c:423-451
  *     consumes acc/pot on the host right after sim_solv());
  *   - the *device* entry points (sfe_dev_*) take device pointers and a cudaStream_t
- *     passed as void*, enqueue work and return without synchronising;
+ *     passed as void*, enqueue work and return without synchronising.  All of them share the
+ *     context's scratch buffers (reduction partials, cell lists, scan temporaries, the tree):
+ *     issue them on ONE stream per context (any stream, but the same one for a whole sequence),
+ *     and never concurrently with a host entry point;
  *   - there is NO CPU fallback: every entry point fails with -1 when no sm_100 device
  *     is usable.
  */
@@ -90,7 +93,10 @@ int sfe_tree_build(const float bounds[6], const float* pos, const float* mas, ui
                    int depth_max, uint32_t nodes_max);
 /* Replaces solve_gravity_part_tree() (gravity.h:14-18, gravity.c:245-663) using the tree of the last
  * sfe_tree_build() on the same pos/mas.  theta is TREE_THETA (config.h:44), compared against
- * width^2/dist^2 exactly as gravity.c:377,448. */
+ * width^2/dist^2 exactly as gravity.c:377,448.  The particle records are the ones sfe_tree_build() uploaded (the
+ * reference calls build and walk back to back on the same arrays, simulation.c:312-321): pos / mas are not copied
+ * again, and a host call that uploads other particles in between (sfe_pp, sfe_sph) retires the tree - sfe_bh() then
+ * fails with "no tree" instead of walking a stale one. */
 int sfe_bh(const float* pos, const float* mas, float* acc, float* pot, uint32_t N,
            float grav_g, float eps2, float theta, uint32_t flavour);
 int sfe_bh_slice(const float* pos, const float* mas, float* acc, float* pot, uint32_t N,

@@ -26,8 +26,8 @@
 # In all other variants: ENABLE_VIS / SOLVER_VIS / VIS_FILENAME off (no rasteriser dependency),
 # CSV logs and timing prints off, Kahan flags ON (shipped default), fp32.
 #
-# Flags: the reference Makefile's performance set is -O3 -march=native -fopenmp -std=c99
-# (Makefile:27-28,58,88).  -march=native is replaced by x86-64-v3 because the .so is
+# Flags: the reference Makefile's performance set is -O3 -march=native -flto=auto -fopenmp -std=c99
+# (Makefile:27-28,58,88; BASELINE.md section 3).  -march=native is replaced by x86-64-v3 because the .so is
 # built in the dev container and executed on the GPU box's (different) host CPU; the
 # hot loops are scalar (volatile Kahan) so the ISA level does not change their speed,
 # and -std=c99 keeps -ffp-contract=off so results are bit-identical.
@@ -72,7 +72,7 @@ build_variant() {
     extra="sfref_matmvp.c"
   fi
   if [ "$vis" = 2 ]; then extra="visualization.c"; fi
-  ( cd "$d" && "$CC" -shared -fPIC -fopenmp -O3 -march=x86-64-v3 -std=c99 -w \
+  ( cd "$d" && "$CC" -shared -fPIC -fopenmp -O3 -march=x86-64-v3 -flto=auto -std=c99 -w \
       simulation.c gravity.c tree.c sph.c initcond.c log.c grid.c $extra \
       -o "$OUT/libsfref_$name.so" -lm )
   echo "built $OUT/libsfref_$name.so"

@@ -271,6 +271,30 @@ def ref_available(variant="pp"):
     return os.path.exists(os.path.join(REF_DIR, "libsfref_%s.so" % variant))
 
 
+# Flags oracle/build_ref.sh compiles the reference with (reported next to every CPU number, bench.py cpu_baseline)
+REF_BUILD_FLAGS = "-fopenmp -O3 -march=x86-64-v3 -flto=auto -std=c99"
+
+
+def omp_threads(n=None):
+    """Thread count of the OpenMP runtime the reference libraries run on (libgomp.so.1, the one libsfref_*.so link).
+    With n: omp_set_num_threads(n) first.  An environment variable is not enough: a launcher may have exported
+    OMP_NUM_THREADS=1 (torch.distributed.run does) and libgomp reads it only once, when it is loaded - so the count is
+    set and read back through the runtime's own API (README.md:242-248 of the reference: OMP_NUM_THREADS=$(nproc))."""
+    g = C.CDLL("libgomp.so.1")
+    if n is not None:
+        g.omp_set_num_threads(int(n))
+    g.omp_get_max_threads.restype = C.c_int
+    return int(g.omp_get_max_threads())
+
+
+def host_cores():
+    """Host cores this process may run on (what $(nproc) prints)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 class quiet_stdout:
     """The reference printf()s from inside the solvers; silence fd 1 around calls."""
     def __enter__(self):

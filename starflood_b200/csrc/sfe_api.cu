@@ -72,8 +72,6 @@ static bool is_pinned(const void* p) {
 static int ensure_bounce(const char* fn, size_t bytes) {
     Ctx* c = g_ctx;
     if (bytes <= c->bounce_cap) return SFE_SUCCESS;
-    c->ov_lines.release(); c->ov_rows.release();
-    if (c->ov_info) cudaFreeHost(c->ov_info);
     if (c->bounce) cudaFreeHost(c->bounce);
     c->bounce = nullptr; c->bounce_cap = 0;
     SFE_CUDA(fn, cudaMallocHost(&c->bounce, bytes));
@@ -148,7 +146,13 @@ static int t_end(Ctx* c, const char* fn, bool has_build) {
     return SFE_SUCCESS;
 }
 
-static int upload_particles(Ctx* c, const char* fn, const float* pos, const float* mas, uint32_t N) {
+// `for_tree`: the upload feeds sfe_tree_build().  Any other upload overwrites (or reallocates) the records the device
+// tree was built from, so the tree of an earlier sfe_tree_build() is retired: sfe_bh() / sfe_bh_overlay() then fail
+// instead of walking a stale tree against different particles.
+static int upload_particles(Ctx* c, const char* fn, const float* pos, const float* mas, uint32_t N, bool for_tree = false) {
+    if (!for_tree && c->tree.valid && (c->tree.pm4_of_build == c->d_pm4.p || c->tree.pm4_of_build == nullptr)) {
+        c->tree.valid = false; c->tree.pm4_of_build = nullptr;
+    }
     if (c->d_pos.reserve((size_t)N * 12, fn) || c->d_mas.reserve((size_t)N * 4, fn) ||
         c->d_pm4.reserve((size_t)N * 16, fn))
         return SFE_FAILURE;
@@ -273,7 +277,8 @@ extern "C" int sfe_tree_build(const float bounds[6], const float* pos, const flo
     if (!bounds || ((!pos || !mas) && N > 0)) { set_error(fn, "null pointer argument"); return SFE_FAILURE; }
     Ctx* c = g_ctx;
     t_begin(c);
-    if (upload_particles(c, fn, pos, mas, N)) return SFE_FAILURE;
+    c->tree.valid = false;
+    if (upload_particles(c, fn, pos, mas, N, /*for_tree=*/true)) return SFE_FAILURE;
     t_mark(c, 1);
     if (launch_tree_build(c, bounds, c->d_pm4.as<float4>(), N, depth_max, nodes_max, c->stream)) return SFE_FAILURE;
     t_mark(c, 2);

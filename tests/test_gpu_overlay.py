@@ -99,3 +99,40 @@ def test_overlay_errors(engine):
     M = matrix()
     assert L.sfe_bh_overlay(3, 0.5, None, rb.ctypes.data, 4, 4) == engine.STARFLOOD_FAILURE
     assert L.sfe_bh_overlay(3, 0.5, M.ctypes.data, rb.ctypes.data, 0, 4) == engine.STARFLOOD_FAILURE
+
+
+def test_overlay_with_pinned_state_and_pageable_render_buffer_in_a_fresh_context(engine):
+    """The first pageable copy of a context allocates the pinned bounce buffer.  When that first copy happens INSIDE
+    sfe_bh_overlay() - the state block pinned with sfe_host_register (what the shims do), the render buffer pageable - the
+    overlay's own buffers must survive it (an earlier version released them from ensure_bounce(): use after free)."""
+    engine.shutdown(); engine.init()                              # no bounce buffer yet
+    N, sx, sy = 6000, 320, 200
+    pos, vel, mas = sfo.initcond(N)
+    box = sfo.root_box(pos, 0)
+    sim = engine.Sim(N, pinned=True); sim.pos[:] = pos; sim.mas[:] = mas
+    engine.tree_init(sim.tree, 2 * N); sim.tree.bounds[:] = box
+    assert engine.tree_build(sim.tree, N, sim.pos, sim.mas) == 0, engine.last_error()
+    rc, nodes, n, *_ = sfo.tree_build_sorted(box, pos, mas, 2 * N)
+    start = np.random.default_rng(11).random(sx * sy * 4).astype(np.float32)
+    for rep in range(3):                                          # the second and third call reuse the overlay buffers
+        rb = start.copy()                                         # pageable
+        assert engine.solve_gravity_part_tree_vis(sim, matrix(), rb, sx, sy) == 0, engine.last_error()
+        assert np.array_equal(rb, sfo.bh_overlay(nodes[:n], pos, mas, 3, matrix(), start.copy(), sx, sy)), rep
+    acc, pot, st = sfo.bh_walk(nodes[:n], pos, mas)
+    assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)
+
+
+def test_host_upload_of_other_particles_retires_the_tree(engine):
+    """sfe_bh() walks the records sfe_tree_build() uploaded; a host PP / SPH call in between uploads other records into
+    the same device buffer, so the tree is retired instead of being walked against them."""
+    N = 3000
+    pos, vel, mas = sfo.initcond(N)
+    sim = engine.Sim(N); sim.pos[:] = pos; sim.mas[:] = mas
+    engine.tree_init(sim.tree, 2 * N); sim.tree.bounds[:] = sfo.root_box(pos, 0)
+    assert engine.tree_build(sim.tree, N, sim.pos, sim.mas) == 0
+    assert engine.solve_gravity_part_tree(sim) == 0
+    other = engine.Sim(N); other.pos[:] = pos[::-1]; other.mas[:] = mas
+    assert engine.solve_gravity_part_part(other) == 0
+    assert engine.solve_gravity_part_tree(sim) == engine.STARFLOOD_FAILURE and "no tree" in engine.last_error()
+    rb = np.zeros(4 * 64 * 64, np.float32)
+    assert engine.lib().sfe_bh_overlay(3, 0.5, matrix().ctypes.data, rb.ctypes.data, 64, 64) == engine.STARFLOOD_FAILURE
