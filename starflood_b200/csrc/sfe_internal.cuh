@@ -71,6 +71,7 @@ struct Tree {
     DevBuf nmid;         // float4[nodes_max]      split planes of internal nodes
     DevBuf lookback;     // tickets + look-back descriptors + long-node lists of one build (zeroed per build)
     DevBuf xl_sum, xl_map;   // scratch of the exact chunked fold
+    DevBuf sub_list;         // uint2[N / 9 + 1]  subtree roots (sfe_subtree.cuh)
     uint32_t* summary_host = nullptr;  // mapped pinned: per-level summaries written by the device
     uint32_t* summary_dev = nullptr;
     uint32_t build_id = 0;

@@ -31,6 +31,7 @@
 #include "sfe_scan.cuh"
 #include <chrono>
 #include <stdlib.h>
+#include <vector>
 
 namespace sfe {
 
@@ -309,6 +310,16 @@ __global__ void __launch_bounds__(PT_THREADS, 4) rank_kernel(TreeDev t, int d) {
     }
 }
 
+// a node of 9 .. sub_max bodies is a subtree root: the grid-wide passes stop there, subtree_kernel finishes it
+__device__ __forceinline__ bool sub_owns(const TreeDev& t, uint32_t cn) { return cn > 8u && cn <= t.sub_max; }
+__device__ __forceinline__ void sub_append(const TreeDev& t, uint32_t node, uint32_t level) {
+    t.sub_list[atomicAdd(t.sub_count, 1u)] = make_uint2(node, level);
+}
+
+}  // namespace sfe
+#include "sfe_subtree.cuh"
+namespace sfe {
+
 // ---------------------------------------------------------------------------- children_kernel
 // level summary for the host (mapped pinned memory): {build id, internal nodes of the level, status, node count}
 __device__ __forceinline__ void publish_summary(const TreeDev& t, int level, uint32_t internal, uint32_t status, uint32_t count) {
@@ -339,12 +350,13 @@ __device__ __forceinline__ void open_level(const TreeDev& t, int lv, uint32_t in
 __global__ void root_kernel(TreeDev t, int depth_max) {
     // runs after the compaction: the root is internal when it holds more than 8 bodies
     const uint32_t M = t.meta[M_NUM_INBOX];
-    const bool internal = M > 8u;
+    const bool internal = M > t.sub_max;                 // split by the grid-wide passes
+    if (sub_owns(t, M)) sub_append(t, 0u, 0u);           // the whole tree is one subtree
     t.child_base[0] = internal ? 1u : NODE_END;
     const float* b = t.bounds;
     t.nmid[0] = make_float4(__fmul_rn(0.5f, __fadd_rn(b[0], b[3])), __fmul_rn(0.5f, __fadd_rn(b[1], b[4])),
                             __fmul_rn(0.5f, __fadd_rn(b[2], b[5])), 0.f);
-    if (M > t.xl_min) { t.xl_count[0] = 1u; t.xl_nodes[0] = 0u; }
+    if (M > t.xl_min && !sub_owns(t, M)) { t.xl_count[0] = 1u; t.xl_nodes[0] = 0u; }
     open_level(t, 0, internal ? 1u : 0u, depth_max);
     if (t.meta[M_STATUS] != 0u) t.child_base[0] = NODE_END;
 }
@@ -378,7 +390,7 @@ __global__ void __launch_bounds__(CH_THREADS) children_kernel(TreeDev t, int d, 
             const uint4 c1 = *reinterpret_cast<const uint4*>(&t.counts[(size_t)n * 8u + 4u]);
             cnt[0] = c0.x; cnt[1] = c0.y; cnt[2] = c0.z; cnt[3] = c0.w; cnt[4] = c1.x; cnt[5] = c1.y; cnt[6] = c1.z; cnt[7] = c1.w;
 #pragma unroll
-            for (int o = 0; o < 8; o++) ki += cnt[o] > 8u ? 1u : 0u;
+            for (int o = 0; o < 8; o++) ki += cnt[o] > t.sub_max ? 1u : 0u;
         }
         uint32_t tile_total;
         const uint32_t ex = block_excl_scan(ki, &tile_total, sm);
@@ -441,7 +453,7 @@ __global__ void __launch_bounds__(CH_THREADS) children_kernel(TreeDev t, int d, 
                 cell[0] = make_float4(clo[0], clo[1], clo[2], chi[0]);
                 cell[1] = make_float4(chi[1], chi[2], __uint_as_float(n), 0.f);
                 t.rec1[c] = make_float4(0.f, 0.f, 0.f, 0.f);          // moments of empty nodes stay zero (tree.c:302-310)
-                if (cn > 8u) {
+                if (cn > t.sub_max) {
                     t.child_base[c] = child_level_end + 8u * r; r++;
                     t.nmid[c] = make_float4(__fmul_rn(0.5f, __fadd_rn(clo[0], chi[0])), __fmul_rn(0.5f, __fadd_rn(clo[1], chi[1])),
                                             __fmul_rn(0.5f, __fadd_rn(clo[2], chi[2])), 0.f);
@@ -449,7 +461,9 @@ __global__ void __launch_bounds__(CH_THREADS) children_kernel(TreeDev t, int d, 
                     t.child_base[c] = NODE_END;
                 }
                 t.seg[c] = make_uint2(start, start + cn);
-                if (d + 1 <= XL_DEPTH_MAX && cn > t.xl_min) {     // very long fold: chunked exact evaluation (moments_xl)
+                if (sub_owns(t, cn)) {
+                    sub_append(t, c, (uint32_t)d + 1u);           // finished (moments included) by subtree_kernel
+                } else if (d + 1 <= XL_DEPTH_MAX && cn > t.xl_min) {     // very long fold: chunked exact evaluation (moments_xl)
                     const uint32_t k = atomicAdd(&t.xl_count[d + 1], 1u);
                     if (k < t.xl_max) t.xl_nodes[(size_t)(d + 1) * t.xl_max + k] = c;
                 } else if (cn > ML_MIN) {
@@ -490,7 +504,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(TreeDev t, int d) {
             const uint32_t c = t.child_base[n] + o;
             const uint2 sg = t.seg[c];
             dest = sg.x + t.rank[s];
-            owner = (sg.y - sg.x) > 8u ? c : NODE_END;      // only slots of internal nodes stay active
+            owner = (sg.y - sg.x) > t.sub_max ? c : NODE_END;   // only slots of nodes the grid-wide passes split stay active
             key |= (uint64_t)o << (45 - 3 * d);             // digit d of the 48-bit path key
         }
         perm_next[dest] = perm[s];
@@ -534,8 +548,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // which kernel folds a node with cn members at level d
-__device__ __forceinline__ bool xl_owns(const TreeDev& t, int d, uint32_t cn) { return d <= XL_DEPTH_MAX && cn > t.xl_min; }
-__device__ __forceinline__ bool ml_owns(const TreeDev& t, int d, uint32_t cn) { return cn > ML_MIN && !xl_owns(t, d, cn); }
+__device__ __forceinline__ bool xl_owns(const TreeDev& t, int d, uint32_t cn) { return d <= XL_DEPTH_MAX && cn > t.xl_min && !sub_owns(t, cn); }
+__device__ __forceinline__ bool ml_owns(const TreeDev& t, int d, uint32_t cn) { return cn > ML_MIN && !xl_owns(t, d, cn) && !sub_owns(t, cn); }
 
 __global__ void __launch_bounds__(ML_THREADS) moments_long_kernel(TreeDev t, int d,
                                                                   uint32_t* __restrict__ gate /* {needed, done} or null */) {
@@ -650,7 +664,7 @@ __global__ void __launch_bounds__(256) moments_short_kernel(TreeDev t, int d, ui
         const bool live = n < e;
         const uint2 sg = live ? t.seg[n] : make_uint2(0u, 0u);
         uint32_t cnt = sg.y - sg.x;
-        if (cnt > ML_MIN) cnt = 0u;                               // the pipelined kernel owns the long nodes
+        if (cnt > ML_MIN || sub_owns(t, cnt)) cnt = 0u;           // the pipelined kernel owns the long nodes, subtree_kernel its roots
         const float* __restrict__ src = reinterpret_cast<const float*>(spm4 + sg.x);
         float sum = 0.f;
 #pragma unroll 4
@@ -968,6 +982,12 @@ static bool trace_enabled() {
 static cudaEvent_t g_trace_ev[2 * (SFE_MAX_LEVELS + 3)];
 static cudaEvent_t g_trace_k[2 * (SFE_MAX_LEVELS + 3)];   // SFE_TRACE: after rank_kernel / children_kernel of every level
 
+static uint32_t sub_max_members() {   // SFE_SUBTREE_MAX: 8 switches the subtree path off (grid-wide passes down to the leaves)
+    static uint32_t v = 0;
+    if (v == 0) { const char* e = getenv("SFE_SUBTREE_MAX"); v = e ? (uint32_t)atoi(e) : (uint32_t)ST_MAX; if (v < 8u) v = 8u; if (v > (uint32_t)ST_MAX) v = (uint32_t)ST_MAX; }
+    return v;
+}
+
 static uint32_t xl_min_members() {   // SFE_XL_MIN lowers the threshold so that small test trees exercise the chunked fold
     static uint32_t v = 0;
     if (v == 0) { const char* e = getenv("SFE_XL_MIN"); v = e ? (uint32_t)atoi(e) : 8192u; if (v < 64u) v = 64u; }
@@ -1007,6 +1027,8 @@ static TreeDev make_dev(Tree& t) {
     d.cdesc_stride = (t.nodes_max + CH_THREADS - 1) / CH_THREADS + 1;
     uint32_t* w = t.lookback.as<uint32_t>();
     d.ticket = w;                 w += 2 * levels;
+    d.sub_count = w;              w += 1;
+    d.sub_ticket = w;             w += 1;
     d.xl_count = w;               w += levels;
     d.ml_count = w;               w += levels;
     d.xl_nodes = w;               w += (size_t)(XL_DEPTH_MAX + 1) * d.xl_max;
@@ -1014,6 +1036,8 @@ static TreeDev make_dev(Tree& t) {
     d.cdesc = reinterpret_cast<unsigned long long*>(t.lookback.as<char>() + ((size_t)(w - t.lookback.as<uint32_t>()) * 4 + 7) / 8 * 8);
     d.xl_sum = t.xl_sum.as<double>();
     d.xl_map = t.xl_map.as<long long>();
+    d.sub_max = sub_max_members();
+    d.sub_list = t.sub_list.as<uint2>();
     d.summary = t.summary_dev;
     d.build_id = t.build_id;
     d.rec0 = t.rec0.as<WalkRec0>();
@@ -1024,7 +1048,7 @@ static TreeDev make_dev(Tree& t) {
 
 static size_t lookback_bytes(const TreeDev& d) {
     const size_t levels = SFE_MAX_LEVELS + 2;
-    const size_t words = 2 * levels + levels + levels + (size_t)(XL_DEPTH_MAX + 1) * d.xl_max + levels * d.tdesc_stride;
+    const size_t words = 2 * levels + 2 + levels + levels + (size_t)(XL_DEPTH_MAX + 1) * d.xl_max + levels * d.tdesc_stride;
     return (words * 4 + 7) / 8 * 8 + levels * (size_t)d.cdesc_stride * 8;
 }
 
@@ -1048,7 +1072,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         t.meta.reserve(M_WORDS * 4, fn) || t.root_gate.reserve(8, fn) || t.rec0.reserve((size_t)nodes_max * sizeof(WalkRec0), fn) ||
         t.rec1.reserve((size_t)nodes_max * 16, fn) || t.rec2.reserve((size_t)nodes_max * sizeof(WalkRec2), fn) ||
         t.perm[0].reserve(n1 * 4, fn) || t.perm[1].reserve(n1 * 4, fn) || t.spm4[0].reserve(n1 * 16, fn) ||
-        t.spm4[1].reserve(n1 * 16, fn))
+        t.spm4[1].reserve(n1 * 16, fn) || t.sub_list.reserve((n1 / 9 + 2) * 8, fn))
         return SFE_FAILURE;
     if (!t.meta_host) SFE_CUDA(fn, cudaMallocHost(&t.meta_host, sizeof(uint32_t) * M_WORDS));
     if (!t.summary_host) {
@@ -1152,6 +1176,27 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
             cudaEventElapsedTime(&ch, g_trace_k[2 * d], g_trace_k[2 * d + 1]);
             cudaEventElapsedTime(&sc, g_trace_k[2 * d + 1], t.ev_perm[d + 1]);
             fprintf(stderr, "[sfe trace] level %2d: device %8.1f us (rank %.1f children %.1f scatter %.1f)   host enqueue at %8.1f us (+%.1f)\n", d, ms * 1e3, r * 1e3, ch * 1e3, sc * 1e3, host_us[d], host_us[d + 1] - host_us[d]);
+        }
+    }
+    // everything below the subtree roots: one CTA per root, drawn from a ticket (the final slot arrays are rewritten in
+    // place range by range; the folds on the side streams read other ranges or other levels' arrays)
+    if (dv.sub_max > 8u) {
+        static bool st_attr = false;
+        if (!st_attr) {
+            SFE_CUDA(fn, cudaFuncSetAttribute(subtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StShared)));
+            st_attr = true;
+        }
+        const uint32_t roots_max = N / 9u + 1u;
+        const uint32_t sg = roots_max < (uint32_t)c->sm_count * 2u ? roots_max : (uint32_t)c->sm_count * 2u;
+        if (trace_enabled()) cudaEventRecord(g_trace_ev[0], s);
+        subtree_kernel<<<sg, ST_THREADS, sizeof(StShared), s>>>(dv, depth_max);
+        if (check_launch(fn)) return SFE_FAILURE;
+        if (trace_enabled()) {
+            cudaEventRecord(g_trace_ev[1], s);
+            cudaStreamSynchronize(s);
+            float a = 0.f;
+            cudaEventElapsedTime(&a, g_trace_ev[0], g_trace_ev[1]);
+            fprintf(stderr, "[sfe trace] subtree_kernel: %8.1f us\n", a * 1e3);
         }
     }
     // join the side streams, then build the walk records
@@ -1261,8 +1306,37 @@ extern "C" int sfe_tree_download(sfe_node_t* nodes, uint32_t max_nodes, uint32_t
     if (t.nodes.reserve((size_t)t.num_nodes * sizeof(sfe_node_t), fn)) return SFE_FAILURE;
     table_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(tree_dev(c));
     if (check_launch(fn)) return SFE_FAILURE;
-    SFE_CUDA(fn, cudaMemcpyAsync(nodes, t.nodes.p, (size_t)t.num_nodes * sizeof(sfe_node_t), cudaMemcpyDeviceToHost, c->stream));
+    if (sub_max_members() <= 8u) {     // grid-wide passes only: the engine's numbering already is the breadth-first one
+        SFE_CUDA(fn, cudaMemcpyAsync(nodes, t.nodes.p, (size_t)t.num_nodes * sizeof(sfe_node_t), cudaMemcpyDeviceToHost, c->stream));
+        SFE_CUDA(fn, cudaStreamSynchronize(c->stream));
+        return SFE_SUCCESS;
+    }
+    // Node ids below the subtree roots are handed out in CTA arrival order (sfe_subtree.cuh): renumber breadth-first -
+    // the children of a level allocated eight at a time in parent order, which is the canonical numbering of the
+    // level-by-level construction - on the way out.  The queue holds old ids; the position in the queue is the new id.
+    const uint32_t n = t.num_nodes;
+    std::vector<sfe_node_t> raw(n);
+    std::vector<uint32_t> queue(n);
+    SFE_CUDA(fn, cudaMemcpyAsync(raw.data(), t.nodes.p, (size_t)n * sizeof(sfe_node_t), cudaMemcpyDeviceToHost, c->stream));
     SFE_CUDA(fn, cudaStreamSynchronize(c->stream));
+    uint32_t head = 0, tail = 0;
+    queue[tail++] = 0u;
+    nodes[0] = raw[0];
+    nodes[0].parent = 0u;
+    while (head < tail) {
+        const uint32_t nid = head, oid = queue[head++];
+        if (raw[oid].bodies <= 8u) continue;
+        if (tail + 8u > n) { set_error(fn, "inconsistent node table (more children than nodes)"); return SFE_FAILURE; }
+        for (uint32_t o = 0; o < 8u; o++) {
+            const uint32_t child = raw[oid].branch[o];
+            if (child >= n) { set_error(fn, "inconsistent node table (child %u of node %u outside the table)", child, oid); return SFE_FAILURE; }
+            nodes[tail] = raw[child];
+            nodes[tail].parent = nid;
+            nodes[nid].branch[o] = tail;
+            queue[tail++] = child;
+        }
+    }
+    if (tail != n) { set_error(fn, "inconsistent node table (%u of %u nodes reachable)", tail, n); return SFE_FAILURE; }
     return SFE_SUCCESS;
 }
 

@@ -70,6 +70,11 @@ struct TreeDev {
     uint32_t xl_min;              // nodes with more members than this use the chunked exact fold
     double* xl_sum;               // [SFE_SIDE_STREAMS][xl_slots][4] chunk sums, then exclusive prefixes, of the rounded products
     long long* xl_map;            // [SFE_SIDE_STREAMS][xl_slots][4][8] {a0, a1, min0, max0, min1, max1, exponent, usable}
+    // lower part of the build (sfe_subtree.cuh): nodes of 9 .. sub_max bodies are finished by one CTA each
+    uint32_t sub_max;             // 8 switches the subtree path off (every level goes through the grid-wide kernels)
+    uint2* sub_list;              // {node id, level} of every subtree root, in no particular order
+    uint32_t* sub_count;
+    uint32_t* sub_ticket;
     volatile uint32_t* summary;   // mapped host memory: {build id, internal nodes, status, node count} per level
     uint32_t build_id;
     WalkRec0* rec0;

@@ -110,3 +110,22 @@ def test_full_size(engine):
     leaves = nodes[nodes["bodies"] <= 8]
     assert int(leaves["bodies"].sum()) == nin == int(nodes["bodies"][0])
     assert len(nodes) == 1 + 8 * int((nodes["bodies"] > 8).sum())
+
+
+@pytest.mark.parametrize("sub_max,xl_min", [(8, None), (40, None), (300, 64), (2048, 64)])
+def test_build_variants_in_a_fresh_process(sub_max, xl_min):
+    """The build has two halves: grid-wide passes for the upper levels and one CTA per subtree root below
+    (SFE_SUBTREE_MAX bodies at most; 8 switches the subtree path off).  The library reads the thresholds once, so every
+    setting runs this file's parity cases in a process of its own: all passes grid-wide (8), subtrees of a few dozen
+    bodies so that small trees mix both halves over several levels (40, 300), and with the exact chunked fold of very
+    long nodes lowered to 64 members (SFE_XL_MIN) so that small trees exercise it next to the subtrees."""
+    if os.environ.get("SFE_TREE_VARIANT_CHILD"):
+        pytest.skip("already inside a variant run")
+    import subprocess, sys
+    env = dict(os.environ, SFE_SUBTREE_MAX=str(sub_max), SFE_TREE_VARIANT_CHILD="1")
+    if xl_min:
+        env["SFE_XL_MIN"] = str(xl_min)
+    sel = "golden or sizes or ties or outside or clustered or failures" + (" or full_size" if sub_max in (8, 300) else "")
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel],
+                       capture_output=True, text=True, env=env, timeout=1200)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
