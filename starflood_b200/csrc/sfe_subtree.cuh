@@ -252,14 +252,24 @@ __global__ void __launch_bounds__(ST_THREADS, 2) subtree_kernel(TreeDev t, int d
                     } else if (wq < items) {
                         cn = cnt; s0 = 0u; gid = root; order = nullptr;
                     }
+                    // scalar component loads (no select on a loaded float4: ptxas turned that into a branch per element);
+                    // the loads do not depend on the running sum, so the unrolled body issues them ahead of the FADD chain
+                    const float* __restrict__ recf = reinterpret_cast<const float*>(S.rec);
                     float sum = 0.f;
-                    for (uint32_t i = 0; i < cn; i++) {
-                        const uint32_t l = order ? order[s0 + i] : i;
-                        const float4 p = S.rec[l];
-                        const float m = p.w;
-                        const float v = comp == 0u ? p.x : comp == 1u ? p.y : p.z;
-                        const float term = comp == 3u ? m : __fmul_rn(m, v);   // product rounded, then added
-                        sum = __fadd_rn(sum, term);
+                    if (order) {
+                        const uint16_t* __restrict__ op = order + s0;
+#pragma unroll 8
+                        for (uint32_t i = 0; i < cn; i++) {
+                            const uint32_t l = op[i];
+                            const float m = recf[4u * l + 3u], v = recf[4u * l + comp];
+                            sum = __fadd_rn(sum, comp == 3u ? m : __fmul_rn(m, v));   // product rounded, then added
+                        }
+                    } else {
+#pragma unroll 8
+                        for (uint32_t i = 0; i < cn; i++) {
+                            const float m = recf[4u * i + 3u], v = recf[4u * i + comp];
+                            sum = __fadd_rn(sum, comp == 3u ? m : __fmul_rn(m, v));
+                        }
                     }
                     const float mass = __shfl_sync(0xFFFFFFFFu, sum, (int)(lane | 3u));
                     if (cn) {
