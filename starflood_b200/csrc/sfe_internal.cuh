@@ -61,17 +61,15 @@ struct Tree {
     DevBuf child_base;   // uint32_t[nodes_max]    first child of internal nodes
     DevBuf counts;       // uint32_t[8*nodes_max]  per-octant member counts of internal nodes
     DevBuf keys;         // uint64_t[N]            48-bit path keys by particle index (on demand)
-    DevBuf skey[2];      // uint64_t[N]            path key of every slot, ping-pong between levels
-    DevBuf perm[SFE_MAX_LEVELS + 3];   // uint32_t[N] slot -> particle index, one array per level
-    DevBuf spm4[SFE_MAX_LEVELS + 3];   // float4[N]  slot-ordered particle records, one array per level
+    DevBuf srec[SFE_MAX_LEVELS + 3];   // SlotRec[N]  the particle order of every level: {x,y,z,m | key | index | owning node}
     DevBuf perm_out;     // uint32_t[N]            out-of-box particles in ascending index
-    DevBuf slot_node[2]; // uint32_t[N]            node owning each slot (ping-pong between levels)
     DevBuf oct;          // uint8_t[N]
     DevBuf rank;         // uint32_t[N]            stable rank inside (node, octant)
     DevBuf nmid;         // float4[nodes_max]      split planes of internal nodes
     DevBuf lookback;     // tickets + look-back descriptors + long-node lists of one build (zeroed per build)
     DevBuf xl_sum, xl_map;   // scratch of the exact chunked fold
     DevBuf sub_list;         // uint2[N / 9 + 1]  subtree roots (sfe_subtree.cuh)
+    DevBuf top_table, top_cols, top_rank;   // one-pass construction of the upper levels (sfe_top.cuh)
     uint32_t* summary_host = nullptr;  // mapped pinned: per-level summaries written by the device
     uint32_t* summary_dev = nullptr;
     uint32_t build_id = 0;

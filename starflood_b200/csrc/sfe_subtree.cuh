@@ -61,9 +61,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) subtree_kernel(TreeDev t, int d
     if (t.meta[M_STATUS] != 0u) return;
     const uint32_t nsub = *t.sub_count;
     const uint32_t fin = t.meta[M_FINAL];
-    uint32_t* __restrict__ g_perm = t.perm[fin];
-    float4* __restrict__ g_spm4 = t.spm4[fin];
-    unsigned long long* __restrict__ g_skey = reinterpret_cast<unsigned long long*>(t.skey[fin & 1u]);
+    SlotRec* __restrict__ g_rec = t.srec[fin];
     for (;;) {
         __syncthreads();                                   // the previous subtree is completely written back
         if (tid == 0) { S.ticket = atomicAdd(t.sub_ticket, 1u); S.abort = 0u; }
@@ -77,9 +75,10 @@ __global__ void __launch_bounds__(ST_THREADS, 2) subtree_kernel(TreeDev t, int d
         // ---------------------------------------------------------------- load the members (ascending index order)
         for (uint32_t i = tid; i < (uint32_t)ST_MAX; i += ST_THREADS) {
             if (i < cnt) {
-                S.rec[i] = g_spm4[slot0 + i];
-                S.pidx[i] = g_perm[slot0 + i];
-                S.key[i] = g_skey[slot0 + i];
+                const SlotRec r = slot_load(&g_rec[slot0 + i]);
+                S.rec[i] = r.pm;
+                S.pidx[i] = r.idx;
+                S.key[i] = r.key;
                 S.ord[0][i] = (uint16_t)i;
                 S.snode[0][i] = 0u;
             } else {
@@ -287,9 +286,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) subtree_kernel(TreeDev t, int d
         // ---------------------------------------------------------------- final (key, index) order of the range, in place
         for (uint32_t s = tid; s < cnt; s += ST_THREADS) {
             const uint32_t l = S.ord[cur][s];
-            g_perm[slot0 + s] = S.pidx[l];
-            g_spm4[slot0 + s] = S.rec[l];
-            g_skey[slot0 + s] = S.key[l];
+            slot_store(&g_rec[slot0 + s], S.rec[l], S.key[l], S.pidx[l], NODE_END);
         }
     }
 }

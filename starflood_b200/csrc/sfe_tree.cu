@@ -47,7 +47,7 @@ struct CompactOp {
     __device__ uint32_t load(uint32_t i) const { return in_box(t.bounds, pm4[i]) ? 1u : 0u; }
     __device__ void store(uint32_t i, uint32_t ex) const {
         const float4 p = pm4[i];
-        if (in_box(t.bounds, p)) { t.perm0[ex] = i; t.slot_node0[ex] = 0u; t.skey[0][ex] = 0ull; t.spm4[0][ex] = p; }
+        if (in_box(t.bounds, p)) slot_store(&t.srec[0][ex], p, 0ull, i, 0u);
         else t.perm_out[i - ex] = i;
     }
     __device__ void total(uint32_t M) const {
@@ -191,8 +191,7 @@ __global__ void __launch_bounds__(PT_THREADS, 4) rank_kernel(TreeDev t, int d) {
     if (level_idle(t, d)) return;
     const uint32_t M = t.meta[M_NUM_INBOX];
     const uint32_t ntiles = (M + PT_TILE - 1) / PT_TILE;
-    const float4* __restrict__ spm4 = t.spm4[d];
-    const uint32_t* __restrict__ slot_node = t.slot_node[d & 1];
+    const SlotRec* __restrict__ rec = t.srec[d];
     uint32_t* __restrict__ desc_base = t.tdesc + (size_t)d * t.tdesc_stride;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, myo = lane & 7u;
     const uint32_t lt = (1u << lane) - 1u, le = lt | (1u << lane);
@@ -210,11 +209,12 @@ __global__ void __launch_bounds__(PT_THREADS, 4) rank_kernel(TreeDev t, int d) {
             const uint32_t s = w0 + 32u * g;
             uint32_t byte = 0u, n = NODE_END;
             if (s < M) {
-                n = slot_node[s];
+                const SlotRec r = slot_load(&rec[s]);
+                n = r.owner;
                 if (n != NODE_END) {                       // slot of an internal node (scatter marks the others)
                     const float4 mid = t.nmid[n];
                     const uint2 sg = t.seg[n];
-                    byte = pick_octant(mid, spm4[s], s - sg.x < 8u) | SB_ACTIVE | (s == sg.x ? SB_HEAD : 0u) | (s + 1u == sg.y ? SB_LAST : 0u);
+                    byte = pick_octant(mid, r.pm, s - sg.x < 8u) | SB_ACTIVE | (s == sg.x ? SB_HEAD : 0u) | (s + 1u == sg.y ? SB_LAST : 0u);
                 }
             }
             b[g] = byte; nn[g] = n;
@@ -487,30 +487,22 @@ __global__ void __launch_bounds__(CH_THREADS) children_kernel(TreeDev t, int d, 
 __global__ void __launch_bounds__(256) scatter_kernel(TreeDev t, int d) {
     if (level_idle(t, d)) return;
     const uint32_t M = t.meta[M_NUM_INBOX];
-    const uint32_t* __restrict__ perm = t.perm[d];
-    uint32_t* __restrict__ perm_next = t.perm[d + 1];
-    const uint32_t* __restrict__ slot_node = t.slot_node[d & 1];
-    uint32_t* __restrict__ slot_node_next = t.slot_node[(d + 1) & 1];
-    const float4* __restrict__ spm4 = t.spm4[d];
-    float4* __restrict__ spm4_next = t.spm4[d + 1];
-    const uint64_t* __restrict__ skey = t.skey[d & 1];
-    uint64_t* __restrict__ skey_next = t.skey[(d + 1) & 1];
+    const SlotRec* __restrict__ rec = t.srec[d];
+    SlotRec* __restrict__ rec_next = t.srec[d + 1];
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < M; s += gridDim.x * blockDim.x) {
-        const uint32_t n = slot_node[s];
+        const SlotRec r = slot_load(&rec[s]);
+        const uint32_t n = r.owner;
         uint32_t dest = s, owner = NODE_END;
-        uint64_t key = skey[s];
+        unsigned long long key = r.key;
         if (n != NODE_END) {
             const uint32_t o = t.oct[s];
             const uint32_t c = t.child_base[n] + o;
             const uint2 sg = t.seg[c];
             dest = sg.x + t.rank[s];
             owner = (sg.y - sg.x) > t.sub_max ? c : NODE_END;   // only slots of nodes the grid-wide passes split stay active
-            key |= (uint64_t)o << (45 - 3 * d);             // digit d of the 48-bit path key
+            key |= (unsigned long long)o << (45 - 3 * d);   // digit d of the 48-bit path key
         }
-        perm_next[dest] = perm[s];
-        slot_node_next[dest] = owner;
-        spm4_next[dest] = spm4[s];
-        skey_next[dest] = key;
+        slot_store(&rec_next[dest], r.pm, key, r.idx, owner);
     }
 }
 
@@ -518,9 +510,14 @@ __global__ void __launch_bounds__(256) scatter_kernel(TreeDev t, int d) {
 __global__ void keys_gather_kernel(TreeDev t, uint32_t N) {
     const uint32_t M = t.meta[M_NUM_INBOX], fin = t.meta[M_FINAL];
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < N; s += gridDim.x * blockDim.x) {
-        if (s < M) t.keys[t.perm[fin][s]] = t.skey[fin & 1u][s];
+        if (s < M) { const SlotRec r = slot_load(&t.srec[fin][s]); t.keys[r.idx] = r.key; }
         else t.keys[t.perm_out[s - M]] = ~0ull;
     }
+}
+
+__global__ void perm_gather_kernel(TreeDev t, uint32_t* __restrict__ out) {
+    const uint32_t M = t.meta[M_NUM_INBOX], fin = t.meta[M_FINAL];
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < M; s += gridDim.x * blockDim.x) out[s] = t.srec[fin][s].idx;
 }
 
 // ============================================================================ moments (tree.c:166-169, :302-310)
@@ -562,7 +559,7 @@ __global__ void __launch_bounds__(ML_THREADS) moments_long_kernel(TreeDev t, int
     if (d > 0 && t.ml_count[d] == 0u) return;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t b = t.meta[M_LV_BEGIN + d], e = t.meta[M_LV_END + d];
-    const float4* __restrict__ spm4 = t.spm4[d];
+    const SlotRec* __restrict__ rec = t.srec[d];
     for (uint32_t base = b + blockIdx.x * 8u; base < e; base += gridDim.x * 8u) {
         // every thread looks at the 8 segments of the group (uniform loads) for the trip count
         uint32_t maxcnt = 0u;
@@ -601,7 +598,7 @@ __global__ void __launch_bounds__(ML_THREADS) moments_long_kernel(TreeDev t, int
             const uint32_t node = warp - 1u;
             const uint2 sg = base + node < e ? t.seg[base + node] : make_uint2(0u, 0u);
             const uint32_t cnt = ml_owns(t, d, sg.y - sg.x) ? (sg.y - sg.x) : 0u;
-            const float4* __restrict__ src = spm4 + sg.x;
+            const SlotRec* __restrict__ src = rec + sg.x;
             auto issue = [&](uint32_t k) {       // raw batch k -> ring slot k % ML_R
                 const uint32_t j0 = k * ML_B;
                 if (j0 < cnt) {
@@ -609,7 +606,7 @@ __global__ void __launch_bounds__(ML_THREADS) moments_long_kernel(TreeDev t, int
 #pragma unroll
                     for (int h = 0; h < ML_B / 32; h++) {
                         const uint32_t j = lane + 32u * h;
-                        if (j0 + j < cnt) cp_async16(dst + j, src + j0 + j);
+                        if (j0 + j < cnt) cp_async16(dst + j, &src[j0 + j].pm);
                     }
                 }
                 cp_async_commit();               // one (possibly empty) group per batch index keeps the wait arithmetic uniform
@@ -657,7 +654,7 @@ __global__ void __launch_bounds__(256) moments_short_kernel(TreeDev t, int d, ui
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
     const uint32_t c = threadIdx.x & 3u;
     const uint32_t b = t.meta[M_LV_BEGIN + d], e = t.meta[M_LV_END + d];
-    const float4* __restrict__ spm4 = t.spm4[d];
+    const SlotRec* __restrict__ rec = t.srec[d];
     const uint32_t quads = (e - b);
     for (uint32_t qd = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; qd < ((quads + 7u) & ~7u); qd += (gridDim.x * blockDim.x) >> 2) {
         const uint32_t n = b + qd;
@@ -665,12 +662,12 @@ __global__ void __launch_bounds__(256) moments_short_kernel(TreeDev t, int d, ui
         const uint2 sg = live ? t.seg[n] : make_uint2(0u, 0u);
         uint32_t cnt = sg.y - sg.x;
         if (cnt > ML_MIN || sub_owns(t, cnt)) cnt = 0u;           // the pipelined kernel owns the long nodes, subtree_kernel its roots
-        const float* __restrict__ src = reinterpret_cast<const float*>(spm4 + sg.x);
+        const float* __restrict__ src = reinterpret_cast<const float*>(rec + sg.x);   // {x, y, z, m} lead every 32-byte record
         float sum = 0.f;
 #pragma unroll 4
         for (uint32_t j = 0; j < cnt; j++) {
-            const float m = __ldg(src + 4u * j + 3u);
-            const float p = __fmul_rn(m, __ldg(src + 4u * j + c));  // tree.c:166-168: product rounded, then added
+            const float m = __ldg(src + 8u * j + 3u);
+            const float p = __fmul_rn(m, __ldg(src + 8u * j + c));  // tree.c:166-168: product rounded, then added
             sum = __fadd_rn(sum, c == 3u ? m : p);                  // tree.c:169
         }
         const float mass = __shfl_sync(0xFFFFFFFFu, sum, (threadIdx.x & 31u) | 3u);
@@ -689,12 +686,17 @@ __global__ void __launch_bounds__(256) moments_short_kernel(TreeDev t, int d, ui
 // parallel, into a map k -> k + a[k & 1], together with the extremes of the running value inside the chunk.
 //   xl_sums / xl_prefix   approximate value of the fold at every chunk boundary (double sums of the rounded products),
 //                         good enough to GUESS the binade, i.e. u, of each chunk;
-//   xl_maps               per chunk and component: the parity map and the prefix extremes for the guessed u;
-//   xl_chain              the only serial part: one step per CHUNK.  The map is used only if the actual s is a
-//                         multiple of u strictly inside the binade and the extremes keep every intermediate value
-//                         inside it; otherwise (binade crossings, the first chunks, wrong guesses) that chunk is folded
-//                         member by member.  The result is the reference's bit pattern either way.
-constexpr int XL_CHUNK = 1024;
+//   xl_maps               per chunk and component: the parity map and the prefix extremes for the guessed u (a lane
+//                         composes its eight consecutive members, an ordered warp reduction composes the lanes);
+//   xl_chain              the only serial part, one warp per (node, component): the maps of 32 consecutive chunks are
+//                         composed with a warp scan (lane i: chunks 0..i of the batch, as long as they share u), every
+//                         lane tests its prefix against the actual s - a multiple of u strictly inside the binade, with
+//                         the extremes keeping every intermediate value inside it - and the longest valid prefix is
+//                         applied at once, so a run of chunks inside one binade costs one step per 32 chunks.  A chunk
+//                         whose map does not apply (binade crossings, the first chunks, wrong guesses) is folded member
+//                         by member.  The result is the reference's bit pattern either way.
+constexpr int XL_CHUNK = 256;
+constexpr int XL_PER_LANE = XL_CHUNK / 32;
 constexpr long long XL_INF = 1ll << 62;
 struct XlMap { long long a0, a1, mn0, mx0, mn1, mx1, e2, usable; };   // 64 B
 
@@ -716,6 +718,16 @@ __device__ __forceinline__ long long shfl_down_ll(long long v, int off) {
     const int hi = __shfl_down_sync(0xFFFFFFFFu, (int)(v >> 32), off);
     return ((long long)hi << 32) | (unsigned int)lo;
 }
+__device__ __forceinline__ long long shfl_up_ll(long long v, int off) {
+    const int lo = __shfl_up_sync(0xFFFFFFFFu, (int)(v & 0xFFFFFFFFll), off);
+    const int hi = __shfl_up_sync(0xFFFFFFFFu, (int)(v >> 32), off);
+    return ((long long)hi << 32) | (unsigned int)lo;
+}
+__device__ __forceinline__ long long shfl_ll(long long v, int src) {
+    const int lo = __shfl_sync(0xFFFFFFFFu, (int)(v & 0xFFFFFFFFll), src);
+    const int hi = __shfl_sync(0xFFFFFFFFu, (int)(v >> 32), src);
+    return ((long long)hi << 32) | (unsigned int)lo;
+}
 __device__ __forceinline__ float xl_term(float4 p, uint32_t q) {   // the q-th summand of tree.c:166-169
     return q == 0u ? __fmul_rn(p.w, p.x) : q == 1u ? __fmul_rn(p.w, p.y) : q == 2u ? __fmul_rn(p.w, p.z) : p.w;
 }
@@ -734,18 +746,28 @@ __device__ __forceinline__ bool xl_node(const TreeDev& t, int d, uint32_t k, XlN
 
 __global__ void __launch_bounds__(256) xl_sums_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
-    XlNode nd;
-    if (!xl_node(t, d, blockIdx.y, &nd)) return;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const float4* __restrict__ src = t.spm4[d] + nd.first;
+    // the chunks of all long nodes of the level are dealt out to the warps of the grid round robin
+    const uint32_t nxl = min(t.xl_count[d], t.xl_max), gw = blockIdx.x * 8u + warp, nw = gridDim.x * 8u;
+    uint32_t dealt = 0u;
+    __shared__ XlNode s_nd[128];                                   // the descriptors of the next 128 long nodes, fetched side by side
+    for (uint32_t kb = 0; kb < nxl; kb += 128u) {
+    __syncthreads();
+    if (threadIdx.x < 128u && kb + threadIdx.x < nxl) xl_node(t, d, kb + threadIdx.x, &s_nd[threadIdx.x]);
+    __syncthreads();
+    for (uint32_t kn = 0; kn < min(128u, nxl - kb); kn++) {
+    const XlNode nd = s_nd[kn];
+    const SlotRec* __restrict__ src = t.srec[d] + nd.first;
     double* __restrict__ sums = t.xl_sum + ((size_t)area * t.xl_slots + nd.slot0) * 4u;
-    for (uint32_t c = blockIdx.x * 8u + warp; c < nd.nchunks; c += gridDim.x * 8u) {
+    const uint32_t c_first = (gw + nw - dealt % nw) % nw;
+    dealt += nd.nchunks;
+    for (uint32_t c = c_first; c < nd.nchunks; c += nw) {
         double a[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-        for (uint32_t i = 0; i < XL_CHUNK / 32; i++) {
+#pragma unroll
+        for (uint32_t i = 0; i < (uint32_t)XL_PER_LANE; i++) {
             const uint32_t j = c * XL_CHUNK + i * 32u + lane;
             if (j < nd.cnt) {
-                const float4 p = src[j];
+                const float4 p = src[j].pm;
                 a[0] += (double)__fmul_rn(p.w, p.x); a[1] += (double)__fmul_rn(p.w, p.y);
                 a[2] += (double)__fmul_rn(p.w, p.z); a[3] += (double)p.w;
             }
@@ -756,37 +778,61 @@ __global__ void __launch_bounds__(256) xl_sums_kernel(TreeDev t, int d, uint32_t
             for (int sh = 16; sh >= 1; sh >>= 1) a[q] += __shfl_xor_sync(0xFFFFFFFFu, a[q], sh);
         if (lane < 4u) sums[(size_t)c * 4u + lane] = a[lane];
     }
+    }
+    }
 }
 
-// exclusive prefix over the chunks of every long node (in place; slot nchunks receives the total)
-__global__ void __launch_bounds__(32) xl_prefix_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
+// exclusive prefix over the chunks of every long node (in place; slot nchunks receives the total): one warp per component,
+// a lane owns a contiguous block of chunks (its loads do not wait for each other), the blocks are joined by a warp scan
+__global__ void __launch_bounds__(128) xl_prefix_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
     XlNode nd;
     if (!xl_node(t, d, blockIdx.x, &nd)) return;
-    if (threadIdx.x >= 4u) return;
-    double* __restrict__ sums = t.xl_sum + ((size_t)area * t.xl_slots + nd.slot0) * 4u + threadIdx.x;
-    double run = 0.0;
-    for (uint32_t c = 0; c < nd.nchunks; c++) { const double v = sums[(size_t)c * 4u]; sums[(size_t)c * 4u] = run; run += v; }
-    sums[(size_t)nd.nchunks * 4u] = run;
+    const uint32_t lane = threadIdx.x & 31u, q = threadIdx.x >> 5;
+    double* __restrict__ sums = t.xl_sum + ((size_t)area * t.xl_slots + nd.slot0) * 4u + q;
+    const uint32_t per = (nd.nchunks + 31u) / 32u, c0 = min(nd.nchunks, lane * per), c1 = min(nd.nchunks, c0 + per);
+    double mine = 0.0;
+#pragma unroll 8
+    for (uint32_t c = c0; c < c1; c++) mine += sums[(size_t)c * 4u];
+    double x = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const double y = __shfl_up_sync(0xFFFFFFFFu, x, off); if (lane >= (uint32_t)off) x += y; }
+    double run = x - mine;
+#pragma unroll 8
+    for (uint32_t c = c0; c < c1; c++) { const double v = sums[(size_t)c * 4u]; sums[(size_t)c * 4u] = run; run += v; }
+    if (lane == 31u) sums[(size_t)nd.nchunks * 4u] = x;
 }
 
 __global__ void __launch_bounds__(256) xl_maps_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
-    XlNode nd;
-    if (!xl_node(t, d, blockIdx.y, &nd)) return;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const float4* __restrict__ src = t.spm4[d] + nd.first;
+    const uint32_t nxl = min(t.xl_count[d], t.xl_max), gw = blockIdx.x * 8u + warp, nw = gridDim.x * 8u;
+    uint32_t dealt = 0u;
+    __shared__ XlNode s_nd[128];                                   // the descriptors of the next 128 long nodes, fetched side by side
+    for (uint32_t kb = 0; kb < nxl; kb += 128u) {
+    __syncthreads();
+    if (threadIdx.x < 128u && kb + threadIdx.x < nxl) xl_node(t, d, kb + threadIdx.x, &s_nd[threadIdx.x]);
+    __syncthreads();
+    for (uint32_t kn = 0; kn < min(128u, nxl - kb); kn++) {
+    const XlNode nd = s_nd[kn];
+    const SlotRec* __restrict__ src = t.srec[d] + nd.first;
     const double* __restrict__ pre = t.xl_sum + ((size_t)area * t.xl_slots + nd.slot0) * 4u;
     XlMap* __restrict__ maps = reinterpret_cast<XlMap*>(t.xl_map) + ((size_t)area * t.xl_slots + nd.slot0) * 4u;
-    for (uint32_t c = blockIdx.x * 8u + warp; c < nd.nchunks; c += gridDim.x * 8u) {
-        // the lane's 32 consecutive members, kept in registers for the four components
-        float4 mem[32];
-        const uint32_t j0 = c * XL_CHUNK + lane * 32u;
+    const uint32_t c_first = (gw + nw - dealt % nw) % nw;
+    dealt += nd.nchunks;
+    for (uint32_t c = c_first; c < nd.nchunks; c += nw) {
+        // the lane's consecutive members, kept in registers for the four components
+        float4 mem[XL_PER_LANE];
+        const uint32_t j0 = c * XL_CHUNK + lane * XL_PER_LANE;
 #pragma unroll
-        for (int i = 0; i < 32; i++) mem[i] = j0 + i < nd.cnt ? src[j0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < XL_PER_LANE; i++) mem[i] = j0 + i < nd.cnt ? src[j0 + i].pm : make_float4(0.f, 0.f, 0.f, 0.f);
+        double pe[8];                                                // approximate fold value at both ends of the chunk
+#pragma unroll
+        for (int i = 0; i < 8; i++) pe[i] = pre[(size_t)c * 4u + i];
+#pragma unroll
         for (uint32_t q = 0; q < 4u; q++) {
             // binade guess from the approximate fold value at both ends of the chunk
-            const float fs = (float)pre[(size_t)c * 4u + q], fe = (float)pre[(size_t)(c + 1u) * 4u + q];
+            const float fs = (float)pe[q], fe = (float)pe[4u + q];
             const uint32_t es = (__float_as_uint(fs) >> 23) & 0xFFu, ee = (__float_as_uint(fe) >> 23) & 0xFFu;
             const bool usable = es == ee && es > 40u && es < 250u && ((__float_as_uint(fs) ^ __float_as_uint(fe)) >> 31) == 0u;
             XlMap m;
@@ -796,7 +842,7 @@ __global__ void __launch_bounds__(256) xl_maps_kernel(TreeDev t, int d, uint32_t
                 const double inv_u = __longlong_as_double((long long)(1023 - m.e2) << 52);
                 long long S0 = 0, S1 = 0;
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
+                for (int i = 0; i < XL_PER_LANE; i++) {
                     if (j0 + i < nd.cnt) {
                         const double tt = (double)xl_term(mem[i], q) * inv_u;   // exact: scaling by a power of two
                         const double fl = floor(tt);
@@ -825,6 +871,28 @@ __global__ void __launch_bounds__(256) xl_maps_kernel(TreeDev t, int d, uint32_t
             if (lane == 0u) maps[(size_t)c * 4u + q] = m;
         }
     }
+    }
+    }
+}
+
+struct XlLane { long long a0, a1, mn0, mx0, mn1, mx1; int e2, usable; };   // a chunk map as a lane carries it
+__device__ __forceinline__ XlLane xl_load(const XlMap* __restrict__ maps, uint32_t c, uint32_t nchunks, uint32_t q) {
+    XlLane m;
+    m.a0 = m.a1 = 0; m.mn0 = m.mn1 = XL_INF; m.mx0 = m.mx1 = -XL_INF; m.e2 = 0; m.usable = 0;
+    if (c < nchunks) {
+        const XlMap g = maps[(size_t)c * 4u + q];
+        m.a0 = g.a0; m.a1 = g.a1; m.mn0 = g.mn0; m.mx0 = g.mx0; m.mn1 = g.mn1; m.mx1 = g.mx1; m.e2 = (int)g.e2; m.usable = (int)g.usable;
+    }
+    return m;
+}
+// the window of 32 maps moves on by nv chunks: lane i takes what lane i + nv held, the tail comes from the next window
+__device__ __forceinline__ long long xl_shift_ll(long long cur, long long nxt, uint32_t nv, uint32_t lane) {
+    const long long a = shfl_ll(cur, (int)((lane + nv) & 31u)), b = shfl_ll(nxt, (int)((lane + nv) & 31u));
+    return lane + nv < 32u ? a : b;
+}
+__device__ __forceinline__ int xl_shift_i(int cur, int nxt, uint32_t nv, uint32_t lane) {
+    const int a = __shfl_sync(0xFFFFFFFFu, cur, (int)((lane + nv) & 31u)), b = __shfl_sync(0xFFFFFFFFu, nxt, (int)((lane + nv) & 31u));
+    return lane + nv < 32u ? a : b;
 }
 
 __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
@@ -834,33 +902,68 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d, uint32_
     XlNode nd;
     if (!xl_node(t, d, blockIdx.x, &nd)) return;
     const uint32_t lane = threadIdx.x & 31u, q = threadIdx.x >> 5;   // one warp per component
-    const float4* __restrict__ src = t.spm4[d] + nd.first;
+    const SlotRec* __restrict__ src = t.srec[d] + nd.first;
     const XlMap* __restrict__ maps = reinterpret_cast<const XlMap*>(t.xl_map) + ((size_t)area * t.xl_slots + nd.slot0) * 4u;
+    const long long B0 = (1ll << 23) + 1, B1 = (1ll << 24) - 1;
     float s = 0.f;
-    for (uint32_t c = 0; c < nd.nchunks; c++) {
-        const XlMap m = maps[(size_t)c * 4u + q];
-        bool ok = m.usable != 0;
-        long long k = 0;
-        double u = 0.0;
-        if (ok) {
-            u = __longlong_as_double((long long)(1023 + m.e2) << 52);
-            const double kd = (double)s * __longlong_as_double((long long)(1023 - m.e2) << 52);   // exact
-            k = (long long)kd;
+    uint32_t c = 0u;
+    // `cur`: the maps of chunks c .. c+31 (lane i: chunk c+i); `nxt`: those of chunks c+32 .. c+63, in flight while cur is used
+    XlLane cur = xl_load(maps, c + lane, nd.nchunks, q);
+    XlLane nxt = xl_load(maps, c + 32u + lane, nd.nchunks, q);
+    float ft[XL_PER_LANE];                                           // summands of the chunk that will need the member-by-member fold
+    uint32_t ft_c = 0xFFFFFFFFu;
+    while (c < nd.nchunks) {
+        const int e2 = __shfl_sync(0xFFFFFFFFu, cur.e2, 0);
+        const uint32_t okmask = __ballot_sync(0xFFFFFFFFu, cur.usable != 0 && cur.e2 == e2);
+        const uint32_t nlead = okmask == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~okmask) - 1u;
+        if (nlead < 32u && c + nlead < nd.nchunks && ft_c != c + nlead) {   // fetch the summands of the first chunk that cannot be composed
+            ft_c = c + nlead;
+#pragma unroll
+            for (uint32_t i = 0; i < (uint32_t)XL_PER_LANE; i++) {
+                const uint32_t j = ft_c * XL_CHUNK + i * 32u + lane;
+                ft[i] = j < nd.cnt ? xl_term(src[j].pm, q) : 0.f;    // pads are +0: s + 0 == s
+            }
+        }
+        uint32_t nv = 0u;
+        if (nlead > 0u) {                                            // warp-uniform
+            // compose in order: lane i holds chunks c .. c+i (meaningful below nlead)
+            XlMap m;
+            m.a0 = cur.a0; m.a1 = cur.a1; m.mn0 = cur.mn0; m.mx0 = cur.mx0; m.mn1 = cur.mn1; m.mx1 = cur.mx1; m.e2 = 0; m.usable = 0;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                XlMap o;
+                o.a0 = shfl_up_ll(m.a0, off); o.a1 = shfl_up_ll(m.a1, off);
+                o.mn0 = shfl_up_ll(m.mn0, off); o.mx0 = shfl_up_ll(m.mx0, off);
+                o.mn1 = shfl_up_ll(m.mn1, off); o.mx1 = shfl_up_ll(m.mx1, off);
+                o.e2 = 0; o.usable = 0;
+                if (lane >= (uint32_t)off) m = xl_combine(o, m);
+            }
+            const double u = __longlong_as_double((long long)(1023 + e2) << 52);
+            const double kd = (double)s * __longlong_as_double((long long)(1023 - e2) << 52);   // exact
+            const long long k = (long long)kd;
             const long long par = k & 1ll;
             const long long lo = k + (par ? m.mn1 : m.mn0), hi = k + (par ? m.mx1 : m.mx0);
-            const long long B0 = (1ll << 23) + 1, B1 = (1ll << 24) - 1;
-            ok = (double)k == kd &&
-                 ((k >= B0 && k <= B1 && lo >= B0 && hi <= B1) || (k <= -B0 && k >= -B1 && hi <= -B0 && lo >= -B1));
-            if (ok) { k += par ? m.a1 : m.a0; s = (float)((double)k * u); }
-        }
-        if (!ok) {
-            // member-by-member fold of this chunk (tree.c:166-169): the warp stages the summands, lane 0 adds them up
-            const uint32_t j0 = c * XL_CHUNK;
-#pragma unroll 4
-            for (uint32_t i = 0; i < XL_CHUNK / 32; i++) {
-                const uint32_t j = j0 + i * 32u + lane;
-                buf[q][i * 32u + lane] = j < nd.cnt ? xl_term(src[j], q) : 0.f;    // pads are +0: s + 0 == s
+            const bool valid = lane < nlead && (double)k == kd &&
+                               ((k >= B0 && k <= B1 && lo >= B0 && hi <= B1) || (k <= -B0 && k >= -B1 && hi <= -B0 && lo >= -B1));
+            const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
+            nv = vmask == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~vmask) - 1u;
+            if (nv > 0u) {
+                const long long kn = shfl_ll(k + (par ? m.a1 : m.a0), (int)nv - 1);
+                s = (float)((double)kn * u);
             }
+        }
+        if (nv == 0u) {
+            // member-by-member fold of chunk c (tree.c:166-169): the warp stages the summands, lane 0 adds them up
+            if (ft_c != c) {
+#pragma unroll
+                for (uint32_t i = 0; i < (uint32_t)XL_PER_LANE; i++) {
+                    const uint32_t j = c * XL_CHUNK + i * 32u + lane;
+                    ft[i] = j < nd.cnt ? xl_term(src[j].pm, q) : 0.f;
+                }
+            }
+#pragma unroll
+            for (uint32_t i = 0; i < (uint32_t)XL_PER_LANE; i++) buf[q][i * 32u + lane] = ft[i];
+            ft_c = 0xFFFFFFFFu;
             __syncwarp();
             if (lane == 0u) {
                 const float4* row = reinterpret_cast<const float4*>(&buf[q][0]);
@@ -872,7 +975,18 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d, uint32_
             }
             s = __shfl_sync(0xFFFFFFFFu, s, 0);
             __syncwarp();
+            nv = 1u;
         }
+        // move the window on by nv chunks
+        c += nv;
+        if (nv == 32u) cur = nxt;
+        else {
+            cur.a0 = xl_shift_ll(cur.a0, nxt.a0, nv, lane); cur.a1 = xl_shift_ll(cur.a1, nxt.a1, nv, lane);
+            cur.mn0 = xl_shift_ll(cur.mn0, nxt.mn0, nv, lane); cur.mx0 = xl_shift_ll(cur.mx0, nxt.mx0, nv, lane);
+            cur.mn1 = xl_shift_ll(cur.mn1, nxt.mn1, nv, lane); cur.mx1 = xl_shift_ll(cur.mx1, nxt.mx1, nv, lane);
+            cur.e2 = xl_shift_i(cur.e2, nxt.e2, nv, lane); cur.usable = xl_shift_i(cur.usable, nxt.usable, nv, lane);
+        }
+        nxt = xl_load(maps, c + 32u + lane, nd.nchunks, q);
     }
     if (threadIdx.x == 96u) s_mass = s;
     __syncthreads();
@@ -883,6 +997,10 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d, uint32_
     }
 }
 
+}  // namespace sfe
+#include "sfe_top.cuh"
+namespace sfe {
+
 static int launch_moments(Ctx* c, const TreeDev& dv, int d, uint32_t* gate, bool single, cudaStream_t s, const char* fn) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -891,10 +1009,10 @@ static int launch_moments(Ctx* c, const TreeDev& dv, int d, uint32_t* gate, bool
     }
     if (d <= XL_DEPTH_MAX) {
         const uint32_t area = (uint32_t)(d % SFE_SIDE_STREAMS);   // one scratch area per side stream; the deferred root uses area 0 after the join
-        const dim3 g2(16, dv.xl_max);
+        const uint32_t g2 = single ? 8u : (uint32_t)c->sm_count * 4u;
         xl_sums_kernel<<<g2, 256, 0, s>>>(dv, d, area, gate);
         if (check_launch(fn)) return SFE_FAILURE;
-        xl_prefix_kernel<<<dv.xl_max, 32, 0, s>>>(dv, d, area, gate);
+        xl_prefix_kernel<<<dv.xl_max, 128, 0, s>>>(dv, d, area, gate);
         if (check_launch(fn)) return SFE_FAILURE;
         xl_maps_kernel<<<g2, 256, 0, s>>>(dv, d, area, gate);
         if (check_launch(fn)) return SFE_FAILURE;
@@ -951,7 +1069,7 @@ __global__ void finalize_kernel(TreeDev t, uint32_t* __restrict__ gate /* null: 
 // the reference-layout node table (tree.h:18-24) for sfe_tree_download(): assembled from the engine's own records
 __global__ void table_kernel(TreeDev t) {
     const uint32_t count = t.meta[M_COUNT];
-    const uint32_t* __restrict__ perm_final = t.perm[t.meta[M_FINAL]];
+    const SlotRec* __restrict__ rec_final = t.srec[t.meta[M_FINAL]];
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < count; n += gridDim.x * blockDim.x) {
         const WalkRec2 cell = t.rec2[n];
         const float4 cm = t.rec1[n];
@@ -964,7 +1082,7 @@ __global__ void table_kernel(TreeDev t) {
             // internal: the eight children; leaf: its members in arrival (= ascending index) order (tree.c:172-175) -
             // a leaf's slot range does not move once the leaf exists, so the final order serves every level
             if (nd.bodies > 8u) nd.branch[k] = base + k;
-            else nd.branch[k] = k < nd.bodies ? perm_final[sg.x + k] : 0u;
+            else nd.branch[k] = k < nd.bodies ? rec_final[sg.x + k].idx : 0u;
         }
         for (int k = 0; k < 3; k++) { nd.bounds[k] = cell.lo[k]; nd.bounds[3 + k] = cell.hi[k]; }
         nd.params[0] = cm.x; nd.params[1] = cm.y; nd.params[2] = cm.z; nd.params[3] = cm.w;
@@ -988,6 +1106,12 @@ static uint32_t sub_max_members() {   // SFE_SUBTREE_MAX: 8 switches the subtree
     return v;
 }
 
+static uint32_t top_min_particles() {   // SFE_TOP_MIN: builds of at least this many particles take the one-pass top levels (sfe_top.cuh)
+    static long v = -1;
+    if (v < 0) { const char* e = getenv("SFE_TOP_MIN"); v = e ? atol(e) : 65536; if (v < 0) v = 0; }
+    return (uint32_t)(v > 0xFFFFFFFFl ? 0xFFFFFFFFl : v);
+}
+
 static uint32_t xl_min_members() {   // SFE_XL_MIN lowers the threshold so that small test trees exercise the chunked fold
     static uint32_t v = 0;
     if (v == 0) { const char* e = getenv("SFE_XL_MIN"); v = e ? (uint32_t)atoi(e) : 8192u; if (v < 64u) v = 64u; }
@@ -1005,13 +1129,8 @@ static TreeDev make_dev(Tree& t) {
     d.child_base = t.child_base.as<uint32_t>();
     d.counts = t.counts.as<uint32_t>();
     d.keys = t.keys.as<uint64_t>();
-    d.skey[0] = t.skey[0].as<uint64_t>(); d.skey[1] = t.skey[1].as<uint64_t>();
     d.perm_out = t.perm_out.as<uint32_t>();
-    for (int k = 0; k < SFE_MAX_LEVELS + 3; k++) { d.perm[k] = t.perm[k].as<uint32_t>(); d.spm4[k] = t.spm4[k].as<float4>(); }
-    d.perm0 = d.perm[0];
-    d.slot_node[0] = t.slot_node[0].as<uint32_t>();
-    d.slot_node[1] = t.slot_node[1].as<uint32_t>();
-    d.slot_node0 = d.slot_node[0];
+    for (int k = 0; k < SFE_MAX_LEVELS + 3; k++) d.srec[k] = t.srec[k].as<SlotRec>();
     d.oct = t.oct.as<uint8_t>();
     d.rank = t.rank.as<uint32_t>();
     d.meta = t.meta.as<uint32_t>();
@@ -1022,7 +1141,7 @@ static TreeDev make_dev(Tree& t) {
     const size_t n1 = t.N ? t.N : 1;
     d.xl_min = xl_min_members();
     d.xl_max = (uint32_t)(n1 / d.xl_min) + 2u;
-    d.xl_slots = (uint32_t)(n1 / 1024u) + 3u * d.xl_max + 8u;
+    d.xl_slots = (uint32_t)(n1 / (uint32_t)XL_CHUNK) + 3u * d.xl_max + 8u;
     d.tdesc_stride = (uint32_t)((n1 + PT_TILE - 1) / PT_TILE + 1) * DESC_WORDS;
     d.cdesc_stride = (t.nodes_max + CH_THREADS - 1) / CH_THREADS + 1;
     uint32_t* w = t.lookback.as<uint32_t>();
@@ -1038,6 +1157,13 @@ static TreeDev make_dev(Tree& t) {
     d.xl_map = t.xl_map.as<long long>();
     d.sub_max = sub_max_members();
     d.sub_list = t.sub_list.as<uint2>();
+    d.top_table = t.top_table.as<uint32_t>();
+    d.top_tot = t.top_cols.as<uint32_t>();
+    d.top_start = d.top_tot ? d.top_tot + TOP_COLS_PAD : nullptr;
+    d.top_info = d.top_tot ? d.top_tot + 2 * TOP_COLS_PAD : nullptr;
+    d.top_flag = d.top_tot ? d.top_tot + 3 * TOP_COLS_PAD : nullptr;
+    d.top_cand = d.top_tot ? reinterpret_cast<uint2*>(d.top_tot + 3 * TOP_COLS_PAD + 4) : nullptr;
+    d.top_rank = t.top_rank.as<TopRank>();
     d.summary = t.summary_dev;
     d.build_id = t.build_id;
     d.rec0 = t.rec0.as<WalkRec0>();
@@ -1066,13 +1192,13 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     const size_t n1 = N ? N : 1;
     if (t.seg.reserve((size_t)nodes_max * 8, fn) ||
         t.next.reserve((size_t)nodes_max * 4, fn) || t.child_base.reserve((size_t)nodes_max * 4, fn) ||
-        t.counts.reserve((size_t)nodes_max * 32, fn) || t.nmid.reserve((size_t)nodes_max * 16, fn) || t.skey[0].reserve(n1 * 8, fn) || t.skey[1].reserve(n1 * 8, fn) ||
-        t.perm_out.reserve(n1 * 4, fn) || t.slot_node[0].reserve(n1 * 4, fn) || t.slot_node[1].reserve(n1 * 4, fn) ||
+        t.counts.reserve((size_t)nodes_max * 32, fn) || t.nmid.reserve((size_t)nodes_max * 16, fn) ||
+        t.perm_out.reserve(n1 * 4, fn) ||
         t.oct.reserve(n1, fn) || t.rank.reserve(n1 * 4, fn) ||
         t.meta.reserve(M_WORDS * 4, fn) || t.root_gate.reserve(8, fn) || t.rec0.reserve((size_t)nodes_max * sizeof(WalkRec0), fn) ||
         t.rec1.reserve((size_t)nodes_max * 16, fn) || t.rec2.reserve((size_t)nodes_max * sizeof(WalkRec2), fn) ||
-        t.perm[0].reserve(n1 * 4, fn) || t.perm[1].reserve(n1 * 4, fn) || t.spm4[0].reserve(n1 * 16, fn) ||
-        t.spm4[1].reserve(n1 * 16, fn) || t.sub_list.reserve((n1 / 9 + 2) * 8, fn))
+        t.srec[0].reserve(n1 * sizeof(SlotRec), fn) || t.srec[1].reserve(n1 * sizeof(SlotRec), fn) ||
+        t.sub_list.reserve((n1 / 9 + 2) * 8, fn))
         return SFE_FAILURE;
     if (!t.meta_host) SFE_CUDA(fn, cudaMallocHost(&t.meta_host, sizeof(uint32_t) * M_WORDS));
     if (!t.summary_host) {
@@ -1091,6 +1217,18 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     t.build_id++;
     if (t.build_id == 0u) t.build_id = 1u;
 
+    // upper levels in one pass (sfe_top.cuh) when the build is large enough for it to pay
+    const bool use_top = N > 0u && N >= top_min_particles() && depth_max > TOP_L && N <= (1u << 26);
+    uint32_t range_len = 0u, ranges = 0u;
+    if (use_top) {
+        const uint32_t tiles = (N + TP_TILE - 1) / TP_TILE;
+        range_len = (uint32_t)TP_TILE * ((tiles + TOP_RANGES_MAX - 1u) / TOP_RANGES_MAX);
+        ranges = (N + range_len - 1u) / range_len;
+        if (t.top_table.reserve((size_t)ranges * TOP_COLS * 4, fn) || t.top_cols.reserve((size_t)(3 * TOP_COLS_PAD + 4 + 2 * TOP_CAND_MAX) * 4, fn) ||
+            t.top_rank.reserve(n1 * sizeof(TopRank), fn))
+            return SFE_FAILURE;
+        for (int k = 2; k <= TOP_L; k++) if (t.srec[k].reserve(n1 * sizeof(SlotRec), fn)) return SFE_FAILURE;
+    }
     TreeDev dv = make_dev(t);
     if (t.lookback.reserve(lookback_bytes(dv), fn) || t.xl_sum.reserve((size_t)SFE_SIDE_STREAMS * dv.xl_slots * 4 * 8, fn) ||
         t.xl_map.reserve((size_t)SFE_SIDE_STREAMS * dv.xl_slots * 4 * 64, fn))
@@ -1101,14 +1239,6 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     const uint32_t cgrid = [&] { uint32_t g = (nodes_max + CH_THREADS - 1) / CH_THREADS; uint32_t cap = (uint32_t)c->sm_count * 4; return g < 1 ? 1u : (g < cap ? g : cap); }();
     const uint32_t sgrid = [&] { uint32_t g = (N + 255) / 256; uint32_t cap = (uint32_t)c->sm_count * 16; return g < 1 ? 1u : (g < cap ? g : cap); }();
 
-    // level 0: in-box compaction + root
-    {
-        CompactOp op{pm4, N, dv};
-        if (run_scan(c, op, N, s, fn)) return SFE_FAILURE;
-    }
-    root_kernel<<<1, 1, 0, s>>>(dv, depth_max);
-    if (check_launch(fn)) return SFE_FAILURE;
-    SFE_CUDA(fn, cudaEventRecord(t.ev_perm[0], s));
 
     // summary[lv] = {build id, internal nodes of level lv, status, node count}, written by the device into mapped
     // host memory; the host only spins on it (no stream operation), two levels behind the device
@@ -1129,10 +1259,58 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         return SFE_SUCCESS;
     };
 
+    int first_level = 0;
+    if (use_top) {
+        static bool tn_attr = false;
+        const size_t tn_smem = (size_t)(3 * TOP_COLS_PAD) * 4;
+        if (!tn_attr) {
+            SFE_CUDA(fn, cudaFuncSetAttribute(top_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tn_smem));
+            tn_attr = true;
+        }
+        SFE_CUDA(fn, cudaMemsetAsync(dv.top_flag, 0, 8, s));
+        if (trace_enabled()) cudaEventRecord(t.ev_perm[0], s);
+        top_rank_kernel<<<ranges, TP_THREADS, 0, s>>>(dv, pm4, N, range_len);
+        if (check_launch(fn)) return SFE_FAILURE;
+        top_scan_kernel<<<(TOP_COLS + 31u) / 32u, TSC_WARPS * 32, 0, s>>>(dv, ranges);
+        if (check_launch(fn)) return SFE_FAILURE;
+        top_nodes_kernel<<<1, TN_THREADS, tn_smem, s>>>(dv, depth_max, range_len);
+        if (check_launch(fn)) return SFE_FAILURE;
+        top_scatter_kernel<<<ranges, TP_THREADS, 0, s>>>(dv, pm4, N, range_len);
+        if (check_launch(fn)) return SFE_FAILURE;
+        SFE_CUDA(fn, cudaEventRecord(t.ev_perm[TOP_L], s));
+        uint32_t not_applicable = 0, status = 0;
+        if (wait_summary((int)TOP_SUMMARY_SLOT, &not_applicable, &status)) return SFE_FAILURE;
+        if (!not_applicable) {
+            first_level = TOP_L;
+            // the folds of levels 1 .. TOP_L
+            for (int d = 1; d <= TOP_L; d++) {
+                cudaStream_t side = c->side[d % SFE_SIDE_STREAMS];
+                SFE_CUDA(fn, cudaStreamWaitEvent(side, t.ev_perm[TOP_L], 0));
+                if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d], side);
+                if (launch_moments(c, dv, d, nullptr, false, side, fn)) return SFE_FAILURE;
+                if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d + 1], side);
+            }
+            if (trace_enabled()) {
+                cudaStreamSynchronize(s);
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, t.ev_perm[0], t.ev_perm[TOP_L]);
+                fprintf(stderr, "[sfe trace] top levels 0..%d in one pass: %8.1f us\n", TOP_L - 1, ms * 1e3);
+            }
+        }
+    }
+    if (first_level == 0) {
+        // level 0: in-box compaction + root
+        CompactOp op{pm4, N, dv};
+        if (run_scan(c, op, N, s, fn)) return SFE_FAILURE;
+        root_kernel<<<1, 1, 0, s>>>(dv, depth_max);
+        if (check_launch(fn)) return SFE_FAILURE;
+        SFE_CUDA(fn, cudaEventRecord(t.ev_perm[0], s));
+    }
+
     int levels_run = 0;
     double host_us[SFE_MAX_LEVELS + 4];
     const auto host_t0 = std::chrono::steady_clock::now();
-    for (int d = 0; d <= depth_max; d++) {
+    for (int d = first_level; d <= depth_max; d++) {
         host_us[d] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count();
         // level d only exists if level d-1 has internal nodes; the host learns that one level late, so the kernels
         // of at most one empty level are enqueued (they return at once)
@@ -1142,13 +1320,19 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
             if (internal == 0u || status != 0u) break;
         }
         // make sure perm[d+1] exists (first build at this depth only) and refresh the device view
-        if (t.perm[d + 1].cap < n1 * 4 || t.spm4[d + 1].cap < n1 * 16) {
-            if (t.perm[d + 1].reserve(n1 * 4, fn) || t.spm4[d + 1].reserve(n1 * 16, fn)) return SFE_FAILURE;
+        if (t.srec[d + 1].cap < n1 * sizeof(SlotRec)) {
+            if (t.srec[d + 1].reserve(n1 * sizeof(SlotRec), fn)) return SFE_FAILURE;
             dv = make_dev(t);
+        }
+        // the top levels left nothing to split at level TOP_L (its summary is already there): no passes at all
+        if (first_level > 0 && d == first_level) {
+            uint32_t internal = 0, status = 0;
+            if (wait_summary(d, &internal, &status)) return SFE_FAILURE;
+            if (internal == 0u || status != 0u) break;
         }
         levels_run = d + 1;
         // moments of level d on a side stream (needs perm[d]); the root's fold is deferred
-        if (d > 0) {
+        if (d > 0 && !(first_level > 0 && d == first_level)) {
             cudaStream_t side = c->side[d % SFE_SIDE_STREAMS];
             SFE_CUDA(fn, cudaStreamWaitEvent(side, t.ev_perm[d], 0));
             if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d], side);
@@ -1168,7 +1352,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     if (trace_enabled()) {   // SFE_TRACE=1: where does the build spend its time (device time per level vs host enqueue time)
         host_us[levels_run] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count();
         cudaStreamSynchronize(s);
-        for (int d = 0; d < levels_run; d++) {
+        for (int d = first_level; d < levels_run; d++) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, t.ev_perm[d], t.ev_perm[d + 1]);
             float r = 0.f, ch = 0.f, sc = 0.f;
@@ -1211,7 +1395,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         cudaEventRecord(g_trace_ev[1], s);
         cudaStreamSynchronize(s);
         float a = 0.f, b = 0.f;
-        for (int d = 1; d < levels_run; d++) {
+        for (int d = 1; d < (first_level && levels_run <= TOP_L ? TOP_L + 1 : levels_run); d++) {
             cudaEventElapsedTime(&a, t.ev_perm[0], g_trace_ev[2 * d]);
             cudaEventElapsedTime(&b, t.ev_perm[0], g_trace_ev[2 * d + 1]);
             fprintf(stderr, "[sfe trace] moments level %2d: start %8.1f us  end %8.1f us\n", d, a * 1e3, b * 1e3);
@@ -1357,7 +1541,12 @@ extern "C" int sfe_tree_keys_download(uint64_t* keys, uint32_t* perm, uint32_t N
         SFE_CUDA(fn, cudaMemcpyAsync(keys, t.keys.p, (size_t)N * 8, cudaMemcpyDeviceToHost, c->stream));
     }
     if (perm) {
-        SFE_CUDA(fn, cudaMemcpyAsync(perm, t.perm[t.final_perm].p, (size_t)t.num_inbox * 4, cudaMemcpyDeviceToHost, c->stream));
+        // the sort permutation = the index column of the final slot records (gathered into the build's rank scratch)
+        if (t.num_inbox) {
+            perm_gather_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(tree_dev(c), t.rank.as<uint32_t>());
+            if (check_launch(fn)) return SFE_FAILURE;
+        }
+        SFE_CUDA(fn, cudaMemcpyAsync(perm, t.rank.p, (size_t)t.num_inbox * 4, cudaMemcpyDeviceToHost, c->stream));
         SFE_CUDA(fn, cudaMemcpyAsync(perm + t.num_inbox, t.perm_out.p, (size_t)(N - t.num_inbox) * 4, cudaMemcpyDeviceToHost, c->stream));
     }
     SFE_CUDA(fn, cudaStreamSynchronize(c->stream));

@@ -38,6 +38,34 @@ struct __align__(16) WalkRec2 {   // 32 B: the cell itself - bounds (gravity.c:4
 };
 static_assert(sizeof(WalkRec0) == 32 && sizeof(WalkRec2) == 32, "walk records are 32 bytes");
 
+// One slot of a level's particle order: everything that moves with a particle from level to level, as ONE 32-byte record
+// (= one sector, written with one 256-bit store).  Separate 16 / 8 / 4-byte arrays made every scattered store a partial
+// sector write, which the memory system punishes (measured: 87 us for the top-level scatter against 48 us with the final
+// slot as one record, profiles/r02_scatter_store_masks.txt).
+struct __align__(32) SlotRec {
+    float4 pm;                    // {x, y, z, m}
+    unsigned long long key;       // path key so far (3 bits per level, digit d at bit 45 - 3d)
+    uint32_t idx;                 // particle index
+    uint32_t owner;               // node that still has to be split by the grid-wide passes, NODE_END otherwise
+};
+static_assert(sizeof(SlotRec) == 32, "slot records are one sector");
+#ifdef __CUDACC__
+__device__ __forceinline__ SlotRec slot_load(const SlotRec* p) {
+    uint32_t r[8];
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p) : "memory");
+    SlotRec s;
+    s.pm = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+    s.key = ((unsigned long long)r[5] << 32) | r[4]; s.idx = r[6]; s.owner = r[7];
+    return s;
+}
+__device__ __forceinline__ void slot_store(SlotRec* p, float4 pm, unsigned long long key, uint32_t idx, uint32_t owner) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(__float_as_uint(pm.x)), "r"(__float_as_uint(pm.y)),
+                 "r"(__float_as_uint(pm.z)), "r"(__float_as_uint(pm.w)), "r"((uint32_t)key), "r"((uint32_t)(key >> 32)), "r"(idx), "r"(owner) : "memory");
+}
+#endif
+
+struct TopRank;
 struct TreeDev {
     float bounds[6];
     uint32_t nodes_max;
@@ -47,13 +75,8 @@ struct TreeDev {
     uint32_t* child_base;
     uint32_t* counts;
     uint64_t* keys;               // 48-bit path keys by particle index (filled on demand by sfe_tree_keys_download)
-    uint64_t* skey[2];            // path key of every slot, ping-pong between levels (level d lives in skey[d & 1])
-    uint32_t* perm[SFE_MAX_LEVELS + 3];
-    float4* spm4[SFE_MAX_LEVELS + 3];   // slot-ordered copy of pm4 per level
-    uint32_t* perm0;
+    SlotRec* srec[SFE_MAX_LEVELS + 3];   // the particle order of every level (nodes own contiguous slot ranges)
     uint32_t* perm_out;
-    uint32_t* slot_node[2];
-    uint32_t* slot_node0;
     uint8_t* oct;
     uint32_t* rank;
     uint32_t* meta;
@@ -75,6 +98,14 @@ struct TreeDev {
     uint2* sub_list;              // {node id, level} of every subtree root, in no particular order
     uint32_t* sub_count;
     uint32_t* sub_ticket;
+    // upper levels in one pass (sfe_top.cuh)
+    uint32_t* top_table;          // [ranges][TOP_COLS] per-range histograms, then exclusive prefixes over the ranges
+    uint32_t* top_tot;            // [TOP_COLS] bodies of every cell of the top levels
+    uint32_t* top_start;          // [TOP_COLS] first slot of every cell
+    uint32_t* top_info;           // [TOP_COLS] node id | split << 31, NODE_END when the cell has no node
+    struct TopRank* top_rank;     // [N] path code + stable rank inside every cell on the path
+    uint32_t* top_flag;           // [0] non-zero: the one-pass construction does not apply to this build; [1] candidates noted
+    uint2* top_cand;              // particles on a split plane: {particle, level}
     volatile uint32_t* summary;   // mapped host memory: {build id, internal nodes, status, node count} per level
     uint32_t build_id;
     WalkRec0* rec0;

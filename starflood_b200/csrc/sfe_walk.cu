@@ -127,8 +127,9 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
     const uint32_t M = t.meta[M_NUM_INBOX];
     const uint32_t s = slots ? slots[k] : s0 + k;
     const uint32_t fin = t.meta[M_FINAL];
-    const uint32_t idx = s < M ? t.perm[fin][s] : t.perm_out[s - M];
-    const float4 me = s < M ? t.spm4[fin][s] : pm4[idx];
+    uint32_t idx; float4 me;
+    if (s < M) { const SlotRec r = slot_load(&t.srec[fin][s]); idx = r.idx; me = r.pm; }   // one sector: particle and index
+    else { idx = t.perm_out[s - M]; me = pm4[idx]; }
     const float x = me.x, y = me.y, z = me.z, mi = me.w;
 
     KahanRef2 kxy = {{0.f, 0.f}, {0.f, 0.f}}, kzp = {{0.f, 0.f}, {0.f, 0.f}};   // (acc x, acc y) and (acc z, pot)
@@ -244,7 +245,7 @@ struct SliceOp {
     __device__ uint32_t n() const { return N; }
     __device__ uint32_t idx_of(uint32_t s) const {
         const uint32_t M = t.meta[M_NUM_INBOX];
-        return s < M ? t.perm[t.meta[M_FINAL]][s] : t.perm_out[s - M];
+        return s < M ? t.srec[t.meta[M_FINAL]][s].idx : t.perm_out[s - M];
     }
     __device__ uint32_t load(uint32_t s) const { const uint32_t i = idx_of(s); return (i >= i0 && i < i1) ? 1u : 0u; }
     __device__ void store(uint32_t s, uint32_t ex) const { const uint32_t i = idx_of(s); if (i >= i0 && i < i1) out[ex] = s; }

@@ -112,19 +112,24 @@ def test_full_size(engine):
     assert len(nodes) == 1 + 8 * int((nodes["bodies"] > 8).sum())
 
 
-@pytest.mark.parametrize("sub_max,xl_min", [(8, None), (40, None), (300, 64), (2048, 64)])
-def test_build_variants_in_a_fresh_process(sub_max, xl_min):
-    """The build has two halves: grid-wide passes for the upper levels and one CTA per subtree root below
-    (SFE_SUBTREE_MAX bodies at most; 8 switches the subtree path off).  The library reads the thresholds once, so every
-    setting runs this file's parity cases in a process of its own: all passes grid-wide (8), subtrees of a few dozen
-    bodies so that small trees mix both halves over several levels (40, 300), and with the exact chunked fold of very
-    long nodes lowered to 64 members (SFE_XL_MIN) so that small trees exercise it next to the subtrees."""
+@pytest.mark.parametrize("sub_max,xl_min,top_min", [(8, None, None), (40, None, None), (300, 64, None), (2048, 64, None),
+                                                    (8, None, 0), (40, 64, 0), (2048, None, 0)])
+def test_build_variants_in_a_fresh_process(sub_max, xl_min, top_min):
+    """The build has three parts: the upper four levels in one pass over the particles (sfe_top.cuh; builds of at least
+    SFE_TOP_MIN particles, 65536 by default), grid-wide passes level by level below them, and one CTA per subtree root at
+    the bottom (SFE_SUBTREE_MAX bodies at most; 8 switches the subtree path off).  The library reads the thresholds once,
+    so every setting runs this file's parity cases in a process of its own: all passes grid-wide (8), subtrees of a few
+    dozen bodies so that small trees mix the parts over several levels (40, 300), the exact chunked fold of very long
+    nodes lowered to 64 members (SFE_XL_MIN) so that small trees exercise it next to the subtrees, and the one-pass top
+    levels for every size (SFE_TOP_MIN=0: trees that end inside the top levels, out-of-box particles, the fall-back to
+    the level-by-level passes on an exact tie)."""
     if os.environ.get("SFE_TREE_VARIANT_CHILD"):
         pytest.skip("already inside a variant run")
     import subprocess, sys
     env = dict(os.environ, SFE_SUBTREE_MAX=str(sub_max), SFE_TREE_VARIANT_CHILD="1")
     if xl_min:
         env["SFE_XL_MIN"] = str(xl_min)
+    env["SFE_TOP_MIN"] = str(top_min) if top_min is not None else str(1 << 30)
     sel = "golden or sizes or ties or outside or clustered or failures" + (" or full_size" if sub_max in (8, 300) else "")
     p = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel],
                        capture_output=True, text=True, env=env, timeout=1200)
