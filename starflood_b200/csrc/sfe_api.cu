@@ -52,7 +52,11 @@ static int do_init(int device, const char* fn) {
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
     c->clock_khz = khz;
     SFE_CUDA(fn, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (auto& sd : c->side) SFE_CUDA(fn, cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+    {   // the side streams carry the moment folds: short kernels that must not queue behind the long ones of the engine stream
+        int lo = 0, hi = 0;
+        SFE_CUDA(fn, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        for (auto& sd : c->side) SFE_CUDA(fn, cudaStreamCreateWithPriority(&sd, cudaStreamNonBlocking, hi));
+    }
     for (auto& ev : c->ev) SFE_CUDA(fn, cudaEventCreate(&ev));
     memset(&c->timings, 0, sizeof c->timings);
     g_ctx = c;
@@ -191,6 +195,7 @@ extern "C" int sfe_shutdown(void) {
     if (t.ev_init) {
         for (auto& ev : t.ev_perm) cudaEventDestroy(ev);
         for (auto& ev : t.ev_side) cudaEventDestroy(ev);
+        for (auto& ev : t.ev_pre) cudaEventDestroy(ev);
         t.ev_init = false;
     }
     t.valid = false;

@@ -79,7 +79,7 @@ struct Tree {
     DevBuf meta;         // uint32_t[M_WORDS]
     DevBuf rec0, rec1, rec2;   // walk records
     uint32_t* meta_host = nullptr;     // pinned, (SFE_MAX_LEVELS + 2) snapshots of meta
-    cudaEvent_t ev_perm[SFE_MAX_LEVELS + 3], ev_side[SFE_SIDE_STREAMS];
+    cudaEvent_t ev_perm[SFE_MAX_LEVELS + 3], ev_side[SFE_SIDE_STREAMS], ev_pre[SFE_SIDE_STREAMS];
     bool ev_init = false;
 };
 

@@ -1001,12 +1001,20 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d, uint32_
 #include "sfe_top.cuh"
 namespace sfe {
 
-static int launch_moments(Ctx* c, const TreeDev& dv, int d, uint32_t* gate, bool single, cudaStream_t s, const char* fn) {
+// All fold kernels of level d.  `pre` (optional) is recorded in front of the serial chains of the very long nodes: the
+// top-level path lets subtree_kernel - which fills every SM for its whole duration - wait for the parallel part of the folds
+// and run beside the chains (a few small CTAs that are resident by then).
+static int launch_moments(Ctx* c, const TreeDev& dv, int d, uint32_t* gate, bool single, cudaStream_t s, const char* fn,
+                          cudaEvent_t pre = nullptr) {
     static bool attr_set = false;
     if (!attr_set) {
         SFE_CUDA(fn, cudaFuncSetAttribute(moments_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ML_SMEM));
         attr_set = true;
     }
+    moments_long_kernel<<<single ? 1 : c->sm_count * 2, ML_THREADS, ML_SMEM, s>>>(dv, d, gate);
+    if (check_launch(fn)) return SFE_FAILURE;
+    moments_short_kernel<<<single ? 1 : c->sm_count * 8, 256, 0, s>>>(dv, d, gate);
+    if (check_launch(fn)) return SFE_FAILURE;
     if (d <= XL_DEPTH_MAX) {
         const uint32_t area = (uint32_t)(d % SFE_SIDE_STREAMS);   // one scratch area per side stream; the deferred root uses area 0 after the join
         const uint32_t g2 = single ? 8u : (uint32_t)c->sm_count * 4u;
@@ -1016,13 +1024,11 @@ static int launch_moments(Ctx* c, const TreeDev& dv, int d, uint32_t* gate, bool
         if (check_launch(fn)) return SFE_FAILURE;
         xl_maps_kernel<<<g2, 256, 0, s>>>(dv, d, area, gate);
         if (check_launch(fn)) return SFE_FAILURE;
+        if (pre) SFE_CUDA(fn, cudaEventRecord(pre, s));
         xl_chain_kernel<<<dv.xl_max, 128, 0, s>>>(dv, d, area, gate);
         if (check_launch(fn)) return SFE_FAILURE;
-    }
-    moments_long_kernel<<<single ? 1 : c->sm_count * 2, ML_THREADS, ML_SMEM, s>>>(dv, d, gate);
-    if (check_launch(fn)) return SFE_FAILURE;
-    moments_short_kernel<<<single ? 1 : c->sm_count * 8, 256, 0, s>>>(dv, d, gate);
-    return check_launch(fn);
+    } else if (pre) SFE_CUDA(fn, cudaEventRecord(pre, s));
+    return SFE_SUCCESS;
 }
 
 // ============================================================================ finalize: walk records
@@ -1114,7 +1120,7 @@ static uint32_t top_min_particles() {   // SFE_TOP_MIN: builds of at least this 
 
 static uint32_t xl_min_members() {   // SFE_XL_MIN lowers the threshold so that small test trees exercise the chunked fold
     static uint32_t v = 0;
-    if (v == 0) { const char* e = getenv("SFE_XL_MIN"); v = e ? (uint32_t)atoi(e) : 8192u; if (v < 64u) v = 64u; }
+    if (v == 0) { const char* e = getenv("SFE_XL_MIN"); v = e ? (uint32_t)atoi(e) : 16384u; if (v < 64u) v = 64u; }
     return v;
 }
 
@@ -1210,6 +1216,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         for (int k = 0; k < SFE_MAX_LEVELS + 3; k++)
             SFE_CUDA(fn, cudaEventCreateWithFlags(&t.ev_perm[k], trace_enabled() ? cudaEventDefault : cudaEventDisableTiming));
         for (auto& ev : t.ev_side) SFE_CUDA(fn, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& ev : t.ev_pre) SFE_CUDA(fn, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         if (trace_enabled()) for (auto& ev : g_trace_ev) SFE_CUDA(fn, cudaEventCreate(&ev));
         if (trace_enabled()) for (auto& ev : g_trace_k) SFE_CUDA(fn, cudaEventCreate(&ev));
         t.ev_init = true;
@@ -1287,7 +1294,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
                 cudaStream_t side = c->side[d % SFE_SIDE_STREAMS];
                 SFE_CUDA(fn, cudaStreamWaitEvent(side, t.ev_perm[TOP_L], 0));
                 if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d], side);
-                if (launch_moments(c, dv, d, nullptr, false, side, fn)) return SFE_FAILURE;
+                if (launch_moments(c, dv, d, nullptr, false, side, fn, t.ev_pre[d % SFE_SIDE_STREAMS])) return SFE_FAILURE;
                 if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d + 1], side);
             }
             if (trace_enabled()) {
@@ -1364,6 +1371,11 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     }
     // everything below the subtree roots: one CTA per root, drawn from a ticket (the final slot arrays are rewritten in
     // place range by range; the folds on the side streams read other ranges or other levels' arrays)
+    if (first_level > 0) {
+        // the parallel part of the top levels' folds goes first (subtree_kernel fills every SM for its whole duration);
+        // the serial chains of the very long nodes - a few small CTAs - run beside it
+        for (int d = 1; d <= TOP_L; d++) SFE_CUDA(fn, cudaStreamWaitEvent(s, t.ev_pre[d % SFE_SIDE_STREAMS], 0));
+    }
     if (dv.sub_max > 8u) {
         static bool st_attr = false;
         if (!st_attr) {
