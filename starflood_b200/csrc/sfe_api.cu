@@ -56,6 +56,7 @@ static int do_init(int device, const char* fn) {
         int lo = 0, hi = 0;
         SFE_CUDA(fn, cudaDeviceGetStreamPriorityRange(&lo, &hi));
         for (auto& sd : c->side) SFE_CUDA(fn, cudaStreamCreateWithPriority(&sd, cudaStreamNonBlocking, hi));
+        for (auto& sd : c->side2) SFE_CUDA(fn, cudaStreamCreateWithPriority(&sd, cudaStreamNonBlocking, hi));
     }
     for (auto& ev : c->ev) SFE_CUDA(fn, cudaEventCreate(&ev));
     memset(&c->timings, 0, sizeof c->timings);
@@ -187,7 +188,7 @@ extern "C" int sfe_shutdown(void) {
                       &c->pp_src, &c->pp_partial, &c->pp_flag, &c->sph_src, &c->sph_partial,
                       &c->sph_cells.desc, &c->sph_cells.count, &c->sph_cells.start, &c->sph_cells.key[0], &c->sph_cells.key[1],
                       &c->sph_cells.val[0], &c->sph_cells.val[1], &c->sph_cells.hist, &c->sph_cells.rec, &c->sph_cells.tlist, &c->sph_cells.part, &c->sph_cells.arrive,
-                      &t.nodes, &t.seg, &t.next, &t.child_base, &t.counts, &t.keys, &t.perm_out, &t.oct, &t.rank, &t.nmid, &t.lookback, &t.xl_sum, &t.xl_map, &t.scan_tmp, &t.slice_count, &t.root_gate, &t.meta, &t.rec0, &t.rec1, &t.rec2,
+                      &t.nodes, &t.seg, &t.next, &t.child_base, &t.counts, &t.keys, &t.perm_out, &t.oct, &t.rank, &t.nmid, &t.lookback, &t.xl_sum, &t.xl_map, &t.xl_flag, &t.xl_list, &t.scan_tmp, &t.slice_count, &t.root_gate, &t.meta, &t.rec0, &t.rec1, &t.rec2,
                       &t.sub_list, &t.top_table, &t.top_cols, &t.top_rank};
     for (DevBuf& b : t.srec) b.release();
     if (t.meta_host) { cudaFreeHost(t.meta_host); t.meta_host = nullptr; }
@@ -196,6 +197,7 @@ extern "C" int sfe_shutdown(void) {
         for (auto& ev : t.ev_perm) cudaEventDestroy(ev);
         for (auto& ev : t.ev_side) cudaEventDestroy(ev);
         for (auto& ev : t.ev_pre) cudaEventDestroy(ev);
+        for (auto& ev : t.ev_pre2) cudaEventDestroy(ev);
         t.ev_init = false;
     }
     t.valid = false;
@@ -207,6 +209,7 @@ extern "C" int sfe_shutdown(void) {
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto& sd : c->side) if (sd) cudaStreamDestroy(sd);
+    for (auto& sd : c->side2) if (sd) cudaStreamDestroy(sd);
     delete c;
     g_ctx = nullptr;
     return SFE_SUCCESS;

@@ -67,7 +67,7 @@ struct Tree {
     DevBuf rank;         // uint32_t[N]            stable rank inside (node, octant)
     DevBuf nmid;         // float4[nodes_max]      split planes of internal nodes
     DevBuf lookback;     // tickets + look-back descriptors + long-node lists of one build (zeroed per build)
-    DevBuf xl_sum, xl_map;   // scratch of the exact chunked fold
+    DevBuf xl_sum, xl_map, xl_flag, xl_list;   // scratch of the exact chunked fold
     DevBuf sub_list;         // uint2[N / 9 + 1]  subtree roots (sfe_subtree.cuh)
     DevBuf top_table, top_cols, top_rank;   // one-pass construction of the upper levels (sfe_top.cuh)
     uint32_t* summary_host = nullptr;  // mapped pinned: per-level summaries written by the device
@@ -79,7 +79,7 @@ struct Tree {
     DevBuf meta;         // uint32_t[M_WORDS]
     DevBuf rec0, rec1, rec2;   // walk records
     uint32_t* meta_host = nullptr;     // pinned, (SFE_MAX_LEVELS + 2) snapshots of meta
-    cudaEvent_t ev_perm[SFE_MAX_LEVELS + 3], ev_side[SFE_SIDE_STREAMS], ev_pre[SFE_SIDE_STREAMS];
+    cudaEvent_t ev_perm[SFE_MAX_LEVELS + 3], ev_side[SFE_SIDE_STREAMS], ev_pre[SFE_SIDE_STREAMS], ev_pre2[SFE_SIDE_STREAMS];
     bool ev_init = false;
 };
 
@@ -144,6 +144,7 @@ struct Ctx {
     int clock_khz = 0;
     cudaStream_t stream = nullptr;     // engine stream for the host entry points
     cudaStream_t side[SFE_SIDE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // overlapped work (moment folds)
+    cudaStream_t side2[SFE_SIDE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};  // the folds of the shorter nodes of the top levels, beside the chunked fold
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // device copies of the host arrays
     DevBuf d_pos, d_mas, d_pm4, d_acc, d_pot, d_rad, d_rho, d_prs;

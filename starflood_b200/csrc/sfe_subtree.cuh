@@ -137,11 +137,16 @@ __global__ void __launch_bounds__(ST_THREADS, 2) subtree_kernel(TreeDev t, int d
                 b[g] = byte; nn[g] = n; lid[g] = l; r[g] = 0u;
             }
             int gl = -1;
+            uint32_t live = 0u;                            // groups with an active slot (most slots of the deeper levels sit in leaves)
 #pragma unroll
             for (int g = 0; g < ST_GROUPS; g++) {
-                hm[g] = __ballot_sync(0xFFFFFFFFu, (b[g] & SB_HEAD) != 0u);
-                if (hm[g]) gl = g;
-                bo[g] = octant_mask((b[g] & SB_ACTIVE) != 0u, b[g] & 7u, lane);
+                hm[g] = 0u; bo[g] = 0u;
+                if (__any_sync(0xFFFFFFFFu, (b[g] & SB_ACTIVE) != 0u)) {
+                    live |= 1u << g;
+                    hm[g] = __ballot_sync(0xFFFFFFFFu, (b[g] & SB_HEAD) != 0u);
+                    if (hm[g]) gl = g;
+                    bo[g] = octant_mask(true, b[g] & 7u, lane) & __ballot_sync(0xFFFFFFFFu, (b[g] & SB_ACTIVE) != 0u);
+                }
             }
             uint32_t tr = 0u;
 #pragma unroll
@@ -157,6 +162,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) subtree_kernel(TreeDev t, int d
             }
 #pragma unroll
             for (int g = 0; g < ST_GROUPS; g++) {
+                if (!((live >> g) & 1u)) continue;         // nothing to rank, nothing open across the group (ranges are contiguous)
                 const uint32_t byte = b[g], oc = byte & 7u;
                 const bool act = (byte & SB_ACTIVE) != 0u;
                 const uint32_t headmask = hm[g];
@@ -237,10 +243,10 @@ __global__ void __launch_bounds__(ST_THREADS, 2) subtree_kernel(TreeDev t, int d
             }
             __syncthreads();
             // ------------------------------------------------------------ moments of the new children (tree.c:166-169, :302-310)
-            // one lane per (node, component); item 8*ncur is the subtree root itself (first level only: its range is
-            // the whole order array of the level above, i.e. the identity)
+            // one lane per (node, component).  A subtree root's own fold is done by the fold kernels of its level like any
+            // other node's - except the tree root's (the whole tree is one subtree): item 8*ncur, its range is the identity
             {
-                const uint32_t items = 8u * ncur + (first ? 1u : 0u);
+                const uint32_t items = 8u * ncur + ((first && root == 0u) ? 1u : 0u);
                 const uint32_t comp = tid & 3u;
                 for (uint32_t wq = tid >> 2; wq < ((items + 7u) & ~7u); wq += ST_THREADS / 4) {
                     uint32_t s0 = 0u, cn = 0u, gid = 0u;

@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(TN_THREADS) top_nodes_kernel(TreeDev t, int de
     extern __shared__ __align__(16) uint32_t tn_smem[];
     uint32_t* tot = tn_smem;                   // bodies of every cell of the top levels
     uint32_t* exb = tot + TOP_COLS_PAD;        // bodies in the columns before this one (all levels concatenated)
-    uint32_t* exs = exb + TOP_COLS_PAD;        // split cells in the columns before this one
+    uint32_t* exs = exb + TOP_COLS_PAD;        // split cells (low half) and subtree roots (high half) in the columns before this one
     __shared__ unsigned long long sw[33];
     __shared__ uint32_t s_lvb[TOP_L + 3], s_int[TOP_L + 2], s_bad;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -377,7 +377,11 @@ __global__ void __launch_bounds__(TN_THREADS) top_nodes_kernel(TreeDev t, int de
 #pragma unroll
         for (int k = 0; k < TN_ITEMS; k++) {
             const uint32_t c = tid * TN_ITEMS + k;
-            v[k] = c < TOP_COLS ? ((unsigned long long)(tot[c] > sub_max ? 1u : 0u) << 32) | tot[c] : 0ull;
+            // a subtree root further down is only real if its parent is split, which the nesting of the counts guarantees
+            // for every cell but the root's own children - and those are real as soon as the root is split
+            const uint32_t cn = c < TOP_COLS ? tot[c] : 0u;
+            const bool real = c == 0u || (c < TOP_COLS && tot[top_off(top_level_of(c) - 1) + ((c - top_off(top_level_of(c))) >> 3)] > sub_max);
+            v[k] = c < TOP_COLS ? ((unsigned long long)((cn > sub_max ? 1u : 0u) | ((real && cn > 8u && cn <= sub_max) ? 0x10000u : 0u)) << 32) | cn : 0ull;
             sum += v[k];
         }
         unsigned long long inc = sum;
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(TN_THREADS) top_nodes_kernel(TreeDev t, int de
             const uint32_t rank = t.top_table[(size_t)(cd.x / range_len) * TOP_COLS + col] + rr;
             if (rank < 8u && tot[col] > sub_max) bad = 1u;
         }
-        const uint32_t nsplit = exs[TOP_COLS];                   // split cells of all top levels
+        const uint32_t nsplit = exs[TOP_COLS] & 0xFFFFu;         // split cells of all top levels
         if ((unsigned long long)1u + 8ull * nsplit >= (unsigned long long)t.nodes_max || depth_max <= TOP_L) bad = 1u;
         if (bad) s_bad = 1u;
         __syncthreads();
@@ -438,7 +442,7 @@ __global__ void __launch_bounds__(TN_THREADS) top_nodes_kernel(TreeDev t, int de
         uint32_t end = 1u;
         s_lvb[0] = 0u; s_lvb[1] = 1u;
         for (int d = 0; d <= TOP_L; d++) {
-            const uint32_t internal = exs[d == TOP_L ? TOP_COLS : top_off(d + 1)] - exs[top_off(d)];
+            const uint32_t internal = (exs[d == TOP_L ? TOP_COLS : top_off(d + 1)] - exs[top_off(d)]) & 0xFFFFu;
             s_int[d] = internal;
             end += 8u * internal;
             s_lvb[d + 2] = end;                                  // first id of level d + 2 = one past the last of level d + 1
@@ -454,9 +458,9 @@ __global__ void __launch_bounds__(TN_THREADS) top_nodes_kernel(TreeDev t, int de
         if (d > 0) {
             const uint32_t pc = top_off(d - 1) + (q >> 3);
             if (tot[pc] <= sub_max) { t.top_info[c] = NODE_END; continue; }          // the parent is not split: no node
-            id = s_lvb[d] + 8u * (exs[pc] - exs[top_off(d - 1)]) + (q & 7u);
+            id = s_lvb[d] + 8u * ((exs[pc] - exs[top_off(d - 1)]) & 0xFFFFu) + (q & 7u);
             const uint32_t ppc = d > 1 ? top_off(d - 2) + (q >> 6) : 0u;
-            pid = d > 1 ? s_lvb[d - 1] + 8u * (exs[ppc] - exs[top_off(d - 2)]) + ((q >> 3) & 7u) : 0u;
+            pid = d > 1 ? s_lvb[d - 1] + 8u * ((exs[ppc] - exs[top_off(d - 2)]) & 0xFFFFu) + ((q >> 3) & 7u) : 0u;
         }
         t.top_info[c] = id | (split ? 0x80000000u : 0u);
         float lo[3], hi[3];
@@ -475,20 +479,20 @@ __global__ void __launch_bounds__(TN_THREADS) top_nodes_kernel(TreeDev t, int de
             for (int lev = d; lev >= 1 && succ == NODE_END; lev--, qq >>= 3) {
                 const uint32_t sib0 = top_off(lev) + (qq & ~7u);
                 for (uint32_t o2 = 7u; o2 > (qq & 7u); o2--)
-                    if (tot[sib0 + o2] > 0u) succ = s_lvb[lev] + 8u * (exs[top_off(lev - 1) + (qq >> 3)] - exs[top_off(lev - 1)]) + o2;
+                    if (tot[sib0 + o2] > 0u) succ = s_lvb[lev] + 8u * ((exs[top_off(lev - 1) + (qq >> 3)] - exs[top_off(lev - 1)]) & 0xFFFFu) + o2;
             }
         }
         t.next[id] = succ;
         if (split) {
-            t.child_base[id] = s_lvb[d + 1] + 8u * (exs[c] - exs[off]);
+            t.child_base[id] = s_lvb[d + 1] + 8u * ((exs[c] - exs[off]) & 0xFFFFu);
             t.nmid[id] = make_float4(__fmul_rn(0.5f, __fadd_rn(lo[0], hi[0])), __fmul_rn(0.5f, __fadd_rn(lo[1], hi[1])),
                                      __fmul_rn(0.5f, __fadd_rn(lo[2], hi[2])), 0.f);
         } else {
             t.child_base[id] = NODE_END;
-            if (sub_owns(t, cn)) sub_append(t, id, (uint32_t)d);                     // finished (moments included) by subtree_kernel
+            if (sub_owns(t, cn)) t.sub_list[exs[c] >> 16] = make_uint2(id, (uint32_t)d);   // finished (moments included) by subtree_kernel
         }
-        if (!sub_owns(t, cn)) {
-            if (d <= XL_DEPTH_MAX && cn > t.xl_min) {             // very long fold: chunked exact evaluation (moments_xl)
+        if (!(d == 0 && sub_owns(t, cn))) {                        // (the tree root as a subtree root is folded by subtree_kernel)
+            if (!sub_owns(t, cn) && d <= XL_DEPTH_MAX && cn > t.xl_min) {   // very long fold: chunked exact evaluation (moments_xl)
                 const uint32_t k = atomicAdd(&t.xl_count[d], 1u);
                 if (k < t.xl_max) t.xl_nodes[(size_t)d * t.xl_max + k] = id;
             } else if (cn > ML_MIN && d > 0) t.ml_count[d] = 1u;
@@ -508,6 +512,7 @@ __global__ void __launch_bounds__(TN_THREADS) top_nodes_kernel(TreeDev t, int de
             h[1] = s_int[d]; h[2] = 0u; h[3] = s_lvb[d + 2];
         }
         t.meta[M_COUNT] = s_lvb[TOP_L + 2];
+        *t.sub_count = exs[TOP_COLS] >> 16;                       // the subtree roots of the top levels (later levels append)
         hs[1] = 0u; hs[2] = 0u; hs[3] = s_lvb[TOP_L + 2];
         __threadfence_system();
         for (int d = 0; d <= TOP_L; d++) t.summary[4 * d] = t.build_id;

@@ -461,9 +461,8 @@ __global__ void __launch_bounds__(CH_THREADS) children_kernel(TreeDev t, int d, 
                     t.child_base[c] = NODE_END;
                 }
                 t.seg[c] = make_uint2(start, start + cn);
-                if (sub_owns(t, cn)) {
-                    sub_append(t, c, (uint32_t)d + 1u);           // finished (moments included) by subtree_kernel
-                } else if (d + 1 <= XL_DEPTH_MAX && cn > t.xl_min) {     // very long fold: chunked exact evaluation (moments_xl)
+                if (sub_owns(t, cn)) sub_append(t, c, (uint32_t)d + 1u);   // everything below it is subtree_kernel's
+                if (!sub_owns(t, cn) && d + 1 <= XL_DEPTH_MAX && cn > t.xl_min) {   // very long fold: chunked exact evaluation (moments_xl)
                     const uint32_t k = atomicAdd(&t.xl_count[d + 1], 1u);
                     if (k < t.xl_max) t.xl_nodes[(size_t)(d + 1) * t.xl_max + k] = c;
                 } else if (cn > ML_MIN) {
@@ -545,8 +544,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // which kernel folds a node with cn members at level d
-__device__ __forceinline__ bool xl_owns(const TreeDev& t, int d, uint32_t cn) { return d <= XL_DEPTH_MAX && cn > t.xl_min && !sub_owns(t, cn); }
-__device__ __forceinline__ bool ml_owns(const TreeDev& t, int d, uint32_t cn) { return cn > ML_MIN && !xl_owns(t, d, cn) && !sub_owns(t, cn); }
+// (a subtree root is folded here like any other node of its level - only the TREE root, when the whole tree is one subtree,
+// is folded by subtree_kernel itself, because the deferred root fold would find its slots already reordered)
+__device__ __forceinline__ bool sub_folds(const TreeDev& t, int d, uint32_t cn) { return d == 0 && sub_owns(t, cn); }
+__device__ __forceinline__ bool xl_owns(const TreeDev& t, int d, uint32_t cn) { return d <= XL_DEPTH_MAX && cn > t.xl_min && !sub_owns(t, cn); }   // (its chains run beside subtree_kernel)
+__device__ __forceinline__ bool ml_owns(const TreeDev& t, int d, uint32_t cn) { return cn > ML_MIN && !xl_owns(t, d, cn) && !sub_folds(t, d, cn); }
 
 __global__ void __launch_bounds__(ML_THREADS) moments_long_kernel(TreeDev t, int d,
                                                                   uint32_t* __restrict__ gate /* {needed, done} or null */) {
@@ -661,7 +663,7 @@ __global__ void __launch_bounds__(256) moments_short_kernel(TreeDev t, int d, ui
         const bool live = n < e;
         const uint2 sg = live ? t.seg[n] : make_uint2(0u, 0u);
         uint32_t cnt = sg.y - sg.x;
-        if (cnt > ML_MIN || sub_owns(t, cnt)) cnt = 0u;           // the pipelined kernel owns the long nodes, subtree_kernel its roots
+        if (cnt > ML_MIN || sub_folds(t, d, cnt)) cnt = 0u;       // the pipelined kernel owns the long nodes, subtree_kernel the tree root it owns
         const float* __restrict__ src = reinterpret_cast<const float*>(rec + sg.x);   // {x, y, z, m} lead every 32-byte record
         float sum = 0.f;
 #pragma unroll 4
@@ -683,214 +685,230 @@ __global__ void __launch_bounds__(256) moments_short_kernel(TreeDev t, int d, ui
 // integer step on k = s / u:  k <- RNE(k + p_j / u) = k + floor(t_j) + [frac(t_j) > 1/2] (+1 on an exact tie when
 // k + floor(t_j) is odd).  As a function of k such a step only depends on the PARITY of k, steps of that kind are
 // closed under composition, and composition is associative - so a whole chunk of XL_CHUNK members collapses, in
-// parallel, into a map k -> k + a[k & 1], together with the extremes of the running value inside the chunk.
-//   xl_sums / xl_prefix   approximate value of the fold at every chunk boundary (double sums of the rounded products),
-//                         good enough to GUESS the binade, i.e. u, of each chunk;
-//   xl_maps               per chunk and component: the parity map and the prefix extremes for the guessed u (a lane
-//                         composes its eight consecutive members, an ordered warp reduction composes the lanes);
-//   xl_chain              the only serial part, one warp per (node, component): the maps of 32 consecutive chunks are
-//                         composed with a warp scan (lane i: chunks 0..i of the batch, as long as they share u), every
-//                         lane tests its prefix against the actual s - a multiple of u strictly inside the binade, with
-//                         the extremes keeping every intermediate value inside it - and the longest valid prefix is
-//                         applied at once, so a run of chunks inside one binade costs one step per 32 chunks.  A chunk
-//                         whose map does not apply (binade crossings, the first chunks, wrong guesses) is folded member
-//                         by member.  The result is the reference's bit pattern either way.
+// parallel, into a map k -> k + a[k & 1], together with the extremes of the running value inside the chunk.  (All of
+// these are below 2^25 in magnitude whenever the map can apply at all, so a map is eight 32-bit words - one sector.)
+//   xl_index   one CTA: the level's long nodes with their chunk counts, as a flat list of chunks;
+//   xl_prep    one warp per chunk, ONE pass over the members: double sums of the rounded products, their prefix over
+//              the node's chunks by decoupled look-back (chunks are handed out in order by a ticket) - the approximate
+//              value of the fold at both ends of the chunk, good enough to GUESS its binade, i.e. u - and, with the
+//              members still in registers, the parity map and the extremes for that u (a lane composes its eight
+//              consecutive members, an ordered warp reduction composes the lanes);
+//   xl_chain   the only serial part, one warp per (node, component): the maps of 32 consecutive chunks are composed
+//              with a warp scan (lane i: chunks 0..i of the window, as long as they share u), every lane tests its
+//              prefix against the actual s - a multiple of u strictly inside the binade, with the extremes keeping
+//              every intermediate value inside it - and the longest valid prefix is applied at once, so a run of chunks
+//              inside one binade costs one step per 32 chunks.  A chunk whose map does not apply (binade crossings,
+//              the first chunks, wrong guesses) is folded member by member.  The reference's bit pattern either way.
 constexpr int XL_CHUNK = 256;
 constexpr int XL_PER_LANE = XL_CHUNK / 32;
-constexpr long long XL_INF = 1ll << 62;
-struct XlMap { long long a0, a1, mn0, mx0, mn1, mx1, e2, usable; };   // 64 B
+constexpr int XL_LIM = 1 << 26;                 // bound on every entry of a usable map
+struct __align__(32) XlMap { int a0, a1, mn0, mx0, mn1, mx1, e2, usable; };
+struct __align__(32) XlNode { uint32_t n, first, cnt, nchunks, slot0, choff, pad0, pad1; };   // choff: chunks of the nodes listed before
 
+__device__ __forceinline__ XlMap xl_identity(int e2, int usable) {
+    XlMap m;
+    m.a0 = m.a1 = 0; m.mn0 = m.mn1 = XL_LIM; m.mx0 = m.mx1 = -XL_LIM; m.e2 = e2; m.usable = usable;
+    return m;
+}
 __device__ __forceinline__ XlMap xl_combine(const XlMap& A, const XlMap& B) {   // A first, then B
     XlMap C;
-    const bool p0 = (A.a0 & 1ll) != 0;            // parity after A when entering even
-    const bool p1 = ((1ll + A.a1) & 1ll) != 0;    // parity after A when entering odd
+    const bool p0 = (A.a0 & 1) != 0;              // parity after A when entering even
+    const bool p1 = ((1 + A.a1) & 1) != 0;        // parity after A when entering odd
     C.a0 = A.a0 + (p0 ? B.a1 : B.a0);
     C.a1 = A.a1 + (p1 ? B.a1 : B.a0);
     C.mn0 = min(A.mn0, A.a0 + (p0 ? B.mn1 : B.mn0));
     C.mx0 = max(A.mx0, A.a0 + (p0 ? B.mx1 : B.mx0));
     C.mn1 = min(A.mn1, A.a1 + (p1 ? B.mn1 : B.mn0));
     C.mx1 = max(A.mx1, A.a1 + (p1 ? B.mx1 : B.mx0));
-    C.e2 = A.e2; C.usable = A.usable;
+    C.e2 = A.e2;
+    const int big = max(max(abs(C.a0), abs(C.a1)), max(max(abs(C.mn0), abs(C.mx0)), max(abs(C.mn1), abs(C.mx1))));
+    C.usable = (A.usable != 0 && B.usable != 0 && big <= XL_LIM) ? 1 : 0;
+    if (!C.usable) { C.a0 = C.a1 = 0; C.mn0 = C.mn1 = 0; C.mx0 = C.mx1 = 0; }   // cannot apply any more; keeps later sums small
     return C;
 }
-__device__ __forceinline__ long long shfl_down_ll(long long v, int off) {
-    const int lo = __shfl_down_sync(0xFFFFFFFFu, (int)(v & 0xFFFFFFFFll), off);
-    const int hi = __shfl_down_sync(0xFFFFFFFFu, (int)(v >> 32), off);
-    return ((long long)hi << 32) | (unsigned int)lo;
+__device__ __forceinline__ XlMap xl_shfl_down(const XlMap& m, int off) {
+    XlMap o;
+    o.a0 = __shfl_down_sync(0xFFFFFFFFu, m.a0, off); o.a1 = __shfl_down_sync(0xFFFFFFFFu, m.a1, off);
+    o.mn0 = __shfl_down_sync(0xFFFFFFFFu, m.mn0, off); o.mx0 = __shfl_down_sync(0xFFFFFFFFu, m.mx0, off);
+    o.mn1 = __shfl_down_sync(0xFFFFFFFFu, m.mn1, off); o.mx1 = __shfl_down_sync(0xFFFFFFFFu, m.mx1, off);
+    o.e2 = m.e2; o.usable = __shfl_down_sync(0xFFFFFFFFu, m.usable, off);
+    return o;
 }
-__device__ __forceinline__ long long shfl_up_ll(long long v, int off) {
-    const int lo = __shfl_up_sync(0xFFFFFFFFu, (int)(v & 0xFFFFFFFFll), off);
-    const int hi = __shfl_up_sync(0xFFFFFFFFu, (int)(v >> 32), off);
-    return ((long long)hi << 32) | (unsigned int)lo;
-}
-__device__ __forceinline__ long long shfl_ll(long long v, int src) {
-    const int lo = __shfl_sync(0xFFFFFFFFu, (int)(v & 0xFFFFFFFFll), src);
-    const int hi = __shfl_sync(0xFFFFFFFFu, (int)(v >> 32), src);
-    return ((long long)hi << 32) | (unsigned int)lo;
+__device__ __forceinline__ XlMap xl_shfl_up(const XlMap& m, int off) {
+    XlMap o;
+    o.a0 = __shfl_up_sync(0xFFFFFFFFu, m.a0, off); o.a1 = __shfl_up_sync(0xFFFFFFFFu, m.a1, off);
+    o.mn0 = __shfl_up_sync(0xFFFFFFFFu, m.mn0, off); o.mx0 = __shfl_up_sync(0xFFFFFFFFu, m.mx0, off);
+    o.mn1 = __shfl_up_sync(0xFFFFFFFFu, m.mn1, off); o.mx1 = __shfl_up_sync(0xFFFFFFFFu, m.mx1, off);
+    o.e2 = m.e2; o.usable = __shfl_up_sync(0xFFFFFFFFu, m.usable, off);
+    return o;
 }
 __device__ __forceinline__ float xl_term(float4 p, uint32_t q) {   // the q-th summand of tree.c:166-169
     return q == 0u ? __fmul_rn(p.w, p.x) : q == 1u ? __fmul_rn(p.w, p.y) : q == 2u ? __fmul_rn(p.w, p.z) : p.w;
 }
-struct XlNode { uint32_t n, first, cnt, nchunks, slot0; };
-__device__ __forceinline__ bool xl_node(const TreeDev& t, int d, uint32_t k, XlNode* out) {
-    if (k >= t.xl_count[d]) return false;
-    out->n = t.xl_nodes[(size_t)d * t.xl_max + k];
-    const uint2 sg = t.seg[out->n];
-    out->first = sg.x; out->cnt = sg.y - sg.x;
-    out->nchunks = (out->cnt + XL_CHUNK - 1) / XL_CHUNK;
-    // disjoint chunk-slot ranges with one spare slot per node for the grand total, independent of the (arbitrary) list
-    // order: a long node has more than xl_min members, so the next one starts at least one xl_min block later
-    out->slot0 = sg.x / XL_CHUNK + 3u * (sg.x / t.xl_min);
-    return true;
+
+// the level's long nodes as a flat list of chunks: descriptors + running chunk count, [xl_max] holds the total
+__global__ void __launch_bounds__(1024) xl_index_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
+    __shared__ uint32_t sm[33];
+    __shared__ uint32_t carry;
+    if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
+    XlNode* __restrict__ list = reinterpret_cast<XlNode*>(t.xl_list) + (size_t)area * (t.xl_max + 1u);
+    const uint32_t nxl = min(t.xl_count[d], t.xl_max);
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    for (uint32_t base = 0; base < nxl; base += blockDim.x) {
+        const uint32_t k = base + threadIdx.x;
+        XlNode nd;
+        nd.n = 0u; nd.first = 0u; nd.cnt = 0u; nd.nchunks = 0u; nd.slot0 = 0u; nd.choff = 0u; nd.pad0 = 0u; nd.pad1 = 0u;
+        if (k < nxl) {
+            nd.n = t.xl_nodes[(size_t)d * t.xl_max + k];
+            const uint2 sg = t.seg[nd.n];
+            nd.first = sg.x; nd.cnt = sg.y - sg.x;
+            nd.nchunks = (nd.cnt + XL_CHUNK - 1) / XL_CHUNK;
+            // disjoint chunk-slot ranges, independent of the (arbitrary) list order: a long node has more than xl_min
+            // members, so the next one starts at least one xl_min block later
+            nd.slot0 = sg.x / XL_CHUNK + 3u * (sg.x / t.xl_min);
+        }
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan(nd.nchunks, &tot, sm);
+        nd.choff = carry + ex;
+        if (k < nxl) list[k] = nd;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        XlNode end;
+        end.n = nxl; end.first = 0u; end.cnt = 0u; end.nchunks = 0u; end.slot0 = 0u; end.choff = carry; end.pad0 = 0u; end.pad1 = 0u;
+        list[t.xl_max] = end;                       // {number of long nodes, -, -, -, -, total chunks}
+    }
 }
 
-__global__ void __launch_bounds__(256) xl_sums_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
+constexpr uint32_t XLF_AGG = 1u, XLF_INCL = 2u;   // chunk flag = epoch << 2 | state; other epochs read as "nothing yet"
+
+__global__ void __launch_bounds__(256) xl_prep_kernel(TreeDev t, int d, uint32_t area, uint32_t epoch, uint32_t* __restrict__ gate) {
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    // the chunks of all long nodes of the level are dealt out to the warps of the grid round robin
-    const uint32_t nxl = min(t.xl_count[d], t.xl_max), gw = blockIdx.x * 8u + warp, nw = gridDim.x * 8u;
-    uint32_t dealt = 0u;
-    __shared__ XlNode s_nd[128];                                   // the descriptors of the next 128 long nodes, fetched side by side
-    for (uint32_t kb = 0; kb < nxl; kb += 128u) {
-    __syncthreads();
-    if (threadIdx.x < 128u && kb + threadIdx.x < nxl) xl_node(t, d, kb + threadIdx.x, &s_nd[threadIdx.x]);
-    __syncthreads();
-    for (uint32_t kn = 0; kn < min(128u, nxl - kb); kn++) {
-    const XlNode nd = s_nd[kn];
-    const SlotRec* __restrict__ src = t.srec[d] + nd.first;
-    double* __restrict__ sums = t.xl_sum + ((size_t)area * t.xl_slots + nd.slot0) * 4u;
-    const uint32_t c_first = (gw + nw - dealt % nw) % nw;
-    dealt += nd.nchunks;
-    for (uint32_t c = c_first; c < nd.nchunks; c += nw) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const XlNode* __restrict__ list = reinterpret_cast<const XlNode*>(t.xl_list) + (size_t)area * (t.xl_max + 1u);
+    const uint32_t nxl = list[t.xl_max].n, total = list[t.xl_max].choff;
+    double* __restrict__ sums_all = t.xl_sum + (size_t)area * t.xl_slots * 8u;           // per chunk slot: aggregate[4], inclusive prefix[4]
+    volatile uint32_t* flags = t.xl_flag + (size_t)area * t.xl_slots;
+    XlMap* __restrict__ maps_all = reinterpret_cast<XlMap*>(t.xl_map) + (size_t)area * t.xl_slots * 4u;
+    uint32_t* ticket = &t.xl_ticket[d];
+    for (;;) {
+        // chunks are handed out in list order, so a chunk only ever waits for chunks that are already being worked on
+        uint32_t w = 0u;
+        if (lane == 0u) w = atomicAdd(ticket, 1u);
+        w = __shfl_sync(0xFFFFFFFFu, w, 0);
+        if (w >= total) return;
+        uint32_t lo = 0u, hi = nxl;                 // the node whose chunks include w: last k with choff[k] <= w
+        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (list[mid].choff <= w) lo = mid; else hi = mid; }
+        const XlNode nd = list[lo];
+        const uint32_t c = w - nd.choff;
+        const SlotRec* __restrict__ src = t.srec[d] + nd.first;
+        const size_t slot = (size_t)nd.slot0 + c;
+        // the lane's consecutive members
+        float4 mem[XL_PER_LANE];
+        const uint32_t j0 = c * XL_CHUNK + lane * XL_PER_LANE;
+#pragma unroll
+        for (int i = 0; i < XL_PER_LANE; i++) mem[i] = j0 + i < nd.cnt ? src[j0 + i].pm : make_float4(0.f, 0.f, 0.f, 0.f);
         double a[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (uint32_t i = 0; i < (uint32_t)XL_PER_LANE; i++) {
-            const uint32_t j = c * XL_CHUNK + i * 32u + lane;
-            if (j < nd.cnt) {
-                const float4 p = src[j].pm;
-                a[0] += (double)__fmul_rn(p.w, p.x); a[1] += (double)__fmul_rn(p.w, p.y);
-                a[2] += (double)__fmul_rn(p.w, p.z); a[3] += (double)p.w;
-            }
+        for (int i = 0; i < XL_PER_LANE; i++) {    // pads add +0
+            a[0] += (double)__fmul_rn(mem[i].w, mem[i].x); a[1] += (double)__fmul_rn(mem[i].w, mem[i].y);
+            a[2] += (double)__fmul_rn(mem[i].w, mem[i].z); a[3] += (double)mem[i].w;
         }
 #pragma unroll
         for (int q = 0; q < 4; q++)
 #pragma unroll
             for (int sh = 16; sh >= 1; sh >>= 1) a[q] += __shfl_xor_sync(0xFFFFFFFFu, a[q], sh);
-        if (lane < 4u) sums[(size_t)c * 4u + lane] = a[lane];
-    }
-    }
-    }
-}
-
-// exclusive prefix over the chunks of every long node (in place; slot nchunks receives the total): one warp per component,
-// a lane owns a contiguous block of chunks (its loads do not wait for each other), the blocks are joined by a warp scan
-__global__ void __launch_bounds__(128) xl_prefix_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
-    if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
-    XlNode nd;
-    if (!xl_node(t, d, blockIdx.x, &nd)) return;
-    const uint32_t lane = threadIdx.x & 31u, q = threadIdx.x >> 5;
-    double* __restrict__ sums = t.xl_sum + ((size_t)area * t.xl_slots + nd.slot0) * 4u + q;
-    const uint32_t per = (nd.nchunks + 31u) / 32u, c0 = min(nd.nchunks, lane * per), c1 = min(nd.nchunks, c0 + per);
-    double mine = 0.0;
-#pragma unroll 8
-    for (uint32_t c = c0; c < c1; c++) mine += sums[(size_t)c * 4u];
-    double x = mine;
+        // publish the aggregate (the inclusive prefix at once for a node's first chunk), then look back
+        double pre[4] = {0.0, 0.0, 0.0, 0.0};
+        if (lane < 4u) { sums_all[slot * 8u + lane] = a[lane]; if (c == 0u) sums_all[slot * 8u + 4u + lane] = a[lane]; }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0u) flags[slot] = (epoch << 2) | (c == 0u ? XLF_INCL : XLF_AGG);
+        if (c > 0u) {
+            int jb = (int)c - 1;                    // nearest predecessor of the current window
+            for (;;) {
+                const int j = jb - (int)lane;
+                const bool valid = j >= 0;
+                uint32_t st;
+                do {
+                    const uint32_t f = valid ? flags[(size_t)nd.slot0 + (uint32_t)j] : ((epoch << 2) | XLF_INCL);
+                    st = (f >> 2) == epoch ? (f & 3u) : 0u;
+                } while (__any_sync(0xFFFFFFFFu, st == 0u));
+                __threadfence();
+                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, !valid || st == XLF_INCL);
+                const uint32_t first = (uint32_t)__ffs((int)ballot) - 1u;          // nearest chunk that knows its inclusive prefix (or the node's start)
+                double v[4] = {0.0, 0.0, 0.0, 0.0};
+                if (valid && lane <= first) {
+                    const volatile double* sp = sums_all + ((size_t)nd.slot0 + (uint32_t)j) * 8u + (st == XLF_INCL ? 4u : 0u);
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) { const double y = __shfl_up_sync(0xFFFFFFFFu, x, off); if (lane >= (uint32_t)off) x += y; }
-    double run = x - mine;
-#pragma unroll 8
-    for (uint32_t c = c0; c < c1; c++) { const double v = sums[(size_t)c * 4u]; sums[(size_t)c * 4u] = run; run += v; }
-    if (lane == 31u) sums[(size_t)nd.nchunks * 4u] = x;
-}
-
-__global__ void __launch_bounds__(256) xl_maps_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
-    if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t nxl = min(t.xl_count[d], t.xl_max), gw = blockIdx.x * 8u + warp, nw = gridDim.x * 8u;
-    uint32_t dealt = 0u;
-    __shared__ XlNode s_nd[128];                                   // the descriptors of the next 128 long nodes, fetched side by side
-    for (uint32_t kb = 0; kb < nxl; kb += 128u) {
-    __syncthreads();
-    if (threadIdx.x < 128u && kb + threadIdx.x < nxl) xl_node(t, d, kb + threadIdx.x, &s_nd[threadIdx.x]);
-    __syncthreads();
-    for (uint32_t kn = 0; kn < min(128u, nxl - kb); kn++) {
-    const XlNode nd = s_nd[kn];
-    const SlotRec* __restrict__ src = t.srec[d] + nd.first;
-    const double* __restrict__ pre = t.xl_sum + ((size_t)area * t.xl_slots + nd.slot0) * 4u;
-    XlMap* __restrict__ maps = reinterpret_cast<XlMap*>(t.xl_map) + ((size_t)area * t.xl_slots + nd.slot0) * 4u;
-    const uint32_t c_first = (gw + nw - dealt % nw) % nw;
-    dealt += nd.nchunks;
-    for (uint32_t c = c_first; c < nd.nchunks; c += nw) {
-        // the lane's consecutive members, kept in registers for the four components
-        float4 mem[XL_PER_LANE];
-        const uint32_t j0 = c * XL_CHUNK + lane * XL_PER_LANE;
+                    for (int q = 0; q < 4; q++) v[q] = sp[q];
+                }
 #pragma unroll
-        for (int i = 0; i < XL_PER_LANE; i++) mem[i] = j0 + i < nd.cnt ? src[j0 + i].pm : make_float4(0.f, 0.f, 0.f, 0.f);
-        double pe[8];                                                // approximate fold value at both ends of the chunk
+                for (int q = 0; q < 4; q++) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) pe[i] = pre[(size_t)c * 4u + i];
+                    for (int sh = 16; sh >= 1; sh >>= 1) v[q] += __shfl_xor_sync(0xFFFFFFFFu, v[q], sh);
+                    pre[q] += v[q];
+                }
+                if (ballot) break;
+                jb -= 32;
+            }
+            if (lane < 4u) sums_all[slot * 8u + 4u + lane] = pre[lane] + a[lane];
+            __threadfence();
+            __syncwarp();
+            if (lane == 0u) flags[slot] = (epoch << 2) | XLF_INCL;
+        }
+        // maps: binade guess from the approximate fold value at both ends of the chunk
+        XlMap* __restrict__ maps = maps_all + slot * 4u;
 #pragma unroll
         for (uint32_t q = 0; q < 4u; q++) {
-            // binade guess from the approximate fold value at both ends of the chunk
-            const float fs = (float)pe[q], fe = (float)pe[4u + q];
+            const float fs = (float)pre[q], fe = (float)(pre[q] + a[q]);
             const uint32_t es = (__float_as_uint(fs) >> 23) & 0xFFu, ee = (__float_as_uint(fe) >> 23) & 0xFFu;
             const bool usable = es == ee && es > 40u && es < 250u && ((__float_as_uint(fs) ^ __float_as_uint(fe)) >> 31) == 0u;
-            XlMap m;
-            m.a0 = m.a1 = 0; m.mn0 = m.mn1 = XL_INF; m.mx0 = m.mx1 = -XL_INF;
-            m.e2 = (long long)es - 127 - 23; m.usable = usable ? 1 : 0;
+            XlMap m = xl_identity((int)es - 127 - 23, usable ? 1 : 0);
             if (usable) {                                            // warp-uniform
                 const double inv_u = __longlong_as_double((long long)(1023 - m.e2) << 52);
-                long long S0 = 0, S1 = 0;
+                int S0 = 0, S1 = 0;
 #pragma unroll
                 for (int i = 0; i < XL_PER_LANE; i++) {
                     if (j0 + i < nd.cnt) {
                         const double tt = (double)xl_term(mem[i], q) * inv_u;   // exact: scaling by a power of two
+                        if (!(fabs(tt) < 33554432.0)) m.usable = 0;              // a summand this large leaves the binade anyway
                         const double fl = floor(tt);
                         const double fr = tt - fl;                               // exact
-                        const long long fll = (long long)fl;
-                        const long long bi = fll + (fr > 0.5 ? 1 : 0);
+                        const int fll = m.usable ? (int)fl : 0;
+                        const int bi = fll + (fr > 0.5 ? 1 : 0);
                         const bool tie = fr == 0.5;
-                        S0 += bi + ((tie && ((S0 + fll) & 1ll)) ? 1 : 0);        // entering even: k + S0 + floor odd -> round up
-                        S1 += bi + ((tie && ((1ll + S1 + fll) & 1ll)) ? 1 : 0);  // entering odd
+                        S0 += bi + ((tie && ((S0 + fll) & 1)) ? 1 : 0);          // entering even: k + S0 + floor odd -> round up
+                        S1 += bi + ((tie && ((1 + S1 + fll) & 1)) ? 1 : 0);      // entering odd
                         m.mn0 = min(m.mn0, S0); m.mx0 = max(m.mx0, S0);
                         m.mn1 = min(m.mn1, S1); m.mx1 = max(m.mx1, S1);
                     }
                 }
                 m.a0 = S0; m.a1 = S1;
+                if (max(max(abs(S0), abs(S1)), max(max(abs(m.mn0), abs(m.mx0)), max(abs(m.mn1), abs(m.mx1)))) > XL_LIM) m.usable = 0;
+                if (!m.usable) { m.a0 = m.a1 = 0; m.mn0 = m.mn1 = 0; m.mx0 = m.mx1 = 0; }
                 // ordered reduction: lane i absorbs lane i + off
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
-                    XlMap o;
-                    o.a0 = shfl_down_ll(m.a0, off); o.a1 = shfl_down_ll(m.a1, off);
-                    o.mn0 = shfl_down_ll(m.mn0, off); o.mx0 = shfl_down_ll(m.mx0, off);
-                    o.mn1 = shfl_down_ll(m.mn1, off); o.mx1 = shfl_down_ll(m.mx1, off);
-                    o.e2 = m.e2; o.usable = m.usable;
+                    const XlMap o = xl_shfl_down(m, off);
                     if ((lane & (2u * off - 1u)) == 0u) m = xl_combine(m, o);
                 }
             }
-            if (lane == 0u) maps[(size_t)c * 4u + q] = m;
+            if (lane == 0u) maps[q] = m;
         }
-    }
-    }
     }
 }
 
-struct XlLane { long long a0, a1, mn0, mx0, mn1, mx1; int e2, usable; };   // a chunk map as a lane carries it
-__device__ __forceinline__ XlLane xl_load(const XlMap* __restrict__ maps, uint32_t c, uint32_t nchunks, uint32_t q) {
-    XlLane m;
-    m.a0 = m.a1 = 0; m.mn0 = m.mn1 = XL_INF; m.mx0 = m.mx1 = -XL_INF; m.e2 = 0; m.usable = 0;
-    if (c < nchunks) {
-        const XlMap g = maps[(size_t)c * 4u + q];
-        m.a0 = g.a0; m.a1 = g.a1; m.mn0 = g.mn0; m.mx0 = g.mx0; m.mn1 = g.mn1; m.mx1 = g.mx1; m.e2 = (int)g.e2; m.usable = (int)g.usable;
-    }
-    return m;
+struct XlWin { XlMap cur, nxt; };
+__device__ __forceinline__ XlMap xl_load(const XlMap* __restrict__ maps, uint32_t c, uint32_t nchunks, uint32_t q) {
+    if (c < nchunks) return maps[(size_t)c * 4u + q];
+    return xl_identity(0, 0);
 }
 // the window of 32 maps moves on by nv chunks: lane i takes what lane i + nv held, the tail comes from the next window
-__device__ __forceinline__ long long xl_shift_ll(long long cur, long long nxt, uint32_t nv, uint32_t lane) {
-    const long long a = shfl_ll(cur, (int)((lane + nv) & 31u)), b = shfl_ll(nxt, (int)((lane + nv) & 31u));
-    return lane + nv < 32u ? a : b;
-}
-__device__ __forceinline__ int xl_shift_i(int cur, int nxt, uint32_t nv, uint32_t lane) {
+__device__ __forceinline__ int xl_shift(int cur, int nxt, uint32_t nv, uint32_t lane) {
     const int a = __shfl_sync(0xFFFFFFFFu, cur, (int)((lane + nv) & 31u)), b = __shfl_sync(0xFFFFFFFFu, nxt, (int)((lane + nv) & 31u));
     return lane + nv < 32u ? a : b;
 }
@@ -899,17 +917,18 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d, uint32_
     __shared__ __align__(16) float buf[4][XL_CHUNK];
     __shared__ float s_mass;
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
-    XlNode nd;
-    if (!xl_node(t, d, blockIdx.x, &nd)) return;
+    const XlNode* __restrict__ list = reinterpret_cast<const XlNode*>(t.xl_list) + (size_t)area * (t.xl_max + 1u);
+    if (blockIdx.x >= list[t.xl_max].n) return;
+    const XlNode nd = list[blockIdx.x];
     const uint32_t lane = threadIdx.x & 31u, q = threadIdx.x >> 5;   // one warp per component
     const SlotRec* __restrict__ src = t.srec[d] + nd.first;
     const XlMap* __restrict__ maps = reinterpret_cast<const XlMap*>(t.xl_map) + ((size_t)area * t.xl_slots + nd.slot0) * 4u;
-    const long long B0 = (1ll << 23) + 1, B1 = (1ll << 24) - 1;
+    const int B0 = (1 << 23) + 1, B1 = (1 << 24) - 1;
     float s = 0.f;
     uint32_t c = 0u;
     // `cur`: the maps of chunks c .. c+31 (lane i: chunk c+i); `nxt`: those of chunks c+32 .. c+63, in flight while cur is used
-    XlLane cur = xl_load(maps, c + lane, nd.nchunks, q);
-    XlLane nxt = xl_load(maps, c + 32u + lane, nd.nchunks, q);
+    XlMap cur = xl_load(maps, c + lane, nd.nchunks, q);
+    XlMap nxt = xl_load(maps, c + 32u + lane, nd.nchunks, q);
     float ft[XL_PER_LANE];                                           // summands of the chunk that will need the member-by-member fold
     uint32_t ft_c = 0xFFFFFFFFu;
     while (c < nd.nchunks) {
@@ -927,28 +946,24 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d, uint32_
         uint32_t nv = 0u;
         if (nlead > 0u) {                                            // warp-uniform
             // compose in order: lane i holds chunks c .. c+i (meaningful below nlead)
-            XlMap m;
-            m.a0 = cur.a0; m.a1 = cur.a1; m.mn0 = cur.mn0; m.mx0 = cur.mx0; m.mn1 = cur.mn1; m.mx1 = cur.mx1; m.e2 = 0; m.usable = 0;
+            XlMap m = cur;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
-                XlMap o;
-                o.a0 = shfl_up_ll(m.a0, off); o.a1 = shfl_up_ll(m.a1, off);
-                o.mn0 = shfl_up_ll(m.mn0, off); o.mx0 = shfl_up_ll(m.mx0, off);
-                o.mn1 = shfl_up_ll(m.mn1, off); o.mx1 = shfl_up_ll(m.mx1, off);
-                o.e2 = 0; o.usable = 0;
+                const XlMap o = xl_shfl_up(m, off);
                 if (lane >= (uint32_t)off) m = xl_combine(o, m);
             }
             const double u = __longlong_as_double((long long)(1023 + e2) << 52);
             const double kd = (double)s * __longlong_as_double((long long)(1023 - e2) << 52);   // exact
-            const long long k = (long long)kd;
-            const long long par = k & 1ll;
-            const long long lo = k + (par ? m.mn1 : m.mn0), hi = k + (par ? m.mx1 : m.mx0);
-            const bool valid = lane < nlead && (double)k == kd &&
+            const bool small = fabs(kd) < 33554432.0;
+            const int k = small ? (int)kd : 0;
+            const int par = k & 1;
+            const int lo = k + (par ? m.mn1 : m.mn0), hi = k + (par ? m.mx1 : m.mx0);
+            const bool valid = lane < nlead && m.usable != 0 && small && (double)k == kd &&
                                ((k >= B0 && k <= B1 && lo >= B0 && hi <= B1) || (k <= -B0 && k >= -B1 && hi <= -B0 && lo >= -B1));
             const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
             nv = vmask == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~vmask) - 1u;
             if (nv > 0u) {
-                const long long kn = shfl_ll(k + (par ? m.a1 : m.a0), (int)nv - 1);
+                const int kn = __shfl_sync(0xFFFFFFFFu, k + (par ? m.a1 : m.a0), (int)nv - 1);
                 s = (float)((double)kn * u);
             }
         }
@@ -981,10 +996,10 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d, uint32_
         c += nv;
         if (nv == 32u) cur = nxt;
         else {
-            cur.a0 = xl_shift_ll(cur.a0, nxt.a0, nv, lane); cur.a1 = xl_shift_ll(cur.a1, nxt.a1, nv, lane);
-            cur.mn0 = xl_shift_ll(cur.mn0, nxt.mn0, nv, lane); cur.mx0 = xl_shift_ll(cur.mx0, nxt.mx0, nv, lane);
-            cur.mn1 = xl_shift_ll(cur.mn1, nxt.mn1, nv, lane); cur.mx1 = xl_shift_ll(cur.mx1, nxt.mx1, nv, lane);
-            cur.e2 = xl_shift_i(cur.e2, nxt.e2, nv, lane); cur.usable = xl_shift_i(cur.usable, nxt.usable, nv, lane);
+            cur.a0 = xl_shift(cur.a0, nxt.a0, nv, lane); cur.a1 = xl_shift(cur.a1, nxt.a1, nv, lane);
+            cur.mn0 = xl_shift(cur.mn0, nxt.mn0, nv, lane); cur.mx0 = xl_shift(cur.mx0, nxt.mx0, nv, lane);
+            cur.mn1 = xl_shift(cur.mn1, nxt.mn1, nv, lane); cur.mx1 = xl_shift(cur.mx1, nxt.mx1, nv, lane);
+            cur.e2 = xl_shift(cur.e2, nxt.e2, nv, lane); cur.usable = xl_shift(cur.usable, nxt.usable, nv, lane);
         }
         nxt = xl_load(maps, c + 32u + lane, nd.nchunks, q);
     }
@@ -1005,24 +1020,26 @@ namespace sfe {
 // top-level path lets subtree_kernel - which fills every SM for its whole duration - wait for the parallel part of the folds
 // and run beside the chains (a few small CTAs that are resident by then).
 static int launch_moments(Ctx* c, const TreeDev& dv, int d, uint32_t* gate, bool single, cudaStream_t s, const char* fn,
-                          cudaEvent_t pre = nullptr) {
+                          cudaEvent_t pre = nullptr, cudaStream_t s2 = nullptr, cudaEvent_t pre2 = nullptr) {
     static bool attr_set = false;
     if (!attr_set) {
         SFE_CUDA(fn, cudaFuncSetAttribute(moments_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ML_SMEM));
         attr_set = true;
     }
-    moments_long_kernel<<<single ? 1 : c->sm_count * 2, ML_THREADS, ML_SMEM, s>>>(dv, d, gate);
+    // the folds of the shorter nodes; on a stream of their own (s2) when the caller has one, beside the chunked fold
+    cudaStream_t sl = s2 ? s2 : s;
+    moments_long_kernel<<<single ? 1 : c->sm_count * 2, ML_THREADS, ML_SMEM, sl>>>(dv, d, gate);
     if (check_launch(fn)) return SFE_FAILURE;
-    moments_short_kernel<<<single ? 1 : c->sm_count * 8, 256, 0, s>>>(dv, d, gate);
+    moments_short_kernel<<<single ? 1 : c->sm_count * 8, 256, 0, sl>>>(dv, d, gate);
     if (check_launch(fn)) return SFE_FAILURE;
+    if (pre2) SFE_CUDA(fn, cudaEventRecord(pre2, sl));
     if (d <= XL_DEPTH_MAX) {
         const uint32_t area = (uint32_t)(d % SFE_SIDE_STREAMS);   // one scratch area per side stream; the deferred root uses area 0 after the join
         const uint32_t g2 = single ? 8u : (uint32_t)c->sm_count * 4u;
-        xl_sums_kernel<<<g2, 256, 0, s>>>(dv, d, area, gate);
+        const uint32_t epoch = ((dv.build_id << 5) + (uint32_t)d + 1u) & 0x3FFFFFFFu;   // tells this pass's chunk flags from older ones
+        xl_index_kernel<<<1, 1024, 0, s>>>(dv, d, area, gate);
         if (check_launch(fn)) return SFE_FAILURE;
-        xl_prefix_kernel<<<dv.xl_max, 128, 0, s>>>(dv, d, area, gate);
-        if (check_launch(fn)) return SFE_FAILURE;
-        xl_maps_kernel<<<g2, 256, 0, s>>>(dv, d, area, gate);
+        xl_prep_kernel<<<g2, 256, 0, s>>>(dv, d, area, epoch, gate);
         if (check_launch(fn)) return SFE_FAILURE;
         if (pre) SFE_CUDA(fn, cudaEventRecord(pre, s));
         xl_chain_kernel<<<dv.xl_max, 128, 0, s>>>(dv, d, area, gate);
@@ -1120,7 +1137,7 @@ static uint32_t top_min_particles() {   // SFE_TOP_MIN: builds of at least this 
 
 static uint32_t xl_min_members() {   // SFE_XL_MIN lowers the threshold so that small test trees exercise the chunked fold
     static uint32_t v = 0;
-    if (v == 0) { const char* e = getenv("SFE_XL_MIN"); v = e ? (uint32_t)atoi(e) : 16384u; if (v < 64u) v = 64u; }
+    if (v == 0) { const char* e = getenv("SFE_XL_MIN"); v = e ? (uint32_t)atoi(e) : 8192u; if (v < 64u) v = 64u; }
     return v;
 }
 
@@ -1154,13 +1171,16 @@ static TreeDev make_dev(Tree& t) {
     d.ticket = w;                 w += 2 * levels;
     d.sub_count = w;              w += 1;
     d.sub_ticket = w;             w += 1;
+    d.xl_ticket = w;              w += levels;
     d.xl_count = w;               w += levels;
     d.ml_count = w;               w += levels;
     d.xl_nodes = w;               w += (size_t)(XL_DEPTH_MAX + 1) * d.xl_max;
     d.tdesc = w;                  w += (size_t)levels * d.tdesc_stride;
     d.cdesc = reinterpret_cast<unsigned long long*>(t.lookback.as<char>() + ((size_t)(w - t.lookback.as<uint32_t>()) * 4 + 7) / 8 * 8);
     d.xl_sum = t.xl_sum.as<double>();
-    d.xl_map = t.xl_map.as<long long>();
+    d.xl_map = t.xl_map.as<int>();
+    d.xl_flag = t.xl_flag.as<uint32_t>();
+    d.xl_list = t.xl_list.p;
     d.sub_max = sub_max_members();
     d.sub_list = t.sub_list.as<uint2>();
     d.top_table = t.top_table.as<uint32_t>();
@@ -1180,7 +1200,7 @@ static TreeDev make_dev(Tree& t) {
 
 static size_t lookback_bytes(const TreeDev& d) {
     const size_t levels = SFE_MAX_LEVELS + 2;
-    const size_t words = 2 * levels + 2 + levels + levels + (size_t)(XL_DEPTH_MAX + 1) * d.xl_max + levels * d.tdesc_stride;
+    const size_t words = 2 * levels + 2 + levels + levels + levels + (size_t)(XL_DEPTH_MAX + 1) * d.xl_max + levels * d.tdesc_stride;
     return (words * 4 + 7) / 8 * 8 + levels * (size_t)d.cdesc_stride * 8;
 }
 
@@ -1217,6 +1237,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
             SFE_CUDA(fn, cudaEventCreateWithFlags(&t.ev_perm[k], trace_enabled() ? cudaEventDefault : cudaEventDisableTiming));
         for (auto& ev : t.ev_side) SFE_CUDA(fn, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : t.ev_pre) SFE_CUDA(fn, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& ev : t.ev_pre2) SFE_CUDA(fn, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         if (trace_enabled()) for (auto& ev : g_trace_ev) SFE_CUDA(fn, cudaEventCreate(&ev));
         if (trace_enabled()) for (auto& ev : g_trace_k) SFE_CUDA(fn, cudaEventCreate(&ev));
         t.ev_init = true;
@@ -1237,9 +1258,14 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         for (int k = 2; k <= TOP_L; k++) if (t.srec[k].reserve(n1 * sizeof(SlotRec), fn)) return SFE_FAILURE;
     }
     TreeDev dv = make_dev(t);
-    if (t.lookback.reserve(lookback_bytes(dv), fn) || t.xl_sum.reserve((size_t)SFE_SIDE_STREAMS * dv.xl_slots * 4 * 8, fn) ||
-        t.xl_map.reserve((size_t)SFE_SIDE_STREAMS * dv.xl_slots * 4 * 64, fn))
+    if (t.lookback.reserve(lookback_bytes(dv), fn) || t.xl_sum.reserve((size_t)SFE_SIDE_STREAMS * dv.xl_slots * 8 * 8, fn) ||
+        t.xl_map.reserve((size_t)SFE_SIDE_STREAMS * dv.xl_slots * 4 * 32, fn) ||
+        t.xl_list.reserve((size_t)SFE_SIDE_STREAMS * (dv.xl_max + 1) * 32, fn))
         return SFE_FAILURE;
+    if (t.xl_flag.cap < (size_t)SFE_SIDE_STREAMS * dv.xl_slots * 4) {   // fresh memory: no stale epoch may look current
+        if (t.xl_flag.reserve((size_t)SFE_SIDE_STREAMS * dv.xl_slots * 4, fn)) return SFE_FAILURE;
+        SFE_CUDA(fn, cudaMemsetAsync(t.xl_flag.p, 0, t.xl_flag.cap, s));
+    }
     dv = make_dev(t);
     SFE_CUDA(fn, cudaMemsetAsync(t.lookback.p, 0, lookback_bytes(dv), s));
     const uint32_t pgrid = [&] { uint32_t g = (N + PT_TILE - 1) / PT_TILE; uint32_t cap = (uint32_t)c->sm_count * 6; return g < 1 ? 1u : (g < cap ? g : cap); }();
@@ -1294,7 +1320,9 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
                 cudaStream_t side = c->side[d % SFE_SIDE_STREAMS];
                 SFE_CUDA(fn, cudaStreamWaitEvent(side, t.ev_perm[TOP_L], 0));
                 if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d], side);
-                if (launch_moments(c, dv, d, nullptr, false, side, fn, t.ev_pre[d % SFE_SIDE_STREAMS])) return SFE_FAILURE;
+                cudaStream_t side2 = c->side2[d % SFE_SIDE_STREAMS];
+                SFE_CUDA(fn, cudaStreamWaitEvent(side2, t.ev_perm[TOP_L], 0));
+                if (launch_moments(c, dv, d, nullptr, false, side, fn, t.ev_pre[d % SFE_SIDE_STREAMS], side2, t.ev_pre2[d % SFE_SIDE_STREAMS])) return SFE_FAILURE;
                 if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d + 1], side);
             }
             if (trace_enabled()) {
@@ -1315,6 +1343,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     }
 
     int levels_run = 0;
+    int last_fold[2] = {-1, -1};                 // the last two levels whose folds went to a side stream inside the loop below
     double host_us[SFE_MAX_LEVELS + 4];
     const auto host_t0 = std::chrono::steady_clock::now();
     for (int d = first_level; d <= depth_max; d++) {
@@ -1345,6 +1374,8 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
             if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d], side);
             if (launch_moments(c, dv, d, nullptr, false, side, fn)) return SFE_FAILURE;
             if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d + 1], side);
+            SFE_CUDA(fn, cudaEventRecord(t.ev_pre[d % SFE_SIDE_STREAMS], side));
+            last_fold[1] = last_fold[0]; last_fold[0] = d;
         }
         rank_kernel<<<pgrid, PT_THREADS, 0, s>>>(dv, d);
         if (check_launch(fn)) return SFE_FAILURE;
@@ -1374,8 +1405,14 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     if (first_level > 0) {
         // the parallel part of the top levels' folds goes first (subtree_kernel fills every SM for its whole duration);
         // the serial chains of the very long nodes - a few small CTAs - run beside it
-        for (int d = 1; d <= TOP_L; d++) SFE_CUDA(fn, cudaStreamWaitEvent(s, t.ev_pre[d % SFE_SIDE_STREAMS], 0));
+        for (int d = 1; d <= TOP_L; d++) {
+            SFE_CUDA(fn, cudaStreamWaitEvent(s, t.ev_pre[d % SFE_SIDE_STREAMS], 0));
+            SFE_CUDA(fn, cudaStreamWaitEvent(s, t.ev_pre2[d % SFE_SIDE_STREAMS], 0));
+        }
     }
+    // subtree_kernel reorders the final slot array in place: the folds that read the subtree roots living there (the last
+    // levels') come first
+    for (int k = 0; k < 2; k++) if (last_fold[k] >= 0) SFE_CUDA(fn, cudaStreamWaitEvent(s, t.ev_pre[last_fold[k] % SFE_SIDE_STREAMS], 0));
     if (dv.sub_max > 8u) {
         static bool st_attr = false;
         if (!st_attr) {

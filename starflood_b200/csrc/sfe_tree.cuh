@@ -91,8 +91,11 @@ struct TreeDev {
     uint32_t* xl_nodes;           // [levels][xl_max]
     uint32_t xl_max, xl_slots;    // list capacity per level, chunk slots per scratch area
     uint32_t xl_min;              // nodes with more members than this use the chunked exact fold
-    double* xl_sum;               // [SFE_SIDE_STREAMS][xl_slots][4] chunk sums, then exclusive prefixes, of the rounded products
-    long long* xl_map;            // [SFE_SIDE_STREAMS][xl_slots][4][8] {a0, a1, min0, max0, min1, max1, exponent, usable}
+    double* xl_sum;               // [SFE_SIDE_STREAMS][xl_slots][8] per chunk: sums of the rounded products, their inclusive prefix
+    int* xl_map;                  // [SFE_SIDE_STREAMS][xl_slots][4][8] {a0, a1, min0, max0, min1, max1, exponent, usable}
+    uint32_t* xl_flag;            // [SFE_SIDE_STREAMS][xl_slots] look-back state of every chunk (epoch << 2 | state)
+    void* xl_list;                // [SFE_SIDE_STREAMS][xl_max + 1] the level's long nodes as a flat list of chunks (XlNode)
+    uint32_t* xl_ticket;          // [levels] chunk tickets of xl_prep_kernel
     // lower part of the build (sfe_subtree.cuh): nodes of 9 .. sub_max bodies are finished by one CTA each
     uint32_t sub_max;             // 8 switches the subtree path off (every level goes through the grid-wide kernels)
     uint2* sub_list;              // {node id, level} of every subtree root, in no particular order
