@@ -90,6 +90,17 @@ __device__ __forceinline__ uint32_t mask6(const Votes6& v, uint32_t bin) {     /
     return v.ba & ((bin & 1u) ? v.b0 : ~v.b0) & ((bin & 2u) ? v.b1 : ~v.b1) & ((bin & 4u) ? v.b2 : ~v.b2) &
            ((bin & 8u) ? v.b3 : ~v.b3) & ((bin & 16u) ? v.b4 : ~v.b4) & ((bin & 32u) ? v.b5 : ~v.b5);
 }
+// the masks of bins `lane` and `lane + 32` at once: lb[k] = all ones when bit k of the lane number is set
+struct LaneBits { uint32_t l0, l1, l2, l3, l4; };
+__device__ __forceinline__ LaneBits lane_bits(uint32_t lane) {
+    LaneBits b;
+    b.l0 = 0u - (lane & 1u); b.l1 = 0u - ((lane >> 1) & 1u); b.l2 = 0u - ((lane >> 2) & 1u); b.l3 = 0u - ((lane >> 3) & 1u); b.l4 = 0u - ((lane >> 4) & 1u);
+    return b;
+}
+__device__ __forceinline__ void mask6_pair(const Votes6& v, const LaneBits& b, uint32_t* lo, uint32_t* hi) {
+    const uint32_t common = v.ba & ~(v.b0 ^ b.l0) & ~(v.b1 ^ b.l1) & ~(v.b2 ^ b.l2) & ~(v.b3 ^ b.l3) & ~(v.b4 ^ b.l4);
+    *lo = common & ~v.b5; *hi = common & v.b5;
+}
 __device__ __forceinline__ uint32_t mask3hi(const Votes6& v, uint32_t bin) {   // active lanes whose upper three bits are `bin`
     return v.ba & ((bin & 1u) ? v.b3 : ~v.b3) & ((bin & 2u) ? v.b4 : ~v.b4) & ((bin & 4u) ? v.b5 : ~v.b5);
 }
@@ -120,6 +131,7 @@ __global__ void __launch_bounds__(TP_THREADS, 4) top_rank_kernel(TreeDev t, cons
     __shared__ TopShared S;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u, le = lt | (1u << lane);
+    const LaneBits lb = lane_bits(lane);
     const uint32_t range = blockIdx.x;
     const uint32_t i_begin = range * range_len, i_end = min(N, i_begin + range_len);
     for (uint32_t k = tid; k < TOP_COLS; k += TP_THREADS) S.row[k] = 0u;
@@ -151,7 +163,9 @@ __global__ void __launch_bounds__(TP_THREADS, 4) top_rank_kernel(TreeDev t, cons
 #pragma unroll
         for (int g = 0; g < TP_GROUPS; g++) {
             const Votes6 v = vote6(cd[g] != TOP_NONE, cd[g] >> 6);
-            tot_lo += __popc(mask6(v, lane)); tot_hi += __popc(mask6(v, lane + 32u));
+            uint32_t m_lo, m_hi;
+            mask6_pair(v, lb, &m_lo, &m_hi);
+            tot_lo += __popc(m_lo); tot_hi += __popc(m_hi);
         }
         S.wtr[warp][lane] = tot_lo; S.wtr[warp][lane + 32u] = tot_hi;
         __syncthreads();
@@ -183,7 +197,9 @@ __global__ void __launch_bounds__(TP_THREADS, 4) top_rank_kernel(TreeDev t, cons
             const uint32_t r0 = __popc(v.ba & lt) + run0;
             r01[g] = r0 | (r1 << 16); r2l[g] = r2;
             if (act) S.a2[S.lstart[q2] + r2] = (uint16_t)(id0 + 32u * g);
-            run_lo += __popc(mask6(v, lane)); run_hi += __popc(mask6(v, lane + 32u));
+            uint32_t m_lo, m_hi;
+            mask6_pair(v, lb, &m_lo, &m_hi);
+            run_lo += __popc(m_lo); run_hi += __popc(m_hi);
             run8 += __popc(mask3hi(v, lane & 7u));
             run0 += __popc(v.ba);
         }
@@ -212,7 +228,9 @@ __global__ void __launch_bounds__(TP_THREADS, 4) top_rank_kernel(TreeDev t, cons
             if (g >= gl) {                          // uniform across the warp
                 const Votes6 v = vote6((e[g] >> 25) & 1u, e[g] & 63u);
                 const uint32_t from = g == gl ? (0xFFFFFFFFu << (31 - __clz(hm[g]))) : 0xFFFFFFFFu;
-                tot_lo += __popc(mask6(v, lane) & from); tot_hi += __popc(mask6(v, lane + 32u) & from);
+                uint32_t m_lo, m_hi;
+                mask6_pair(v, lb, &m_lo, &m_hi);
+                tot_lo += __popc(m_lo & from); tot_hi += __popc(m_hi & from);
             }
         }
         S.wtr[warp][lane] = tot_lo; S.wtr[warp][lane + 32u] = tot_hi;
@@ -238,7 +256,8 @@ __global__ void __launch_bounds__(TP_THREADS, 4) top_rank_kernel(TreeDev t, cons
             const uint32_t r4 = __popc(mask6(v, d34) & lt & from) + (in_open ? (d34 < 32u ? b_lo : b_hi) : 0u);
             const uint32_t r3 = __popc(mask3hi(v, d3) & lt & from) + (in_open ? b8 : 0u);
             if (act) { S.r3[id] = (uint16_t)r3; S.r4[id] = (uint16_t)r4; }
-            const uint32_t m_lo = mask6(v, lane), m_hi = mask6(v, lane + 32u);
+            uint32_t m_lo, m_hi;
+            mask6_pair(v, lb, &m_lo, &m_hi);
             // last member of a segment: the 64 totals of its two-digit bin
             for (uint32_t m = __ballot_sync(0xFFFFFFFFu, (e[g] >> 24) & 1u); m; m &= m - 1u) {
                 const uint32_t L = (uint32_t)__ffs(m) - 1u, upto = 0xFFFFFFFFu >> (31u - L);
@@ -347,6 +366,7 @@ __device__ __forceinline__ void top_cell(const float* b, uint32_t q, int d, floa
 
 constexpr int TN_THREADS = 1024;
 constexpr int TN_ITEMS = 5;                    // columns per thread (TN_THREADS * TN_ITEMS >= TOP_COLS)
+constexpr int TN_CTAS = 5;                     // CTAs that share the per-cell work
 constexpr uint32_t TOP_COLS_PAD = 4684u;
 static_assert(TN_THREADS * TN_ITEMS >= (int)TOP_COLS, "one scan covers all columns");
 
@@ -433,7 +453,7 @@ __global__ void __launch_bounds__(TN_THREADS) top_nodes_kernel(TreeDev t, int de
         if (bad) s_bad = 1u;
         __syncthreads();
         if (s_bad != 0u) {
-            if (tid == 0) { t.top_flag[0] = 1u; hs[1] = 1u; hs[2] = 0u; hs[3] = 0u; __threadfence_system(); hs[0] = t.build_id; }
+            if (tid == 0 && blockIdx.x == 0) { t.top_flag[0] = 1u; hs[1] = 1u; hs[2] = 0u; hs[3] = 0u; __threadfence_system(); hs[0] = t.build_id; }
             return;
         }
     }
@@ -449,8 +469,8 @@ __global__ void __launch_bounds__(TN_THREADS) top_nodes_kernel(TreeDev t, int de
         }
     }
     __syncthreads();
-    // ---- every cell writes the records of its node
-    for (uint32_t c = tid; c < TOP_COLS; c += TN_THREADS) {
+    // ---- every cell writes the records of its node (the CTAs of the grid - each has done the scan for itself - share the cells)
+    for (uint32_t c = blockIdx.x * TN_THREADS + tid; c < TOP_COLS; c += gridDim.x * TN_THREADS) {
         const int d = top_level_of(c);
         const uint32_t off = top_off(d), q = c - off, cn = tot[c];
         const bool split = cn > sub_max;
@@ -500,7 +520,7 @@ __global__ void __launch_bounds__(TN_THREADS) top_nodes_kernel(TreeDev t, int de
         t.top_start[c] = start;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && blockIdx.x == 0) {
         // the per-build counters and level summaries, as CompactOp::total, root_kernel and open_level() leave them
         t.meta[M_NUM_INBOX] = M; t.meta[M_STATUS] = 0u; t.meta[M_DEPTH] = 0u; t.meta[M_FINAL] = 0u;
         t.meta[M_LV_BEGIN + 0] = 0u; t.meta[M_LV_END + 0] = 1u;

@@ -1306,7 +1306,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         if (check_launch(fn)) return SFE_FAILURE;
         top_scan_kernel<<<(TOP_COLS + 31u) / 32u, TSC_WARPS * 32, 0, s>>>(dv, ranges);
         if (check_launch(fn)) return SFE_FAILURE;
-        top_nodes_kernel<<<1, TN_THREADS, tn_smem, s>>>(dv, depth_max, range_len);
+        top_nodes_kernel<<<TN_CTAS, TN_THREADS, tn_smem, s>>>(dv, depth_max, range_len);
         if (check_launch(fn)) return SFE_FAILURE;
         top_scatter_kernel<<<ranges, TP_THREADS, 0, s>>>(dv, pm4, N, range_len);
         if (check_launch(fn)) return SFE_FAILURE;
