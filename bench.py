@@ -3,14 +3,14 @@
 
 Workload (config.workload): C2 = Barnes-Hut gravity, N = 2^20 uniform sphere from the reference's
 initcond_generate(), theta = 0.5 monopole, root box of sim_solv().  One "step" = one pass of the hot path over
-one snapshot: tree_build + solve_gravity_part_tree for all N particles (the root box is caller-side code that
-stays in the reference, simulation.c:245-308, and is computed once per snapshot at set-up).
+one snapshot: the SOLVER_TREE branch of sim_solv() (simulation.c:245-325) - root box of the step, tree_build,
+solve_gravity_part_tree for all N particles - which is exactly what the reference arm times.
 
     value   particle-steps/s with the snapshot already resident in HBM (device entry points, sfe_dev_*)
-    e2e     the same through the host C ABI (sfe_tree_build + sfe_bh on pinned HOST buffers): every step copies
+    e2e     the same through the host C ABI (sfe_solv_tree on pinned HOST buffers): every step copies
             pos/mas host->device and acc/pot device->host inside the timed region
     pp      PP direct-sum interactions/s at the same N (second half of BASELINE.json's metric), FP32-bound
-    roofline  the walk kernel against measured HBM bandwidth with SURVEY 8(d)'s algorithmic bytes
+    roofline  the walk kernel against the roof that binds it (instruction issue), with SURVEY 8(d)'s HBM byte model beside it
     cpu_baseline  the unmodified reference (oracle/_ref/libsfref_tree.so) timed on this box's host cores
 
 N > 1 (torchrun, one rank per GPU): strong scaling at the same total N.  Every rank owns a target slice,
@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--no-sph", action="store_true", help="skip the C3 (PP + SPH) legs")
     ap.add_argument("--no-resident", action="store_true", help="skip the device-resident leapfrog legs")
     ap.add_argument("--no-vis", action="store_true", help="skip the vis_draw() leg")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 leg (PP N=2^22 by target slice; runs on 2/4/8 GPUs)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 leg (Barnes-Hut N=2^24 galaxy pair)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: all-gather of {x,y,z,m} by the engine's peer-memory kernels (sfe_dev_peer_put) or by NCCL")
     return ap.parse_args()
@@ -386,6 +388,156 @@ def resident_leg(e, L, torch, dist, world, rank, N, tree, with_sph, flavour, all
             "l2": "the state evolves in place (a real trajectory); its working set is what the workload has"}
 
 
+def slot_hash(torch, acc, pot):
+    """Order-independent 64-bit checksum of the bit patterns of acc / pot (the EXACT walk is bit-reproducible, so the
+    value is the same at every GPU count when every rank's slice is right)."""
+    a = acc.view(torch.int32).to(torch.int64).reshape(-1, 3)
+    p = pot.view(torch.int32).to(torch.int64)
+    h = (a[:, 0] * 1000003 + a[:, 1]) * 1000003 + a[:, 2]
+    h = h * 1000003 + p
+    return int((h ^ (h >> 29)).sum().item()) & 0xFFFFFFFFFFFFFFFF
+
+
+def c5_leg(e, L, torch, dist, world, rank, dev, stream, flavour, barrier, max_over_ranks):
+    """BASELINE.json C5: Barnes-Hut N = 2^24 galaxy-pair collision ICs, theta = 0.5, tree per GPU.  A step = root box +
+    full tree build on every rank + walk of the rank's target slice (index slices: sfe_dev_bh).  Parity: rank 0 walks ALL
+    particles on its own tree afterwards and compares the bits of every rank's slice with it."""
+    from starflood_b200 import ics
+    N = 1 << 24
+    nodes_max = 1 << 23
+    sptr = stream.cuda_stream
+    pos, vel, mas = ics.galaxy_pair(N)
+    pm = np.empty((N, 4), np.float32); pm[:, :3] = pos.reshape(-1, 3); pm[:, 3] = mas
+    del pos, vel
+    pm4 = torch.from_numpy(pm).to(dev).reshape(-1)
+    del pm
+    i0, i1 = (N * rank) // world, (N * (rank + 1)) // world
+    ni = i1 - i0
+    acc = torch.zeros(3 * N, dtype=torch.float32, device=dev)
+    pot = torch.zeros(N, dtype=torch.float32, device=dev)
+    box = np.zeros(6, np.float32)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+    def step(k, timed=False, lo=i0, n=ni):
+        rc = L.sfe_dev_root_box(pm4.data_ptr(), N, k, box.ctypes.data, sptr)
+        if timed: ev[0].record(stream)
+        rc |= L.sfe_dev_tree_build(box.ctypes.data, pm4.data_ptr(), N, e.TREE_DEPTH_MAX, nodes_max, sptr)
+        if timed: ev[1].record(stream)
+        rc |= L.sfe_dev_bh(pm4.data_ptr(), N, lo, n, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, THETA, flavour, sptr)
+        if timed: ev[2].record(stream)
+        if rc != 0:
+            raise SystemExit("bench.py: C5 leg failed: " + e.last_error())
+    step(0); step(1)
+    barrier()
+    import ctypes as C
+    st = (C.c_uint32(), C.c_uint32(), C.c_uint32())
+    if L.sfe_dev_tree_status(sptr, C.byref(st[0]), C.byref(st[1]), C.byref(st[2])) != 0:
+        raise SystemExit("bench.py: C5 tree build failed: " + e.last_error())
+    reps = 3
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    build_ms = walk_ms = 0.0
+    l0 = L.sfe_launch_count()
+    a.record(stream)
+    for r in range(reps):
+        step(2 + r, timed=True)
+        stream.synchronize()
+        build_ms += ev[0].elapsed_time(ev[1]); walk_ms += ev[1].elapsed_time(ev[2])
+    b.record(stream)
+    barrier()
+    launches = int(L.sfe_launch_count() - l0)
+    ms = max_over_ranks(a.elapsed_time(b)) / reps
+    build_ms = max_over_ranks(build_ms / reps); walk_ms = max_over_ranks(walk_ms / reps)
+    # parity on the last snapshot's box: every rank's slice against a single-rank walk of all particles on rank 0
+    mine_acc = acc[3 * i0:3 * i1].clone(); mine_pot = pot[i0:i1].clone()
+    parity = None
+    if world > 1:
+        even = N % world == 0
+        ga = [torch.empty_like(mine_acc) for _ in range(world)] if even else None
+        gp = [torch.empty_like(mine_pot) for _ in range(world)] if even else None
+        if even:
+            dist.all_gather(ga, mine_acc); dist.all_gather(gp, mine_pot)
+        if rank == 0 and even:
+            step(2 + reps - 1, lo=0, n=N)
+            torch.cuda.synchronize()
+            ok = bool(torch.equal(torch.cat(ga).view(torch.int32), acc.view(torch.int32)) and
+                      torch.equal(torch.cat(gp).view(torch.int32), pot.view(torch.int32)))
+            parity = {"bit_identical_to_single_rank": ok, "checked": "acc and pot of all %d particles, gathered from the %d ranks, "
+                      "against a walk of all particles on rank 0's own tree" % (N, world),
+                      "checksum": "%016x" % slot_hash(torch, acc, pot)}
+    else:
+        parity = {"bit_identical_to_single_rank": True, "checked": "single rank (this value is the one the multi-GPU runs must reproduce)",
+                  "checksum": "%016x" % slot_hash(torch, acc, pot)}
+    hbm, hbm_src = measured_peaks()
+    out = {"workload": "C5: Barnes-Hut gravity N=%d galaxy-pair collision ICs (initcond.c:265-329), theta=0.5 monopole, tree per GPU; "
+                       "one sim_solv() per step: root box + tree_build + solve_gravity_part_tree" % N,
+           "N": N, "ms_per_step": ms, "particle_steps_per_s": N / (ms * 1e-3), "build_ms": build_ms, "walk_ms": walk_ms,
+           "tree_nodes": int(st[0].value), "tree_depth": int(st[2].value), "gpu_launches": launches, "steps": reps,
+           "partition": "target index slices, full tree on every GPU" if world > 1 else "single GPU",
+           "parity": parity,
+           "build_hbm": {"algorithmic_bytes": (16.0 + 24.0 * int(st[2].value)) * N + 32.0 * int(st[0].value),
+                         "achieved_gbs": ((16.0 + 24.0 * int(st[2].value)) * N + 32.0 * int(st[0].value)) / (build_ms * 1e-3) / 1e9,
+                         "frac": ((16.0 + 24.0 * int(st[2].value)) * N + 32.0 * int(st[0].value)) / (build_ms * 1e-3) / 1e9 / hbm,
+                         "model": "SURVEY 8(d): B_build = 16 + 24 D + 32 nodes/N bytes per particle", "peak_source": hbm_src},
+           "l2": "inputs of 256 MiB > L2; every step rebuilds the tree (a new root box per step)"}
+    del pm4, acc, pot
+    torch.cuda.empty_cache()
+    return out
+
+
+def c4_leg(e, L, torch, dist, world, rank, dev, stream, barrier, max_over_ranks):
+    """BASELINE.json C4: PP direct-sum gravity N = 2^22 sharded by target slice.  Every rank evaluates its slice over all
+    sources (sfe_dev_pp).  Parity: rank 0 re-evaluates the first 256 targets of every rank's slice on its own and compares
+    (the j-split of the kernel depends on the number of targets, so the comparison is to 1e-6 relative, not bitwise)."""
+    from starflood_b200 import ics
+    N = 1 << 22
+    sptr = stream.cuda_stream
+    pos, vel, mas = ics.uniform_ball(N)
+    pm = np.empty((N, 4), np.float32); pm[:, :3] = pos.reshape(-1, 3); pm[:, 3] = mas
+    pm4 = torch.from_numpy(pm).to(dev).reshape(-1)
+    i0, i1 = (N * rank) // world, (N * (rank + 1)) // world
+    ni = i1 - i0
+    acc = torch.zeros(3 * N, dtype=torch.float32, device=dev)
+    pot = torch.zeros(N, dtype=torch.float32, device=dev)
+
+    def solve(lo, n):
+        if L.sfe_dev_pp(pm4.data_ptr(), N, lo, n, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, sptr) != 0:
+            raise SystemExit("bench.py: C4 leg failed: " + e.last_error())
+    solve(i0, min(ni, 65536))                                  # warm-up on a small slice (the full one takes a second)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream); solve(i0, ni); b.record(stream)
+    barrier()
+    ms = max_over_ranks(a.elapsed_time(b))
+    inter = float(N) * float(N) / (ms * 1e-3)
+    info = e.device_info()
+    K = 256
+    head_a = acc[3 * i0:3 * (i0 + K)].clone(); head_p = pot[i0:i0 + K].clone()
+    ga = [torch.empty_like(head_a) for _ in range(world)]; gp = [torch.empty_like(head_p) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(ga, head_a); dist.all_gather(gp, head_p)
+    else:
+        ga, gp = [head_a], [head_p]
+    parity = None
+    if rank == 0:
+        worst = 0.0
+        for r in range(world):
+            lo = (N * r) // world
+            solve(lo, K)
+            torch.cuda.synchronize()
+            ra = acc[3 * lo:3 * (lo + K)].double(); rp = pot[lo:lo + K].double()
+            worst = max(worst, float(((ga[r].double() - ra).norm() / ra.norm()).item()), float(((gp[r].double() - rp).norm() / rp.norm()).item()))
+        parity = {"max_rel_rms_vs_rank0": worst, "tolerance": 1e-6, "ok": worst <= 1e-6,
+                  "checked": "the first %d targets of every rank's slice, re-evaluated on rank 0" % K}
+    out = {"workload": "C4: PP direct-sum gravity N=%d sharded by target slice, one solve_gravity_part_part per step" % N,
+           "N": N, "ms_per_solve": ms, "interactions_per_s": inter, "flop_per_interaction": 20,
+           "achieved_tflops": 20.0 * inter / 1e12, "fp32_peak_tflops": info["fp32_peak_tflops"] * world,
+           "frac": 20.0 * inter / 1e12 / (info["fp32_peak_tflops"] * world), "parity": parity,
+           "partition": "target index slices, all sources on every GPU", "steps": 1}
+    del pm4, acc, pot
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------ engine arm
 def run_engine(args):
     import torch
@@ -481,9 +633,13 @@ def run_engine(args):
             pm4_full.copy_(slices[k])      # at N=1 the "gather" is a device copy of the resident snapshot
         return pm4_full
 
+    box_host = np.zeros(6, np.float32)
+
     def step_dev(k, ev=None):
         pm4 = gather(k)
-        rc = L.sfe_dev_tree_build(boxes[k].ctypes.data, pm4.data_ptr(), N, e.TREE_DEPTH_MAX, nodes_max, sptr)
+        # root box of sim_solv() on the device (bit-identical to simulation.c:245-301; boxes[k] is the host mirror's)
+        rc = L.sfe_dev_root_box(pm4.data_ptr(), N, k, box_host.ctypes.data, sptr)
+        rc |= L.sfe_dev_tree_build(box_host.ctypes.data, pm4.data_ptr(), N, e.TREE_DEPTH_MAX, nodes_max, sptr)
         if ev is not None:
             ev[0].record(stream)
         if use_peer:
@@ -511,6 +667,8 @@ def run_engine(args):
     # ---- warm-up
     for w in range(max(args.warmup, 3)):
         step_dev(w % ring)
+        if not np.array_equal(box_host, boxes[w % ring]):
+            raise SystemExit("bench.py: the device root box differs from the reference's")
     barrier()
     st = (C.c_uint32(), C.c_uint32(), C.c_uint32())
     if L.sfe_dev_tree_status(sptr, C.byref(st[0]), C.byref(st[1]), C.byref(st[2])) != 0:
@@ -554,6 +712,35 @@ def run_engine(args):
     alt_ms = max_over_ranks(a0.elapsed_time(a1)) / args.steps
     flavour = main_flavour
 
+    # ---- parity of the multi-GPU path on real devices: every rank's slice of one step against a single-rank walk of all
+    # particles on rank 0's own tree (the EXACT walk is bit-reproducible), plus a checksum that is the same at every GPU count
+    step_dev(0)
+    barrier()
+    parity = None
+    mine_acc = acc[3 * i0:3 * i1].clone(); mine_pot = pot[i0:i1].clone()
+    if world > 1 and N % world == 0:
+        ga = [torch.empty_like(mine_acc) for _ in range(world)]; gp = [torch.empty_like(mine_pot) for _ in range(world)]
+        dist.all_gather(ga, mine_acc); dist.all_gather(gp, mine_pot)
+        if rank == 0:
+            full_acc = torch.zeros(3 * N, dtype=torch.float32, device=dev); full_pot = torch.zeros(N, dtype=torch.float32, device=dev)
+            pm4_now = pm4_regions[(xstate["n"] - 1) & 1] if use_peer else pm4_full
+            if L.sfe_dev_bh(pm4_now.data_ptr(), N, 0, N, full_acc.data_ptr(), full_pot.data_ptr(), e.G, e.EPS2, THETA, flavour, sptr) != 0:
+                raise SystemExit("bench.py: parity walk failed: " + e.last_error())
+            torch.cuda.synchronize()
+            same = bool(torch.equal(torch.cat(ga).view(torch.int32), full_acc.view(torch.int32)) and
+                        torch.equal(torch.cat(gp).view(torch.int32), full_pot.view(torch.int32)))
+            parity = {"bit_identical_to_single_rank": same, "flavour": args.flavour,
+                      "checked": "acc and pot of all %d particles of one step, gathered from the %d ranks, against a walk of all "
+                                 "particles on rank 0's own tree" % (N, world),
+                      "checksum": "%016x" % slot_hash(torch, full_acc, full_pot)}
+            del full_acc, full_pot
+        del ga, gp
+    elif world == 1:
+        parity = {"bit_identical_to_single_rank": True, "flavour": args.flavour,
+                  "checked": "single rank (the checksum is the one the multi-GPU runs must reproduce)",
+                  "checksum": "%016x" % slot_hash(torch, acc, pot)}
+    barrier()
+
     # ---- e2e: host buffers through the host C ABI (N=1) / pinned slices + collective + device ABI (N>1)
     e2e_ms = None
     h2d_b = d2h_b = 0
@@ -562,9 +749,8 @@ def run_engine(args):
             L.sfe_host_register(sim.mem.ctypes.data, sim.mem.nbytes)
         def step_host(k):
             sim, box = snaps[k]
-            rc = L.sfe_tree_build(boxes[k].ctypes.data, sim.pos.ctypes.data, sim.mas.ctypes.data, N, e.TREE_DEPTH_MAX, nodes_max)
-            rc |= L.sfe_bh(sim.pos.ctypes.data, sim.mas.ctypes.data, sim.acc.ctypes.data, sim.pot.ctypes.data, N,
-                           e.G, e.EPS2, THETA, flavour)
+            rc = L.sfe_solv_tree(sim.pos.ctypes.data, sim.mas.ctypes.data, sim.acc.ctypes.data, sim.pot.ctypes.data, N, k,
+                                 e.TREE_DEPTH_MAX, nodes_max, e.G, e.EPS2, THETA, flavour, box_host.ctypes.data)
             if rc != 0:
                 raise SystemExit("bench.py: engine call failed: " + e.last_error())
         for w in range(3):
@@ -621,11 +807,28 @@ def run_engine(args):
         info = e.device_info()
         inter = float(N) * float(N) / (pp_ms * 1e-3)
         tf = 20.0 * inter / 1e12
+        # the same solve with unequal masses (the general kernel: the m_j multiply stays in the loop, 13 FMA-pipe operations per
+        # interaction instead of 12); the reference's own ICs have equal masses, which is what `value` / `frac` are measured on
+        pm4m = gather(0).clone()
+        pm4m.view(-1, 4)[:, 3] *= torch.linspace(0.5, 1.5, N, device=dev)
+        L.sfe_dev_pp(pm4m.data_ptr(), N, i0, min(ni, 65536), acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, sptr)
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record(stream)
+        L.sfe_dev_pp(pm4m.data_ptr(), N, i0, ni, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, sptr)
+        q1.record(stream)
+        barrier()
+        mix_ms = max_over_ranks(q0.elapsed_time(q1))
+        del pm4m
+        tf_mix = 20.0 * float(N) * float(N) / (mix_ms * 1e-3) / 1e12
         pp = {"metric": "PP interactions/s", "value": inter, "ms_per_solve": pp_ms, "N": N,
               "flop_per_interaction": 20, "achieved_tflops": tf,
               "fp32_peak_tflops": info["fp32_peak_tflops"] * world,
               "peak_note": "2*128 lanes*%d SMs*%.0f MHz per GPU (cudaDevAttrClockRate)" % (info["sm_count"], info["clock_khz"] / 1e3),
-              "frac": tf / (info["fp32_peak_tflops"] * world)}
+              "frac": tf / (info["fp32_peak_tflops"] * world),
+              "frac_equal_mass": tf / (info["fp32_peak_tflops"] * world),
+              "frac_mixed": tf_mix / (info["fp32_peak_tflops"] * world), "ms_per_solve_mixed": mix_ms, "achieved_tflops_mixed": tf_mix,
+              "note": "frac counts 20 flop per interaction in both cases; the equal-mass kernel (every IC the reference generates) executes 19"}
 
     # ---- C3 SPH kernels alone (single rank): density + EOS + pressure force on a resident snapshot
     sph = None
@@ -636,6 +839,13 @@ def run_engine(args):
     vis = None
     if not args.no_vis and world == 1:
         vis = vis_leg(e, L, torch, dev, stream, N, gather(0), pot, not args.no_cpu)
+
+    # ---- BASELINE.json's larger configurations: C5 at every GPU count (it fits one GPU), C4 where it is defined (2/4/8)
+    c5 = c4 = None
+    if not args.no_c5:
+        c5 = c5_leg(e, L, torch, dist, world, rank, dev, stream, flavour, barrier, max_over_ranks)
+    if not args.no_c4 and world > 1:
+        c4 = c4_leg(e, L, torch, dist, world, rank, dev, stream, barrier, max_over_ranks)
 
     # ---- device-resident leapfrog: whole sim_step()s with the state in HBM, through sfe_sim_run()
     resident = None
@@ -662,31 +872,45 @@ def run_engine(args):
     walk_bytes = (32.0 * V_C2 + 32.0) * ni            # 32 B per node visit + 32 B particle I/O
     step_bytes = (32.0 * V_C2 + 32.0 + 16.0 + 24.0 * 8 + 32.0 * 0.382) * N
     achieved = walk_bytes / (walk_ms * 1e-3) / 1e9
-    traffic, winst = None, None
+    traffic, winst, lanes = None, None, None
     prof = os.path.join(ROOT, "profiles", "walk_traffic.json")
     if os.path.exists(prof):
         try:
             rec = json.load(open(prof)).get(args.flavour, {})
             traffic = rec.get("dram_bytes_per_launch")
             winst = rec.get("warp_instructions_per_launch")
+            lanes = rec.get("lanes_per_instruction")
         except Exception:
             traffic = None
-    roofline = {"kernel": "walk_kernel (sfe_dev_bh)", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                "frac": achieved / hbm, "traffic": traffic, "peak_source": hbm_src,
-                "algorithmic_bytes_per_launch": walk_bytes, "launch_ms": walk_ms,
-                "model": "32 B x V(=%.1f node visits/particle, oracle-counted) + 32 B particle I/O, x %d targets" % (V_C2, ni),
-                # the bound the walk actually runs into (DRAM traffic is 0.3 % of the algorithmic bytes: the node table is
-                # L1/L2 resident): warp instructions of one full-N launch (ncu capture under profiles/) per second against
-                # 4 issue slots per SM per clock
-                "issue": ({"warp_instructions_per_launch": winst * (ni / float(N)),
-                           "achieved": winst * (ni / float(N)) / (walk_ms * 1e-3),
-                           "peak": 4.0 * e.device_info()["sm_count"] * e.device_info()["clock_khz"] * 1e3,
-                           "unit": "warp-instructions/s",
-                           "frac": winst * (ni / float(N)) / (walk_ms * 1e-3) / (4.0 * e.device_info()["sm_count"] * e.device_info()["clock_khz"] * 1e3)}
-                          if winst and N == N_DEFAULT else None),
-                "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
-                               "frac": step_bytes / (ms_step * 1e-3) / 1e9 / hbm,
-                               "model": "SURVEY 8(d) B = 32 V + 32 + B_build = 16710 B per particle-step"}}
+    info = e.device_info()
+    issue_peak = 4.0 * info["sm_count"] * info["clock_khz"] * 1e3          # 4 schedulers per SM, one warp instruction per clock each
+    hbm_model = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": hbm_src,
+                 "algorithmic_bytes_per_launch": walk_bytes,
+                 "model": "SURVEY 8(d): 32 B x V(=%.1f node visits/particle, oracle-counted) + 32 B particle I/O, x %d targets" % (V_C2, ni),
+                 "note": "not the binding roof: the node table is L1/L2 resident (DRAM traffic is 0.3 % of these bytes), so this "
+                         "fraction exceeds 1; kept because SURVEY 8(d) and the north star quote the walk against HBM"}
+    if winst and N == N_DEFAULT:
+        wi = winst * (ni / float(N))
+        roofline = {"kernel": "walk_kernel (sfe_dev_bh)", "bound": "issue", "achieved": wi / (walk_ms * 1e-3), "peak": issue_peak,
+                    "unit": "warp-instructions/s", "frac": wi / (walk_ms * 1e-3) / issue_peak,
+                    "traffic": traffic, "traffic_source": "profiles/walk_traffic.json: dram__bytes_read+write of one full-N launch under "
+                                                          "ncu --set full (not measured inside this run)",
+                    "warp_instructions_per_launch": wi,
+                    "instruction_source": "profiles/walk_traffic.json: smsp__inst_executed.sum of the same capture, scaled by the rank's share of the targets",
+                    "launch_ms": walk_ms, "lanes_active_per_instruction": lanes,
+                    "model": "the walk is bound by instruction issue (ncu: issue slots ~80 % busy, 21 of 32 lanes active), not by memory",
+                    "hbm_model": hbm_model}
+    else:
+        roofline = dict(hbm_model, kernel="walk_kernel (sfe_dev_bh)", traffic=traffic, launch_ms=walk_ms)
+    roofline["whole_step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
+                              "frac": step_bytes / (ms_step * 1e-3) / 1e9 / hbm,
+                              "model": "SURVEY 8(d) B = 32 V + 32 + B_build = 16710 B per particle-step (HBM model, see hbm_model.note)"}
+    # the tree build against its own HBM model (B_build = 16 + 24 D + 32 nodes/N bytes per particle)
+    build_ms = ms_step - walk_ms
+    build_bytes = (16.0 + 24.0 * int(st[2].value)) * N + 32.0 * int(st[0].value)
+    roofline["tree_build"] = {"bound": "hbm", "ms": build_ms, "algorithmic_bytes": build_bytes, "achieved": build_bytes / (build_ms * 1e-3) / 1e9,
+                              "peak": hbm, "unit": "GB/s", "frac": build_bytes / (build_ms * 1e-3) / 1e9 / hbm,
+                              "model": "SURVEY 8(d): 16 + 24 D + 32 nodes/N bytes per particle; ms = step - walk (root box, exchange and build)"}
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only, bounded sample)
     cpu = None
@@ -703,8 +927,10 @@ def run_engine(args):
         "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: Barnes-Hut gravity N=%d uniform sphere (reference initcond), theta=0.5 monopole, "
-                               "tree_build + solve_gravity_part_tree per step" % N,
+        "config": {"workload": workload_name(N),
+                   "arm": "the engine on z-rotated copies of the reference IC, root box of step_number = ring position (the "
+                          "reference arm re-solves the un-rotated IC with the root box of step_number = 0, 1, 2, ...: "
+                          "statistically the same work)",
                    "N": N, "theta": THETA, "depth_max": 16, "walk": args.flavour,
                    "partition": ("tree per GPU; " + ("all-gather of {x,y,z,m} by the engine's peer-memory put + flag kernels "
                                  "(NVLink, sfe_dev_peer_put), walk by Morton slot range with results stored into the owner's window "
@@ -715,7 +941,7 @@ def run_engine(args):
                    **({"note": peer_note} if peer_note else {})},
         "e2e": {"value": N / (e2e_ms * 1e-3), "unit": "particle-steps/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
-                "api": "sfe_tree_build + sfe_bh on pinned host arrays" if world == 1 else
+                "api": "sfe_solv_tree (root box + tree_build + walk in one call) on pinned host arrays" if world == 1 else
                        "pinned slice H2D + exchange + sfe_dev_tree_build + walk + slice D2H"},
         "gpu_launches": launches,
         "clocks": clocks,
@@ -723,7 +949,10 @@ def run_engine(args):
         "cpu_baseline": cpu,
         "alt_walk": {"walk": "fast" if args.flavour == "exact" else "exact", "ms_per_step": alt_ms, "value": N / (alt_ms * 1e-3),
                      "unit": "particle-steps/s"},
+        "parity": parity,
         "pp": pp,
+        "c4": c4,
+        "c5": c5,
         "sph": sph,
         "vis": vis,
         "resident": resident,

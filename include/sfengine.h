@@ -133,6 +133,14 @@ int sfe_vis_draw(const float* pos, const float* pot, uint32_t N, uint32_t step_n
                  double pixel_value_scale, int tonemap, int32_t* atomic_buffer, float* render_buffer,
                  double* average_radius, float mvp[16]);
 
+/* sim_solv()'s SOLVER_TREE branch in one call (simulation.c:245-325): root box of `step_number` (simulation.c:245-301,
+ * returned in bounds_out when not NULL), tree_build (tree.c:74-318), solve_gravity_part_tree (gravity.c:245-663).
+ * One upload of pos / mas, one download of acc / pot, no host synchronisation in between; a failed build is reported with
+ * the reference's messages (tree.c:181,187); acc / pot are undefined then. */
+int sfe_solv_tree(const float* pos, const float* mas, float* acc, float* pot, uint32_t N, uint32_t step_number,
+                  int depth_max, uint32_t nodes_max, float grav_g, float eps2, float theta, uint32_t flavour,
+                  float bounds_out[6]);
+
 /* Replaces solve_sph() (sph.h:6, sph.c:14-283): density (all pairs, no cutoff), EOS
  * P = (eos_k rho)^(1/eos_n + 1), pressure force added to acc (read-modify-write) for r^2 <= cutoff2. */
 int sfe_sph(const float* pos, const float* mas, const float* rad, float* rho, float* prs, float* acc,

@@ -324,6 +324,37 @@ extern "C" int sfe_bh(const float* pos, const float* mas, float* acc, float* pot
     return sfe_bh_slice(pos, mas, acc, pot, N, 0, N, G, eps2, theta, flavour);
 }
 
+// The SOLVER_TREE branch of sim_solv() (simulation.c:245-325) in one call on host arrays: root box, tree_build,
+// solve_gravity_part_tree.  Nothing waits for the host between the upload and the download but the root box (six floats
+// through mapped memory, because the box is a kernel argument of the build); the build's status is raised at the end
+// (a walk on a failed build returns at once on the device).
+extern "C" int sfe_solv_tree(const float* pos, const float* mas, float* acc, float* pot, uint32_t N, uint32_t step_number,
+                             int depth_max, uint32_t nodes_max, float G, float eps2, float theta, uint32_t flavour,
+                             float bounds_out[6]) {
+    const char* fn = "sfe_solv_tree";
+    if (ensure_init(fn)) return SFE_FAILURE;
+    if (!pos || !mas || !acc || !pot) { set_error(fn, "null pointer argument"); return SFE_FAILURE; }
+    if (N == 0) { set_error(fn, "N must be at least 1 (the reference divides by N, simulation.c:277)"); return SFE_FAILURE; }
+    Ctx* c = g_ctx;
+    t_begin(c);
+    c->tree.valid = false;
+    if (upload_particles(c, fn, pos, mas, N, /*for_tree=*/true)) return SFE_FAILURE;
+    if (c->d_acc.reserve((size_t)N * 12, fn) || c->d_pot.reserve((size_t)N * 4, fn)) return SFE_FAILURE;
+    t_mark(c, 1);
+    float b[6];
+    if (launch_root_box(c, c->d_pm4.as<float4>(), N, step_number, b, c->stream)) return SFE_FAILURE;
+    if (bounds_out) for (int k = 0; k < 6; k++) bounds_out[k] = b[k];
+    if (launch_tree_build(c, b, c->d_pm4.as<float4>(), N, depth_max, nodes_max, c->stream)) return SFE_FAILURE;
+    t_mark(c, 2);
+    if (launch_bh(c, c->d_pm4.as<float4>(), N, 0, N, c->d_acc.as<float>(), c->d_pot.as<float>(), G, eps2, theta, flavour, c->stream))
+        return SFE_FAILURE;
+    t_mark(c, 3);
+    if (d2h(fn, acc, c->d_acc.p, (size_t)N * 12, c->stream)) return SFE_FAILURE;
+    if (d2h(fn, pot, c->d_pot.p, (size_t)N * 4, c->stream)) return SFE_FAILURE;
+    if (t_end(c, fn, true)) return SFE_FAILURE;
+    return tree_status(c, c->stream);
+}
+
 extern "C" int sfe_sph(const float* pos, const float* mas, const float* rad, float* rho, float* prs, float* acc,
                        uint32_t N, float eos_k, float eos_n, float cutoff2) {
     const char* fn = "sfe_sph";

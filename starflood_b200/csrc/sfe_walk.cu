@@ -124,6 +124,7 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
             float* __restrict__ acc, float* __restrict__ pot, WalkRoute route) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nslots) return;
+    if (t.meta[M_STATUS] != 0u) return;          // the build failed (tree.c:180-189): nothing consistent to walk; tree_status() raises it
     const uint32_t M = t.meta[M_NUM_INBOX];
     const uint32_t s = slots ? slots[k] : s0 + k;
     const uint32_t fin = t.meta[M_FINAL];

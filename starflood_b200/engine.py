@@ -90,6 +90,7 @@ SIGNATURES = {
     "sfe_tree_build": ([_P, _P, _P, _u32, C.c_int, _u32], C.c_int),
     "sfe_bh": ([_P, _P, _P, _P, _u32, _f, _f, _f, _u32], C.c_int),
     "sfe_bh_slice": ([_P, _P, _P, _P, _u32, _u32, _u32, _f, _f, _f, _u32], C.c_int),
+    "sfe_solv_tree": ([_P, _P, _P, _P, _u32, _u32, C.c_int, _u32, _f, _f, _f, _u32, _P], C.c_int),
     "sfe_tree_download": ([_P, _u32, C.POINTER(_u32)], C.c_int),
     "sfe_tree_keys_download": ([_P, _P, _u32, C.POINTER(_u32)], C.c_int),
     "sfe_selftest_exact_math": ([C.POINTER(C.c_uint64)], C.c_int),
@@ -287,6 +288,13 @@ def solve_gravity_part_tree(sim, flavour=WALK_EXACT, i0=0, ni=None, theta=TREE_T
     ni = sim.N - i0 if ni is None else ni
     return lib().sfe_bh_slice(_ptr(sim.pos), _ptr(sim.mas), _ptr(sim.acc), _ptr(sim.pot), sim.N, i0, ni,
                               G, EPS2, theta, flavour)
+
+
+def solv_tree(sim, flavour=WALK_EXACT, theta=TREE_THETA, depth_max=TREE_DEPTH_MAX):
+    """The SOLVER_TREE branch of sim_solv() (simulation.c:245-325) as ONE engine call: root box of sim.step_number
+    (left in sim.tree.bounds), tree_build, solve_gravity_part_tree."""
+    return lib().sfe_solv_tree(_ptr(sim.pos), _ptr(sim.mas), _ptr(sim.acc), _ptr(sim.pot), sim.N, sim.step_number,
+                               depth_max, sim.tree.max_nodes, G, EPS2, theta, flavour, _ptr(sim.tree.bounds))
 
 
 SOLVER_VIS = 3   # config.h:32

@@ -59,3 +59,30 @@ def uniform_ball(N, outflow=4.0e-3, G=1.0):
     vel = np.stack([vx * speed + k * p64[:, 0], vy * speed + k * p64[:, 1], vz * speed + k * p64[:, 2]], axis=1).astype(np.float32)
     mas = np.full(N, np.float32((PI_4_3 * 1.0) / N), np.float32)
     return pos.ravel(), vel.ravel(), mas
+
+
+def galaxy_pair(N, G=1.0):
+    """BASELINE.json C5: the author's disabled galaxy-pair sketch (initcond.c:265-329) on top of initcond_generate():
+    85 % of the particles are squashed into a disc (y * 0.025) on circular-ish orbits, every particle joins one of two
+    galaxies at x = +-2 approaching each other with +-0.005."""
+    pos, vel, mas = uniform_ball(N, 4.0e-3, G)
+    p = pos.reshape(-1, 3).astype(np.float64)
+    v = vel.reshape(-1, 3).astype(np.float64)
+    i = np.arange(N, dtype=np.uint32)
+    full = lambda c: np.full(N, c, np.uint32)
+    with np.errstate(over="ignore"):
+        s = pcg4d(np.uint32(0x5D20CDF7) + i, full(0xE5C4E174), full(0xCB77B51E), full(0xA82C87A3))
+    u = [INV_PCG32_MAX * x.astype(np.float64) for x in s]
+    disc = u[0] < 0.850
+    p[disc, 1] *= 0.025
+    r2 = (p[:, 0] * p[:, 0]) + (p[:, 1] * p[:, 1]) + (p[:, 2] * p[:, 2])
+    with np.errstate(divide="ignore"):
+        inv_r1 = np.where(0.0 < r2, 1.0 / np.sqrt(r2), 0.0)
+    k = 1.000e-2 * np.sqrt(PI_8_3 * G)
+    v[disc, 0] = (k * inv_r1 * p[:, 2])[disc]
+    v[disc, 1] = 0.0
+    v[disc, 2] = (k * inv_r1 * -p[:, 0])[disc]
+    first = u[1] < 0.500
+    p[:, 0] += np.where(first, 2.000, -2.000)
+    v[:, 0] += np.where(first, -0.005, 0.005)
+    return p.astype(np.float32).ravel(), v.astype(np.float32).ravel(), mas

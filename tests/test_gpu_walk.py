@@ -100,3 +100,29 @@ def test_full_size(engine):
 def test_exact_math_exhaustive(engine):
     """The EXACT flavour's 1/q, sqrt(q), 1/sqrt(q) sequences give the IEEE result for every float in [2^-24, 2^16)."""
     assert engine.selftest_exact_math() == [0, 0, 0]
+
+
+@pytest.mark.parametrize("N,step", [(9, 0), (20000, 0), (20000, 5), (200000, 2)])
+def test_solv_tree_is_the_tree_branch_of_sim_solv(engine, N, step):
+    """sfe_solv_tree(): root box of step_number + tree_build + walk in one call on host arrays (simulation.c:245-325) -
+    the box equals the reference's bit for bit, acc / pot equal the oracle's walk on the oracle's tree."""
+    pos, vel, mas = sfo.initcond(N)
+    sim = engine.Sim(N); sim.pos[:] = pos; sim.mas[:] = mas; sim.step_number = step
+    engine.tree_init(sim.tree, N + 64)
+    assert engine.solv_tree(sim) == 0, engine.last_error()
+    b = sfo.root_box(pos, step)
+    assert np.array_equal(sim.tree.bounds, b)
+    rc, onodes, oc, *_ = sfo.tree_build_sorted(b, pos, mas, N + 64)
+    acc, pot, st = sfo.bh_walk(onodes[:oc], pos, mas)
+    assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)
+
+
+def test_solv_tree_reports_a_failed_build_like_the_reference(engine):
+    N = 20000
+    pos, vel, mas = sfo.initcond(N)
+    sim = engine.Sim(N); sim.pos[:] = pos; sim.mas[:] = mas
+    engine.tree_init(sim.tree, 1000)                                   # far too few nodes (tree.c:180-183)
+    assert engine.solv_tree(sim) == engine.STARFLOOD_FAILURE
+    assert "Exceeded maximum number of tree nodes" in engine.last_error()
+    engine.tree_init(sim.tree, N + 64)
+    assert engine.solv_tree(sim) == 0, engine.last_error()             # and the engine is usable afterwards

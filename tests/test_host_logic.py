@@ -27,6 +27,13 @@ def test_ics_match_reference_generator():
     assert np.abs(v0 - V0).max() <= 1e-9
 
 
+def test_galaxy_pair_ics_match_the_oracle():
+    for N in (1000, 50000):
+        p, v, m = ics.galaxy_pair(N)
+        P, V, M = sfo.initcond_galaxy_pair(N)
+        assert np.array_equal(m, M) and np.abs(p - P).max() <= 2.4e-7 and np.abs(v - V).max() <= 1e-9
+
+
 def test_pcg4d_matches_oracle():
     seeds = np.array([0x638FE17B, 0xB10BDCE7, 0x7B8ADB9B, 0xD8C5850E], np.uint32)
     want = sfo.pcg4d(seeds)
