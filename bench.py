@@ -253,9 +253,15 @@ def sph_leg(e, L, torch, dev, stream):
                                   acc.data_ptr(), sptr)
         if rc != 0:
             raise SystemExit("bench.py: SPH call failed: " + e.last_error())
+    import ctypes as C
+    pairs = C.c_uint64()
     for _ in range(3):
         solve()
     torch.cuda.synchronize()
+    L.sfe_sph_pairs_evaluated(C.byref(pairs), sptr)     # reset the counter
+    solve()
+    L.sfe_sph_pairs_evaluated(C.byref(pairs), sptr)     # (target, source) pairs the two cell-list passes of ONE solve evaluated
+    pairs_eval = float(pairs.value)
     reps, tot = 10, 0.0
     for _ in range(reps):
         flush.fill_(1)                                  # 160 MiB > L2: the snapshot is read from HBM again
@@ -272,8 +278,24 @@ def sph_leg(e, L, torch, dev, stream):
     hbm, hbm_src = measured_peaks()
     bytes_alg = (20.0 * nn + 24.0 * nn + 64.0) * N
     ach = bytes_alg / (ms * 1e-3) / 1e9
+    # the bound the pair passes actually run into: FP32 FMA-pipe lane operations and MUFU.EX2 per EVALUATED pair (one common h:
+    # density 3 add + 2 mul + 4 fma = 9, force 4 add + 4 mul + 5 fma + 2 select = 15; one ex2 each), against
+    # 128 FMA lanes and 16 MUFU lanes per SM per clock
+    info = e.device_info()
+    clk = info["clock_khz"] * 1e3
+    fma_peak, mufu_peak = 128.0 * info["sm_count"] * clk, 16.0 * info["sm_count"] * clk
+    pairs_in = 2.0 * nn * N
+    compute = {"bound": "fp32 fma pipe", "pairs_evaluated_per_solve": pairs_eval, "pairs_in_range_per_solve": pairs_in,
+               "evaluated_over_in_range": pairs_eval / pairs_in if pairs_in else None,
+               "pairs_per_s": pairs_eval / (ms * 1e-3),
+               "fma_lane_ops_per_pair": 12.0, "fma_frac": 12.0 * pairs_eval / (ms * 1e-3) / fma_peak,
+               "mufu_per_pair": 1.0, "mufu_frac": pairs_eval / (ms * 1e-3) / mufu_peak,
+               "useful_fma_frac": 12.0 * pairs_in / (ms * 1e-3) / fma_peak,
+               "note": "evaluated pairs are counted on the device (sfe_sph_pairs_evaluated); in-range = sources within R = 4 h of a target "
+                       "(sampled); the whole solve_sph time (grid, sort, records, two pair passes, EOS) is charged to the pair work"}
     return {"workload": "C3 snapshot: SPH density + EOS + pressure force, N=%d, h=0.1 (solve_sph replacement), device resident" % N,
             "ms_per_solve": ms, "particle_solves_per_s": N / (ms * 1e-3),
+            "compute_roofline": compute,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": hbm_src,
                          "model": "SURVEY 8(d): (20 B + 24 B) x n + 64 B per particle, n = %.0f sources within R = 4 h = 0.4 "
                                   "(sampled); source tiles are shared through shared memory, so DRAM traffic is far below this" % nn,

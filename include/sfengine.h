@@ -166,6 +166,9 @@ int sfe_dev_bh(const void* pm4, uint32_t N, uint32_t i0, uint32_t ni, float* acc
                float grav_g, float eps2, float theta, uint32_t flavour, void* stream);
 int sfe_dev_sph_density(const void* pm4, const float* rad, uint32_t N, uint32_t i0, uint32_t ni,
                         float* rho, void* stream);
+/* Statistics hook of the SPH cell-list passes: (target, source) pairs evaluated since the last call (read and reset;
+ * 0 when the all-pairs kernels did the work).  bench.py reports it against the pairs inside the cutoff radius. */
+int sfe_sph_pairs_evaluated(uint64_t* pairs, void* stream);
 int sfe_dev_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float eos_n, void* stream);
 int sfe_dev_sph_force(const void* pm4, const float* rad, const float* rho, const float* prs, uint32_t N,
                       uint32_t i0, uint32_t ni, float cutoff2, float* acc, void* stream);

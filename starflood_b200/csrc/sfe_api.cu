@@ -422,6 +422,15 @@ extern "C" int sfe_dev_sph_density(const void* pm4, const float* rad, uint32_t N
     return launch_sph_density(g_ctx, (const float4*)pm4, rad, N, i0, ni, rho, (cudaStream_t)stream);
 }
 
+extern "C" int sfe_sph_pairs_evaluated(uint64_t* pairs, void* stream) {
+    if (ensure_init("sfe_sph_pairs_evaluated")) return SFE_FAILURE;
+    if (!pairs) { set_error("sfe_sph_pairs_evaluated", "null pointer argument"); return SFE_FAILURE; }
+    unsigned long long v = 0ull;
+    if (cells_stats(g_ctx, &v, stream ? (cudaStream_t)stream : g_ctx->stream, "sfe_sph_pairs_evaluated")) return SFE_FAILURE;
+    *pairs = v;
+    return SFE_SUCCESS;
+}
+
 extern "C" int sfe_dev_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float eos_n, void* stream) {
     if (ensure_init("sfe_dev_sph_eos")) return SFE_FAILURE;
     return launch_sph_eos(rho, prs, n, eos_k, eos_n, (cudaStream_t)stream);

@@ -93,6 +93,7 @@ struct CellGrid {                 // device-resident descriptor, written by cl_g
 };
 struct SphCells {
     DevBuf desc, count, start, key[2], val[2], hist, rec, tlist;
+    DevBuf stat;                  // pairs evaluated (statistics hook)
     DevBuf part, arrive;          // j-split of the pair pass: partial sums of both halves of a group, arrival counters
     bool maybe = false;           // host-side: the cell kernels were enqueued for the current snapshot
 };
@@ -209,6 +210,7 @@ int peer_status(Ctx* c, const char* fn);                                   // ra
 void peer_release(Ctx* c);
 void saver_release();        // sfe_save.cu: drains pending snapshots, stops the writer thread
 // SPH neighbour search (sfe_sph_cells.cu): grid + sort for one snapshot, then one gated pass per mode
+int cells_stats(Ctx* c, unsigned long long* pairs, cudaStream_t s, const char* fn);
 int cells_prepare(Ctx* c, const float4* pm4, const float* rad, uint32_t N, bool force_all_pairs, cudaStream_t s, const char* fn);
 int cells_run(Ctx* c, int mode, const float4* pm4, const float* rad, const float* rho, const float* prs, uint32_t N,
               uint32_t i0, uint32_t ni, float cutoff2, float* out, cudaStream_t s, const char* fn, const SphRoute* route = nullptr);

@@ -26,6 +26,7 @@
 #include "sfe_internal.cuh"
 #include "sfe_scan.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace sfe {
 
@@ -33,7 +34,7 @@ constexpr uint32_t CL_CELLS_MAX = 1u << 18;
 constexpr int CL_SORT_BITS = 9, CL_SORT_BINS = 1 << CL_SORT_BITS;     // 2 passes cover 2^18 cells
 constexpr int CL_SORT_WARPS = 8, CL_SORT_ROWS = 16;
 constexpr int CL_SORT_CHUNK = CL_SORT_WARPS * 32 * CL_SORT_ROWS;       // keys per CTA
-constexpr int CL_CPR_MAX = 5;                                          // reach in cells
+constexpr int CL_CPR_MAX = 8;                                          // reach in cells
 constexpr int CL_RUNS_MAX = (2 * CL_CPR_MAX + 1) * (2 * CL_CPR_MAX + 1);
 constexpr int CL_THREADS = 64;                                         // 2 targets per thread
 constexpr int CL_CHUNK = 128;                                          // sources per shared-memory stage
@@ -41,9 +42,27 @@ constexpr int CL_STAGES = 2;
 constexpr uint32_t CL_SPLIT_MAX = 8;                                   // at most this many CTAs per target group (the source runs are dealt out)
 constexpr uint32_t CL_SPLIT_CTAS = 16384;                              // ... and only until a pass has about this many CTAs
 constexpr float CL_KAPPA = 4.0f;                                       // R = CL_KAPPA * h_max
-constexpr float CL_TARGET_PER_CELL = 32.0f;
+constexpr float CL_TARGET_PER_CELL = 32.0f;                            // (default; see cl_tuning())
 constexpr uint32_t CL_MIN_N = 8192;                                    // below this the all-pairs kernel is as fast
 constexpr float CL_FAR = 1.0e15f;
+
+// Cell size: s = max(R / div, edge of a cube that holds `tpc` particles on average).  Finer cells follow the sphere of
+// radius R more closely (fewer pairs evaluated beyond R) at the price of more, shorter source runs.
+// SFE_SPH_CELL_DIV / SFE_SPH_TPC / SFE_SPH_CULL override the defaults (read once).
+struct ClTuning { float div, tpc; int cull; };
+static ClTuning cl_tuning() {
+    static ClTuning t = {0.f, 0.f, -1};
+    if (t.cull < 0) {
+        const char* e;
+        t.div = (e = getenv("SFE_SPH_CELL_DIV")) ? (float)atof(e) : 4.0f;
+        t.tpc = (e = getenv("SFE_SPH_TPC")) ? (float)atof(e) : CL_TARGET_PER_CELL;
+        t.cull = (e = getenv("SFE_SPH_CULL")) ? atoi(e) : 1;
+        if (!(t.div >= 1.0f)) t.div = 1.0f;
+        if (t.div > (float)CL_CPR_MAX) t.div = (float)CL_CPR_MAX;
+        if (!(t.tpc >= 1.0f)) t.tpc = 1.0f;
+    }
+    return t;
+}
 
 // monotone float <-> uint mapping for atomicMin/atomicMax on floats of either sign
 __device__ __forceinline__ uint32_t f2ord(float f) { uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
@@ -78,7 +97,7 @@ __global__ void cl_bbox_kernel(const float4* __restrict__ pm4, const float* __re
     }
 }
 
-__global__ void cl_grid_kernel(CellGrid* g, uint32_t N, uint32_t force_all_pairs) {
+__global__ void cl_grid_kernel(CellGrid* g, uint32_t N, uint32_t force_all_pairs, float cell_div, float tpc) {
     const float hmax = ord2f(g->hmax), hmin = ord2f(g->hmin);
     g->uniform_h = g->hmax == g->hmin ? 1u : 0u;
     float lo[3], ext[3];
@@ -94,7 +113,7 @@ __global__ void cl_grid_kernel(CellGrid* g, uint32_t N, uint32_t force_all_pairs
     const float tiny = fmaxf(emax * 1.0e-3f, 1.0e-30f);
     float vol = 1.0f;
     for (int k = 0; k < 3; k++) vol *= fmaxf(ext[k], tiny);
-    float s = fmaxf(R / 4.0f, cbrtf(vol * CL_TARGET_PER_CELL / (float)N));
+    float s = fmaxf(R / cell_div, cbrtf(vol * tpc / (float)N));
     uint32_t n[3];
     for (int it = 0; it < 200; it++) {
         uint64_t cells = 1;
@@ -296,7 +315,7 @@ __global__ void __launch_bounds__(CL_THREADS)
 cl_pair_kernel(const CellGrid* __restrict__ g, const uint32_t* __restrict__ start, const uint32_t* __restrict__ key,
                const float4* __restrict__ rec, const uint32_t* __restrict__ tlist, uint32_t slot0, uint32_t nt,
                const float4* __restrict__ pm4, float cutoff2, float* __restrict__ out, SphRoute route, uint32_t N,
-               float4* __restrict__ part, uint32_t* __restrict__ arrive) {
+               float4* __restrict__ part, uint32_t* __restrict__ arrive, unsigned long long* __restrict__ stat, int cull) {
     if (!g->use_cells) return;
     // C3-sized problems (N = 2^18: 2048 groups of 128 targets) do not even fill the machine once, so a pass lasts as long
     // as its slowest group while the cheap groups near the surface leave their SMs idle.  Every group is therefore worked
@@ -309,23 +328,29 @@ cl_pair_kernel(const CellGrid* __restrict__ g, const uint32_t* __restrict__ star
     __shared__ __align__(128) float4 tile[CL_STAGES][CL_CHUNK * 2];
     __shared__ __align__(8) uint64_t full[CL_STAGES];
     __shared__ uint32_t run_lo[CL_RUNS_MAX], run_len[CL_RUNS_MAX];
+    __shared__ float run_rem[CL_RUNS_MAX];             // (R/s)^2 minus the squared cell distance in y and z of the run's row
+    __shared__ float ch_rem[CL_STAGES];                // ... of the staged chunk's run
     __shared__ uint32_t s_x[2];
+    unsigned long long npairs = 0ull;                   // pairs this thread evaluates (statistics)
     const uint32_t tid = threadIdx.x;
     const uint32_t nx_ = g->n[0], ny_ = g->n[1], nz_ = g->n[2];
     const int cpr = (int)g->cpr;
     const int w = 2 * cpr + 1;
     const uint32_t nruns = (uint32_t)(w * w);
     const float rr = g->rr;
+    const float org_x = g->origin[0], inv_s = g->inv_s;
     const bool uniform_h = g->uniform_h != 0u;
     if (tid == 0) {
         for (int s = 0; s < CL_STAGES; s++) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     uint32_t gc = 0;   // chunks consumed so far by this CTA: stage = gc % STAGES, parity = (gc / STAGES) & 1
+    uint32_t s_run = 0;   // run of the chunk next_chunk() returned last
 
     auto next_chunk = [&](uint32_t& r, uint32_t& off, uint32_t& slot, uint32_t& cnt) -> bool {
         while (r < nruns && off >= run_len[r]) { r++; off = 0; }
         if (r >= nruns) return false;
+        s_run = r;
         cnt = min((uint32_t)CL_CHUNK, run_len[r] - off);
         slot = run_lo[r] + off;
         off += cnt;
@@ -371,9 +396,11 @@ cl_pair_kernel(const CellGrid* __restrict__ g, const uint32_t* __restrict__ star
             const int dy = (int)(r % (uint32_t)w) - cpr, dz = (int)(r / (uint32_t)w) - cpr;
             const int yy = (int)cy + dy, zz = (int)cz + dz;
             uint32_t rl = 0, rn = 0;
+            float remv = 0.f;
             if (yy >= 0 && yy < (int)ny_ && zz >= 0 && zz < (int)nz_) {
                 const float ty = (float)max(abs(dy) - 1, 0), tz = (float)max(abs(dz) - 1, 0);
                 const float rem = rr - ty * ty - tz * tz;
+                remv = rem;
                 if (rem > 0.f) {
                     const int amax = (int)ceilf(sqrtf(rem));
                     const int x0 = max((int)xa - amax, 0), x1 = min((int)xb + amax, (int)nx_ - 1);
@@ -382,7 +409,7 @@ cl_pair_kernel(const CellGrid* __restrict__ g, const uint32_t* __restrict__ star
                     rn = start[rbase + (uint32_t)x1 + 1u] - rl;
                 }
             }
-            run_lo[r] = rl; run_len[r] = (r % nsplit) == half ? rn : 0u;
+            run_lo[r] = rl; run_len[r] = (r % nsplit) == half ? rn : 0u; run_rem[r] = remv;
         }
         __syncthreads();
 
@@ -391,6 +418,10 @@ cl_pair_kernel(const CellGrid* __restrict__ g, const uint32_t* __restrict__ star
         const float2 ny = make_float2(aa ? -Aa.y : -CL_FAR, ab ? -Ab.y : -CL_FAR);
         const float2 nz = make_float2(aa ? -Aa.z : -CL_FAR, ab ? -Ab.z : -CL_FAR);
         const bool warp_active = __any_sync(0xFFFFFFFFu, aa || ab);
+        // x cells of this WARP's targets in the row: a staged chunk whose cells all lie farther than R from every one of them
+        // (whole cells apart, like the run selection) is skipped by the warp
+        const uint32_t wxa = __reduce_min_sync(0xFFFFFFFFu, min(aa ? ca % nx_ : 0xFFFFFFFFu, ab ? cb % nx_ : 0xFFFFFFFFu));
+        const uint32_t wxb = __reduce_max_sync(0xFFFFFFFFu, max(aa ? ca % nx_ : 0u, ab ? cb % nx_ : 0u));
 
         uint32_t pr = 0, poff = 0, cr = 0, coff = 0, slot = 0, cnt = 0;
         if (tid == 0) {
@@ -398,6 +429,7 @@ cl_pair_kernel(const CellGrid* __restrict__ g, const uint32_t* __restrict__ star
                 uint32_t ps, pc;
                 if (!next_chunk(pr, poff, ps, pc)) break;
                 uint64_t* bar = &full[(gc + s) % CL_STAGES];
+                ch_rem[(gc + s) % CL_STAGES] = run_rem[s_run];       // (before the arrive: released with it)
                 mbar_expect_tx(bar, pc * 32u);
                 bulk_g2s(&tile[(gc + s) % CL_STAGES][0], rec + 2u * (size_t)ps, pc * 32u, bar);
             }
@@ -405,7 +437,18 @@ cl_pair_kernel(const CellGrid* __restrict__ g, const uint32_t* __restrict__ star
         while (next_chunk(cr, coff, slot, cnt)) {
             const uint32_t st = gc % CL_STAGES;
             mbar_wait(&full[st], (gc / CL_STAGES) & 1u);
-            if (warp_active) {
+            bool near = true;
+            if (cull) {
+                // the chunk is a piece of one x-run, sorted by cell: its x cells span those of its first and last source
+                // (same expression as cl_cellid_kernel)
+                const float xf = tile[st][0].x, xl = tile[st][2u * (cnt - 1u)].x;
+                const uint32_t c0 = (uint32_t)fminf(fmaxf(floorf((xf - org_x) * inv_s), 0.0f), (float)(nx_ - 1u));
+                const uint32_t c1 = (uint32_t)fminf(fmaxf(floorf((xl - org_x) * inv_s), 0.0f), (float)(nx_ - 1u));
+                const float gap = c0 > wxb + 1u ? (float)(c0 - wxb - 1u) : (wxa > c1 + 1u ? (float)(wxa - c1 - 1u) : 0.f);
+                near = gap * gap < ch_rem[st];
+            }
+            if (warp_active && near) {
+                npairs += (unsigned long long)cnt * ((aa ? 1u : 0u) + (ab ? 1u : 0u));
                 float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
                 if (uniform_h) cl_chunk<MODE, true>(&tile[st][0], cnt, nx, ny, nz, ki, qi, ci, cutoff2, a0, a1, a2);
                 else cl_chunk<MODE, false>(&tile[st][0], cnt, nx, ny, nz, ki, qi, ci, cutoff2, a0, a1, a2);
@@ -421,12 +464,18 @@ cl_pair_kernel(const CellGrid* __restrict__ g, const uint32_t* __restrict__ star
             if (tid == 0) {
                 uint32_t ps, pc;
                 if (next_chunk(pr, poff, ps, pc)) {
+                    ch_rem[st] = run_rem[s_run];
                     mbar_expect_tx(&full[st], pc * 32u);
                     bulk_g2s(&tile[st][0], rec + 2u * (size_t)ps, pc * 32u, &full[st]);
                 }
             }
             gc++;
         }
+    }
+    if (stat) {                                             // statistics: pairs evaluated by this pass
+#pragma unroll
+        for (int sh = 16; sh >= 1; sh >>= 1) npairs += __shfl_xor_sync(0xFFFFFFFFu, npairs, sh);
+        if ((tid & 31u) == 0u && npairs) atomicAdd(stat, npairs);
     }
     // hand-over between the gridDim.y CTAs of the group: partials to global memory, the last arrival combines
     float4* mine = part + ((size_t)(blockIdx.x * nsplit + half) * 3u) * CL_THREADS;
@@ -491,7 +540,7 @@ int cells_prepare(Ctx* c, const float4* pm4, const float* rad, uint32_t N, bool 
     const uint32_t rb = std::min<uint32_t>((N + 255) / 256, 4u * (uint32_t)c->sm_count);
     cl_bbox_kernel<<<rb, 256, 0, s>>>(pm4, rad, N, g);
     if (check_launch(fn)) return SFE_FAILURE;
-    cl_grid_kernel<<<1, 1, 0, s>>>(g, N, (force_all_pairs || N < CL_MIN_N) ? 1u : 0u);
+    cl_grid_kernel<<<1, 1, 0, s>>>(g, N, (force_all_pairs || N < CL_MIN_N) ? 1u : 0u, cl_tuning().div, cl_tuning().tpc);
     if (check_launch(fn)) return SFE_FAILURE;
     k.maybe = !(force_all_pairs || N < CL_MIN_N);
     if (!k.maybe) return SFE_SUCCESS;
@@ -548,14 +597,29 @@ int cells_run(Ctx* c, int mode, const float4* pm4, const float* rad, const float
         if (k.arrive.reserve((size_t)groups * 4, fn)) return SFE_FAILURE;
         SFE_CUDA(fn, cudaMemsetAsync(k.arrive.p, 0, k.arrive.cap, s));
     }
+    if (!k.stat.p) {
+        if (k.stat.reserve(8, fn)) return SFE_FAILURE;
+        SFE_CUDA(fn, cudaMemsetAsync(k.stat.p, 0, 8, s));
+    }
     const dim3 grid(groups, nsplit);
     if (mode == 0)
         cl_pair_kernel<0><<<grid, CL_THREADS, 0, s>>>(g, k.start.as<uint32_t>(), k.key[0].as<uint32_t>(), k.rec.as<float4>(), tlist, slot0, ni, pm4, cutoff2, out, rt, N,
-                                                      k.part.as<float4>(), k.arrive.as<uint32_t>());
+                                                      k.part.as<float4>(), k.arrive.as<uint32_t>(), k.stat.as<unsigned long long>(), cl_tuning().cull);
     else
         cl_pair_kernel<1><<<grid, CL_THREADS, 0, s>>>(g, k.start.as<uint32_t>(), k.key[0].as<uint32_t>(), k.rec.as<float4>(), tlist, slot0, ni, pm4, cutoff2, out, rt, N,
-                                                      k.part.as<float4>(), k.arrive.as<uint32_t>());
+                                                      k.part.as<float4>(), k.arrive.as<uint32_t>(), k.stat.as<unsigned long long>(), cl_tuning().cull);
     return check_launch(fn);
+}
+
+// statistics hook: pairs evaluated by the cell-list passes since the last call (read and reset)
+int cells_stats(Ctx* c, unsigned long long* pairs, cudaStream_t s, const char* fn) {
+    SphCells& k = c->sph_cells;
+    *pairs = 0ull;
+    if (!k.stat.p) return SFE_SUCCESS;
+    SFE_CUDA(fn, cudaMemcpyAsync(pairs, k.stat.p, 8, cudaMemcpyDeviceToHost, s));
+    SFE_CUDA(fn, cudaMemsetAsync(k.stat.p, 0, 8, s));
+    SFE_CUDA(fn, cudaStreamSynchronize(s));
+    return SFE_SUCCESS;
 }
 
 }  // namespace sfe

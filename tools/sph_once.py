@@ -1,12 +1,18 @@
+"""solve_sph() replacement on a C3-like snapshot: python tools/sph_once.py [N]; prints the solve time and the pairs the
+cell-list passes evaluated (SFE_SPH_CELL_DIV / SFE_SPH_TPC / SFE_SPH_CULL select the tuning)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes as C
 import numpy as np
-from oracle import sfo
-from starflood_b200 import engine as e
+from starflood_b200 import engine as e, ics
 e.init()
-N = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
-pos, vel, mas, rad = sfo.initcond(N, outflow=0.0, sph=True)
-sim = e.Sim(N, sph=True); sim.pos[:] = pos; sim.mas[:] = mas; sim.rad[:] = rad
-for r in range(2):
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+pos, vel, mas = ics.uniform_ball(N, outflow=0.0)
+sim = e.Sim(N, sph=True, pinned=True); sim.pos[:] = pos; sim.mas[:] = mas; sim.rad[:] = 0.1
+pairs = C.c_uint64()
+for r in range(3):
     sim.acc[:] = 0
-    e.solve_sph(sim); t = e.timings(); print('SPH N', N, 'solve_ms', t.solve_ms, flush=True)
+    rc = e.solve_sph(sim); t = e.timings()
+    e.lib().sfe_sph_pairs_evaluated(C.byref(pairs), None)
+    print('SPH N', N, rc, 'solve_ms %.3f' % t.solve_ms, 'pairs evaluated per pass and target %.0f' % (pairs.value / 2.0 / N),
+          'tuning', os.environ.get('SFE_SPH_CELL_DIV', '-'), os.environ.get('SFE_SPH_TPC', '-'), os.environ.get('SFE_SPH_CULL', '-'), flush=True)
