@@ -220,8 +220,15 @@ extern "C" const char* sfe_last_error(void) { return g_err; }
 extern "C" int sfe_host_register(void* ptr, uint64_t bytes) {
     const char* fn = "sfe_host_register";
     if (ensure_init(fn)) return SFE_FAILURE;
-    if (g_registered.count(ptr)) return SFE_SUCCESS;
-    if (is_pinned(ptr)) return SFE_SUCCESS;  // e.g. already pinned by the caller
+    // ranges may nest or overlap (a shim that first sees pos / mas and later the whole sim.mem block): a range inside an
+    // existing registration needs nothing; existing registrations the new range touches are given up first
+    const char* lo = (const char*)ptr; const char* hi = lo + bytes;
+    for (auto it = g_registered.begin(); it != g_registered.end();) {
+        const char* a = (const char*)it->first; const char* b = a + it->second;
+        if (lo >= a && hi <= b) return SFE_SUCCESS;
+        if (a < hi && lo < b) { cudaHostUnregister(it->first); it = g_registered.erase(it); } else ++it;
+    }
+    if (is_pinned(ptr) && is_pinned(hi - 1)) return SFE_SUCCESS;  // already pinned by the caller
     SFE_CUDA(fn, cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
     g_registered[ptr] = bytes;
     return SFE_SUCCESS;

@@ -550,7 +550,9 @@ __device__ __forceinline__ bool sub_folds(const TreeDev& t, int d, uint32_t cn) 
 __device__ __forceinline__ bool xl_owns(const TreeDev& t, int d, uint32_t cn) { return d <= XL_DEPTH_MAX && cn > t.xl_min && !sub_owns(t, cn); }   // (its chains run beside subtree_kernel)
 __device__ __forceinline__ bool ml_owns(const TreeDev& t, int d, uint32_t cn) { return cn > ML_MIN && !xl_owns(t, d, cn) && !sub_folds(t, d, cn); }
 
-__global__ void __launch_bounds__(ML_THREADS) moments_long_kernel(TreeDev t, int d,
+// (all fold kernels take a range of levels d0..d1: the top-level path folds levels 1..TOP_L with one launch of each kernel -
+// with four launches per level the host, not the device, was what the folds waited for)
+__global__ void __launch_bounds__(ML_THREADS) moments_long_kernel(TreeDev t, int d0, int d1,
                                                                   uint32_t* __restrict__ gate /* {needed, done} or null */) {
     extern __shared__ __align__(16) unsigned char ml_smem[];
     float4 (*raw)[8][ML_B] = reinterpret_cast<float4 (*)[8][ML_B]>(ml_smem);                                  // [ML_R][8][ML_B]
@@ -558,11 +560,14 @@ __global__ void __launch_bounds__(ML_THREADS) moments_long_kernel(TreeDev t, int
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
     // children_kernel(d-1) notes whether level d has a node for this kernel at all: deep levels have hundreds of thousands of
     // nodes and none that long, and finding that out group by group costs a 100 us of dependent loads (level 7 at C2)
-    if (d > 0 && t.ml_count[d] == 0u) return;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (int d = d0; d <= d1; d++) {
+    if (d > 0 && t.ml_count[d] == 0u) continue;
     const uint32_t b = t.meta[M_LV_BEGIN + d], e = t.meta[M_LV_END + d];
     const SlotRec* __restrict__ rec = t.srec[d];
-    for (uint32_t base = b + blockIdx.x * 8u; base < e; base += gridDim.x * 8u) {
+    // (the groups of a level are dealt out from a different CTA on every level, so that the few groups of the top levels
+    // do not all land on the same CTAs)
+    for (uint32_t base = b + ((blockIdx.x + (uint32_t)d * 37u) % gridDim.x) * 8u; base < e; base += gridDim.x * 8u) {
         // every thread looks at the 8 segments of the group (uniform loads) for the trip count
         uint32_t maxcnt = 0u;
 #pragma unroll
@@ -650,11 +655,13 @@ __global__ void __launch_bounds__(ML_THREADS) moments_long_kernel(TreeDev t, int
             __syncthreads();
         }
     }
+    }
 }
 
-__global__ void __launch_bounds__(256) moments_short_kernel(TreeDev t, int d, uint32_t* __restrict__ gate) {
+__global__ void __launch_bounds__(256) moments_short_kernel(TreeDev t, int d0, int d1, uint32_t* __restrict__ gate) {
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
     const uint32_t c = threadIdx.x & 3u;
+    for (int d = d0; d <= d1; d++) {
     const uint32_t b = t.meta[M_LV_BEGIN + d], e = t.meta[M_LV_END + d];
     const SlotRec* __restrict__ rec = t.srec[d];
     const uint32_t quads = (e - b);
@@ -677,6 +684,7 @@ __global__ void __launch_bounds__(256) moments_short_kernel(TreeDev t, int d, ui
             const float inv = 0.f < mass ? __fdiv_rn(1.0f, mass) : 1.0f;   // tree.c:303-304
             reinterpret_cast<float*>(&t.rec1[n])[c] = c < 3u ? __fmul_rn(sum, inv) : sum;
         }
+    }
     }
 }
 
@@ -747,10 +755,13 @@ __device__ __forceinline__ float xl_term(float4 p, uint32_t q) {   // the q-th s
 }
 
 // the level's long nodes as a flat list of chunks: descriptors + running chunk count, [xl_max] holds the total
-__global__ void __launch_bounds__(1024) xl_index_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
+__global__ void __launch_bounds__(1024) xl_index_kernel(TreeDev t, int d0, uint32_t* __restrict__ gate) {
     __shared__ uint32_t sm[33];
     __shared__ uint32_t carry;
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
+    const int d = d0 + (int)blockIdx.x;                 // one CTA per level
+    if (d > XL_DEPTH_MAX) return;
+    const uint32_t area = (uint32_t)(d % SFE_SIDE_STREAMS);
     XlNode* __restrict__ list = reinterpret_cast<XlNode*>(t.xl_list) + (size_t)area * (t.xl_max + 1u);
     const uint32_t nxl = min(t.xl_count[d], t.xl_max);
     if (threadIdx.x == 0) carry = 0u;
@@ -784,14 +795,27 @@ __global__ void __launch_bounds__(1024) xl_index_kernel(TreeDev t, int d, uint32
 }
 
 constexpr uint32_t XLF_AGG = 1u, XLF_INCL = 2u;   // chunk flag = epoch << 2 | state; other epochs read as "nothing yet"
+constexpr int XP_WARPS = 8;
+constexpr int XP_ROW = 33;                        // staged members: one float4 of padding per 32 (conflict-free strided reads)
 
-__global__ void __launch_bounds__(256) xl_prep_kernel(TreeDev t, int d, uint32_t area, uint32_t epoch, uint32_t* __restrict__ gate) {
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+// One warp per chunk.  The 256 members are staged in shared memory with coalesced loads; then lane 8g + k (g = component
+// 0..3, k = 0..7) owns the 32 consecutive members 32k .. 32k+31 of component g: their double sum (for the prefix), and - once
+// the look-back has delivered the approximate fold value at the chunk's start - their parity map, composed in order over
+// the eight lanes of the group.  Four components in four lane groups: a quarter of the shuffles and no members in registers.
+__global__ void __launch_bounds__(XP_WARPS * 32) xl_prep_kernel(TreeDev t, int d0, int d1, uint32_t epoch0, uint32_t* __restrict__ gate) {
+    __shared__ float4 stage[XP_WARPS][8 * XP_ROW];
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, q = lane >> 3, sub = lane & 7u;
+    float4* __restrict__ st = stage[warp];
+    for (int d = d0; d <= d1 && d <= XL_DEPTH_MAX; d++) {      // a warp that finds one level's chunks dealt out moves on to the next
+    const uint32_t area = (uint32_t)(d % SFE_SIDE_STREAMS), epoch = (epoch0 + (uint32_t)(d - d0)) & 0x3FFFFFFFu;
     const XlNode* __restrict__ list = reinterpret_cast<const XlNode*>(t.xl_list) + (size_t)area * (t.xl_max + 1u);
     const uint32_t nxl = list[t.xl_max].n, total = list[t.xl_max].choff;
     double* __restrict__ sums_all = t.xl_sum + (size_t)area * t.xl_slots * 8u;           // per chunk slot: aggregate[4], inclusive prefix[4]
-    volatile uint32_t* flags = t.xl_flag + (size_t)area * t.xl_slots;
+    uint32_t* __restrict__ flags = t.xl_flag + (size_t)area * t.xl_slots;
     XlMap* __restrict__ maps_all = reinterpret_cast<XlMap*>(t.xl_map) + (size_t)area * t.xl_slots * 4u;
     uint32_t* ticket = &t.xl_ticket[d];
     for (;;) {
@@ -799,106 +823,101 @@ __global__ void __launch_bounds__(256) xl_prep_kernel(TreeDev t, int d, uint32_t
         uint32_t w = 0u;
         if (lane == 0u) w = atomicAdd(ticket, 1u);
         w = __shfl_sync(0xFFFFFFFFu, w, 0);
-        if (w >= total) return;
+        if (w >= total) break;
         uint32_t lo = 0u, hi = nxl;                 // the node whose chunks include w: last k with choff[k] <= w
         while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (list[mid].choff <= w) lo = mid; else hi = mid; }
         const XlNode nd = list[lo];
         const uint32_t c = w - nd.choff;
         const SlotRec* __restrict__ src = t.srec[d] + nd.first;
         const size_t slot = (size_t)nd.slot0 + c;
-        // the lane's consecutive members
-        float4 mem[XL_PER_LANE];
-        const uint32_t j0 = c * XL_CHUNK + lane * XL_PER_LANE;
+        const uint32_t left = nd.cnt - c * XL_CHUNK;                 // members of this chunk (>= 1)
+        __syncwarp();                                                // the previous chunk's staged members are no longer read
 #pragma unroll
-        for (int i = 0; i < XL_PER_LANE; i++) mem[i] = j0 + i < nd.cnt ? src[j0 + i].pm : make_float4(0.f, 0.f, 0.f, 0.f);
-        double a[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int i = 0; i < XL_PER_LANE; i++) {    // pads add +0
-            a[0] += (double)__fmul_rn(mem[i].w, mem[i].x); a[1] += (double)__fmul_rn(mem[i].w, mem[i].y);
-            a[2] += (double)__fmul_rn(mem[i].w, mem[i].z); a[3] += (double)mem[i].w;
+        for (uint32_t i = 0; i < (uint32_t)XL_PER_LANE; i++) {       // member 32 i + lane -> row i (pads are {0,0,0,0}: +0 summands)
+            const uint32_t j = i * 32u + lane;
+            st[i * XP_ROW + lane] = j < left ? src[c * XL_CHUNK + j].pm : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-#pragma unroll
-            for (int sh = 16; sh >= 1; sh >>= 1) a[q] += __shfl_xor_sync(0xFFFFFFFFu, a[q], sh);
-        // publish the aggregate (the inclusive prefix at once for a node's first chunk), then look back
-        double pre[4] = {0.0, 0.0, 0.0, 0.0};
-        if (lane < 4u) { sums_all[slot * 8u + lane] = a[lane]; if (c == 0u) sums_all[slot * 8u + 4u + lane] = a[lane]; }
-        __threadfence();
         __syncwarp();
-        if (lane == 0u) flags[slot] = (epoch << 2) | (c == 0u ? XLF_INCL : XLF_AGG);
+        // this lane's 32 summands of component q: members 32 sub .. 32 sub + 31, i.e. row `sub`
+        const float4* __restrict__ mine = st + sub * XP_ROW;
+        const uint32_t have = left > sub * 32u ? min(32u, left - sub * 32u) : 0u;
+        double a = 0.0;
+#pragma unroll 8
+        for (uint32_t i = 0; i < 32u; i++) a += (double)xl_term(mine[i], q);
+        a += __shfl_xor_sync(0xFFFFFFFFu, a, 1); a += __shfl_xor_sync(0xFFFFFFFFu, a, 2); a += __shfl_xor_sync(0xFFFFFFFFu, a, 4);
+        // publish the aggregate (the inclusive prefix at once for a node's first chunk), then look back
+        if (sub == 0u) { sums_all[slot * 8u + q] = a; if (c == 0u) sums_all[slot * 8u + 4u + q] = a; }
+        __syncwarp();
+        if (lane == 0u) st_release_u32(&flags[slot], (epoch << 2) | (c == 0u ? XLF_INCL : XLF_AGG));
+        double pre = 0.0;                                            // component q: approximate fold value at the chunk's start
         if (c > 0u) {
             int jb = (int)c - 1;                    // nearest predecessor of the current window
             for (;;) {
                 const int j = jb - (int)lane;
                 const bool valid = j >= 0;
-                uint32_t st;
+                uint32_t stt;
                 do {
-                    const uint32_t f = valid ? flags[(size_t)nd.slot0 + (uint32_t)j] : ((epoch << 2) | XLF_INCL);
-                    st = (f >> 2) == epoch ? (f & 3u) : 0u;
-                } while (__any_sync(0xFFFFFFFFu, st == 0u));
-                __threadfence();
-                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, !valid || st == XLF_INCL);
+                    const uint32_t f = valid ? ld_acquire_u32(&flags[(size_t)nd.slot0 + (uint32_t)j]) : ((epoch << 2) | XLF_INCL);
+                    stt = (f >> 2) == epoch ? (f & 3u) : 0u;
+                } while (__any_sync(0xFFFFFFFFu, stt == 0u));
+                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, !valid || stt == XLF_INCL);
                 const uint32_t first = (uint32_t)__ffs((int)ballot) - 1u;          // nearest chunk that knows its inclusive prefix (or the node's start)
                 double v[4] = {0.0, 0.0, 0.0, 0.0};
                 if (valid && lane <= first) {
-                    const volatile double* sp = sums_all + ((size_t)nd.slot0 + (uint32_t)j) * 8u + (st == XLF_INCL ? 4u : 0u);
+                    const double* sp = sums_all + ((size_t)nd.slot0 + (uint32_t)j) * 8u + (stt == XLF_INCL ? 4u : 0u);
 #pragma unroll
-                    for (int q = 0; q < 4; q++) v[q] = sp[q];
+                    for (int k = 0; k < 4; k++) v[k] = __ldcg(sp + k);
                 }
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
+                for (int k = 0; k < 4; k++)
 #pragma unroll
-                    for (int sh = 16; sh >= 1; sh >>= 1) v[q] += __shfl_xor_sync(0xFFFFFFFFu, v[q], sh);
-                    pre[q] += v[q];
-                }
+                    for (int sh = 16; sh >= 1; sh >>= 1) v[k] += __shfl_xor_sync(0xFFFFFFFFu, v[k], sh);
+                pre += q == 0u ? v[0] : q == 1u ? v[1] : q == 2u ? v[2] : v[3];
                 if (ballot) break;
                 jb -= 32;
             }
-            if (lane < 4u) sums_all[slot * 8u + 4u + lane] = pre[lane] + a[lane];
-            __threadfence();
+            if (sub == 0u) sums_all[slot * 8u + 4u + q] = pre + a;
             __syncwarp();
-            if (lane == 0u) flags[slot] = (epoch << 2) | XLF_INCL;
+            if (lane == 0u) st_release_u32(&flags[slot], (epoch << 2) | XLF_INCL);
         }
-        // maps: binade guess from the approximate fold value at both ends of the chunk
-        XlMap* __restrict__ maps = maps_all + slot * 4u;
-#pragma unroll
-        for (uint32_t q = 0; q < 4u; q++) {
-            const float fs = (float)pre[q], fe = (float)(pre[q] + a[q]);
-            const uint32_t es = (__float_as_uint(fs) >> 23) & 0xFFu, ee = (__float_as_uint(fe) >> 23) & 0xFFu;
-            const bool usable = es == ee && es > 40u && es < 250u && ((__float_as_uint(fs) ^ __float_as_uint(fe)) >> 31) == 0u;
-            XlMap m = xl_identity((int)es - 127 - 23, usable ? 1 : 0);
-            if (usable) {                                            // warp-uniform
-                const double inv_u = __longlong_as_double((long long)(1023 - m.e2) << 52);
-                int S0 = 0, S1 = 0;
-#pragma unroll
-                for (int i = 0; i < XL_PER_LANE; i++) {
-                    if (j0 + i < nd.cnt) {
-                        const double tt = (double)xl_term(mem[i], q) * inv_u;   // exact: scaling by a power of two
-                        if (!(fabs(tt) < 33554432.0)) m.usable = 0;              // a summand this large leaves the binade anyway
-                        const double fl = floor(tt);
-                        const double fr = tt - fl;                               // exact
-                        const int fll = m.usable ? (int)fl : 0;
-                        const int bi = fll + (fr > 0.5 ? 1 : 0);
-                        const bool tie = fr == 0.5;
-                        S0 += bi + ((tie && ((S0 + fll) & 1)) ? 1 : 0);          // entering even: k + S0 + floor odd -> round up
-                        S1 += bi + ((tie && ((1 + S1 + fll) & 1)) ? 1 : 0);      // entering odd
-                        m.mn0 = min(m.mn0, S0); m.mx0 = max(m.mx0, S0);
-                        m.mn1 = min(m.mn1, S1); m.mx1 = max(m.mx1, S1);
-                    }
-                }
-                m.a0 = S0; m.a1 = S1;
-                if (max(max(abs(S0), abs(S1)), max(max(abs(m.mn0), abs(m.mx0)), max(abs(m.mn1), abs(m.mx1)))) > XL_LIM) m.usable = 0;
-                if (!m.usable) { m.a0 = m.a1 = 0; m.mn0 = m.mn1 = 0; m.mx0 = m.mx1 = 0; }
-                // ordered reduction: lane i absorbs lane i + off
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const XlMap o = xl_shfl_down(m, off);
-                    if ((lane & (2u * off - 1u)) == 0u) m = xl_combine(m, o);
+        // maps: binade guess from the approximate fold value at both ends of the chunk (uniform inside a lane group)
+        const float fs = (float)pre, fe = (float)(pre + a);
+        const uint32_t es = (__float_as_uint(fs) >> 23) & 0xFFu, ee = (__float_as_uint(fe) >> 23) & 0xFFu;
+        const bool usable = es == ee && es > 40u && es < 250u && ((__float_as_uint(fs) ^ __float_as_uint(fe)) >> 31) == 0u;
+        XlMap m = xl_identity((int)es - 127 - 23, usable ? 1 : 0);
+        {
+            const double inv_u = __longlong_as_double((long long)(1023 - m.e2) << 52);
+            int S0 = 0, S1 = 0;
+#pragma unroll 4
+            for (uint32_t i = 0; i < 32u; i++) {
+                if (i < have) {
+                    const double tt = (double)xl_term(mine[i], q) * inv_u;       // exact: scaling by a power of two
+                    const bool okm = fabs(tt) < 33554432.0;                      // a summand this large leaves the binade anyway
+                    if (!okm) m.usable = 0;
+                    const double fl = floor(tt);
+                    const double fr = tt - fl;                                   // exact
+                    const int fll = okm ? (int)fl : 0;
+                    const int bi = fll + (fr > 0.5 ? 1 : 0);
+                    const bool tie = fr == 0.5;
+                    S0 += bi + ((tie && ((S0 + fll) & 1)) ? 1 : 0);              // entering even: k + S0 + floor odd -> round up
+                    S1 += bi + ((tie && ((1 + S1 + fll) & 1)) ? 1 : 0);          // entering odd
+                    m.mn0 = min(m.mn0, S0); m.mx0 = max(m.mx0, S0);
+                    m.mn1 = min(m.mn1, S1); m.mx1 = max(m.mx1, S1);
+                    if (max(abs(S0), abs(S1)) > XL_LIM) m.usable = 0;
                 }
             }
-            if (lane == 0u) maps[q] = m;
+            m.a0 = S0; m.a1 = S1;
+            if (max(max(abs(m.mn0), abs(m.mx0)), max(abs(m.mn1), abs(m.mx1))) > XL_LIM && have) m.usable = 0;
+            if (!m.usable) { m.a0 = m.a1 = 0; m.mn0 = m.mn1 = 0; m.mx0 = m.mx1 = 0; }
+            // ordered reduction over the eight lanes of the group: lane k absorbs lane k + off
+#pragma unroll
+            for (int off = 1; off < 8; off <<= 1) {
+                const XlMap o = xl_shfl_down(m, off);
+                if ((sub & (2u * off - 1u)) == 0u) m = xl_combine(m, o);
+            }
         }
+        if (sub == 0u) maps_all[slot * 4u + q] = m;
+    }
     }
 }
 
@@ -913,10 +932,13 @@ __device__ __forceinline__ int xl_shift(int cur, int nxt, uint32_t nv, uint32_t 
     return lane + nv < 32u ? a : b;
 }
 
-__global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d, uint32_t area, uint32_t* __restrict__ gate) {
+__global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d0, uint32_t* __restrict__ gate) {
     __shared__ __align__(16) float buf[4][XL_CHUNK];
     __shared__ float s_mass;
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
+    const int d = d0 + (int)blockIdx.y;                 // grid.y: levels
+    if (d > XL_DEPTH_MAX) return;
+    const uint32_t area = (uint32_t)(d % SFE_SIDE_STREAMS);
     const XlNode* __restrict__ list = reinterpret_cast<const XlNode*>(t.xl_list) + (size_t)area * (t.xl_max + 1u);
     if (blockIdx.x >= list[t.xl_max].n) return;
     const XlNode nd = list[blockIdx.x];
@@ -1016,10 +1038,11 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d, uint32_
 #include "sfe_top.cuh"
 namespace sfe {
 
-// All fold kernels of level d.  `pre` (optional) is recorded in front of the serial chains of the very long nodes: the
-// top-level path lets subtree_kernel - which fills every SM for its whole duration - wait for the parallel part of the folds
-// and run beside the chains (a few small CTAs that are resident by then).
-static int launch_moments(Ctx* c, const TreeDev& dv, int d, uint32_t* gate, bool single, cudaStream_t s, const char* fn,
+// All fold kernels of the levels d0..d1 (at most SFE_SIDE_STREAMS of them: the chunked fold keeps one scratch area per level
+// modulo SFE_SIDE_STREAMS).  `pre` / `pre2` (optional) are recorded in front of the serial chains of the very long nodes and
+// behind the folds of the shorter ones: the top-level path lets subtree_kernel - which fills every SM for its whole
+// duration - wait for the parallel part of the folds and run beside the chains (a few small CTAs that are resident by then).
+static int launch_moments(Ctx* c, const TreeDev& dv, int d0, int d1, uint32_t* gate, bool single, cudaStream_t s, const char* fn,
                           cudaEvent_t pre = nullptr, cudaStream_t s2 = nullptr, cudaEvent_t pre2 = nullptr) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -1028,21 +1051,21 @@ static int launch_moments(Ctx* c, const TreeDev& dv, int d, uint32_t* gate, bool
     }
     // the folds of the shorter nodes; on a stream of their own (s2) when the caller has one, beside the chunked fold
     cudaStream_t sl = s2 ? s2 : s;
-    moments_long_kernel<<<single ? 1 : c->sm_count * 2, ML_THREADS, ML_SMEM, sl>>>(dv, d, gate);
+    moments_long_kernel<<<single ? 1 : c->sm_count * 2, ML_THREADS, ML_SMEM, sl>>>(dv, d0, d1, gate);
     if (check_launch(fn)) return SFE_FAILURE;
-    moments_short_kernel<<<single ? 1 : c->sm_count * 8, 256, 0, sl>>>(dv, d, gate);
+    moments_short_kernel<<<single ? 1 : c->sm_count * 8, 256, 0, sl>>>(dv, d0, d1, gate);
     if (check_launch(fn)) return SFE_FAILURE;
     if (pre2) SFE_CUDA(fn, cudaEventRecord(pre2, sl));
-    if (d <= XL_DEPTH_MAX) {
-        const uint32_t area = (uint32_t)(d % SFE_SIDE_STREAMS);   // one scratch area per side stream; the deferred root uses area 0 after the join
+    if (d0 <= XL_DEPTH_MAX) {
+        const int dl = d1 < XL_DEPTH_MAX ? d1 : XL_DEPTH_MAX;
         const uint32_t g2 = single ? 8u : (uint32_t)c->sm_count * 4u;
-        const uint32_t epoch = ((dv.build_id << 5) + (uint32_t)d + 1u) & 0x3FFFFFFFu;   // tells this pass's chunk flags from older ones
-        xl_index_kernel<<<1, 1024, 0, s>>>(dv, d, area, gate);
+        const uint32_t epoch0 = ((dv.build_id << 5) + (uint32_t)d0 + 1u) & 0x3FFFFFFFu;   // tells this pass's chunk flags from older ones
+        xl_index_kernel<<<dl - d0 + 1, 1024, 0, s>>>(dv, d0, gate);
         if (check_launch(fn)) return SFE_FAILURE;
-        xl_prep_kernel<<<g2, 256, 0, s>>>(dv, d, area, epoch, gate);
+        xl_prep_kernel<<<g2, 256, 0, s>>>(dv, d0, dl, epoch0, gate);
         if (check_launch(fn)) return SFE_FAILURE;
         if (pre) SFE_CUDA(fn, cudaEventRecord(pre, s));
-        xl_chain_kernel<<<dv.xl_max, 128, 0, s>>>(dv, d, area, gate);
+        xl_chain_kernel<<<dim3(dv.xl_max, dl - d0 + 1), 128, 0, s>>>(dv, d0, gate);
         if (check_launch(fn)) return SFE_FAILURE;
     } else if (pre) SFE_CUDA(fn, cudaEventRecord(pre, s));
     return SFE_SUCCESS;
@@ -1293,6 +1316,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     };
 
     int first_level = 0;
+    bool top_folds = false;                      // the folds of levels 1..TOP_L are on side[1] / side2[1]
     if (use_top) {
         static bool tn_attr = false;
         const size_t tn_smem = (size_t)(3 * TOP_COLS_PAD) * 4;
@@ -1315,15 +1339,17 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         if (wait_summary((int)TOP_SUMMARY_SLOT, &not_applicable, &status)) return SFE_FAILURE;
         if (!not_applicable) {
             first_level = TOP_L;
-            // the folds of levels 1 .. TOP_L
-            for (int d = 1; d <= TOP_L; d++) {
-                cudaStream_t side = c->side[d % SFE_SIDE_STREAMS];
+            // the folds of levels 1 .. TOP_L: one launch of each fold kernel for all of them, the chunked fold of the very
+            // long nodes on one side stream, the folds of the shorter nodes on another
+            {
+                cudaStream_t side = c->side[1], side2 = c->side2[1];
                 SFE_CUDA(fn, cudaStreamWaitEvent(side, t.ev_perm[TOP_L], 0));
-                if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d], side);
-                cudaStream_t side2 = c->side2[d % SFE_SIDE_STREAMS];
                 SFE_CUDA(fn, cudaStreamWaitEvent(side2, t.ev_perm[TOP_L], 0));
-                if (launch_moments(c, dv, d, nullptr, false, side, fn, t.ev_pre[d % SFE_SIDE_STREAMS], side2, t.ev_pre2[d % SFE_SIDE_STREAMS])) return SFE_FAILURE;
-                if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d + 1], side);
+                if (trace_enabled()) cudaEventRecord(g_trace_ev[2], side);
+                if (launch_moments(c, dv, 1, TOP_L, nullptr, false, side, fn, t.ev_pre[1], side2, t.ev_pre2[1])) return SFE_FAILURE;
+                if (trace_enabled()) cudaEventRecord(g_trace_ev[3], side);
+                SFE_CUDA(fn, cudaEventRecord(t.ev_pre2[0], side));   // end of the top levels' chunked folds (their scratch areas are free again)
+                top_folds = true;
             }
             if (trace_enabled()) {
                 cudaStreamSynchronize(s);
@@ -1371,8 +1397,9 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         if (d > 0 && !(first_level > 0 && d == first_level)) {
             cudaStream_t side = c->side[d % SFE_SIDE_STREAMS];
             SFE_CUDA(fn, cudaStreamWaitEvent(side, t.ev_perm[d], 0));
+            if (top_folds) SFE_CUDA(fn, cudaStreamWaitEvent(side, t.ev_pre2[0], 0));   // (levels TOP_L+1.. reuse the scratch areas of the top levels)
             if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d], side);
-            if (launch_moments(c, dv, d, nullptr, false, side, fn)) return SFE_FAILURE;
+            if (launch_moments(c, dv, d, d, nullptr, false, side, fn)) return SFE_FAILURE;
             if (trace_enabled()) cudaEventRecord(g_trace_ev[2 * d + 1], side);
             SFE_CUDA(fn, cudaEventRecord(t.ev_pre[d % SFE_SIDE_STREAMS], side));
             last_fold[1] = last_fold[0]; last_fold[0] = d;
@@ -1402,13 +1429,11 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     }
     // everything below the subtree roots: one CTA per root, drawn from a ticket (the final slot arrays are rewritten in
     // place range by range; the folds on the side streams read other ranges or other levels' arrays)
-    if (first_level > 0) {
+    if (top_folds) {
         // the parallel part of the top levels' folds goes first (subtree_kernel fills every SM for its whole duration);
         // the serial chains of the very long nodes - a few small CTAs - run beside it
-        for (int d = 1; d <= TOP_L; d++) {
-            SFE_CUDA(fn, cudaStreamWaitEvent(s, t.ev_pre[d % SFE_SIDE_STREAMS], 0));
-            SFE_CUDA(fn, cudaStreamWaitEvent(s, t.ev_pre2[d % SFE_SIDE_STREAMS], 0));
-        }
+        SFE_CUDA(fn, cudaStreamWaitEvent(s, t.ev_pre[1], 0));
+        SFE_CUDA(fn, cudaStreamWaitEvent(s, t.ev_pre2[1], 0));
     }
     // subtree_kernel reorders the final slot array in place: the folds that read the subtree roots living there (the last
     // levels') come first
@@ -1444,7 +1469,12 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         cudaEventRecord(g_trace_ev[1], s);
         cudaStreamSynchronize(s);
         float a = 0.f, b = 0.f;
-        for (int d = 1; d < (first_level && levels_run <= TOP_L ? TOP_L + 1 : levels_run); d++) {
+        if (top_folds) {
+            cudaEventElapsedTime(&a, t.ev_perm[0], g_trace_ev[2]);
+            cudaEventElapsedTime(&b, t.ev_perm[0], g_trace_ev[3]);
+            fprintf(stderr, "[sfe trace] moments levels 1..%d: start %8.1f us  end %8.1f us\n", TOP_L, a * 1e3, b * 1e3);
+        }
+        for (int d = first_level > 0 ? first_level + 1 : 1; d < levels_run; d++) {
             cudaEventElapsedTime(&a, t.ev_perm[0], g_trace_ev[2 * d]);
             cudaEventElapsedTime(&b, t.ev_perm[0], g_trace_ev[2 * d + 1]);
             fprintf(stderr, "[sfe trace] moments level %2d: start %8.1f us  end %8.1f us\n", d, a * 1e3, b * 1e3);
@@ -1499,7 +1529,7 @@ int tree_root_moments(Ctx* c, const float4* pm4, uint32_t i0, uint32_t ni, float
     if (force) root_force_kernel<<<1, 1, 0, s>>>(gate);
     else root_gate_kernel<<<(ni + 255) / 256, 256, 0, s>>>(dv, pm4, i0, ni, theta, gate);
     if (check_launch(fn)) return SFE_FAILURE;
-    if (launch_moments(c, dv, 0, gate, true, s, fn)) return SFE_FAILURE;
+    if (launch_moments(c, dv, 0, 0, gate, true, s, fn)) return SFE_FAILURE;
     finalize_kernel<<<1, 32, 0, s>>>(dv, gate);
     if (check_launch(fn)) return SFE_FAILURE;
     root_done_kernel<<<1, 1, 0, s>>>(gate);

@@ -30,6 +30,15 @@ int tree_free(tree_t* restrict tree_ptr) {
 }
 
 int tree_build(tree_t* restrict tree_ptr, unsigned int num_parts, const real* restrict pos, const real* restrict mas) {
+    /* tree_build is the first engine call of a run (main.c:398 -> sim_solv) and does not see sim_t: pin what it does see -
+     * the span of sim.mem from pos to mas - so that the very first upload already runs at PCIe rate; the gravity shim's
+     * registration of the whole block replaces this one later */
+    {
+        const char* a = (const char*)pos < (const char*)mas ? (const char*)pos : (const char*)mas;
+        const char* pe = (const char*)(pos + 3u * (size_t)num_parts); const char* me = (const char*)(mas + (size_t)num_parts);
+        const char* b = pe > me ? pe : me;
+        if (num_parts) sfe_host_register((void*)a, (uint64_t)(b - a));
+    }
     return sfe_tree_build(tree_ptr->bounds, pos, mas, num_parts, TREE_DEPTH_MAX, tree_ptr->max_nodes);
 }
 #endif

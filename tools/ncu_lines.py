@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """Per-source-line stall samples of one kernel: joins `ncu --page source --csv` (SASS, in program order) with
-`nvdisasm --print-line-info` of the same function.  usage: ncu_lines.py sass.csv nvdisasm.txt [top]"""
+`nvdisasm --print-line-info` of the same function.  usage: ncu_lines.py sass.csv nvdisasm.txt [top] [section]"""
 import csv, re, sys
 rows = list(csv.reader(open(sys.argv[1])))
-hi = [i for i, r in enumerate(rows) if len(r) > 5 and 'Source' in r][0]
+his = [i for i, r in enumerate(rows) if len(r) > 5 and 'Source' in r]
+which = int(sys.argv[4]) if len(sys.argv) > 4 else 0          # which kernel of the report (several launches: several sections)
+hi = his[which]
+rows = rows[:his[which + 1] - 1] if which + 1 < len(his) else rows
 hdr = rows[hi]
 si = hdr.index('Source'); wi = hdr.index('Warp Stall Sampling (All Samples)'); ii = hdr.index('Instructions Executed'); ti = hdr.index('Thread Instructions Executed')
 sass = [(r[si].strip(), int(r[wi] or 0), int(r[ii] or 0), int(r[ti] or 0)) for r in rows[hi + 1:] if len(r) > max(si, wi, ii)]

@@ -1,5 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_sph.py -x -q -m gpu 2>&1 | tail -3
-for cfg in "4 32 0" "4 32 1" "5 16 1" "6 12 1" "6 8 1" "8 8 1" "8 4 1" "8 4 0"; do
-  set -- $cfg
-  SFE_SPH_CELL_DIV=$1 SFE_SPH_TPC=$2 SFE_SPH_CULL=$3 timeout 120 python tools/sph_once.py 2>&1 | tail -1
-done
+timeout 900 python -m pytest tests/test_gpu_tree.py tests/test_gpu_configs.py -x -q -m gpu 2>&1 | tail -4
+timeout 120 python tools/bh_once.py 1048576 4 2>&1 | tail -3
+SFE_TRACE=1 timeout 120 python tools/bh_once.py 1048576 2 2>&1 | tail -6
+timeout 300 python tools/c5_once.py 4 2>&1 | tail -3
