@@ -932,6 +932,12 @@ __device__ __forceinline__ int xl_shift(int cur, int nxt, uint32_t nv, uint32_t 
     return lane + nv < 32u ? a : b;
 }
 
+// ... and the window behind it: lane i takes what lane i + nv held, the last nv lanes take the maps they fetched themselves
+__device__ __forceinline__ int xl_slide(int v, int fresh_own, uint32_t nv, uint32_t lane) {
+    const int a = __shfl_sync(0xFFFFFFFFu, v, (int)((lane + nv) & 31u));
+    return lane + nv < 32u ? a : fresh_own;
+}
+
 __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d0, uint32_t* __restrict__ gate) {
     __shared__ __align__(16) float buf[4][XL_CHUNK];
     __shared__ float s_mass;
@@ -951,28 +957,50 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d0, uint32
     // `cur`: the maps of chunks c .. c+31 (lane i: chunk c+i); `nxt`: those of chunks c+32 .. c+63, in flight while cur is used
     XlMap cur = xl_load(maps, c + lane, nd.nchunks, q);
     XlMap nxt = xl_load(maps, c + 32u + lane, nd.nchunks, q);
-    float ft[XL_PER_LANE];                                           // summands of the chunk that will need the member-by-member fold
+    // Summands for the member-by-member fold of chunk ft_c, fetched as soon as the window shows a chunk whose map cannot apply.
+    float ft[XL_PER_LANE];
     uint32_t ft_c = 0xFFFFFFFFu;
+    auto fetch = [&](uint32_t ch) {
+#pragma unroll
+        for (uint32_t i = 0; i < (uint32_t)XL_PER_LANE; i++) {
+            const uint32_t j = ch * XL_CHUNK + i * 32u + lane;
+            ft[i] = j < nd.cnt ? xl_term(src[j].pm, q) : 0.f;       // pads are +0: s + 0 == s
+        }
+    };
+    // A component whose running sum hovers around zero (a symmetric cloud: the y sums of a disc galaxy at C5) changes binade
+    // all the time, and many of its maps do not apply.  After a failure the warp therefore goes chunk by chunk for a while
+    // (`slow`: no composition of 32 maps that would be thrown away), and returns to windows of 32 after eight chunks in a
+    // row whose maps applied.
+    uint32_t slow = 0u;
     while (c < nd.nchunks) {
         const int e2 = __shfl_sync(0xFFFFFFFFu, cur.e2, 0);
         const uint32_t okmask = __ballot_sync(0xFFFFFFFFu, cur.usable != 0 && cur.e2 == e2);
-        const uint32_t nlead = okmask == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~okmask) - 1u;
-        if (nlead < 32u && c + nlead < nd.nchunks && ft_c != c + nlead) {   // fetch the summands of the first chunk that cannot be composed
+        uint32_t nlead = okmask == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~okmask) - 1u;
+        if (nlead < 32u && c + nlead < nd.nchunks && ft_c != c + nlead) {   // the first chunk of the window that cannot be composed
             ft_c = c + nlead;
+            fetch(ft_c);
+        }
+        if (slow) {
+            nlead = min(nlead, 1u);
+            // stream the members of the chunks ahead into L2 (at C5 a level's slot array is far larger than L2, and a
+            // fold that was not foreseen by the window would otherwise wait for DRAM): chunk c + 8, two 128-byte lines per lane
+            const uint32_t ch = c + 8u;
 #pragma unroll
-            for (uint32_t i = 0; i < (uint32_t)XL_PER_LANE; i++) {
-                const uint32_t j = ft_c * XL_CHUNK + i * 32u + lane;
-                ft[i] = j < nd.cnt ? xl_term(src[j].pm, q) : 0.f;    // pads are +0: s + 0 == s
+            for (uint32_t k2 = 0; k2 < 2u; k2++) {
+                const uint32_t rec0 = ch * XL_CHUNK + (lane * 2u + k2) * 4u;       // four 32-byte records per line
+                if (rec0 < nd.cnt) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + rec0));
             }
         }
         uint32_t nv = 0u;
         if (nlead > 0u) {                                            // warp-uniform
             // compose in order: lane i holds chunks c .. c+i (meaningful below nlead)
             XlMap m = cur;
+            if (!slow) {
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const XlMap o = xl_shfl_up(m, off);
-                if (lane >= (uint32_t)off) m = xl_combine(o, m);
+                for (int off = 1; off < 32; off <<= 1) {
+                    const XlMap o = xl_shfl_up(m, off);
+                    if (lane >= (uint32_t)off) m = xl_combine(o, m);
+                }
             }
             const double u = __longlong_as_double((long long)(1023 + e2) << 52);
             const double kd = (double)s * __longlong_as_double((long long)(1023 - e2) << 52);   // exact
@@ -987,17 +1015,12 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d0, uint32
             if (nv > 0u) {
                 const int kn = __shfl_sync(0xFFFFFFFFu, k + (par ? m.a1 : m.a0), (int)nv - 1);
                 s = (float)((double)kn * u);
+                if (slow) slow--;
             }
         }
         if (nv == 0u) {
             // member-by-member fold of chunk c (tree.c:166-169): the warp stages the summands, lane 0 adds them up
-            if (ft_c != c) {
-#pragma unroll
-                for (uint32_t i = 0; i < (uint32_t)XL_PER_LANE; i++) {
-                    const uint32_t j = c * XL_CHUNK + i * 32u + lane;
-                    ft[i] = j < nd.cnt ? xl_term(src[j].pm, q) : 0.f;
-                }
-            }
+            if (ft_c != c) fetch(c);
 #pragma unroll
             for (uint32_t i = 0; i < (uint32_t)XL_PER_LANE; i++) buf[q][i * 32u + lane] = ft[i];
             ft_c = 0xFFFFFFFFu;
@@ -1013,17 +1036,25 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d0, uint32
             s = __shfl_sync(0xFFFFFFFFu, s, 0);
             __syncwarp();
             nv = 1u;
+            slow = 8u;
         }
         // move the window on by nv chunks
         c += nv;
-        if (nv == 32u) cur = nxt;
+        if (nv == 32u) { cur = nxt; nxt = xl_load(maps, c + 32u + lane, nd.nchunks, q); }
         else {
+            // both windows slide; only the last nv lanes of `nxt` need maps from memory (consumed 32 chunks later)
+            const bool tail = lane + nv >= 32u;
+            XlMap fresh = xl_identity(0, 0);
+            if (tail) fresh = xl_load(maps, c + 32u + lane, nd.nchunks, q);
             cur.a0 = xl_shift(cur.a0, nxt.a0, nv, lane); cur.a1 = xl_shift(cur.a1, nxt.a1, nv, lane);
             cur.mn0 = xl_shift(cur.mn0, nxt.mn0, nv, lane); cur.mx0 = xl_shift(cur.mx0, nxt.mx0, nv, lane);
             cur.mn1 = xl_shift(cur.mn1, nxt.mn1, nv, lane); cur.mx1 = xl_shift(cur.mx1, nxt.mx1, nv, lane);
             cur.e2 = xl_shift(cur.e2, nxt.e2, nv, lane); cur.usable = xl_shift(cur.usable, nxt.usable, nv, lane);
+            nxt.a0 = xl_slide(nxt.a0, fresh.a0, nv, lane); nxt.a1 = xl_slide(nxt.a1, fresh.a1, nv, lane);
+            nxt.mn0 = xl_slide(nxt.mn0, fresh.mn0, nv, lane); nxt.mx0 = xl_slide(nxt.mx0, fresh.mx0, nv, lane);
+            nxt.mn1 = xl_slide(nxt.mn1, fresh.mn1, nv, lane); nxt.mx1 = xl_slide(nxt.mx1, fresh.mx1, nv, lane);
+            nxt.e2 = xl_slide(nxt.e2, fresh.e2, nv, lane); nxt.usable = xl_slide(nxt.usable, fresh.usable, nv, lane);
         }
-        nxt = xl_load(maps, c + 32u + lane, nd.nchunks, q);
     }
     if (threadIdx.x == 96u) s_mass = s;
     __syncthreads();
