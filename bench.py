@@ -441,9 +441,8 @@ def c5_leg(e, L, torch, dist, world, rank, dev, stream, flavour, barrier, max_ov
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 
     def step(k, timed=False, lo=i0, n=ni):
-        rc = L.sfe_dev_root_box(pm4.data_ptr(), N, k, box.ctypes.data, sptr)
         if timed: ev[0].record(stream)
-        rc |= L.sfe_dev_tree_build(box.ctypes.data, pm4.data_ptr(), N, e.TREE_DEPTH_MAX, nodes_max, sptr)
+        rc = L.sfe_dev_tree_build_box(pm4.data_ptr(), N, k, e.TREE_DEPTH_MAX, nodes_max, sptr)
         if timed: ev[1].record(stream)
         rc |= L.sfe_dev_bh(pm4.data_ptr(), N, lo, n, acc.data_ptr(), pot.data_ptr(), e.G, e.EPS2, THETA, flavour, sptr)
         if timed: ev[2].record(stream)
@@ -659,9 +658,8 @@ def run_engine(args):
 
     def step_dev(k, ev=None):
         pm4 = gather(k)
-        # root box of sim_solv() on the device (bit-identical to simulation.c:245-301; boxes[k] is the host mirror's)
-        rc = L.sfe_dev_root_box(pm4.data_ptr(), N, k, box_host.ctypes.data, sptr)
-        rc |= L.sfe_dev_tree_build(box_host.ctypes.data, pm4.data_ptr(), N, e.TREE_DEPTH_MAX, nodes_max, sptr)
+        # root box of sim_solv() on the device (bit-identical to simulation.c:245-301; boxes[k] is the host mirror's) + build
+        rc = L.sfe_dev_tree_build_box(pm4.data_ptr(), N, k, e.TREE_DEPTH_MAX, nodes_max, sptr)
         if ev is not None:
             ev[0].record(stream)
         if use_peer:
@@ -689,7 +687,7 @@ def run_engine(args):
     # ---- warm-up
     for w in range(max(args.warmup, 3)):
         step_dev(w % ring)
-        if not np.array_equal(box_host, boxes[w % ring]):
+        if L.sfe_dev_last_box(box_host.ctypes.data, sptr) != 0 or not np.array_equal(box_host, boxes[w % ring]):
             raise SystemExit("bench.py: the device root box differs from the reference's")
     barrier()
     st = (C.c_uint32(), C.c_uint32(), C.c_uint32())

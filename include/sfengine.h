@@ -158,6 +158,10 @@ int sfe_dev_vis_draw(const void* pm4, const float* pot, uint32_t N, uint32_t ste
 int sfe_dev_pack_pm4(const float* pos, const float* mas, void* pm4, uint32_t n, void* stream);
 int sfe_dev_pp(const void* pm4, uint32_t N, uint32_t i0, uint32_t ni, float* acc, float* pot,
                float grav_g, float eps2, void* stream);
+/* Root box of sim_solv() for `step_number` (simulation.c:245-301) + tree_build, the box staying in device memory (no host
+ * round trip between the two); sfe_dev_last_box() returns it once the stream has got there (it waits for the box only). */
+int sfe_dev_tree_build_box(const void* pm4, uint32_t N, uint32_t step_number, int depth_max, uint32_t nodes_max, void* stream);
+int sfe_dev_last_box(float bounds[6], void* stream);
 int sfe_dev_tree_build(const float bounds[6], const void* pm4, uint32_t N, int depth_max,
                        uint32_t nodes_max, void* stream);
 /* Raises the deferred build status (node / depth overflow) after synchronising the stream. */

@@ -189,7 +189,7 @@ extern "C" int sfe_shutdown(void) {
                       &c->sph_cells.desc, &c->sph_cells.count, &c->sph_cells.start, &c->sph_cells.key[0], &c->sph_cells.key[1],
                       &c->sph_cells.val[0], &c->sph_cells.val[1], &c->sph_cells.hist, &c->sph_cells.rec, &c->sph_cells.tlist, &c->sph_cells.part, &c->sph_cells.arrive,
                       &t.nodes, &t.seg, &t.next, &t.child_base, &t.counts, &t.keys, &t.perm_out, &t.oct, &t.rank, &t.nmid, &t.lookback, &t.xl_sum, &t.xl_map, &t.xl_flag, &t.xl_list, &t.scan_tmp, &t.slice_count, &t.root_gate, &t.meta, &t.rec0, &t.rec1, &t.rec2,
-                      &t.sub_list, &t.top_table, &t.top_cols, &t.top_rank};
+                      &t.sub_list, &t.bounds_buf, &t.top_table, &t.top_cols, &t.top_rank};
     for (DevBuf& b : t.srec) b.release();
     if (t.meta_host) { cudaFreeHost(t.meta_host); t.meta_host = nullptr; }
     if (t.summary_host) { cudaFreeHost(t.summary_host); t.summary_host = nullptr; t.summary_dev = nullptr; }
@@ -348,10 +348,10 @@ extern "C" int sfe_solv_tree(const float* pos, const float* mas, float* acc, flo
     if (upload_particles(c, fn, pos, mas, N, /*for_tree=*/true)) return SFE_FAILURE;
     if (c->d_acc.reserve((size_t)N * 12, fn) || c->d_pot.reserve((size_t)N * 4, fn)) return SFE_FAILURE;
     t_mark(c, 1);
-    float b[6];
-    if (launch_root_box(c, c->d_pm4.as<float4>(), N, step_number, b, c->stream)) return SFE_FAILURE;
-    if (bounds_out) for (int k = 0; k < 6; k++) bounds_out[k] = b[k];
-    if (launch_tree_build(c, b, c->d_pm4.as<float4>(), N, depth_max, nodes_max, c->stream)) return SFE_FAILURE;
+    float b[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* box_dev = nullptr;                      // the box stays on the device; the host copy is picked up at the end
+    if (launch_root_box_dev(c, c->d_pm4.as<float4>(), N, step_number, &box_dev, c->stream)) return SFE_FAILURE;
+    if (launch_tree_build(c, b, c->d_pm4.as<float4>(), N, depth_max, nodes_max, c->stream, box_dev)) return SFE_FAILURE;
     t_mark(c, 2);
     if (launch_bh(c, c->d_pm4.as<float4>(), N, 0, N, c->d_acc.as<float>(), c->d_pot.as<float>(), G, eps2, theta, flavour, c->stream))
         return SFE_FAILURE;
@@ -359,6 +359,7 @@ extern "C" int sfe_solv_tree(const float* pos, const float* mas, float* acc, flo
     if (d2h(fn, acc, c->d_acc.p, (size_t)N * 12, c->stream)) return SFE_FAILURE;
     if (d2h(fn, pot, c->d_pot.p, (size_t)N * 4, c->stream)) return SFE_FAILURE;
     if (t_end(c, fn, true)) return SFE_FAILURE;
+    if (bounds_out && root_box_host(c, bounds_out, c->stream, fn)) return SFE_FAILURE;
     return tree_status(c, c->stream);
 }
 
@@ -400,6 +401,25 @@ extern "C" int sfe_dev_pp(const void* pm4, uint32_t N, uint32_t i0, uint32_t ni,
                           float G, float eps2, void* stream) {
     if (ensure_init("sfe_dev_pp")) return SFE_FAILURE;
     return launch_pp(g_ctx, (const float4*)pm4, N, i0, ni, acc, pot, G, eps2, (cudaStream_t)stream);
+}
+
+// root box of sim_solv() (simulation.c:245-301) + tree_build in one call, the box never leaving the device
+extern "C" int sfe_dev_tree_build_box(const void* pm4, uint32_t N, uint32_t step_number, int depth_max, uint32_t nodes_max, void* stream) {
+    const char* fn = "sfe_dev_tree_build_box";
+    if (ensure_init(fn)) return SFE_FAILURE;
+    if (!pm4) { set_error(fn, "null pointer argument"); return SFE_FAILURE; }
+    const float* box_dev = nullptr;
+    const float unused[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (launch_root_box_dev(g_ctx, (const float4*)pm4, N, step_number, &box_dev, (cudaStream_t)stream)) return SFE_FAILURE;
+    return launch_tree_build(g_ctx, unused, (const float4*)pm4, N, depth_max, nodes_max, (cudaStream_t)stream, box_dev);
+}
+// the box of the last sfe_dev_tree_build_box() / sfe_dev_root_box(), once the stream has computed it (waits for it)
+extern "C" int sfe_dev_last_box(float bounds[6], void* stream) {
+    const char* fn = "sfe_dev_last_box";
+    if (ensure_init(fn)) return SFE_FAILURE;
+    if (!bounds) { set_error(fn, "null pointer argument"); return SFE_FAILURE; }
+    if (!g_ctx->sim.box_host || g_ctx->sim.box_seq == 0u) { set_error(fn, "no root box has been computed"); return SFE_FAILURE; }
+    return root_box_host(g_ctx, bounds, (cudaStream_t)stream, fn);
 }
 
 extern "C" int sfe_dev_tree_build(const float bounds[6], const void* pm4, uint32_t N, int depth_max,

@@ -46,7 +46,8 @@ struct Tree {
     // configuration of the last build
     uint32_t N = 0, nodes_max = 0;
     int depth_max = 0;
-    float bounds[6] = {0, 0, 0, 0, 0, 0};
+    DevBuf bounds_buf;            // float[6]  the root box of a build whose caller passed it in host memory
+    const float* bounds_dev = nullptr;   // the root box of the last build (bounds_buf or the root-box kernel's output)
     bool valid = false;
     // results, fetched lazily by tree_status()
     uint32_t num_nodes = 0, num_inbox = 0, depth = 0;
@@ -178,8 +179,10 @@ int d2h(const char* fn, void* dst, const void* src, size_t bytes, cudaStream_t s
 int launch_pack_pm4(const float* pos, const float* mas, float4* pm4, uint32_t n, cudaStream_t s);
 int launch_pp(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, float* acc, float* pot,
               float G, float eps2, cudaStream_t s);
+// `bounds` is host memory; `bounds_dev` (optional) names the same box in device memory instead - the output of
+// launch_root_box_dev() - and spares the host round trip of the six floats
 int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t N, int depth_max,
-                      uint32_t nodes_max, cudaStream_t s);
+                      uint32_t nodes_max, cudaStream_t s, const float* bounds_dev = nullptr);
 int tree_status(Ctx* c, cudaStream_t s);
 int launch_bh(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, float* acc, float* pot,
               float G, float eps2, float theta, uint32_t flavour, cudaStream_t s);
@@ -197,6 +200,10 @@ int launch_sph_force(Ctx* c, const float4* pm4, const float* rad, const float* r
 // resident leapfrog (sfe_sim.cu)
 int launch_kick_drift(Ctx* c, float4* pm4, float* vel, const float* acc, uint32_t i0, uint32_t ni, float dt, cudaStream_t s);
 int launch_root_box(Ctx* c, const float4* pm4, uint32_t N, uint32_t step_number, float bounds[6], cudaStream_t s);
+// the same without waiting for the box on the host: *bounds_dev stays valid until the next root box; the host copy can be
+// read with root_box_host() once the stream has passed the kernel
+int launch_root_box_dev(Ctx* c, const float4* pm4, uint32_t N, uint32_t step_number, const float** bounds_dev, cudaStream_t s);
+int root_box_host(Ctx* c, float bounds[6], cudaStream_t s, const char* fn);
 int launch_kick_energy(Ctx* c, const float4* pm4, float* vel, const float* acc, const float* pot, float* ken, float* pen,
                        uint32_t i0, uint32_t ni, float dt, int do_kick, double* tv_dev, cudaStream_t s);
 int launch_mean_radius(Ctx* c, const float4* pm4, uint32_t N, const double** rbar_dev, cudaStream_t s);

@@ -259,7 +259,7 @@ int launch_kick_drift(Ctx* c, float4* pm4, float* vel, const float* acc, uint32_
     return check_launch("sfe_dev_kick_drift");
 }
 
-int launch_root_box(Ctx* c, const float4* pm4, uint32_t N, uint32_t step_number, float bounds[6], cudaStream_t s) {
+int launch_root_box_dev(Ctx* c, const float4* pm4, uint32_t N, uint32_t step_number, const float** bounds_dev, cudaStream_t s) {
     const char* fn = "sfe_dev_root_box";
     if (N == 0) { set_error(fn, "N must be at least 1 (the reference divides by N, simulation.c:277)"); return SFE_FAILURE; }
     if (sim_scratch(c, fn, s)) return SFE_FAILURE;
@@ -268,7 +268,15 @@ int launch_root_box(Ctx* c, const float4* pm4, uint32_t N, uint32_t step_number,
     root_box_kernel<<<sim_grid(c, N), SIM_THREADS, 0, s>>>(pm4, N, step_number, st.partial.as<dd>(), st.ticket.as<uint32_t>(),
                                                            st.box_dev.as<BoxOut>(), (volatile BoxOut*)st.box_host_dev, seq);
     if (check_launch(fn)) return SFE_FAILURE;
-    // the device writes the box into mapped host memory; spin on its sequence number (no stream operation)
+    *bounds_dev = st.box_dev.as<BoxOut>()->bounds;
+    return SFE_SUCCESS;
+}
+
+// the box of the last launch_root_box_dev() on the host: the device writes it into mapped host memory; spin on its sequence
+// number (no stream operation)
+int root_box_host(Ctx* c, float bounds[6], cudaStream_t s, const char* fn) {
+    SimState& st = c->sim;
+    const uint32_t seq = st.box_seq;
     volatile BoxOut* h = (volatile BoxOut*)st.box_host;
     uint64_t spins = 0;
     while (h->seq != seq) {
@@ -282,6 +290,12 @@ int launch_root_box(Ctx* c, const float4* pm4, uint32_t N, uint32_t step_number,
     }
     for (int k = 0; k < 6; k++) bounds[k] = h->bounds[k];
     return SFE_SUCCESS;
+}
+
+int launch_root_box(Ctx* c, const float4* pm4, uint32_t N, uint32_t step_number, float bounds[6], cudaStream_t s) {
+    const float* dev = nullptr;
+    if (launch_root_box_dev(c, pm4, N, step_number, &dev, s)) return SFE_FAILURE;
+    return root_box_host(c, bounds, s, "sfe_dev_root_box");
 }
 
 // Mean |pos| left in device memory (visualization.c:274-307 computes the same double Kahan mean as simulation.c:245-277):
@@ -510,12 +524,16 @@ static int sim_solv_enqueue(Ctx* c, const sfe_sim_params_t* p, uint32_t step_num
     const uint32_t i0 = st.i0, ni = st.ni;
     if (p->solver & SFE_SOLVER_TREE) {
         float box[6];
-        if (launch_root_box(c, pm4, st.N, step_number, box, s)) return SFE_FAILURE;
-        for (int k = 0; k < 6; k++) st.last_box[k] = box[k];
+        // the box stays on the device: the build reads it there, the host copy (sfe_sim_last_box) is picked up behind the
+        // status check below
+        const float* box_dev = nullptr;
+        if (launch_root_box_dev(c, pm4, st.N, step_number, &box_dev, s)) return SFE_FAILURE;
         // the reference ignores tree_build()'s return value (simulation.c:312) and walks whatever was built; the
         // engine raises the failure instead (a truncated tree has no defined contents here)
-        if (launch_tree_build(c, box, pm4, st.N, p->depth_max, p->nodes_max, s)) return SFE_FAILURE;
+        if (launch_tree_build(c, box, pm4, st.N, p->depth_max, p->nodes_max, s, box_dev)) return SFE_FAILURE;
         if (tree_status(c, s)) return SFE_FAILURE;
+        if (root_box_host(c, box, s, fn)) return SFE_FAILURE;
+        for (int k = 0; k < 6; k++) st.last_box[k] = box[k];
         if (st.peer_mode) {
             // every rank walks a slot range of the (identical) tree and delivers acc / pot to the particles' owners
             if (launch_bh_routed(c, pm4, st.N, st.acc_off, st.pot_off, p->grav_g, p->eps2, p->theta, p->flavour, s)) return SFE_FAILURE;

@@ -1198,7 +1198,7 @@ static uint32_t xl_min_members() {   // SFE_XL_MIN lowers the threshold so that 
 static TreeDev make_dev(Tree& t) {
     TreeDev d;
     memset(&d, 0, sizeof d);
-    for (int k = 0; k < 6; k++) d.bounds[k] = t.bounds[k];
+    d.bounds = t.bounds_dev;
     d.nodes_max = t.nodes_max;
     d.nodes = t.nodes.as<sfe_node_t>();
     d.seg = t.seg.as<uint2>();
@@ -1260,15 +1260,30 @@ static size_t lookback_bytes(const TreeDev& d) {
 
 TreeDev tree_dev(Ctx* c) { return make_dev(c->tree); }
 
+struct Box6 { float v[6]; };
+__global__ void copy_bounds_kernel(float* __restrict__ dst, const float* __restrict__ src) { if (threadIdx.x < 6) dst[threadIdx.x] = src[threadIdx.x]; }
+__global__ void set_bounds_kernel(float* __restrict__ dst, Box6 b) { if (threadIdx.x < 6) dst[threadIdx.x] = b.v[threadIdx.x]; }
+
 int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t N, int depth_max,
-                      uint32_t nodes_max, cudaStream_t s) {
+                      uint32_t nodes_max, cudaStream_t s, const float* bounds_dev) {
     const char* fn = "sfe_tree_build";
     Tree& t = c->tree;
     t.valid = false; t.status_fetched = false;
     if (depth_max < 0 || depth_max > SFE_MAX_LEVELS) { set_error(fn, "depth_max %d outside [0,%d]", depth_max, SFE_MAX_LEVELS); return SFE_FAILURE; }
     if (nodes_max < 1) { set_error(fn, "nodes_max must be at least 1"); return SFE_FAILURE; }
     t.N = N; t.nodes_max = nodes_max; t.depth_max = depth_max;
-    for (int k = 0; k < 6; k++) t.bounds[k] = bounds[k];
+    if (t.bounds_buf.reserve(6 * sizeof(float), fn)) return SFE_FAILURE;
+    if (bounds_dev) {       // the tree keeps its own copy (the root-box kernel's output is overwritten by the next box / mean radius)
+        copy_bounds_kernel<<<1, 32, 0, s>>>(t.bounds_buf.as<float>(), bounds_dev);
+        if (check_launch(fn)) return SFE_FAILURE;
+        t.bounds_dev = t.bounds_buf.as<float>();
+    } else {
+        Box6 b6;
+        for (int k = 0; k < 6; k++) b6.v[k] = bounds[k];
+        set_bounds_kernel<<<1, 32, 0, s>>>(t.bounds_buf.as<float>(), b6);
+        if (check_launch(fn)) return SFE_FAILURE;
+        t.bounds_dev = t.bounds_buf.as<float>();
+    }
     const size_t n1 = N ? N : 1;
     if (t.seg.reserve((size_t)nodes_max * 8, fn) ||
         t.next.reserve((size_t)nodes_max * 4, fn) || t.child_base.reserve((size_t)nodes_max * 4, fn) ||

@@ -67,7 +67,7 @@ __device__ __forceinline__ void slot_store(SlotRec* p, float4 pm, unsigned long 
 
 struct TopRank;
 struct TreeDev {
-    float bounds[6];
+    const float* bounds;          // the root box {lo xyz, hi xyz} in device memory (the build never needs it on the host)
     uint32_t nodes_max;
     sfe_node_t* nodes;            // reference-layout table (tree.h:18-24), materialised on demand by sfe_tree_download()
     uint2* seg;

@@ -103,6 +103,8 @@ SIGNATURES = {
     "sfe_dev_pp": ([_P, _u32, _u32, _u32, _P, _P, _f, _f, _P], C.c_int),
     "sfe_sph_pairs_evaluated": ([C.POINTER(C.c_uint64), _P], C.c_int),
     "sfe_dev_tree_build": ([_P, _P, _u32, C.c_int, _u32, _P], C.c_int),
+    "sfe_dev_tree_build_box": ([_P, _u32, _u32, C.c_int, _u32, _P], C.c_int),
+    "sfe_dev_last_box": ([_P, _P], C.c_int),
     "sfe_dev_tree_status": ([_P, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)], C.c_int),
     "sfe_dev_bh": ([_P, _u32, _u32, _u32, _P, _P, _f, _f, _f, _u32, _P], C.c_int),
     "sfe_dev_sph_density": ([_P, _P, _u32, _u32, _u32, _P, _P], C.c_int),

@@ -1,1 +1,2 @@
-for parts in 8 4 2 1; do for pf in 0 1; do SFE_WALK_PF=$pf timeout 120 python tools/walk_slice_once.py $parts 2>&1 | tail -2; done; done
+timeout 3000 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -4
+timeout 900 python bench.py --no-c5 --no-vis --no-sph --no-cpu > gpurun_out/r02_bench_n1_b.json 2> gpurun_out/r02_bench_n1_b.err; echo rc=$?; tail -3 gpurun_out/r02_bench_n1_b.err
