@@ -968,10 +968,11 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d0, uint32
         }
     };
     // A component whose running sum hovers around zero (a symmetric cloud: the y sums of a disc galaxy at C5) changes binade
-    // all the time, and many of its maps do not apply.  After a failure the warp therefore goes chunk by chunk for a while
-    // (`slow`: no composition of 32 maps that would be thrown away), and returns to windows of 32 after eight chunks in a
-    // row whose maps applied.
-    uint32_t slow = 0u;
+    // all the time, and many of its maps do not apply.  After two failures close to each other the warp therefore goes
+    // chunk by chunk for a while (`slow`: no composition of 32 maps that would be thrown away), and returns to windows of
+    // 32 after eight chunks in a row whose maps applied.  (A sum that only grows fails at its binade crossings - about one
+    // chunk per doubling - and never enters this mode.)
+    uint32_t slow = 0u, last_fail = 0xC0000000u;
     while (c < nd.nchunks) {
         const int e2 = __shfl_sync(0xFFFFFFFFu, cur.e2, 0);
         const uint32_t okmask = __ballot_sync(0xFFFFFFFFu, cur.usable != 0 && cur.e2 == e2);
@@ -1036,7 +1037,8 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d0, uint32
             s = __shfl_sync(0xFFFFFFFFu, s, 0);
             __syncwarp();
             nv = 1u;
-            slow = 8u;
+            if (c - last_fail < 16u) slow = 8u;                      // failures come in clusters: go chunk by chunk for a while
+            last_fail = c;
         }
         // move the window on by nv chunks
         c += nv;
