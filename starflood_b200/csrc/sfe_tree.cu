@@ -973,6 +973,8 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d0, uint32
     // 32 after eight chunks in a row whose maps applied.  (A sum that only grows fails at its binade crossings - about one
     // chunk per doubling - and never enters this mode.)
     uint32_t slow = 0u, last_fail = 0xC0000000u;
+    XlMap pend = xl_identity(0, 0);
+    uint32_t pend_lo = 32u;
     while (c < nd.nchunks) {
         const int e2 = __shfl_sync(0xFFFFFFFFu, cur.e2, 0);
         const uint32_t okmask = __ballot_sync(0xFFFFFFFFu, cur.usable != 0 && cur.e2 == e2);
@@ -1040,23 +1042,30 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d0, uint32
             if (c - last_fail < 16u) slow = 8u;                      // failures come in clusters: go chunk by chunk for a while
             last_fail = c;
         }
-        // move the window on by nv chunks
+        // move the window on by nv chunks.  The maps that enter `nxt` at its tail are fetched now and merged one iteration
+        // later (`pend`, lanes from pend_lo on), so that nothing waits for the load it has just issued.
         c += nv;
-        if (nv == 32u) { cur = nxt; nxt = xl_load(maps, c + 32u + lane, nd.nchunks, q); }
+        if (pend_lo < 32u) {
+            const bool take = lane >= pend_lo;
+            nxt.a0 = take ? pend.a0 : nxt.a0; nxt.a1 = take ? pend.a1 : nxt.a1;
+            nxt.mn0 = take ? pend.mn0 : nxt.mn0; nxt.mx0 = take ? pend.mx0 : nxt.mx0;
+            nxt.mn1 = take ? pend.mn1 : nxt.mn1; nxt.mx1 = take ? pend.mx1 : nxt.mx1;
+            nxt.e2 = take ? pend.e2 : nxt.e2; nxt.usable = take ? pend.usable : nxt.usable;
+        }
+        if (nv == 32u) cur = nxt;
         else {
-            // both windows slide; only the last nv lanes of `nxt` need maps from memory (consumed 32 chunks later)
-            const bool tail = lane + nv >= 32u;
-            XlMap fresh = xl_identity(0, 0);
-            if (tail) fresh = xl_load(maps, c + 32u + lane, nd.nchunks, q);
             cur.a0 = xl_shift(cur.a0, nxt.a0, nv, lane); cur.a1 = xl_shift(cur.a1, nxt.a1, nv, lane);
             cur.mn0 = xl_shift(cur.mn0, nxt.mn0, nv, lane); cur.mx0 = xl_shift(cur.mx0, nxt.mx0, nv, lane);
             cur.mn1 = xl_shift(cur.mn1, nxt.mn1, nv, lane); cur.mx1 = xl_shift(cur.mx1, nxt.mx1, nv, lane);
             cur.e2 = xl_shift(cur.e2, nxt.e2, nv, lane); cur.usable = xl_shift(cur.usable, nxt.usable, nv, lane);
-            nxt.a0 = xl_slide(nxt.a0, fresh.a0, nv, lane); nxt.a1 = xl_slide(nxt.a1, fresh.a1, nv, lane);
-            nxt.mn0 = xl_slide(nxt.mn0, fresh.mn0, nv, lane); nxt.mx0 = xl_slide(nxt.mx0, fresh.mx0, nv, lane);
-            nxt.mn1 = xl_slide(nxt.mn1, fresh.mn1, nv, lane); nxt.mx1 = xl_slide(nxt.mx1, fresh.mx1, nv, lane);
-            nxt.e2 = xl_slide(nxt.e2, fresh.e2, nv, lane); nxt.usable = xl_slide(nxt.usable, fresh.usable, nv, lane);
+            nxt.a0 = xl_slide(nxt.a0, 0, nv, lane); nxt.a1 = xl_slide(nxt.a1, 0, nv, lane);
+            nxt.mn0 = xl_slide(nxt.mn0, 0, nv, lane); nxt.mx0 = xl_slide(nxt.mx0, 0, nv, lane);
+            nxt.mn1 = xl_slide(nxt.mn1, 0, nv, lane); nxt.mx1 = xl_slide(nxt.mx1, 0, nv, lane);
+            nxt.e2 = xl_slide(nxt.e2, 0, nv, lane); nxt.usable = xl_slide(nxt.usable, 0, nv, lane);
         }
+        pend_lo = 32u - nv;
+        pend = xl_identity(0, 0);
+        if (lane >= pend_lo) pend = xl_load(maps, c + 32u + lane, nd.nchunks, q);
     }
     if (threadIdx.x == 96u) s_mass = s;
     __syncthreads();
