@@ -171,7 +171,8 @@ int sfe_dev_bh(const void* pm4, uint32_t N, uint32_t i0, uint32_t ni, float* acc
 int sfe_dev_sph_density(const void* pm4, const float* rad, uint32_t N, uint32_t i0, uint32_t ni,
                         float* rho, void* stream);
 /* Statistics hook of the SPH cell-list passes: (target, source) pairs evaluated since the last call (read and reset;
- * 0 when the all-pairs kernels did the work).  bench.py reports it against the pairs inside the cutoff radius. */
+ * 0 when the all-pairs kernels did the work).  `stream` is the stream the passes were enqueued on (the call synchronises
+ * it).  bench.py reports the count against the pairs inside the cutoff radius. */
 int sfe_sph_pairs_evaluated(uint64_t* pairs, void* stream);
 int sfe_dev_sph_eos(const float* rho, float* prs, uint32_t n, float eos_k, float eos_n, void* stream);
 int sfe_dev_sph_force(const void* pm4, const float* rad, const float* rho, const float* prs, uint32_t N,
@@ -296,6 +297,10 @@ int sfe_peer_close(void);
  * and sfe_sim_run() are collective (every rank calls them with the same arguments; upload ends with an exchange of
  * flags so that no rank stores into a window its owner is still filling). */
 uint64_t sfe_sim_peer_bytes(uint32_t N, uint32_t dof);
+/* The same plus room for the integer accumulation buffer of one sizex x sizey frame: with a window of at least this size
+ * sfe_sim_vis_draw() works in multi-rank mode too (collective: every rank splats the particles of its slice into its
+ * window, the buffers are summed over NVLink - integer adds, so every rank ends up with the single-rank frame bit for bit). */
+uint64_t sfe_sim_peer_bytes_vis(uint32_t N, uint32_t dof, uint32_t sizex, uint32_t sizey);
 
 #ifdef __cplusplus
 }

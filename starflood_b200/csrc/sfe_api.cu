@@ -453,7 +453,8 @@ extern "C" int sfe_sph_pairs_evaluated(uint64_t* pairs, void* stream) {
     if (ensure_init("sfe_sph_pairs_evaluated")) return SFE_FAILURE;
     if (!pairs) { set_error("sfe_sph_pairs_evaluated", "null pointer argument"); return SFE_FAILURE; }
     unsigned long long v = 0ull;
-    if (cells_stats(g_ctx, &v, stream ? (cudaStream_t)stream : g_ctx->stream, "sfe_sph_pairs_evaluated")) return SFE_FAILURE;
+    // (`stream` as given: NULL is the legacy default stream, which is what a caller on that stream has enqueued the passes on)
+    if (cells_stats(g_ctx, &v, (cudaStream_t)stream, "sfe_sph_pairs_evaluated")) return SFE_FAILURE;
     *pairs = v;
     return SFE_SUCCESS;
 }

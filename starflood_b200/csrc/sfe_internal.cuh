@@ -207,7 +207,8 @@ int root_box_host(Ctx* c, float bounds[6], cudaStream_t s, const char* fn);
 int launch_kick_energy(Ctx* c, const float4* pm4, float* vel, const float* acc, const float* pot, float* ken, float* pen,
                        uint32_t i0, uint32_t ni, float dt, int do_kick, double* tv_dev, cudaStream_t s);
 int launch_mean_radius(Ctx* c, const float4* pm4, uint32_t N, const double** rbar_dev, cudaStream_t s);
-int sim_resident_views(Ctx* c, const float4** pm4, const float** pot, uint32_t* N, const char* fn);
+int sim_resident_views(Ctx* c, const float4** pm4, const float** pot, uint32_t* N, const char* fn,
+                       uint32_t* i0, uint32_t* ni, uint64_t* vis_off, bool* sliced);
 void sim_release(Ctx* c);
 // peer exchange (sfe_peer.cu)
 PeerPtrs peer_ptrs(const Ctx* c);

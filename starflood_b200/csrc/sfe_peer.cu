@@ -221,6 +221,11 @@ extern "C" int sfe_peer_close(void) {
     return rc;
 }
 
+// ... plus room for one frame's integer accumulation buffer behind the state blocks (sfe_sim_vis_draw() in multi-rank mode)
+extern "C" uint64_t sfe_sim_peer_bytes_vis(uint32_t N, uint32_t dof, uint32_t sizex, uint32_t sizey) {
+    return sfe_sim_peer_bytes(N, dof) + 16ull * (uint64_t)sizex * (uint64_t)sizey;
+}
+
 extern "C" uint64_t sfe_sim_peer_bytes(uint32_t N, uint32_t dof) {
     const uint64_t n = ((uint64_t)N + 63u) & ~(uint64_t)63u;   // keeps every array 256-byte aligned
     return 2u * 16u * n + 16u * n + (dof == 16u ? 4u * n : 0u);   // {x,y,z,m} x 2, acc + pot, rho

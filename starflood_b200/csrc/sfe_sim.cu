@@ -313,11 +313,19 @@ int launch_mean_radius(Ctx* c, const float4* pm4, uint32_t N, const double** rba
 }
 
 // the resident state's particle records and potentials (single-rank mode), for the splat of sfe_sim_vis_draw()
-int sim_resident_views(Ctx* c, const float4** pm4, const float** pot, uint32_t* N, const char* fn) {
+static float4* sim_pm4(Ctx* c);
+static float* sim_pot(Ctx* c);
+
+// Views of the resident state for vis_draw().  In multi-rank mode every rank holds all positions but only the potentials
+// of its own slice [i0, i0+ni): it splats that slice, and the accumulation buffers are summed over the windows (the frame's
+// region starts at *vis_off, behind the state blocks).
+int sim_resident_views(Ctx* c, const float4** pm4, const float** pot, uint32_t* N, const char* fn,
+                       uint32_t* i0, uint32_t* ni, uint64_t* vis_off, bool* sliced) {
     SimState& st = c->sim;
     if (!st.loaded) { set_error(fn, "no resident state: call sfe_sim_upload() first"); return SFE_FAILURE; }
-    if (st.peer_mode) { set_error(fn, "not available in multi-rank mode (every rank holds the potentials of its slice only)"); return SFE_FAILURE; }
-    *pm4 = st.pm4.as<float4>(); *pot = st.pot.as<float>(); *N = st.N;
+    *pm4 = sim_pm4(c); *pot = sim_pot(c); *N = st.N;
+    *sliced = st.peer_mode; *i0 = st.i0; *ni = st.ni;
+    *vis_off = sfe_sim_peer_bytes(st.N, st.dof);
     return SFE_SUCCESS;
 }
 

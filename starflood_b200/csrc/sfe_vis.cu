@@ -73,7 +73,7 @@ __device__ __forceinline__ void splat_add(int32_t* __restrict__ ab, uint32_t pix
 }
 
 __global__ void __launch_bounds__(VIS_THREADS, SFE_VIS_MINB) vis_splat_kernel(const float4* __restrict__ pm4, const float* __restrict__ pot,
-                                                                uint32_t N, uint32_t step_number,
+                                                                uint32_t i0, uint32_t i1, uint32_t step_number,
                                                                 const VisInfo* __restrict__ info, uint32_t sizex, uint32_t sizey,
                                                                 uint32_t samples, int32_t* __restrict__ ab) {
     __shared__ uint32_t s_win[VIS_WARPS][VIS_WIN * VIS_WIN];
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(VIS_THREADS, SFE_VIS_MINB) vis_splat_kernel(co
     const float hy = __fmul_rn(0.5f, (float)sizey);               // (real)0.5 * (real)sizey
     const float ox = __fmul_rn(0.5f, (float)sizex), oy = hy;
     const uint32_t nwarps = gridDim.x * VIS_WARPS;
-    for (uint32_t idx = blockIdx.x * VIS_WARPS + warp; idx < N; idx += nwarps) {
+    for (uint32_t idx = i0 + blockIdx.x * VIS_WARPS + warp; idx < i1; idx += nwarps) {      // particles [i0, i1): a rank's slice, or all
         const float4 p = __ldg(&pm4[idx]);
         // y = A * x with x[3] = 1 (visualization.c:536-552): ((a0 x0 + a1 x1) + a2 x2) + a3 x3
         const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], p.x), __fmul_rn(m[1], p.y)), __fmul_rn(m[2], p.z)), __fmul_rn(m[3], 1.0f));
@@ -177,21 +177,47 @@ static uint32_t vis_ctas_per_sm() {      // grid size of the splat in CTAs per S
 }
 
 // Enqueue the whole frame on stream s: mean radius -> MVP -> clear -> splat -> finish.  ab / rb / info are device buffers.
+// sums the accumulation buffers of all ranks (their windows, at byte offset `off`) into this rank's own buffer: integer
+// adds commute, so the result is the single-rank buffer bit for bit
+__global__ void vis_reduce_kernel(PeerPtrs pp, uint64_t off, uint32_t words, int32_t* __restrict__ out) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < words / 4u; k += gridDim.x * blockDim.x) {
+        int4 acc = make_int4(0, 0, 0, 0);
+        for (uint32_t r = 0; r < pp.world; r++) {
+            const int4 v = reinterpret_cast<const int4*>(pp.base[r] + off)[k];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<int4*>(out)[k] = acc;
+    }
+}
+
+// `slice`: multi-rank mode - this rank splats the particles [i0, i1) into its window at vis_off, the ranks exchange arrival
+// flags, every rank sums all windows into `ab`, and a second exchange keeps anybody from clearing its window for the
+// next frame while a peer still reads it.
+struct VisSlice { bool on; uint32_t i0, i1; uint64_t vis_off; };
+
 static int launch_vis(Ctx* c, const char* fn, const float4* pm4, const float* pot, uint32_t N, uint32_t step_number,
                       const float mat_vm[16], float ortho_scale, int autoscale, uint32_t sizex, uint32_t sizey,
                       uint32_t samples, double pixel_value_scale, int tonemap, int32_t* ab, float* rb, VisInfo* info,
-                      cudaStream_t s) {
+                      cudaStream_t s, VisSlice slice = VisSlice{false, 0u, 0u, 0u}) {
     const double* rbar = nullptr;
     if (launch_mean_radius(c, pm4, N, &rbar, s)) return SFE_FAILURE;
     Mat16 vm; memcpy(vm.m, mat_vm, sizeof vm.m);
     vis_mvp_kernel<<<1, 32, 0, s>>>(vm, ortho_scale, autoscale, rbar, info);
     if (check_launch(fn)) return SFE_FAILURE;
     const size_t npix = (size_t)sizex * sizey;
-    SFE_CUDA(fn, cudaMemsetAsync(ab, 0, npix * 16, s));                                    // visualization.c:334-342
-    const uint32_t want = (N + VIS_WARPS - 1) / VIS_WARPS, cap = (uint32_t)c->sm_count * vis_ctas_per_sm();
-    vis_splat_kernel<<<want < cap ? (want ? want : 1u) : cap, VIS_THREADS, 0, s>>>(pm4, pot, N, step_number, info, sizex, sizey,
-                                                                                 samples, ab);
+    const uint32_t i0 = slice.on ? slice.i0 : 0u, i1 = slice.on ? slice.i1 : N;
+    int32_t* target = slice.on ? reinterpret_cast<int32_t*>((char*)c->peer.local + slice.vis_off) : ab;
+    SFE_CUDA(fn, cudaMemsetAsync(target, 0, npix * 16, s));                                // visualization.c:334-342
+    const uint32_t want = (i1 - i0 + VIS_WARPS - 1) / VIS_WARPS, cap = (uint32_t)c->sm_count * vis_ctas_per_sm();
+    vis_splat_kernel<<<want < cap ? (want ? want : 1u) : cap, VIS_THREADS, 0, s>>>(pm4, pot, i0, i1, step_number, info, sizex, sizey,
+                                                                                 samples, target);
     if (check_launch(fn)) return SFE_FAILURE;
+    if (slice.on) {
+        if (launch_peer_barrier(c, s, fn)) return SFE_FAILURE;                             // every rank's slice has landed
+        vis_reduce_kernel<<<c->sm_count * 8, 256, 0, s>>>(peer_ptrs(c), slice.vis_off, (uint32_t)(npix * 4), ab);
+        if (check_launch(fn)) return SFE_FAILURE;
+        if (launch_peer_barrier(c, s, fn)) return SFE_FAILURE;                             // ... and has been read by everybody
+    }
     const uint32_t fb = (uint32_t)((npix + 255) / 256), fcap = (uint32_t)c->sm_count * 8u;
     vis_finish_kernel<<<fb < fcap ? (fb ? fb : 1u) : fcap, 256, 0, s>>>(ab, (uint32_t)npix, pixel_value_scale, tonemap, rb);
     return check_launch(fn);
@@ -268,14 +294,20 @@ extern "C" int sfe_sim_vis_draw(uint32_t step_number, const float mat_vm[16], fl
     const char* fn = "sfe_sim_vis_draw";
     if (ensure_init(fn)) return SFE_FAILURE;
     Ctx* c = ctx();
-    const float4* pm4; const float* pot; uint32_t N;
-    if (sim_resident_views(c, &pm4, &pot, &N, fn)) return SFE_FAILURE;
+    const float4* pm4; const float* pot; uint32_t N, i0 = 0u, ni = 0u; uint64_t vis_off = 0u; bool sliced = false;
+    if (sim_resident_views(c, &pm4, &pot, &N, fn, &i0, &ni, &vis_off, &sliced)) return SFE_FAILURE;
     if (vis_args_ok(fn, N, mat_vm, sizex, sizey, render_buffer)) return SFE_FAILURE;
     const size_t npix = (size_t)sizex * sizey;
+    if (sliced && vis_off + npix * 16 > c->peer.bytes) {
+        set_error(fn, "the peer window holds %llu bytes; a %u x %u frame in multi-rank mode needs sfe_sim_peer_bytes_vis() = %llu",
+                  (unsigned long long)c->peer.bytes, sizex, sizey, (unsigned long long)(vis_off + npix * 16));
+        return SFE_FAILURE;
+    }
     if (c->vis_atomic.reserve(npix * 16, fn) || c->vis_render.reserve(npix * 16, fn) || c->vis_info.reserve(sizeof(VisInfo), fn))
         return SFE_FAILURE;
     if (launch_vis(c, fn, pm4, pot, N, step_number, mat_vm, ortho_scale, autoscale, sizex, sizey, samples, pixel_value_scale,
-                   tonemap, c->vis_atomic.as<int32_t>(), c->vis_render.as<float>(), c->vis_info.as<VisInfo>(), c->stream))
+                   tonemap, c->vis_atomic.as<int32_t>(), c->vis_render.as<float>(), c->vis_info.as<VisInfo>(), c->stream,
+                   VisSlice{sliced, i0, i0 + ni, vis_off}))
         return SFE_FAILURE;
     return vis_fetch(c, fn, sizex, sizey, atomic_buffer, render_buffer, average_radius, mvp);
 }

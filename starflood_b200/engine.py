@@ -131,6 +131,7 @@ SIGNATURES = {
     "sfe_peer_detach": ([], C.c_int),
     "sfe_peer_close": ([], C.c_int),
     "sfe_sim_peer_bytes": ([_u32, _u32], C.c_uint64),
+    "sfe_sim_peer_bytes_vis": ([_u32, _u32, _u32, _u32], C.c_uint64),
 }
 
 _lib = None

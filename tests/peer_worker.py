@@ -96,7 +96,8 @@ def main():
     # ---- 2. Barnes-Hut leapfrog on `world` ranks against the oracle-driven run (bit for bit on the rank's slice)
     N, steps = 6000, 5
     pos, vel, mas = sfo.initcond(N)
-    e.peer_setup(rank, world, int(L.sfe_sim_peer_bytes(N, 13)), allgather)
+    VX, VY = 160, 96
+    e.peer_setup(rank, world, int(L.sfe_sim_peer_bytes_vis(N, 13, VX, VY)), allgather)
     sim = e.Sim(N); sim.pos[:] = pos; sim.vel[:] = vel; sim.mas[:] = mas
     prm = e.sim_params(tree=True, nodes_max=2 * N)
     assert e.sim_upload(sim) == 0, e.last_error()
@@ -104,6 +105,16 @@ def main():
     assert e.sim_solv_resident(sim, prm) == 0, e.last_error()
     rc, E = e.sim_step(sim, prm, nsteps=steps)
     assert rc == 0, e.last_error()
+    # vis_draw() in multi-rank mode: every rank splats its slice, the integer buffers are summed over the
+    # windows - every rank must end up with the frame the reference draws from the whole state, bit for bit, twice in a row
+    p_, v_, a_, po_, *_rest = oracle_run(pos, vel, mas, steps, 2 * N)
+    for frame in range(2):
+        vis = e.Vis(); e.vis_init(vis, VX, VY)
+        assert e.sim_vis_draw(vis, steps + frame) == 0, e.last_error()
+        rbar, mvp, ab, rb = sfo.vis_draw(p_.copy(), po_.copy(), steps + frame, VX, VY)
+        assert np.array_equal(vis.matMVP, mvp) and np.array_equal(vis.atomic_buffer, ab), (rank, "multi-rank vis_draw", frame)
+    big = e.Vis(); e.vis_init(big, 4 * VX, 4 * VY)                      # a frame the window has no room for
+    assert e.sim_vis_draw(big, steps) == e.STARFLOOD_FAILURE and "sfe_sim_peer_bytes_vis" in e.last_error()
     sim.mem[:] = -7.0
     assert e.sim_download(sim) == 0, e.last_error()
     p, v, a, po, ken, pen, Eo, box = oracle_run(pos, vel, mas, steps, 2 * N)
