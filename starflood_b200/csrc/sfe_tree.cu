@@ -957,14 +957,20 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d0, uint32
     // `cur`: the maps of chunks c .. c+31 (lane i: chunk c+i); `nxt`: those of chunks c+32 .. c+63, in flight while cur is used
     XlMap cur = xl_load(maps, c + lane, nd.nchunks, q);
     XlMap nxt = xl_load(maps, c + 32u + lane, nd.nchunks, q);
-    // Summands for the member-by-member fold of chunk ft_c, fetched as soon as the window shows a chunk whose map cannot apply.
-    float ft[XL_PER_LANE];
+    // Members for the member-by-member fold of chunk ft_c, fetched as soon as the window shows a chunk whose map cannot
+    // apply: {m, coordinate} as loaded - nothing touches the registers before the fold stages them, so the loads stay in
+    // flight while the warp goes on (a product computed at fetch time would wait for them right there).  `fx`: the same for
+    // a chunk whose map was expected to apply and did not (its own registers, so that it never waits for loads into ft).
+    float ft_m[XL_PER_LANE], ft_v[XL_PER_LANE], fx_m[XL_PER_LANE], fx_v[XL_PER_LANE];
     uint32_t ft_c = 0xFFFFFFFFu;
-    auto fetch = [&](uint32_t ch) {
+    const uint32_t qv = q < 3u ? q : 3u;
+    auto fetch = [&](float* fm, float* fv, uint32_t ch) {
 #pragma unroll
         for (uint32_t i = 0; i < (uint32_t)XL_PER_LANE; i++) {
             const uint32_t j = ch * XL_CHUNK + i * 32u + lane;
-            ft[i] = j < nd.cnt ? xl_term(src[j].pm, q) : 0.f;       // pads are +0: s + 0 == s
+            const float* f = reinterpret_cast<const float*>(&src[j < nd.cnt ? j : 0u].pm);
+            fm[i] = j < nd.cnt ? f[3] : 0.f;                        // pads are +0: s + 0 == s
+            fv[i] = f[qv];
         }
     };
     // A component whose running sum hovers around zero (a symmetric cloud: the y sums of a disc galaxy at C5) changes binade
@@ -973,78 +979,16 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d0, uint32
     // 32 after eight chunks in a row whose maps applied.  (A sum that only grows fails at its binade crossings - about one
     // chunk per doubling - and never enters this mode.)
     uint32_t slow = 0u, last_fail = 0xC0000000u;
+#ifdef SFE_XL_DEBUG
+    long long dbg_t0 = clock64(), dbg_fold = 0, dbg_fetch = 0, dbg_top = 0, dbg_valid = 0, dbg_adv = 0; uint32_t dbg_fail = 0u, dbg_iter = 0u, dbg_slowit = 0u;
+#endif
     XlMap pend = xl_identity(0, 0);
     uint32_t pend_lo = 32u;
-    while (c < nd.nchunks) {
-        const int e2 = __shfl_sync(0xFFFFFFFFu, cur.e2, 0);
-        const uint32_t okmask = __ballot_sync(0xFFFFFFFFu, cur.usable != 0 && cur.e2 == e2);
-        uint32_t nlead = okmask == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~okmask) - 1u;
-        if (nlead < 32u && c + nlead < nd.nchunks && ft_c != c + nlead) {   // the first chunk of the window that cannot be composed
-            ft_c = c + nlead;
-            fetch(ft_c);
-        }
-        if (slow) {
-            nlead = min(nlead, 1u);
-            // stream the members of the chunks ahead into L2 (at C5 a level's slot array is far larger than L2, and a
-            // fold that was not foreseen by the window would otherwise wait for DRAM): chunk c + 8, two 128-byte lines per lane
-            const uint32_t ch = c + 8u;
-#pragma unroll
-            for (uint32_t k2 = 0; k2 < 2u; k2++) {
-                const uint32_t rec0 = ch * XL_CHUNK + (lane * 2u + k2) * 4u;       // four 32-byte records per line
-                if (rec0 < nd.cnt) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + rec0));
-            }
-        }
-        uint32_t nv = 0u;
-        if (nlead > 0u) {                                            // warp-uniform
-            // compose in order: lane i holds chunks c .. c+i (meaningful below nlead)
-            XlMap m = cur;
-            if (!slow) {
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const XlMap o = xl_shfl_up(m, off);
-                    if (lane >= (uint32_t)off) m = xl_combine(o, m);
-                }
-            }
-            const double u = __longlong_as_double((long long)(1023 + e2) << 52);
-            const double kd = (double)s * __longlong_as_double((long long)(1023 - e2) << 52);   // exact
-            const bool small = fabs(kd) < 33554432.0;
-            const int k = small ? (int)kd : 0;
-            const int par = k & 1;
-            const int lo = k + (par ? m.mn1 : m.mn0), hi = k + (par ? m.mx1 : m.mx0);
-            const bool valid = lane < nlead && m.usable != 0 && small && (double)k == kd &&
-                               ((k >= B0 && k <= B1 && lo >= B0 && hi <= B1) || (k <= -B0 && k >= -B1 && hi <= -B0 && lo >= -B1));
-            const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
-            nv = vmask == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~vmask) - 1u;
-            if (nv > 0u) {
-                const int kn = __shfl_sync(0xFFFFFFFFu, k + (par ? m.a1 : m.a0), (int)nv - 1);
-                s = (float)((double)kn * u);
-                if (slow) slow--;
-            }
-        }
-        if (nv == 0u) {
-            // member-by-member fold of chunk c (tree.c:166-169): the warp stages the summands, lane 0 adds them up
-            if (ft_c != c) fetch(c);
-#pragma unroll
-            for (uint32_t i = 0; i < (uint32_t)XL_PER_LANE; i++) buf[q][i * 32u + lane] = ft[i];
-            ft_c = 0xFFFFFFFFu;
-            __syncwarp();
-            if (lane == 0u) {
-                const float4* row = reinterpret_cast<const float4*>(&buf[q][0]);
-#pragma unroll 8
-                for (int v4 = 0; v4 < XL_CHUNK / 4; v4++) {
-                    const float4 v = row[v4];
-                    s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
-                }
-            }
-            s = __shfl_sync(0xFFFFFFFFu, s, 0);
-            __syncwarp();
-            nv = 1u;
-            if (c - last_fail < 16u) slow = 8u;                      // failures come in clusters: go chunk by chunk for a while
-            last_fail = c;
-        }
-        // move the window on by nv chunks.  The maps that enter `nxt` at its tail are fetched now and merged one iteration
-        // later (`pend`, lanes from pend_lo on), so that nothing waits for the load it has just issued.
-        c += nv;
+    uint32_t base = 0u;                                              // chunk of lane 0 of `cur` (== c outside the slow mode)
+    // slides the two windows on by nv chunks (base += nv); the maps that enter `nxt` at its tail are fetched now and merged
+    // one step later (`pend`, lanes from pend_lo on), so that nothing waits for the load it has just issued
+    auto advance = [&](uint32_t nv) {
+        base += nv;
         if (pend_lo < 32u) {
             const bool take = lane >= pend_lo;
             nxt.a0 = take ? pend.a0 : nxt.a0; nxt.a1 = take ? pend.a1 : nxt.a1;
@@ -1065,8 +1009,121 @@ __global__ void __launch_bounds__(128) xl_chain_kernel(TreeDev t, int d0, uint32
         }
         pend_lo = 32u - nv;
         pend = xl_identity(0, 0);
-        if (lane >= pend_lo) pend = xl_load(maps, c + 32u + lane, nd.nchunks, q);
+        if (lane >= pend_lo) pend = xl_load(maps, base + 32u + lane, nd.nchunks, q);
+    };
+    while (c < nd.nchunks) {
+        // p: position of chunk c in the window.  Outside the slow mode the window starts at c (p == 0); inside it the window
+        // stays where it is and the warp steps through it (no slide, no load per chunk), a window at a time
+#ifdef SFE_XL_DEBUG
+        long long dbg_i0 = clock64();
+#endif
+        const uint32_t p = c - base;
+        const int e2 = __shfl_sync(0xFFFFFFFFu, cur.e2, (int)p);
+        const uint32_t okmask = __ballot_sync(0xFFFFFFFFu, cur.usable != 0 && cur.e2 == e2) | ((1u << p) - 1u);
+        uint32_t nlead = (okmask == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~okmask) - 1u) - p;   // composable chunks from c on
+        if (p + nlead < 32u && c + nlead < nd.nchunks && ft_c != c + nlead) {   // the first chunk ahead that cannot be composed
+            ft_c = c + nlead;
+            fetch(ft_m, ft_v, ft_c);
+        }
+#ifdef SFE_XL_DEBUG
+        long long dbg_i1 = clock64(); dbg_top += dbg_i1 - dbg_i0;
+#endif
+        uint32_t nv = 0u;
+        if (slow) {
+            if (nlead > 0u) {                                        // the map of chunk c alone, held by lane p
+                const int a0 = __shfl_sync(0xFFFFFFFFu, cur.a0, (int)p), a1 = __shfl_sync(0xFFFFFFFFu, cur.a1, (int)p);
+                const int mn0 = __shfl_sync(0xFFFFFFFFu, cur.mn0, (int)p), mx0 = __shfl_sync(0xFFFFFFFFu, cur.mx0, (int)p);
+                const int mn1 = __shfl_sync(0xFFFFFFFFu, cur.mn1, (int)p), mx1 = __shfl_sync(0xFFFFFFFFu, cur.mx1, (int)p);
+                const double u = __longlong_as_double((long long)(1023 + e2) << 52);
+                const double kd = (double)s * __longlong_as_double((long long)(1023 - e2) << 52);   // exact
+                const bool small = fabs(kd) < 33554432.0;
+                const int k = small ? (int)kd : 0;
+                const int par = k & 1;
+                const int lo = k + (par ? mn1 : mn0), hi = k + (par ? mx1 : mx0);
+                const bool valid = small && (double)k == kd &&
+                                   ((k >= B0 && k <= B1 && lo >= B0 && hi <= B1) || (k <= -B0 && k >= -B1 && hi <= -B0 && lo >= -B1));
+                if (valid) { s = (float)((double)(k + (par ? a1 : a0)) * u); nv = 1u; slow--; }
+            }
+        } else if (nlead > 0u) {                                     // warp-uniform; p == 0 here
+            // compose in order: lane i holds chunks c .. c+i (meaningful below nlead)
+            XlMap m = cur;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const XlMap o = xl_shfl_up(m, off);
+                if (lane >= (uint32_t)off) m = xl_combine(o, m);
+            }
+            const double u = __longlong_as_double((long long)(1023 + e2) << 52);
+            const double kd = (double)s * __longlong_as_double((long long)(1023 - e2) << 52);   // exact
+            const bool small = fabs(kd) < 33554432.0;
+            const int k = small ? (int)kd : 0;
+            const int par = k & 1;
+            const int lo = k + (par ? m.mn1 : m.mn0), hi = k + (par ? m.mx1 : m.mx0);
+            const bool valid = lane < nlead && m.usable != 0 && small && (double)k == kd &&
+                               ((k >= B0 && k <= B1 && lo >= B0 && hi <= B1) || (k <= -B0 && k >= -B1 && hi <= -B0 && lo >= -B1));
+            const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
+            nv = vmask == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~vmask) - 1u;
+            if (nv > 0u) {
+                const int kn = __shfl_sync(0xFFFFFFFFu, k + (par ? m.a1 : m.a0), (int)nv - 1);
+                s = (float)((double)kn * u);
+            }
+        }
+#ifdef SFE_XL_DEBUG
+        long long dbg_i2 = clock64(); dbg_valid += dbg_i2 - dbg_i1;
+#endif
+        if (nv == 0u) {
+            // member-by-member fold of chunk c (tree.c:166-169): the warp stages the summands, lane 0 adds them up
+#ifdef SFE_XL_DEBUG
+            long long dbg_a = clock64(); dbg_fail++;
+#endif
+            if (ft_c == c) {
+#pragma unroll
+                for (uint32_t i = 0; i < (uint32_t)XL_PER_LANE; i++) buf[q][i * 32u + lane] = q == 3u ? ft_m[i] : __fmul_rn(ft_m[i], ft_v[i]);
+                ft_c = 0xFFFFFFFFu;
+            } else {
+                fetch(fx_m, fx_v, c);
+#pragma unroll
+                for (uint32_t i = 0; i < (uint32_t)XL_PER_LANE; i++) buf[q][i * 32u + lane] = q == 3u ? fx_m[i] : __fmul_rn(fx_m[i], fx_v[i]);
+            }
+#ifdef SFE_XL_DEBUG
+            __syncwarp(); long long dbg_b = clock64(); dbg_fetch += dbg_b - dbg_a;
+#endif
+            __syncwarp();
+            if (lane == 0u) {
+                const float4* row = reinterpret_cast<const float4*>(&buf[q][0]);
+#pragma unroll 8
+                for (int v4 = 0; v4 < XL_CHUNK / 4; v4++) {
+                    const float4 v = row[v4];
+                    s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
+                }
+            }
+            s = __shfl_sync(0xFFFFFFFFu, s, 0);
+            __syncwarp();
+#ifdef SFE_XL_DEBUG
+            dbg_fold += clock64() - dbg_b;
+#endif
+            nv = 1u;
+            if (c - last_fail < 16u) slow = 8u;                      // failures come in clusters: go chunk by chunk for a while
+            last_fail = c;
+        }
+#ifdef SFE_XL_DEBUG
+        dbg_iter++; if (slow) dbg_slowit++;
+#endif
+        c += nv;
+#ifdef SFE_XL_DEBUG
+        long long dbg_i3 = clock64();
+#endif
+        // the windows move when the slow mode has used one up, when it ends, and after every step outside it
+        if (slow) { if (c - base == 32u) advance(32u); }
+        else if (c != base) advance(c - base);
+#ifdef SFE_XL_DEBUG
+        dbg_adv += clock64() - dbg_i3;
+#endif
     }
+#ifdef SFE_XL_DEBUG
+    if (lane == 0u && nd.nchunks > 2000u)
+        printf("xl_chain d=%d node=%u comp=%u chunks=%u iters=%u slow_iters=%u fails=%u cycles=%lld fold=%lld fetch+stage=%lld top=%lld valid=%lld adv=%lld\n", d, nd.n, q, nd.nchunks,
+               dbg_iter, dbg_slowit, dbg_fail, clock64() - dbg_t0, dbg_fold, dbg_fetch, dbg_top, dbg_valid, dbg_adv);
+#endif
     if (threadIdx.x == 96u) s_mass = s;
     __syncthreads();
     if (lane == 0u) {

@@ -1,2 +1,3 @@
-timeout 1500 python -m pytest tests/test_gpu_peer.py -x -q -m gpu 2>&1 | tail -5
-nvidia-smi -L | head -3
+timeout 900 python -m pytest tests/test_gpu_tree.py tests/test_gpu_configs.py -x -q -m gpu 2>&1 | tail -3
+timeout 120 python tools/bh_once.py 1048576 4 2>&1 | tail -3
+timeout 300 python tools/c5_once.py 5 2>&1 | tail -5
