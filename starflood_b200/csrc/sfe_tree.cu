@@ -796,6 +796,7 @@ __global__ void __launch_bounds__(1024) xl_index_kernel(TreeDev t, int d0, uint3
 
 constexpr uint32_t XLF_AGG = 1u, XLF_INCL = 2u;   // chunk flag = epoch << 2 | state; other epochs read as "nothing yet"
 constexpr int XP_WARPS = 8;
+constexpr uint32_t XP_CHOFF = 512u;
 constexpr int XP_ROW = 33;                        // staged members: one float4 of padding per 32 (conflict-free strided reads)
 
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -807,8 +808,10 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) { uint32_t
 // the eight lanes of the group.  Four components in four lane groups: a quarter of the shuffles and no members in registers.
 __global__ void __launch_bounds__(XP_WARPS * 32) xl_prep_kernel(TreeDev t, int d0, int d1, uint32_t epoch0, uint32_t* __restrict__ gate) {
     __shared__ float4 stage[XP_WARPS][8 * XP_ROW];
+    __shared__ uint32_t s_choff[XP_CHOFF];                     // chunk offsets of the level's long nodes (the first XP_CHOFF of them)
     if (gate && (gate[0] == 0u || gate[1] != 0u)) return;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, q = lane >> 3, sub = lane & 7u;
+    const uint32_t qv = q < 3u ? q : 3u;                         // float of {x,y,z,m} that goes into this lane group's product
     float4* __restrict__ st = stage[warp];
     for (int d = d0; d <= d1 && d <= XL_DEPTH_MAX; d++) {      // a warp that finds one level's chunks dealt out moves on to the next
     const uint32_t area = (uint32_t)(d % SFE_SIDE_STREAMS), epoch = (epoch0 + (uint32_t)(d - d0)) & 0x3FFFFFFFu;
@@ -818,6 +821,9 @@ __global__ void __launch_bounds__(XP_WARPS * 32) xl_prep_kernel(TreeDev t, int d
     uint32_t* __restrict__ flags = t.xl_flag + (size_t)area * t.xl_slots;
     XlMap* __restrict__ maps_all = reinterpret_cast<XlMap*>(t.xl_map) + (size_t)area * t.xl_slots * 4u;
     uint32_t* ticket = &t.xl_ticket[d];
+    __syncthreads();                                             // (every warp of the CTA passes here once per level)
+    for (uint32_t k = threadIdx.x; k < min(nxl, XP_CHOFF); k += blockDim.x) s_choff[k] = list[k].choff;
+    __syncthreads();
     for (;;) {
         // chunks are handed out in list order, so a chunk only ever waits for chunks that are already being worked on
         uint32_t w = 0u;
@@ -825,7 +831,10 @@ __global__ void __launch_bounds__(XP_WARPS * 32) xl_prep_kernel(TreeDev t, int d
         w = __shfl_sync(0xFFFFFFFFu, w, 0);
         if (w >= total) break;
         uint32_t lo = 0u, hi = nxl;                 // the node whose chunks include w: last k with choff[k] <= w
-        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (list[mid].choff <= w) lo = mid; else hi = mid; }
+        while (hi - lo > 1u) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((mid < XP_CHOFF ? s_choff[mid] : list[mid].choff) <= w) lo = mid; else hi = mid;
+        }
         const XlNode nd = list[lo];
         const uint32_t c = w - nd.choff;
         const SlotRec* __restrict__ src = t.srec[d] + nd.first;
@@ -839,11 +848,15 @@ __global__ void __launch_bounds__(XP_WARPS * 32) xl_prep_kernel(TreeDev t, int d
         }
         __syncwarp();
         // this lane's 32 summands of component q: members 32 sub .. 32 sub + 31, i.e. row `sub`
-        const float4* __restrict__ mine = st + sub * XP_ROW;
+        // (scalar reads at a lane-dependent offset: a select on the component would be a branch per lane group)
+        const float* __restrict__ mine = reinterpret_cast<const float*>(st + sub * XP_ROW);
         const uint32_t have = left > sub * 32u ? min(32u, left - sub * 32u) : 0u;
         double a = 0.0;
 #pragma unroll 8
-        for (uint32_t i = 0; i < 32u; i++) a += (double)xl_term(mine[i], q);
+        for (uint32_t i = 0; i < 32u; i++) {
+            const float m = mine[4u * i + 3u], v = mine[4u * i + qv];
+            a += (double)(q == 3u ? m : __fmul_rn(m, v));
+        }
         a += __shfl_xor_sync(0xFFFFFFFFu, a, 1); a += __shfl_xor_sync(0xFFFFFFFFu, a, 2); a += __shfl_xor_sync(0xFFFFFFFFu, a, 4);
         // publish the aggregate (the inclusive prefix at once for a node's first chunk), then look back
         if (sub == 0u) { sums_all[slot * 8u + q] = a; if (c == 0u) sums_all[slot * 8u + 4u + q] = a; }
@@ -859,6 +872,7 @@ __global__ void __launch_bounds__(XP_WARPS * 32) xl_prep_kernel(TreeDev t, int d
                 do {
                     const uint32_t f = valid ? ld_acquire_u32(&flags[(size_t)nd.slot0 + (uint32_t)j]) : ((epoch << 2) | XLF_INCL);
                     stt = (f >> 2) == epoch ? (f & 3u) : 0u;
+                    if (stt == 0u) __nanosleep(40);                  // (a spinning warp takes issue slots from the ones it waits for)
                 } while (__any_sync(0xFFFFFFFFu, stt == 0u));
                 const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, !valid || stt == XLF_INCL);
                 const uint32_t first = (uint32_t)__ffs((int)ballot) - 1u;          // nearest chunk that knows its inclusive prefix (or the node's start)
@@ -891,7 +905,8 @@ __global__ void __launch_bounds__(XP_WARPS * 32) xl_prep_kernel(TreeDev t, int d
 #pragma unroll 4
             for (uint32_t i = 0; i < 32u; i++) {
                 if (i < have) {
-                    const double tt = (double)xl_term(mine[i], q) * inv_u;       // exact: scaling by a power of two
+                    const float mm = mine[4u * i + 3u], vv = mine[4u * i + qv];
+                    const double tt = (double)(q == 3u ? mm : __fmul_rn(mm, vv)) * inv_u;   // exact: scaling by a power of two
                     const bool okm = fabs(tt) < 33554432.0;                      // a summand this large leaves the binade anyway
                     if (!okm) m.usable = 0;
                     const double fl = floor(tt);
