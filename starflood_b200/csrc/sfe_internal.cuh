@@ -47,6 +47,7 @@ struct Tree {
     uint32_t N = 0, nodes_max = 0;
     int depth_max = 0;
     DevBuf bounds_buf;            // float[6]  the root box of a build whose caller passed it in host memory
+    uint32_t level0_range_len = 0;       // non-zero: the last build took the one-pass top levels and left srec[0] unwritten (top_level0_kernel)
     const float* bounds_dev = nullptr;   // the root box of the last build (bounds_buf or the root-box kernel's output)
     bool valid = false;
     // results, fetched lazily by tree_status()

@@ -577,7 +577,8 @@ __global__ void __launch_bounds__(TP_THREADS, 4) top_scatter_kernel(TreeDev t, c
         if (code == TOP_NONE) { t.perm_out[i - r0] = i; continue; }
         const float4 p = ps[j];
         // every store is one whole 32-byte record; the folds of level d read the members of its nodes in srec[d]
-        slot_store(&t.srec[0][r0], p, 0ull, i, NODE_END);          // level-0 order: the (deferred) fold of the root reads it
+        // (the level-0 order - the in-box particles in index order - is only read by the deferred fold of the root, which
+        //  hardly ever runs: top_level0_kernel writes it then)
         const uint32_t c1 = comb[TOP_O1 + (code >> 9)], c2 = comb[TOP_O2 + (code >> 6)], c3 = comb[TOP_O3 + (code >> 3)], c4 = comb[TOP_O4 + code];
         const uint32_t p1 = (c1 & 0x7FFFFFFFu) + (raw.y & 0xFFFFu), p2 = (c2 & 0x7FFFFFFFu) + (raw.y >> 16);
         const uint32_t p3 = (c3 & 0x7FFFFFFFu) + (raw.z & 0xFFFFu), p4 = (c4 & 0x7FFFFFFFu) + (raw.z >> 16);
@@ -593,6 +594,19 @@ __global__ void __launch_bounds__(TP_THREADS, 4) top_scatter_kernel(TreeDev t, c
         if (need_owner && d == TOP_L && (c4 >> 31)) own = t.top_info[TOP_O4 + code] & 0x7FFFFFFFu;
         slot_store(&rec[pos], p, key, i, own);
     }
+    }
+}
+
+// The level-0 slot records of a build that took the one-pass top levels, written when the root's fold is needed after all
+// (gate = {needed, done}): slot = in-box particles before this one, from the rank record and the prefix table of the build.
+__global__ void __launch_bounds__(256) top_level0_kernel(TreeDev t, const float4* __restrict__ pm4, uint32_t N, uint32_t range_len,
+                                                         const uint32_t* __restrict__ gate) {
+    if (gate[0] == 0u || gate[1] != 0u) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(&t.top_rank[i]);
+        if ((raw.x & 0xFFFFu) == TOP_NONE) continue;
+        const uint32_t r0 = t.top_table[(size_t)(i / range_len) * TOP_COLS] + (raw.x >> 16);
+        slot_store(&t.srec[0][r0], pm4[i], 0ull, i, NODE_END);
     }
 }
 

@@ -1352,6 +1352,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
     const char* fn = "sfe_tree_build";
     Tree& t = c->tree;
     t.valid = false; t.status_fetched = false;
+    t.level0_range_len = 0u;
     if (depth_max < 0 || depth_max > SFE_MAX_LEVELS) { set_error(fn, "depth_max %d outside [0,%d]", depth_max, SFE_MAX_LEVELS); return SFE_FAILURE; }
     if (nodes_max < 1) { set_error(fn, "nodes_max must be at least 1"); return SFE_FAILURE; }
     t.N = N; t.nodes_max = nodes_max; t.depth_max = depth_max;
@@ -1468,6 +1469,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         if (wait_summary((int)TOP_SUMMARY_SLOT, &not_applicable, &status)) return SFE_FAILURE;
         if (!not_applicable) {
             first_level = TOP_L;
+            t.level0_range_len = range_len;
             // the folds of levels 1 .. TOP_L: one launch of each fold kernel for all of them, the chunked fold of the very
             // long nodes on one side stream, the folds of the shorter nodes on another
             {
@@ -1658,6 +1660,11 @@ int tree_root_moments(Ctx* c, const float4* pm4, uint32_t i0, uint32_t ni, float
     if (force) root_force_kernel<<<1, 1, 0, s>>>(gate);
     else root_gate_kernel<<<(ni + 255) / 256, 256, 0, s>>>(dv, pm4, i0, ni, theta, gate);
     if (check_launch(fn)) return SFE_FAILURE;
+    if (t.level0_range_len) {        // the build left the level-0 records out: write them now if the fold is going to run
+        const float4* src = pm4 ? pm4 : (const float4*)t.pm4_of_build;
+        top_level0_kernel<<<c->sm_count * 8, 256, 0, s>>>(dv, src, t.N, t.level0_range_len, gate);
+        if (check_launch(fn)) return SFE_FAILURE;
+    }
     if (launch_moments(c, dv, 0, 0, gate, true, s, fn)) return SFE_FAILURE;
     finalize_kernel<<<1, 32, 0, s>>>(dv, gate);
     if (check_launch(fn)) return SFE_FAILURE;
