@@ -44,7 +44,7 @@ struct StShared {
     uint16_t ord[2][ST_MAX];         // slot -> local id, ping-pong between levels
     uint8_t snode[2][ST_MAX];        // slot -> index of the owning internal node of the current level (ST_LEAF: leaf slot)
     StNode nodes[2][ST_NODES];
-    float4 nmid[ST_NODES];           // split planes of the current level (tree.c:159-163)
+    float4 nmid[2][ST_NODES];        // split planes of the current / next level (tree.c:159-163)
     uint16_t ncount[ST_NODES][8];    // per-octant member counts
     uint16_t cstart[ST_NODES][8];    // first slot of each child
     uint8_t cidx[ST_NODES][8];       // index of an internal child in the next level's node list
@@ -72,6 +72,27 @@ __global__ void __launch_bounds__(ST_THREADS, 2) subtree_kernel(TreeDev t, int d
         const uint32_t root = ent.x;
         const uint2 rsg = t.seg[root];
         const uint32_t slot0 = rsg.x, cnt = rsg.y - rsg.x;
+        // ids for the children of `count` nodes of level lvl (tree.c:180-189: node budget first, then depth).  One global atomic
+        // per CTA and level, issued by thread 0 a phase ahead of its use so that its latency hides behind other work.
+        auto alloc_ids = [&](uint32_t count, int lvl) {
+            if (depth_max <= lvl) { atomicCAS(&t.meta[M_STATUS], 0u, 2u); S.abort = 1u; }
+            else {
+                const uint32_t b = atomicAdd(&t.meta[M_COUNT], 8u * count);
+                if (t.nodes_max <= b + 8u * count) { atomicCAS(&t.meta[M_STATUS], 0u, 1u); S.abort = 1u; }
+                S.base = b;
+                atomicMax(&t.meta[M_DEPTH], (uint32_t)lvl + 1u);
+            }
+        };
+        // first child of the nodes [0, n) of list `buf`, whose children start at S.base (read two barriers later)
+        auto setup_nodes = [&](uint32_t buf, uint32_t n) {
+            for (uint32_t j = tid; j < n; j += ST_THREADS) {
+                StNode& nd = S.nodes[buf][j];
+                nd.cbase = S.base + 8u * j;
+                t.child_base[nd.gid] = nd.cbase;
+            }
+        };
+        int level = (int)ent.y;
+        if (tid == 0) { S.nnext = 0u; alloc_ids(1u, level); }     // (in flight while the members are loaded)
         // ---------------------------------------------------------------- load the members (ascending index order)
         for (uint32_t i = tid; i < (uint32_t)ST_MAX; i += ST_THREADS) {
             if (i < cnt) {
@@ -93,34 +114,16 @@ __global__ void __launch_bounds__(ST_THREADS, 2) subtree_kernel(TreeDev t, int d
             const WalkRec2 cell = t.rec2[root];
             for (int q = 0; q < 3; q++) { nd.lo[q] = cell.lo[q]; nd.hi[q] = cell.hi[q]; }
             S.nodes[0][0] = nd;
+            S.nmid[0][0] = make_float4(__fmul_rn(0.5f, __fadd_rn(nd.lo[0], nd.hi[0])), __fmul_rn(0.5f, __fadd_rn(nd.lo[1], nd.hi[1])),
+                                       __fmul_rn(0.5f, __fadd_rn(nd.lo[2], nd.hi[2])), 0.f);   // tree.c:159-163
         }
         uint32_t ncur = 1u, cur = 0u;
-        int level = (int)ent.y;
         bool first = true;
         __syncthreads();
         while (ncur > 0u) {
             const uint32_t nxt = cur ^ 1u;
-            // ------------------------------------------------------------ ids for the children of this level (tree.c:180-189)
-            if (tid == 0) {
-                S.nnext = 0u;
-                if (depth_max <= level) { atomicCAS(&t.meta[M_STATUS], 0u, 2u); S.abort = 1u; }
-                else {
-                    const uint32_t b = atomicAdd(&t.meta[M_COUNT], 8u * ncur);
-                    if (t.nodes_max <= b + 8u * ncur) { atomicCAS(&t.meta[M_STATUS], 0u, 1u); S.abort = 1u; }
-                    S.base = b;
-                    atomicMax(&t.meta[M_DEPTH], (uint32_t)level + 1u);
-                }
-            }
-            __syncthreads();
             if (S.abort) return;                           // the build has failed (uniform: read behind the barrier); tree_status() reports it
-            for (uint32_t j = tid; j < ncur; j += ST_THREADS) {
-                StNode& nd = S.nodes[cur][j];
-                nd.cbase = S.base + 8u * j;
-                t.child_base[nd.gid] = nd.cbase;
-                S.nmid[j] = make_float4(__fmul_rn(0.5f, __fadd_rn(nd.lo[0], nd.hi[0])), __fmul_rn(0.5f, __fadd_rn(nd.lo[1], nd.hi[1])),
-                                        __fmul_rn(0.5f, __fadd_rn(nd.lo[2], nd.hi[2])), 0.f);   // tree.c:159-163
-            }
-            __syncthreads();
+            setup_nodes(cur, ncur);                        // (the ids arrived during the previous phase)
             // ------------------------------------------------------------ octants + stable ranks (warp votes)
             uint32_t b[ST_GROUPS], r[ST_GROUPS], lid[ST_GROUPS], nn[ST_GROUPS], hm[ST_GROUPS], bo[ST_GROUPS];
             const uint32_t w0 = warp * (ST_GROUPS * 32) + lane;
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) subtree_kernel(TreeDev t, int d
                 if (n != ST_LEAF) {
                     const uint32_t ns = S.nodes[cur][n].start, ne = S.nodes[cur][n].end;
                     l = S.ord[cur][s];
-                    byte = pick_octant(S.nmid[n], S.rec[l], s - ns < 8u) | SB_ACTIVE | (s == ns ? SB_HEAD : 0u) | (s + 1u == ne ? SB_LAST : 0u);
+                    byte = pick_octant(S.nmid[cur][n], S.rec[l], s - ns < 8u) | SB_ACTIVE | (s == ns ? SB_HEAD : 0u) | (s + 1u == ne ? SB_LAST : 0u);
                 }
                 b[g] = byte; nn[g] = n; lid[g] = l; r[g] = 0u;
             }
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) subtree_kernel(TreeDev t, int d
 #pragma unroll
                 for (uint32_t o2 = 7u; o2 > 0u; o2--) if (o2 > o && S.ncount[j][o2] > 0u) succ = nd.cbase + o2;
                 const uint32_t gid = nd.cbase + o;
-                const float4 mid = S.nmid[j];
+                const float4 mid = S.nmid[cur][j];
                 const float md[3] = {mid.x, mid.y, mid.z};
                 float clo[3], chi[3];
 #pragma unroll
@@ -222,6 +225,8 @@ __global__ void __launch_bounds__(ST_THREADS, 2) subtree_kernel(TreeDev t, int d
                     c.gid = gid; c.cbase = 0u; c.next = succ; c.start = (uint16_t)start; c.end = (uint16_t)(start + cn);
                     for (int a = 0; a < 3; a++) { c.lo[a] = clo[a]; c.hi[a] = chi[a]; }
                     S.nodes[nxt][ci] = c;
+                    S.nmid[nxt][ci] = make_float4(__fmul_rn(0.5f, __fadd_rn(clo[0], chi[0])), __fmul_rn(0.5f, __fadd_rn(clo[1], chi[1])),
+                                                  __fmul_rn(0.5f, __fadd_rn(clo[2], chi[2])), 0.f);
                 }
                 S.cidx[j][o] = (uint8_t)ci;
             }
@@ -242,6 +247,9 @@ __global__ void __launch_bounds__(ST_THREADS, 2) subtree_kernel(TreeDev t, int d
                 }
             }
             __syncthreads();
+            // ids for the next level's children: one thread of the last warp (idle or nearly so in the fold phase) fetches them
+            // while the folds run
+            if (tid == ST_THREADS - 1 && S.nnext > 0u) alloc_ids(S.nnext, level + 1);
             // ------------------------------------------------------------ moments of the new children (tree.c:166-169, :302-310)
             // one lane per (node, component).  A subtree root's own fold is done by the fold kernels of its level like any
             // other node's - except the tree root's (the whole tree is one subtree): item 8*ncur, its range is the identity
@@ -288,6 +296,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) subtree_kernel(TreeDev t, int d
             cur = nxt;
             level++;
             __syncthreads();
+            if (tid == 0) S.nnext = 0u;                    // (everybody has read it; the next atomicAdd on it is two barriers away)
         }
         // ---------------------------------------------------------------- final (key, index) order of the range, in place
         for (uint32_t s = tid; s < cnt; s += ST_THREADS) {
