@@ -13,16 +13,17 @@
 //                       warp votes (lane = slot; 6-bit digits, a lane carries the running counts of two of the 64 bins),
 //                       levels 1-2 in index order, levels 3-4 after a tile-local stable partition by the first two digits
 //                       in shared memory (segmented, same scheme as rank_kernel).  Output: a 16-byte rank record per
-//                       particle, one histogram row (1 + 8 + 64 + 512 + 4096 counters) per range, and a flag when any
-//                       in-box particle lies exactly on a split plane of the top levels.
+//                       particle, one histogram row (1 + 8 + 64 + 512 + 4096 counters) per range, and a note of every
+//                       in-box particle that lies exactly on a split plane of the top levels (see "Ties").
 //   top_scan_kernel     exclusive prefix of every histogram column over the ranges, in place, plus the column totals.
-//   top_nodes_kernel    ONE CTA: which cells exist (the parent holds more than sub_max bodies and is split by the grid-wide
+//   top_nodes_kernel    five CTAs (each does the one scan over the 4681 column totals for itself): which cells exist (the parent holds more than sub_max bodies and is split by the grid-wide
 //                       passes), node ids in the breadth-first order of children_kernel, cell records (bounds, slot range,
 //                       depth-first successor, counts, split planes, fold work lists, subtree roots) for levels 0..TOP_L and
 //                       the bookkeeping of open_level() - everything root_kernel / children_kernel(0..TOP_L-1) leave behind.
 //   top_scatter_kernel  per particle: slot at every level it takes part in (start of the cell + ranges before + own rank),
-//                       written straight into spm4[0..TOP_L] / perm / skey / slot_node of level TOP_L - what
-//                       scatter_kernel(TOP_L-1) would have left.  The grid-wide passes then continue at level TOP_L.
+//                       written as one 32-byte record per level into srec[1..TOP_L] - what scatter_kernel(TOP_L-1) would
+//                       have left (level 0's records only on demand, top_level0_kernel).  The grid-wide passes then
+//                       continue at level TOP_L.
 //
 // Ties: the codes are computed with the rule of an ARRIVING particle (`<=`), which is what every member of a node but its
 // first eight gets.  A particle that lies exactly on a split plane (at N = 2^20 about one per build does - fp32 positions

@@ -17,15 +17,22 @@
 //             reference (tree.c:166-169), i.e. a fold over the node's slot range.  It is evaluated
 //             exactly that way (one warp per node, products rounded separately, no FMA), because a
 //             more accurate reduction changes walk results by 2e-4 rel-RMS at N = 2^20.
-//             The folds run on a second stream, overlapped with the partitioning of deeper levels; the
+//             The folds run on side streams, overlapped with the partitioning of deeper levels; the
 //             root's fold (N dependent adds) is only needed by out-of-box particles and is deferred.
 //
-// The stable partition is slot-centric: one segmented exclusive scan over the whole slot array per level
-// (8 counters per element, reset at range heads), done as tile-local scans + a scan of tile aggregates,
-// so node sizes from 9 to N members go through the same three kernels.  Node numbering is breadth-first
-// (children of a level allocated 8 at a time in parent order) and deterministic.
+// Three parts produce that tree:
+//   sfe_top.cuh      the upper four levels in ONE pass over the particles (path codes + stable ranks by warp votes, a histogram
+//                    table, one-scan node logic, scatter into 32-byte slot records) when the build is large enough;
+//   this file        the grid-wide passes, level by level, for cells that stay large below the top levels (and for every level
+//                    when the one-pass construction does not apply): rank_kernel (one segmented scan over the whole slot
+//                    array per level, warp votes inside a tile, decoupled look-back between tiles), children_kernel,
+//                    scatter_kernel - node sizes from 9 to N members go through the same three kernels, node numbering is
+//                    breadth-first (children of a level allocated 8 at a time in parent order); and the moment folds
+//                    (moments_short / moments_long / the exact chunked fold xl_index + xl_prep + xl_chain) with the
+//                    walk records (finalize_kernel);
+//   sfe_subtree.cuh  one CTA per node of 9 .. 2048 bodies finishes everything below it in shared memory.
 //
-// Bound: HBM / L2 bandwidth - every level streams the slot arrays a few times (B_build).
+// Bound: latency chains, not bandwidth - 231 MB of algorithmic traffic (B_build) in 0.33 ms at N = 2^20.
 #include "sfe_internal.cuh"
 #include "sfe_tree.cuh"
 #include "sfe_scan.cuh"
