@@ -4,7 +4,12 @@
 // kernels decay like exp(-r^2/h^2): beyond R = 4 h_max a pair contributes less than e^-16 = 1.1e-7 of a
 // neighbour at r = 0, and the neglected tail of the kernel integral is 5e-7 of the density.  That is inside
 // the parity gate (<= 1e-5 rel-RMS), so when R is small against the particle cloud the sums only need the
-// sources in the cells that can hold a particle within R of the target's cell:
+// sources in the cells that can hold a particle within R of the target's cell.  (The 1e-7 .. 5e-7 figures are relative to a
+// neighbour at r = 0, i.e. they hold where the density varies slowly over R - the reference's initial conditions and the
+// runs that grow out of them.  A target in a near-empty region next to a clump of N_far particles just beyond R can lose up
+// to N_far e^-16 of ITS density, which no geometric test sees: the <= 1e-5 parity of this path is an RMS statement for such
+// quasi-uniform inputs, checked on the test ICs.  SFE_SPH_ALL_PAIRS=1 selects the untruncated all-pairs kernels for
+// anything else.)
 //
 //   1. bounding box + h_min/h_max (one grid-stride reduction), grid descriptor chosen ON THE DEVICE (cell size
 //      s = max(R/4, cube root of 32 particles' volume), at most 2^18 cells); use_cells = 0 when the neighbourhood
