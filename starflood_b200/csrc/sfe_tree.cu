@@ -1227,8 +1227,9 @@ __global__ void finalize_kernel(TreeDev t, uint32_t* __restrict__ gate /* null: 
             r0.rin2 = (diag + slack) * (diag + slack) * 1.0001f + 1e-30f;
         }
         r0.next = t.next[n];
-        r0.child_kind = (kind << 30) | child;
-        r0.pad = 0.f;
+        r0.child = child;
+        r0.kind = kind;
+        if (kind == KIND_SINGLE) r0.rin2 = -1.0f;
         t.rec0[n] = r0;
     }
 }

@@ -26,10 +26,11 @@ struct __align__(32) WalkRec0 {   // 32 B = one L1 sector, fetched with ONE 256-
                                   // leaf    : centre of mass xyz, mass - a leaf is always a monopole (gravity.c:331), so
                                   //           its visit costs exactly this one sector
     uint32_t next;                // next NON-EMPTY node in depth-first order when this node is not opened
-    uint32_t child_kind;          // kind << 30 | first NON-EMPTY child (internal nodes)
+    uint32_t child;               // first NON-EMPTY child (internal nodes)
     float rin2;                   // beyond this squared distance (internal: from the centre; leaf: from the COM) a point
-                                  // is surely outside the box: filter in front of the exact bounds test (gravity.c:473-476)
-    float pad;
+                                  // is surely outside the box: filter in front of the exact bounds test (gravity.c:473-476);
+                                  // -1 for a single body (nothing to subtract: gravity.c:463-470 only looks at bodies > 1)
+    uint32_t kind;                // KIND_* (a word of its own: no shift / mask on the visit's critical path)
 };
 struct __align__(16) WalkRec2 {   // 32 B: the cell itself - bounds (gravity.c:473-476 self-subtraction test, tree.c:219-226) + parent
     float lo[3], hi[3];

@@ -9,7 +9,7 @@
 //
 // Targets are processed in Morton (slot) order, so the lanes of a warp hold neighbouring particles and
 // follow nearly the same path: node records are fetched through L1 by all lanes at once and control flow
-// stays mostly converged.  The 32-byte decision record {centre, width^2, next, child|kind} is the only thing
+// stays mostly converged.  The 32-byte decision record {centre, width^2, next, child, rin^2, kind} is the only thing
 // touched for an opened or empty node; the monopole {com, mass} is a second 16-byte record and the bounds
 // (self-subtraction test, gravity.c:473-490) a third one that is read only when the target can be inside.
 //
@@ -27,10 +27,12 @@
 #include "sfe_internal.cuh"
 #include "sfe_tree.cuh"
 #include "sfe_scan.cuh"
+#include <stdlib.h>
 
 namespace sfe {
 
 constexpr int WALK_THREADS = 128;
+constexpr int WALK_SP_CTAS = 7;     // resident CTAs per SM of walk_sp_kernel (72 registers)
 
 struct KahanRef {   // gravity.c:771-799: y = F - com; t = sum + y; z = t - sum; com = z - y; sum = t
     float s, c;
@@ -119,6 +121,17 @@ __device__ __forceinline__ bool opens(float w2, float d2, float theta) {
 // plain stores over NVLink peer pointers; the arrival flags follow in peer_barrier_kernel.
 struct WalkRoute { char* base[SFE_PEER_MAX]; uint64_t acc_off, pot_off; uint32_t world, N; };
 
+__device__ __forceinline__ void load_rec0(uint32_t (&r)[8], const WalkRec0* p) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ float4 load_rec1(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 template <int FLAVOUR, bool ROUTED>
 __global__ void __launch_bounds__(WALK_THREADS, 16)
 walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restrict__ slots /* null: the range from s0 */,
@@ -145,13 +158,11 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
     const bool seq_ok = eps2 >= SEQ_LO;
     uint32_t n = M == 0u ? NODE_END : 0u;   // an empty root is never evaluated (gravity.c:324-328)
     while (n != NODE_END) {
-        // one 256-bit load = one L1 sector: {a[4], next, child|kind, rin2, -}
+        // one 256-bit load = one L1 sector: {a[4], next, child, rin2, kind}
         uint32_t r[8];
-        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                     : "l"(rec0 + n));
+        load_rec0(r, rec0 + n);
         const float a0 = __uint_as_float(r[0]), a1 = __uint_as_float(r[1]), a2 = __uint_as_float(r[2]), a3 = __uint_as_float(r[3]);
-        const uint32_t next = r[4], kind = r[5] >> 30;
+        const uint32_t next = r[4], kind = r[7];
         const float rin2 = __uint_as_float(r[6]);
         float rx, ry, rz, mj;
         bool maybe_inside;
@@ -160,14 +171,17 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
             const float2 osq = __fmul2_rn(oxy, oxy);
             const float oz = __fsub_rn(a2, z);
             const float d2 = __fadd_rn(__fadd_rn(osq.x, osq.y), __fmul_rn(oz, oz));
-            if (opens(a3, d2, theta)) { n = r[5] & 0x3FFFFFFFu; continue; }   // gravity.c:448-453 (first non-empty child)
+            if (opens(a3, d2, theta)) {                                          // gravity.c:448-453 (first non-empty child)
+                n = r[5];
+                continue;
+            }
             const float4 cm = __ldg(&rec1[n]);                                   // accepted: monopole of the cell
             rx = cm.x; ry = cm.y; rz = cm.z; mj = cm.w;
             maybe_inside = d2 <= rin2;
         } else {                                                                 // leaf: the record IS the monopole
             rx = a0; ry = a1; rz = a2; mj = a3;
             const float ux = x - rx, uy = y - ry, uz = z - rz;
-            maybe_inside = kind != KIND_SINGLE && (ux * ux + uy * uy + uz * uz) <= rin2;
+            maybe_inside = (ux * ux + uy * uy + uz * uz) <= rin2;      // (rin2 = -1 for a single body)
         }
         // monopole (gravity.c:463-548)
         if (maybe_inside) {
@@ -242,6 +256,205 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
     pot[idx] = __fmul_rn(-G, fp);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// walk_sp_kernel: the same walk as a three-stage software pipeline inside every thread, for launches whose duration is the
+// length of ONE warp's chain of dependent visits (a rank's 1/G share of the targets: 7 warps per scheduler at G = 8, a lone
+// warp needs ~630 cycles per visit in walk_kernel - fixed-latency dependencies 235, node loads 217, divergent branches
+// 122; profiles/r02_walk_slice_ncu.txt).  Per loop iteration a thread
+//     A   visits node n: opening decision, successor, and - when the node is accepted - its monopole as the SOURCE of B1;
+//     B1  starts the source accepted by the previous visit: distance, q = r^2 + eps^2, sqrt(q), reciprocal seeds;
+//     B2  finishes the source of two visits ago: Newton steps, force terms, Kahan accumulation;
+// three independent dependency chains in one basic block (the opened / accepted / leaf cases are selects and predicated
+// loads, not branches; only the rare cases - self-subtraction, an opening test within 1e-5 of theta, q outside the verified
+// range - branch), so the scheduler fills the latency of each with the other two and the lanes of a warp stay converged.
+// The record of `next` is requested as soon as it is known; an opened cell replaces the request by its first child's.
+// Sources reach the accumulators in visit order through the pipeline, with the arithmetic of walk_kernel: same bits.
+__device__ __forceinline__ void load_rec0_if(uint32_t (&r)[8], const WalkRec0* p, bool c) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t@q ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 : "l"(p), "r"((uint32_t)c));
+}
+__device__ __forceinline__ void load_rec1_if(float& a, float& b, float& c_, float& d, const float4* p, bool c) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+                 : "+f"(a), "+f"(b), "+f"(c_), "+f"(d) : "l"(p), "r"((uint32_t)c));
+}
+
+struct SpOut { float fx, fy, fz, fp; };
+
+// RANGE_OK: every q = r^2 + eps^2 this thread can meet lies in the verified range of the Newton sequences (decided once per
+// warp from the root box), so the loop carries no IEEE fallback.
+template <int FLAVOUR, bool RANGE_OK>
+__device__ __forceinline__ SpOut sp_loop(const WalkRec0* __restrict__ rec0, const float4* __restrict__ rec1,
+                                         const WalkRec2* __restrict__ rec2, uint32_t n, float x, float y, float z, float mi,
+                                         float eps2, float theta) {
+    KahanRef2 kxy = {{0.f, 0.f}, {0.f, 0.f}}, kzp = {{0.f, 0.f}, {0.f, 0.f}};   // (acc x, acc y) and (acc z, pot)
+    float fx = 0.f, fy = 0.f, fz = 0.f, fp = 0.f;
+    uint32_t ra[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, rb[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    load_rec0_if(ra, rec0, n != NODE_END);
+    float sx = 0.f, sy = 0.f, sz = 0.f, sm = 0.f; bool v1 = false;                     // A  -> B1
+    float2 b_d = make_float2(0.f, 0.f), b_r = make_float2(1.f, 1.f);                   // B1 -> B2
+    float b_dz = 0.f, b_q = 1.f, b_sr = 1.f, b_m = 0.f; bool v2 = false, b_ieee = false;
+
+    auto step = [&](uint32_t (&cur)[8], uint32_t (&nxt)[8]) {
+        // ---- A, loads: the successor's record is wanted by the next iteration whatever this one decides (87 % of the
+        //      visits)
+        const bool active = n != NODE_END;
+        const uint32_t next = cur[4], child = cur[5], kind = cur[7];
+        const uint32_t succ = (active && next != NODE_END) ? next : 0u;
+        load_rec0(nxt, rec0 + succ);
+        // ---- B2: gravity.c:754-799 for the source of two visits ago
+        if (FLAVOUR == (int)SFE_WALK_EXACT) {
+            const float2 nqs = make_float2(-b_q, -b_sr), one = make_float2(1.0f, 1.0f);
+            float2 rr = b_r;
+            float2 e = __ffma2_rn(nqs, rr, one);
+            rr = __ffma2_rn(rr, e, rr);
+            e = __ffma2_rn(nqs, rr, one);
+            rr = __ffma2_rn(rr, e, rr);
+            const float inv_r2 = (!RANGE_OK && b_ieee) ? b_r.x : rr.x, inv_r1 = (!RANGE_OK && b_ieee) ? b_r.y : rr.y;
+            const float pj = __fmul_rn(b_m, inv_r1);
+            const float w = __fmul_rn(pj, inv_r2);
+            const float2 fxy = make_float2(__fmul_rn(w, b_d.x), __fmul_rn(w, b_d.y));   // scalar products: see walk_kernel
+            const float2 fzp = make_float2(__fmul_rn(w, b_dz), pj);
+            if (v2) { kxy.add(fxy); kzp.add(fzp); }
+        } else {
+            const float inv = b_r.x;
+            const float pj = b_m * inv;
+            const float w = pj * (inv * inv);
+            if (v2) { fx = fmaf(w, b_d.x, fx); fy = fmaf(w, b_d.y, fy); fz = fmaf(w, b_dz, fz); fp += pj; }
+        }
+        // ---- B1: the source accepted by the previous visit
+        bool odd_q = false;
+        if (FLAVOUR == (int)SFE_WALK_EXACT) {
+            const float2 dxy = __fadd2_rn(make_float2(x, y), make_float2(-sx, -sy));
+            const float2 sq = __fmul2_rn(dxy, dxy);
+            const float dz = __fsub_rn(z, sz);
+            const float q = __fadd_rn(__fadd_rn(__fadd_rn(sq.x, sq.y), __fmul_rn(dz, dz)), eps2);
+            const float sr = sqrt_rn_seq(q);
+            b_d = dxy; b_dz = dz; b_q = q; b_sr = sr; b_r = make_float2(rcp_approx(q), rcp_approx(sr));
+            if (!RANGE_OK) odd_q = v1 && !(eps2 >= SEQ_LO && q < SEQ_HI);   // IEEE forms below
+        } else {
+            const float dx = __fsub_rn(x, sx), dy = __fsub_rn(y, sy), dz = __fsub_rn(z, sz);
+            const float q = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)), eps2);
+            b_d = make_float2(dx, dy); b_dz = dz; b_r.x = rsqrt_approx(q);
+        }
+        b_m = sm; v2 = v1; b_ieee = false;
+        // ---- A: opening decision (gravity.c:353-377,448): theta <= fl(w^2 / d^2), settled by the sign of w^2 - theta d^2
+        //      unless that is within 1e-5 of zero (or d^2 is not positive) - then the IEEE division decides, below
+        const float a0 = __uint_as_float(cur[0]), a1 = __uint_as_float(cur[1]), a2 = __uint_as_float(cur[2]), a3 = __uint_as_float(cur[3]);
+        const float rin2 = __uint_as_float(cur[6]);
+        const float2 oxy = __fadd2_rn(make_float2(a0, a1), make_float2(-x, -y));
+        const float2 osq = __fmul2_rn(oxy, oxy);
+        const float oz = __fsub_rn(a2, z);
+        const float d2 = __fadd_rn(__fadd_rn(osq.x, osq.y), __fmul_rn(oz, oz));
+        const bool cell = active && kind == KIND_INTERNAL;
+        const float rhs = theta * d2;
+        const float diff = a3 - rhs;
+        const bool open_fast = cell && diff > 0.0f;
+        const bool amb = cell && !(fabsf(diff) > rhs * 1.0e-5f && 0.0f < d2);
+        load_rec0_if(nxt, rec0 + child, open_fast);      // an opened cell continues at its first non-empty child (gravity.c:448-453)
+        float4 cm = make_float4(a0, a1, a2, a3);          // a leaf's record IS its monopole (gravity.c:331) ...
+        load_rec1_if(cm.x, cm.y, cm.z, cm.w, rec1 + n, cell && !open_fast);   // ... an accepted cell's is the second record
+        bool open = open_fast;
+        const bool near = active && d2 <= rin2;            // the target may be one of the node's bodies (rin2 < 0: single body)
+        // ---- the rare cases, all behind one branch
+        if (amb || near || odd_q) {
+            if (amb) {
+                open = opens(a3, d2, theta);
+                if (open != open_fast) { load_rec0(nxt, rec0 + (open ? child : succ)); if (!open) cm = load_rec1(rec1 + n); }
+            }
+            if (near && !open) {
+                const float4 lo = __ldg(reinterpret_cast<const float4*>(&rec2[n]));
+                const float4 hi = __ldg(reinterpret_cast<const float4*>(&rec2[n]) + 1);
+                if (lo.x <= x && x <= lo.w && lo.y <= y && y <= hi.x && lo.z <= z && z <= hi.y) {
+                    cm.x = __fsub_rn(__fmul_rn(cm.x, cm.w), __fmul_rn(mi, x));            // gravity.c:478-484
+                    cm.y = __fsub_rn(__fmul_rn(cm.y, cm.w), __fmul_rn(mi, y));
+                    cm.z = __fsub_rn(__fmul_rn(cm.z, cm.w), __fmul_rn(mi, z));
+                    cm.w = __fsub_rn(cm.w, mi);
+                    const float inv = 0.0f < cm.w ? __fdiv_rn(1.0f, cm.w) : 1.0f;
+                    cm.x = __fmul_rn(cm.x, inv); cm.y = __fmul_rn(cm.y, inv); cm.z = __fmul_rn(cm.z, inv);
+                }
+            }
+            if (!RANGE_OK && odd_q) { b_r = make_float2(__fdiv_rn(1.0f, b_q), __fdiv_rn(1.0f, __fsqrt_rn(b_q))); b_ieee = true; }
+        }
+        sx = cm.x; sy = cm.y; sz = cm.z; sm = cm.w; v1 = active && !open;
+        n = open ? child : (active ? next : NODE_END);
+    };
+    while (true) {
+        if (!(n != NODE_END || v1 || v2)) break;
+        step(ra, rb);
+        if (!(n != NODE_END || v1 || v2)) break;
+        step(rb, ra);
+    }
+    if (FLAVOUR == (int)SFE_WALK_EXACT) { fx = kxy.s.x; fy = kxy.s.y; fz = kzp.s.x; fp = kzp.s.y; }
+    return SpOut{fx, fy, fz, fp};
+}
+
+template <int FLAVOUR, bool ROUTED>
+__global__ void __launch_bounds__(WALK_THREADS, WALK_SP_CTAS)
+walk_sp_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restrict__ slots /* null: the range from s0 */,
+               uint32_t s0, uint32_t nslots, float G, float eps2, float theta,
+               float* __restrict__ acc, float* __restrict__ pot, WalkRoute route) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nslots) return;
+    if (t.meta[M_STATUS] != 0u) return;
+    const uint32_t M = t.meta[M_NUM_INBOX];
+    const uint32_t s = slots ? slots[k] : s0 + k;
+    const uint32_t fin = t.meta[M_FINAL];
+    uint32_t idx; float4 me;
+    if (s < M) { const SlotRec r = slot_load(&t.srec[fin][s]); idx = r.idx; me = r.pm; }
+    else { idx = t.perm_out[s - M]; me = pm4[idx]; }
+    const float x = me.x, y = me.y, z = me.z, mi = me.w;
+    const uint32_t n0 = M == 0u ? NODE_END : 0u;   // an empty root is never evaluated (gravity.c:324-328)
+
+    // every source (a COM, with or without the target taken out) lies inside the root box: the farthest corner bounds r^2
+    bool range_ok = false;
+    if (FLAVOUR == (int)SFE_WALK_EXACT) {
+        const float ex = fmaxf(fabsf(x - t.bounds[0]), fabsf(x - t.bounds[3]));
+        const float ey = fmaxf(fabsf(y - t.bounds[1]), fabsf(y - t.bounds[4]));
+        const float ez = fmaxf(fabsf(z - t.bounds[2]), fabsf(z - t.bounds[5]));
+        range_ok = eps2 >= SEQ_LO && (ex * ex + ey * ey + ez * ez) * 1.01f + eps2 < 0.5f * SEQ_HI;
+    }
+    SpOut o;
+    if (FLAVOUR != (int)SFE_WALK_EXACT || __all_sync(__activemask(), range_ok))
+        o = sp_loop<FLAVOUR, true>(t.rec0, t.rec1, t.rec2, n0, x, y, z, mi, eps2, theta);
+    else
+        o = sp_loop<FLAVOUR, false>(t.rec0, t.rec1, t.rec2, n0, x, y, z, mi, eps2, theta);
+    const float gm = __fmul_rn(-G, mi);                                            // gravity.c:656-659
+    if (ROUTED) {
+        uint32_t r = (uint32_t)(((uint64_t)idx * route.world) / route.N);
+        while (idx < (uint32_t)(((uint64_t)route.N * r) / route.world)) r--;
+        while (idx >= (uint32_t)(((uint64_t)route.N * (r + 1u)) / route.world)) r++;
+        acc = reinterpret_cast<float*>(route.base[r] + route.acc_off);
+        pot = reinterpret_cast<float*>(route.base[r] + route.pot_off);
+    }
+    acc[3u * idx + 0u] = __fmul_rn(gm, o.fx);
+    acc[3u * idx + 1u] = __fmul_rn(gm, o.fy);
+    acc[3u * idx + 2u] = __fmul_rn(gm, o.fz);
+    pot[idx] = __fmul_rn(-G, o.fp);
+}
+
+// Which kernel: walk_sp_kernel when all its CTAs are resident at once (then the launch lasts as long as one warp's chain of
+// visits, which the pipeline shortens), walk_kernel otherwise (fewer loads and registers: more throughput).  Measured at
+// N = 2^20 (profiles/r02_walk_sp.txt): N/16 targets 0.36 -> 0.24 ms, N/8 0.40 -> 0.34, N/4 0.60 -> 0.60, all 1.83 -> 1.95.
+// SFE_WALK_SP=0 / 1 or sfe_walk_select() forces one of them (test / measurement hook).
+static int g_walk_select = -2;     // -2: not read yet, -1: by size, 0 / 1: forced (SFE_WALK_SP or sfe_walk_select())
+static bool walk_use_sp(Ctx* c, uint32_t ntargets) {
+    if (g_walk_select == -2) { const char* e = getenv("SFE_WALK_SP"); g_walk_select = e ? (atoi(e) != 0) : -1; }
+    if (g_walk_select >= 0) return g_walk_select != 0;
+    return (uint64_t)ntargets <= (uint64_t)c->sm_count * WALK_SP_CTAS * WALK_THREADS;
+}
+
+template <bool ROUTED>
+static void launch_walk(Ctx* c, uint32_t flavour, uint32_t grid, cudaStream_t s, const TreeDev& dv, const float4* pm4,
+                        const uint32_t* slots, uint32_t s0, uint32_t ns, float G, float eps2, float theta, float* acc, float* pot,
+                        const WalkRoute& rt) {
+    const bool sp = walk_use_sp(c, ns);
+#define SFE_WALK_GO(K, FL) K<(int)FL, ROUTED><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, s0, ns, G, eps2, theta, acc, pot, rt)
+    if (flavour == SFE_WALK_EXACT) { if (sp) SFE_WALK_GO(walk_sp_kernel, SFE_WALK_EXACT); else SFE_WALK_GO(walk_kernel, SFE_WALK_EXACT); }
+    else { if (sp) SFE_WALK_GO(walk_sp_kernel, SFE_WALK_FAST); else SFE_WALK_GO(walk_kernel, SFE_WALK_FAST); }
+#undef SFE_WALK_GO
+}
+
 // slots whose particle index lies in [i0, i0+ni), in slot order (multi-GPU target slices)
 struct SliceOp {
     TreeDev t; uint32_t N, i0, i1; uint32_t* out; uint32_t* count;
@@ -279,10 +492,7 @@ int launch_bh(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, f
     if (ni != N && walk_slice_slots(c, N, i0, ni, s, &slots)) return SFE_FAILURE;
     const uint32_t grid = (ni + WALK_THREADS - 1) / WALK_THREADS;
     WalkRoute none; none.world = 0u; none.N = N; none.acc_off = none.pot_off = 0u;
-    if (flavour == SFE_WALK_EXACT)
-        walk_kernel<(int)SFE_WALK_EXACT, false><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, 0u, ni, G, eps2, theta, acc, pot, none);
-    else
-        walk_kernel<(int)SFE_WALK_FAST, false><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, 0u, ni, G, eps2, theta, acc, pot, none);
+    launch_walk<false>(c, flavour, grid, s, dv, pm4, slots, 0u, ni, G, eps2, theta, acc, pot, none);
     return check_launch(fn);
 }
 
@@ -312,10 +522,7 @@ int launch_bh_routed(Ctx* c, const float4* pm4, uint32_t N, uint64_t acc_off, ui
             rt.acc_off = acc_off; rt.pot_off = pot_off; rt.world = pr.world; rt.N = N;
             const uint32_t grid = (ns + WALK_THREADS - 1) / WALK_THREADS;
             TreeDev dv = tree_dev(c);
-            if (flavour == SFE_WALK_EXACT)
-                walk_kernel<(int)SFE_WALK_EXACT, true><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, nullptr, s0, ns, G, eps2, theta, nullptr, nullptr, rt);
-            else
-                walk_kernel<(int)SFE_WALK_FAST, true><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, nullptr, s0, ns, G, eps2, theta, nullptr, nullptr, rt);
+            launch_walk<true>(c, flavour, grid, s, dv, pm4, nullptr, s0, ns, G, eps2, theta, nullptr, nullptr, rt);
             if (check_launch(fn)) return SFE_FAILURE;
         }
     }
@@ -328,6 +535,12 @@ extern "C" int sfe_dev_bh_peer(const void* pm4, uint32_t N, uint64_t acc_off, ui
                                float theta, uint32_t flavour, void* stream) {
     if (sfe::ensure_init("sfe_dev_bh_peer")) return SFE_FAILURE;
     return sfe::launch_bh_routed(sfe::ctx(), (const float4*)pm4, N, acc_off, pot_off, grav_g, eps2, theta, flavour, (cudaStream_t)stream);
+}
+
+extern "C" int sfe_walk_select(int mode) {
+    if (mode < -1 || mode > 1) { sfe::set_error("sfe_walk_select", "mode %d is not -1, 0 or 1", mode); return SFE_FAILURE; }
+    sfe::g_walk_select = mode;
+    return SFE_SUCCESS;
 }
 
 extern "C" int sfe_selftest_exact_math(uint64_t mismatches[3]) {

@@ -94,6 +94,7 @@ SIGNATURES = {
     "sfe_tree_download": ([_P, _u32, C.POINTER(_u32)], C.c_int),
     "sfe_tree_keys_download": ([_P, _P, _u32, C.POINTER(_u32)], C.c_int),
     "sfe_selftest_exact_math": ([C.POINTER(C.c_uint64)], C.c_int),
+    "sfe_walk_select": ([C.c_int], C.c_int),
     "sfe_sph": ([_P, _P, _P, _P, _P, _P, _u32, _f, _f, _f], C.c_int),
     "sfe_bh_overlay": ([_u32, _f, _P, _P, _u32, _u32], C.c_int),
     "sfe_vis_draw": ([_P, _P, _u32, _u32, _P, _f, C.c_int, _u32, _u32, _u32, C.c_double, C.c_int, _P, _P, _P, _P], C.c_int),
@@ -285,6 +286,11 @@ def selftest_exact_math():
     bad = (C.c_uint64 * 3)()
     _check(lib().sfe_selftest_exact_math(bad), "sfe_selftest_exact_math")
     return [int(b) for b in bad]
+
+
+def walk_select(mode):
+    """Test / measurement hook: 0 forces walk_kernel, 1 walk_sp_kernel (same bits, see sfengine.h), -1 chooses by size."""
+    _check(lib().sfe_walk_select(int(mode)), "sfe_walk_select")
 
 
 def solve_gravity_part_tree(sim, flavour=WALK_EXACT, i0=0, ni=None, theta=TREE_THETA):

@@ -13,6 +13,15 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 
 
+@pytest.fixture(params=[0, 1], ids=["walk_kernel", "walk_sp_kernel"])
+def both_kernels(engine, request):
+    """The walk has a throughput kernel and a latency (software-pipelined) kernel, chosen by the number of targets; the tests
+    that use this fixture run with each of them forced, whatever the size."""
+    engine.walk_select(request.param)
+    yield request.param
+    engine.walk_select(-1)
+
+
 def solve(engine, pos, mas, bounds, flavour, theta=0.5, max_nodes=None, **kw):
     N = len(mas)
     sim = engine.Sim(N); sim.pos[:] = pos; sim.mas[:] = mas
@@ -23,7 +32,7 @@ def solve(engine, pos, mas, bounds, flavour, theta=0.5, max_nodes=None, **kw):
 
 
 @pytest.mark.parametrize("name", ["bh_n4096.npz", "bh_n4096_step7.npz"])
-def test_golden(engine, name):
+def test_golden(engine, both_kernels, name):
     g0 = np.load(os.path.join(G, "bh_n4096.npz")); g = np.load(os.path.join(G, name))
     sim = solve(engine, g0["pos"], g0["mas"], g["bounds"], engine.WALK_EXACT)
     assert np.array_equal(sim.acc, g["acc"]) and np.array_equal(sim.pot, g["pot"])
@@ -33,7 +42,7 @@ def test_golden(engine, name):
 
 @pytest.mark.parametrize("N", [1, 9, 100, 5000, 65536])
 @pytest.mark.parametrize("theta", [0.5, 0.2, 1.0, 2.5])
-def test_sizes_and_thetas(engine, N, theta):
+def test_sizes_and_thetas(engine, both_kernels, N, theta):
     if N == 65536 and theta == 0.2:
         pytest.skip("slow on the CPU oracle")
     pos, vel, mas = sfo.initcond(N)
@@ -48,7 +57,7 @@ def test_sizes_and_thetas(engine, N, theta):
         assert rel_rms(sim.acc, acc) <= 1e-4
 
 
-def test_out_of_box_targets_and_self_subtraction(engine):
+def test_out_of_box_targets_and_self_subtraction(engine, both_kernels):
     N = 5000
     pos, vel, mas = sfo.initcond(N)
     b = np.array([-0.5, -0.4, -0.6, 0.7, 0.8, 0.6], np.float32)        # elongated box, 58 % of particles outside
@@ -60,7 +69,28 @@ def test_out_of_box_targets_and_self_subtraction(engine):
     assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)
 
 
-def test_slices_tile_the_answer(engine):
+def test_distances_beyond_the_newton_range(engine, both_kernels):
+    """q = r^2 + eps^2 >= 2^16 leaves the range in which the EXACT walk's Newton sequences were verified: those sources go
+    through the IEEE forms (walk_kernel: per source; walk_sp_kernel: the loop without RANGE_OK for warps that can meet one)."""
+    N = 3000
+    pos, vel, mas = sfo.initcond(N)
+    b = sfo.root_box(pos, 0)
+    pos[3 * 5:3 * 5 + 3] = [300.0, -200.0, 150.0]                      # r^2 = 152 500 to everything else
+    pos[3 * 2100:3 * 2100 + 3] = [-180.0, 10.0, 0.5]                   # r^2 = 32 500: inside the range, outside the warp test
+    rc, onodes, oc, *_ = sfo.tree_build_sorted(b, pos, mas, N + 64)
+    acc, pot, st = sfo.bh_walk(onodes[:oc], pos, mas)
+    sim = solve(engine, pos, mas, b, engine.WALK_EXACT)
+    assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)
+    # ... and with the sources far away too: a root box around everything
+    lo = pos.reshape(-1, 3).min(0) - 1; hi = pos.reshape(-1, 3).max(0) + 1
+    b2 = np.concatenate([lo, hi]).astype(np.float32)
+    rc, onodes, oc, *_ = sfo.tree_build_sorted(b2, pos, mas, N + 64)
+    acc, pot, st = sfo.bh_walk(onodes[:oc], pos, mas)
+    sim = solve(engine, pos, mas, b2, engine.WALK_EXACT)
+    assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)
+
+
+def test_slices_tile_the_answer(engine, both_kernels):
     N = 30000
     pos, vel, mas = sfo.initcond(N)
     b = sfo.root_box(pos, 0)
@@ -93,6 +123,14 @@ def test_full_size(engine):
     assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)
     fast = solve(engine, pos, mas, b, engine.WALK_FAST, max_nodes=N)
     assert rel_rms(fast.acc, acc) <= 1e-4 and rel_rms(fast.pot, pot) <= 1e-4
+    try:                                       # the latency kernel on the same tree: the same bits, both flavours
+        engine.walk_select(1)
+        sp = solve(engine, pos, mas, b, engine.WALK_EXACT, max_nodes=N)
+        assert np.array_equal(sp.acc, acc) and np.array_equal(sp.pot, pot)
+        spf = solve(engine, pos, mas, b, engine.WALK_FAST, max_nodes=N)
+        assert np.array_equal(spf.acc, fast.acc) and np.array_equal(spf.pot, fast.pot)
+    finally:
+        engine.walk_select(-1)
     # walk statistics that the roofline model uses: V = opened + evals + empty = 514.3
     assert abs((st.opened + st.evals + st.empty) / N - 514.3) < 0.1
 
