@@ -10,7 +10,7 @@ solve_gravity_part_tree for all N particles - which is exactly what the referenc
     e2e     the same through the host C ABI (sfe_solv_tree on pinned HOST buffers): every step copies
             pos/mas host->device and acc/pot device->host inside the timed region
     pp      PP direct-sum interactions/s at the same N (second half of BASELINE.json's metric), FP32-bound
-    roofline  the walk kernel against the roof that binds it (instruction issue), with SURVEY 8(d)'s HBM byte model beside it
+    roofline  the walk kernel against the roofs that bind it (instruction issue, L1 data pipe), with SURVEY 8(d)'s HBM byte model beside it
     cpu_baseline  the unmodified reference (oracle/_ref/libsfref_tree.so) timed on this box's host cores
 
 N > 1 (torchrun, one rank per GPU): strong scaling at the same total N.  Every rank owns a target slice,
@@ -83,7 +83,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -93,6 +93,12 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
+
+    def wait_first(self, timeout=8.0):
+        """Blocks until nvidia-smi has delivered its first row (its start-up takes 0.1 - 2 s on a fresh box)."""
+        t_end = time.time() + timeout
+        while self.proc and not self.rows and time.time() < t_end:
+            time.sleep(0.02)
 
     def window(self, t0, t1):
         self.t0, self.t1 = t0, t1
@@ -697,7 +703,8 @@ def run_engine(args):
     # ---- timed region: K steps, device resident
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        time.sleep(0.3)
+        sampler.wait_first()
+        time.sleep(0.1)
     walk_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -892,36 +899,50 @@ def run_engine(args):
     walk_bytes = (32.0 * V_C2 + 32.0) * ni            # 32 B per node visit + 32 B particle I/O
     step_bytes = (32.0 * V_C2 + 32.0 + 16.0 + 24.0 * 8 + 32.0 * 0.382) * N
     achieved = walk_bytes / (walk_ms * 1e-3) / 1e9
-    traffic, winst, lanes = None, None, None
+    traffic, winst, lanes, wavef, rec = None, None, None, None, {}
+    info = e.device_info()
+    # the engine walks a launch that fits the GPU in one wave with its latency kernel (launch_walk() in csrc/sfe_walk.cu)
+    sp = ni <= info["sm_count"] * 7 * 128
+    kernel = "walk_sp_kernel" if sp else "walk_kernel"
     prof = os.path.join(ROOT, "profiles", "walk_traffic.json")
     if os.path.exists(prof):
         try:
-            rec = json.load(open(prof)).get(args.flavour, {})
+            rec = json.load(open(prof)).get(args.flavour + ("_sp" if sp else ""), {})
+            share = ni / float(rec.get("targets", N_DEFAULT))       # the capture's counts, scaled to this launch's targets
             traffic = rec.get("dram_bytes_per_launch")
-            winst = rec.get("warp_instructions_per_launch")
+            winst = rec.get("warp_instructions_per_launch") * share
+            wavef = rec.get("l1_data_pipe_wavefronts_per_launch") * share
             lanes = rec.get("lanes_per_instruction")
         except Exception:
-            traffic = None
-    info = e.device_info()
-    issue_peak = 4.0 * info["sm_count"] * info["clock_khz"] * 1e3          # 4 schedulers per SM, one warp instruction per clock each
+            traffic = winst = wavef = None
+    clock_hz = info["clock_khz"] * 1e3
+    issue_peak = 4.0 * info["sm_count"] * clock_hz          # 4 schedulers per SM, one warp instruction per clock each
+    l1_peak = 1.0 * info["sm_count"] * clock_hz             # one L1 data-pipe wavefront (128 B to the registers) per SM per clock
     hbm_model = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": hbm_src,
                  "algorithmic_bytes_per_launch": walk_bytes,
                  "model": "SURVEY 8(d): 32 B x V(=%.1f node visits/particle, oracle-counted) + 32 B particle I/O, x %d targets" % (V_C2, ni),
                  "note": "not the binding roof: the node table is L1/L2 resident (DRAM traffic is 0.3 % of these bytes), so this "
                          "fraction exceeds 1; kept because SURVEY 8(d) and the north star quote the walk against HBM"}
     if winst and N == N_DEFAULT:
-        wi = winst * (ni / float(N))
-        roofline = {"kernel": "walk_kernel (sfe_dev_bh)", "bound": "issue", "achieved": wi / (walk_ms * 1e-3), "peak": issue_peak,
-                    "unit": "warp-instructions/s", "frac": wi / (walk_ms * 1e-3) / issue_peak,
-                    "traffic": traffic, "traffic_source": "profiles/walk_traffic.json: dram__bytes_read+write of one full-N launch under "
-                                                          "ncu --set full (not measured inside this run)",
-                    "warp_instructions_per_launch": wi,
-                    "instruction_source": "profiles/walk_traffic.json: smsp__inst_executed.sum of the same capture, scaled by the rank's share of the targets",
+        issue = {"achieved": winst / (walk_ms * 1e-3), "peak": issue_peak, "unit": "warp-instructions/s",
+                 "frac": winst / (walk_ms * 1e-3) / issue_peak}
+        l1 = {"achieved": wavef / (walk_ms * 1e-3), "peak": l1_peak, "unit": "wavefronts/s", "frac": wavef / (walk_ms * 1e-3) / l1_peak,
+              "model": "every 256-bit record load of a warp moves 1 KB into registers: >= 8 wavefronts at 128 B per clock per SM"}
+        bound, top = ("issue", issue) if issue["frac"] >= l1["frac"] else ("l1", l1)
+        roofline = {"kernel": "%s (sfe_dev_bh%s)" % (kernel, "_peer" if world > 1 else ""), "bound": bound, "achieved": top["achieved"],
+                    "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "issue": issue, "l1_data_pipe": l1,
+                    "traffic": traffic, "traffic_source": "profiles/walk_traffic.json: dram__bytes_read+write of one launch of this kernel "
+                                                          "under ncu --set full (not measured inside this run)",
+                    "warp_instructions_per_launch": winst, "l1_wavefronts_per_launch": wavef,
+                    "instruction_source": "profiles/walk_traffic.json (%s): smsp__inst_executed.sum and l1tex__data_pipe_lsu_wavefronts "
+                                          "of the same capture (%d targets), scaled to this launch's %d targets; peaks at the device's "
+                                          "maximum SM clock" % (rec.get("source"), rec.get("targets", N_DEFAULT), ni),
                     "launch_ms": walk_ms, "lanes_active_per_instruction": lanes,
-                    "model": "the walk is bound by instruction issue (ncu: issue slots ~80 % busy, 21 of 32 lanes active), not by memory",
+                    "model": "the walk is bound on the SM - instruction issue and the L1 data pipe (node records into registers), both "
+                             "~70-80 % busy under ncu - not by memory: " + ("(N > 1: launch_ms includes the flag exchange)" if world > 1 else "single launch"),
                     "hbm_model": hbm_model}
     else:
-        roofline = dict(hbm_model, kernel="walk_kernel (sfe_dev_bh)", traffic=traffic, launch_ms=walk_ms)
+        roofline = dict(hbm_model, kernel=kernel, traffic=traffic, launch_ms=walk_ms)
     roofline["whole_step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
                               "frac": step_bytes / (ms_step * 1e-3) / 1e9 / hbm,
                               "model": "SURVEY 8(d) B = 32 V + 32 + B_build = 16710 B per particle-step (HBM model, see hbm_model.note)"}
