@@ -1223,8 +1223,15 @@ __global__ void finalize_kernel(TreeDev t, uint32_t* __restrict__ gate /* null: 
         } else {
             const float4 cm = t.rec1[n];
             r0.a[0] = cm.x; r0.a[1] = cm.y; r0.a[2] = cm.z; r0.a[3] = cm.w;
-            // the COM lies inside the box, so does a target that must be self-subtracted: at most one diagonal apart
-            r0.rin2 = (diag + slack) * (diag + slack) * 1.0001f + 1e-30f;
+            // a target that must be self-subtracted lies inside the box: along every axis no farther from the COM than the
+            // box's farther face (true for any point, so it does not matter that the COM is a rounded quotient) - a cube about
+            // the COM, whose half edge goes into rin2 (not squared).  What the filter saves are the scattered loads of the cells
+            // (rec2) of the leaves around a target, on the L1 data pipe the walk is bound by.  [B200] EXACT walk at C2 with the
+            // sphere "one box diagonal about the COM" 1.83 ms, with the sphere through the farthest corner 1.73 ms, with this
+            // cube 1.69 ms (profiles/r02_walk_filter.txt)
+            const float fx = fmaxf(fabsf(cm.x - b[0]), fabsf(b[3] - cm.x)), fy = fmaxf(fabsf(cm.y - b[1]), fabsf(b[4] - cm.y));
+            const float fz = fmaxf(fabsf(cm.z - b[2]), fabsf(b[5] - cm.z));
+            r0.rin2 = (fmaxf(fmaxf(fx, fy), fz) + slack) * 1.0001f + 1e-30f;
         }
         r0.next = t.next[n];
         r0.child = child;

@@ -27,8 +27,9 @@ struct __align__(32) WalkRec0 {   // 32 B = one L1 sector, fetched with ONE 256-
                                   //           its visit costs exactly this one sector
     uint32_t next;                // next NON-EMPTY node in depth-first order when this node is not opened
     uint32_t child;               // first NON-EMPTY child (internal nodes)
-    float rin2;                   // beyond this squared distance (internal: from the centre; leaf: from the COM) a point
-                                  // is surely outside the box: filter in front of the exact bounds test (gravity.c:473-476);
+    float rin2;                   // filter in front of the exact bounds test of the self-subtraction (gravity.c:473-476): a point
+                                  // is surely outside the box when its squared distance from the centre exceeds this (internal),
+                                  // when it is farther than this from the COM along any axis (leaf: the half edge of a cube);
                                   // -1 for a single body (nothing to subtract: gravity.c:463-470 only looks at bodies > 1)
     uint32_t kind;                // KIND_* (a word of its own: no shift / mask on the visit's critical path)
 };

@@ -126,6 +126,11 @@ __device__ __forceinline__ void load_rec0(uint32_t (&r)[8], const WalkRec0* p) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(p));
 }
+// the cell of a node (rare path: self-subtraction test): one request for the whole 32-byte record
+__device__ __forceinline__ void load_rec2(float4& lo, float4& hi, const WalkRec2* p) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "l"(p));
+}
 __device__ __forceinline__ float4 load_rec1(const float4* p) {
     float4 v;
     asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -181,13 +186,12 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
         } else {                                                                 // leaf: the record IS the monopole
             rx = a0; ry = a1; rz = a2; mj = a3;
             const float ux = x - rx, uy = y - ry, uz = z - rz;
-            maybe_inside = (ux * ux + uy * uy + uz * uz) <= rin2;      // (rin2 = -1 for a single body)
+            maybe_inside = fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz)) <= rin2;      // a cube about the COM (rin2 = -1 for a single body)
         }
         // monopole (gravity.c:463-548)
         if (maybe_inside) {
-            const float4 lo = __ldg(reinterpret_cast<const float4*>(&rec2[n]));
-            const float4 hi = __ldg(reinterpret_cast<const float4*>(&rec2[n]) + 1);
-            // lo = {lo.x, lo.y, lo.z, hi.x}, hi = {hi.y, hi.z, -, -}
+            float4 lo, hi;                                       // lo = {lo.x, lo.y, lo.z, hi.x}, hi = {hi.y, hi.z, -, -}
+            load_rec2(lo, hi, &rec2[n]);
             if (lo.x <= x && x <= lo.w && lo.y <= y && y <= hi.x && lo.z <= z && z <= hi.y) {
                 rx = __fsub_rn(__fmul_rn(rx, mj), __fmul_rn(mi, x));              // gravity.c:478-484
                 ry = __fsub_rn(__fmul_rn(ry, mj), __fmul_rn(mi, y));
@@ -355,7 +359,8 @@ __device__ __forceinline__ SpOut sp_loop(const WalkRec0* __restrict__ rec0, cons
         float4 cm = make_float4(a0, a1, a2, a3);          // a leaf's record IS its monopole (gravity.c:331) ...
         load_rec1_if(cm.x, cm.y, cm.z, cm.w, rec1 + n, cell && !open_fast);   // ... an accepted cell's is the second record
         bool open = open_fast;
-        const bool near = active && d2 <= rin2;            // the target may be one of the node's bodies (rin2 < 0: single body)
+        // the target may be one of the node's bodies (rin2 < 0: single body)
+        const bool near = active && (kind == KIND_INTERNAL ? d2 : fmaxf(fmaxf(fabsf(oxy.x), fabsf(oxy.y)), fabsf(oz))) <= rin2;
         // ---- the rare cases, all behind one branch
         if (amb || near || odd_q) {
             if (amb) {
@@ -363,8 +368,8 @@ __device__ __forceinline__ SpOut sp_loop(const WalkRec0* __restrict__ rec0, cons
                 if (open != open_fast) { load_rec0(nxt, rec0 + (open ? child : succ)); if (!open) cm = load_rec1(rec1 + n); }
             }
             if (near && !open) {
-                const float4 lo = __ldg(reinterpret_cast<const float4*>(&rec2[n]));
-                const float4 hi = __ldg(reinterpret_cast<const float4*>(&rec2[n]) + 1);
+                float4 lo, hi;
+                load_rec2(lo, hi, &rec2[n]);
                 if (lo.x <= x && x <= lo.w && lo.y <= y && y <= hi.x && lo.z <= z && z <= hi.y) {
                     cm.x = __fsub_rn(__fmul_rn(cm.x, cm.w), __fmul_rn(mi, x));            // gravity.c:478-484
                     cm.y = __fsub_rn(__fmul_rn(cm.y, cm.w), __fmul_rn(mi, y));

@@ -18,7 +18,7 @@ import weakref
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsfengine.so")
+LIB_PATH = os.environ.get("SFE_ENGINE_LIB") or os.path.join(HERE, "libsfengine.so")   # (the override: A/B builds of the library)
 
 STARFLOOD_SUCCESS = 0   # common.h:31
 STARFLOOD_FAILURE = -1  # common.h:32
