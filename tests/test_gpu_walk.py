@@ -69,6 +69,30 @@ def test_out_of_box_targets_and_self_subtraction(engine, both_kernels):
     assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)
 
 
+@pytest.mark.parametrize("theta", [0.5, 2.0])
+def test_targets_on_cell_faces_and_large_theta(engine, both_kernels, theta):
+    """gravity.c:473-476 tests `lo <= r <= hi` on BOTH sides, so a target that lies exactly on a face shared by two cells is
+    taken out of the monopole of a leaf it does not belong to; with theta = 2 accepted INTERNAL cells contain their target
+    too.  The walk's filters in front of the bounds test (a cube about a leaf's COM, a sphere about a cell's centre) must let
+    all of these through: positions on a dyadic lattice inside a dyadic root box put thousands of targets on cell faces."""
+    rng = np.random.default_rng(7)
+    N = 6000
+    idx = rng.choice(32 ** 3, N, replace=False)
+    g = np.stack([idx % 32, (idx // 32) % 32, idx // 1024], 1).astype(np.float32)
+    pos = (g / 16.0 - 1.0).astype(np.float32)                          # multiples of 1/16 in [-1, 1)
+    pos[::7] += rng.normal(0, 0.01, (len(pos[::7]), 3)).astype(np.float32)
+    pos = np.ascontiguousarray(pos.reshape(-1))
+    mas = ((rng.random(N).astype(np.float32) + 0.5) / N).astype(np.float32)
+    b = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    rc, onodes, oc, *_ = sfo.tree_build_sorted(b, pos, mas, 4 * N)
+    acc, pot, st = sfo.bh_walk(onodes[:oc], pos, mas, theta=theta)
+    assert st.self_sub > 1.5 * N                                       # more subtractions than targets: the shared faces
+    sim = solve(engine, pos, mas, b, engine.WALK_EXACT, theta=theta, max_nodes=4 * N)
+    assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)
+    sim = solve(engine, pos, mas, b, engine.WALK_FAST, theta=theta, max_nodes=4 * N)
+    assert rel_rms(sim.acc, acc) <= 1e-4 and rel_rms(sim.pot, pot) <= 1e-4
+
+
 def test_distances_beyond_the_newton_range(engine, both_kernels):
     """q = r^2 + eps^2 >= 2^16 leaves the range in which the EXACT walk's Newton sequences were verified: those sources go
     through the IEEE forms (walk_kernel: per source; walk_sp_kernel: the loop without RANGE_OK for warps that can meet one)."""
