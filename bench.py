@@ -903,7 +903,7 @@ def run_engine(args):
     info = e.device_info()
     # the engine walks a launch that fits the GPU in one wave with its latency kernel (launch_walk() in csrc/sfe_walk.cu)
     sp = ni <= info["sm_count"] * 7 * 128
-    kernel = "walk_sp_kernel" if sp else "walk_kernel"
+    kernel = "walk_sp_kernel" if sp else ("walk_p_kernel" if args.flavour == "fast" else "walk_kernel")   # (launch_walk() in csrc/sfe_walk.cu)
     prof = os.path.join(ROOT, "profiles", "walk_traffic.json")
     if os.path.exists(prof):
         try:

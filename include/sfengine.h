@@ -109,9 +109,11 @@ int sfe_tree_keys_download(uint64_t* keys, uint32_t* perm, uint32_t N, uint32_t*
  * instead of the IEEE intrinsics; this compares the two for EVERY float of the range in which the sequences are
  * used and returns the number of mismatching bit patterns per function (must be {0, 0, 0}). */
 int sfe_selftest_exact_math(uint64_t mismatches[3]);
-/* Test / measurement hook: the walk has two kernels that produce the same bits - walk_kernel (throughput: launches that
- * fill the GPU) and walk_sp_kernel (latency: a rank's share of the targets in a multi-GPU run, small N) - chosen from the
- * number of targets.  mode 0 / 1 forces the first / second for all later walks of this process, -1 restores the choice. */
+/* Test / measurement hook: the walk has three kernels that produce the same bits - walk_kernel (throughput: launches that
+ * fill the GPU), walk_sp_kernel (latency: a rank's share of the targets in a multi-GPU run, small N) and walk_p_kernel
+ * (throughput on depth-first node records, one load per visit: what the FAST flavour uses for launches that fill the
+ * GPU) - chosen from the number of targets and the flavour.  mode 0 / 1 / 2 forces the first / second / third for all
+ * later walks of this process, -1 restores the choice. */
 int sfe_walk_select(int mode);
 
 /* The SOLVER_VIS part of solve_gravity_part_tree() (gravity.h:14-18 with SOLVER_VIS defined, the reference's default;

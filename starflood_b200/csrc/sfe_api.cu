@@ -188,7 +188,7 @@ extern "C" int sfe_shutdown(void) {
                       &c->pp_src, &c->pp_partial, &c->pp_flag, &c->sph_src, &c->sph_partial,
                       &c->sph_cells.desc, &c->sph_cells.count, &c->sph_cells.start, &c->sph_cells.key[0], &c->sph_cells.key[1],
                       &c->sph_cells.val[0], &c->sph_cells.val[1], &c->sph_cells.hist, &c->sph_cells.rec, &c->sph_cells.tlist, &c->sph_cells.part, &c->sph_cells.arrive,
-                      &t.nodes, &t.seg, &t.next, &t.child_base, &t.counts, &t.keys, &t.perm_out, &t.oct, &t.rank, &t.nmid, &t.lookback, &t.xl_sum, &t.xl_map, &t.xl_flag, &t.xl_list, &t.scan_tmp, &t.slice_count, &t.root_gate, &t.meta, &t.rec0, &t.rec1, &t.rec2,
+                      &t.nodes, &t.seg, &t.next, &t.child_base, &t.counts, &t.keys, &t.perm_out, &t.oct, &t.rank, &t.nmid, &t.lookback, &t.xl_sum, &t.xl_map, &t.xl_flag, &t.xl_list, &t.scan_tmp, &t.slice_count, &t.root_gate, &t.meta, &t.rec0, &t.rec1, &t.rec2, &t.recp, &t.bfs_of, &t.recp_par, &t.recp_hist, &t.recp_pref,
                       &t.sub_list, &t.bounds_buf, &t.top_table, &t.top_cols, &t.top_rank};
     for (DevBuf& b : t.srec) b.release();
     if (t.meta_host) { cudaFreeHost(t.meta_host); t.meta_host = nullptr; }

@@ -50,6 +50,7 @@ struct Tree {
     uint32_t level0_range_len = 0;       // non-zero: the last build took the one-pass top levels and left srec[0] unwritten (top_level0_kernel)
     const float* bounds_dev = nullptr;   // the root box of the last build (bounds_buf or the root-box kernel's output)
     bool valid = false;
+    bool recp_ready = false;   // the pre-order walk records (WalkRecP) of this build exist (made on demand: tree_ensure_recp)
     // results, fetched lazily by tree_status()
     uint32_t num_nodes = 0, num_inbox = 0, depth = 0;
     int status = 0;  // 0 ok, 1 node overflow, 2 depth overflow
@@ -80,6 +81,7 @@ struct Tree {
     DevBuf root_gate;    // uint32_t[1]  set when some target evaluates the root as a monopole
     DevBuf meta;         // uint32_t[M_WORDS]
     DevBuf rec0, rec1, rec2;   // walk records
+    DevBuf recp, bfs_of, recp_par, recp_hist, recp_pref;   // ... in pre-order numbering (sfe_tree.cuh WalkRecP)
     uint32_t* meta_host = nullptr;     // pinned, (SFE_MAX_LEVELS + 2) snapshots of meta
     cudaEvent_t ev_perm[SFE_MAX_LEVELS + 3], ev_side[SFE_SIDE_STREAMS], ev_pre[SFE_SIDE_STREAMS], ev_pre2[SFE_SIDE_STREAMS];
     bool ev_init = false;

@@ -1241,6 +1241,111 @@ __global__ void finalize_kernel(TreeDev t, uint32_t* __restrict__ gate /* null: 
     }
 }
 
+// ============================================================================ pre-order walk records (WalkRecP, sfe_tree.cuh)
+// Pre-order id of node n = (non-empty nodes whose slot range starts before n's) + (ancestors of n that start at the same
+// slot).  The nodes starting at one slot are a chain parent -> first non-empty child -> ..., of consecutive depths, so one
+// atomicAdd per node into recp_hist[first slot] (count << 16 | depth) gives both the count and the chain's top depth, an
+// exclusive scan over the slots gives the ids, and the successor of n (the first node, in pre-order, that starts where n's
+// range ends) is simply the prefix at n's end slot.
+__device__ __forceinline__ int recp_depth(const TreeDev& t, uint32_t n, bool& bad) {
+    // every cell is the root halved `depth` times: read the depth off the extents along the root's longest axis
+    const float* b = t.bounds;
+    const float e0 = b[3] - b[0], e1 = b[4] - b[1], e2 = b[5] - b[2];
+    const int ax = e0 >= e1 ? (e0 >= e2 ? 0 : 2) : (e1 >= e2 ? 1 : 2);
+    const float er = ax == 0 ? e0 : ax == 1 ? e1 : e2;
+    const float e = t.rec2[n].hi[ax] - t.rec2[n].lo[ax];
+    if (!(er > 0.0f) || !(e > 0.0f)) { bad = true; return 0; }
+    const float q = log2f(er / e);
+    const int d = __float2int_rn(q);
+    if (!(fabsf(q - (float)d) <= 0.25f) || d < 0 || d > 31) { bad = true; return 0; }
+    return d;
+}
+__global__ void recp_hist_kernel(TreeDev t) {
+    if (t.meta[M_STATUS] != 0u) return;
+    const uint32_t count = t.meta[M_COUNT];
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < count; n += gridDim.x * blockDim.x) {
+        const uint2 sg = t.seg[n];
+        if (sg.y == sg.x) continue;
+        bool bad = false;
+        const int d = recp_depth(t, n, bad);
+        if (bad) atomicOr(&t.recp_par[RP_BAD], 1u);
+        atomicAdd(&t.recp_hist[sg.x], (1u << 16) | (uint32_t)d);
+    }
+}
+struct RecpScanOp {
+    TreeDev t;
+    __device__ uint32_t n() const { return t.meta[M_STATUS] != 0u ? 0u : t.meta[M_NUM_INBOX] + 1u; }
+    __device__ uint32_t load(uint32_t s) const { return t.recp_hist[s] >> 16; }
+    __device__ void store(uint32_t s, uint32_t ex) const { t.recp_pref[s] = ex; }
+    __device__ void total(uint32_t c) const { t.recp_par[RP_COUNT] = c; }
+};
+__device__ __forceinline__ void recp_fill(const TreeDev& t, uint32_t n, WalkRecP& r, uint32_t& kind, int d, uint32_t w0b, float kr) {
+    const WalkRec0 r0 = t.rec0[n];
+    if (r0.kind == KIND_INTERNAL) {
+        const float4 cm = t.rec1[n];
+        r.a[0] = cm.x; r.a[1] = cm.y; r.a[2] = cm.z; r.a[3] = cm.w; r.a[4] = r0.a[0]; r.a[5] = r0.a[1]; r.a[6] = r0.a[2];
+        // is root width^2 / 4^depth good enough for this cell (and its filter radius covered)?
+        bool sure = (w0b >> 23) > 2u * (uint32_t)d + 1u && (w0b >> 23) < 255u;
+        const float w2a = __uint_as_float(w0b - ((uint32_t)d << 24));
+        sure = sure && fabsf(w2a - r0.a[3]) <= RECP_TOL * r0.a[3] && r0.rin2 <= kr * w2a;
+        kind = sure ? RECP_SURE : RECP_EXACT;
+    } else {
+        r.a[0] = r0.a[0]; r.a[1] = r0.a[1]; r.a[2] = r0.a[2]; r.a[3] = r0.a[3]; r.a[4] = r0.rin2; r.a[5] = 0.f; r.a[6] = 0.f;
+        kind = r0.kind == KIND_SINGLE ? RECP_SINGLE : RECP_LEAF;
+    }
+}
+__global__ void recp_build_kernel(TreeDev t) {
+    if (t.meta[M_STATUS] != 0u) return;
+    const uint32_t count = t.meta[M_COUNT], M = t.meta[M_NUM_INBOX];
+    const WalkRec0 root = t.rec0[0];
+    const uint32_t w0b = __float_as_uint(root.a[3]);
+    const float kr = root.kind == KIND_INTERNAL && root.a[3] > 0.0f ? root.rin2 / root.a[3] * 1.01f : 1.0f;
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < count; n += gridDim.x * blockDim.x) {
+        const uint2 sg = t.seg[n];
+        if (n == 0u) { t.recp_par[RP_W0] = w0b; t.recp_par[RP_KR] = __float_as_uint(kr); }
+        if (sg.y == sg.x) continue;
+        bool bad = false;
+        const int d = recp_depth(t, n, bad);
+        const uint32_t v = t.recp_hist[sg.x], k = v >> 16, dsum = v & 0xFFFFu;
+        const int d0 = k ? (int)((dsum - k * (k - 1u) / 2u) / k) : 0;       // depths d0 .. d0 + k - 1
+        if (k == 0u || d < d0 || d >= d0 + (int)k) bad = true;
+        const uint32_t pre = t.recp_pref[sg.x] + (uint32_t)(d - d0);
+        const uint32_t nxt = sg.y < M ? t.recp_pref[sg.y] : RECP_END;
+        if (pre >= RECP_END || pre >= t.nodes_max || (nxt != RECP_END && nxt >= t.nodes_max)) bad = true;
+        if (bad) { atomicOr(&t.recp_par[RP_BAD], 1u); continue; }
+        WalkRecP r; uint32_t kind;
+        recp_fill(t, n, r, kind, d, w0b, kr);
+        r.w = kind << 30 | (uint32_t)d << 24 | nxt;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&t.recp[pre]);
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(__float_as_uint(r.a[0])), "r"(__float_as_uint(r.a[1])),
+                     "r"(__float_as_uint(r.a[2])), "r"(__float_as_uint(r.a[3])), "r"(__float_as_uint(r.a[4])), "r"(__float_as_uint(r.a[5])),
+                     "r"(__float_as_uint(r.a[6])), "r"(r.w) : "memory");
+        t.bfs_of[pre] = n;
+    }
+}
+// the root's deferred fold (tree_root_moments) has just rewritten rec0[0] / rec1[0]: bring its pre-order record (id 0) up to date
+__global__ void recp_root_kernel(TreeDev t, const uint32_t* __restrict__ gate) {
+    if (gate[0] == 0u || gate[1] != 0u) return;
+    if (t.meta[M_STATUS] != 0u || t.meta[M_NUM_INBOX] == 0u || t.recp_par[RP_BAD] != 0u) return;
+    WalkRecP r; uint32_t kind;
+    const uint32_t w = t.recp[0].w;
+    recp_fill(t, 0u, r, kind, 0, t.recp_par[RP_W0], __uint_as_float(t.recp_par[RP_KR]));
+    r.w = kind << 30 | (w & 0x3FFFFFFFu);   // (depth 0, same successor)
+    t.recp[0] = r;
+}
+static int launch_recp(Ctx* c, const TreeDev& dv, uint32_t N, cudaStream_t s, const char* fn) {
+    Tree& t = c->tree;
+    SFE_CUDA(fn, cudaMemsetAsync(t.recp_hist.p, 0, ((size_t)(N ? N : 1) + 1) * 4, s));
+    SFE_CUDA(fn, cudaMemsetAsync(t.recp_par.p, 0, RP_WORDS * 4, s));
+    recp_hist_kernel<<<c->sm_count * 4, 256, 0, s>>>(dv);
+    if (check_launch(fn)) return SFE_FAILURE;
+    RecpScanOp op{dv};
+    if (run_scan(c, op, N + 1u, s, fn)) return SFE_FAILURE;
+    recp_build_kernel<<<c->sm_count * 4, 256, 0, s>>>(dv);
+    if (check_launch(fn)) return SFE_FAILURE;
+    return walk_publish_recp(c, s, fn);
+}
+
 // the reference-layout node table (tree.h:18-24) for sfe_tree_download(): assembled from the engine's own records
 __global__ void table_kernel(TreeDev t) {
     const uint32_t count = t.meta[M_COUNT];
@@ -1352,6 +1457,11 @@ static TreeDev make_dev(Tree& t) {
     d.rec0 = t.rec0.as<WalkRec0>() + REC_SHIFT;
     d.rec1 = t.rec1.as<float4>() + REC_SHIFT;
     d.rec2 = t.rec2.as<WalkRec2>() + REC_SHIFT;
+    d.recp = t.recp.as<WalkRecP>();
+    d.bfs_of = t.bfs_of.as<uint32_t>();
+    d.recp_par = t.recp_par.as<uint32_t>();
+    d.recp_hist = t.recp_hist.as<uint32_t>();
+    d.recp_pref = t.recp_pref.as<uint32_t>();
     return d;
 }
 
@@ -1363,6 +1473,17 @@ static size_t lookback_bytes(const TreeDev& d) {
 
 TreeDev tree_dev(Ctx* c) { return make_dev(c->tree); }
 
+// On demand (the walk asks for them when it is going to use walk_p_kernel): five launches, ~45 us at N = 2^20 - more than the
+// EXACT flavour gains from them, less than the FAST flavour does (profiles/r02_walk_preorder.txt).
+int tree_ensure_recp(Ctx* c, cudaStream_t s, const char* fn) {
+    Tree& t = c->tree;
+    if (t.recp_ready) return SFE_SUCCESS;
+    if (launch_recp(c, make_dev(t), t.N, s, fn)) return SFE_FAILURE;
+    t.recp_ready = true;
+    return SFE_SUCCESS;
+}
+
+
 struct Box6 { float v[6]; };
 __global__ void copy_bounds_kernel(float* __restrict__ dst, const float* __restrict__ src) { if (threadIdx.x < 6) dst[threadIdx.x] = src[threadIdx.x]; }
 __global__ void set_bounds_kernel(float* __restrict__ dst, Box6 b) { if (threadIdx.x < 6) dst[threadIdx.x] = b.v[threadIdx.x]; }
@@ -1371,7 +1492,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
                       uint32_t nodes_max, cudaStream_t s, const float* bounds_dev) {
     const char* fn = "sfe_tree_build";
     Tree& t = c->tree;
-    t.valid = false; t.status_fetched = false;
+    t.valid = false; t.status_fetched = false; t.recp_ready = false;
     t.level0_range_len = 0u;
     if (depth_max < 0 || depth_max > SFE_MAX_LEVELS) { set_error(fn, "depth_max %d outside [0,%d]", depth_max, SFE_MAX_LEVELS); return SFE_FAILURE; }
     if (nodes_max < 1) { set_error(fn, "nodes_max must be at least 1"); return SFE_FAILURE; }
@@ -1396,6 +1517,8 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         t.oct.reserve(n1, fn) || t.rank.reserve(n1 * 4, fn) ||
         t.meta.reserve(M_WORDS * 4, fn) || t.root_gate.reserve(8, fn) || t.rec0.reserve(((size_t)nodes_max + REC_SHIFT) * sizeof(WalkRec0), fn) ||
         t.rec1.reserve(((size_t)nodes_max + REC_SHIFT) * 16, fn) || t.rec2.reserve(((size_t)nodes_max + REC_SHIFT) * sizeof(WalkRec2), fn) ||
+        t.recp.reserve((size_t)nodes_max * sizeof(WalkRecP), fn) || t.bfs_of.reserve((size_t)nodes_max * 4, fn) ||
+        t.recp_par.reserve(RP_WORDS * 4, fn) || t.recp_hist.reserve((n1 + 1) * 4, fn) || t.recp_pref.reserve((n1 + 1) * 4, fn) ||
         t.srec[0].reserve(n1 * sizeof(SlotRec), fn) || t.srec[1].reserve(n1 * sizeof(SlotRec), fn) ||
         t.sub_list.reserve((n1 / 9 + 2) * 8, fn))
         return SFE_FAILURE;
@@ -1688,6 +1811,10 @@ int tree_root_moments(Ctx* c, const float4* pm4, uint32_t i0, uint32_t ni, float
     if (launch_moments(c, dv, 0, 0, gate, true, s, fn)) return SFE_FAILURE;
     finalize_kernel<<<1, 32, 0, s>>>(dv, gate);
     if (check_launch(fn)) return SFE_FAILURE;
+    if (t.recp_ready) {
+        recp_root_kernel<<<1, 1, 0, s>>>(dv, gate);
+        if (check_launch(fn)) return SFE_FAILURE;
+    }
     root_done_kernel<<<1, 1, 0, s>>>(gate);
     return check_launch(fn);
 }

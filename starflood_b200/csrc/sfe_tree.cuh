@@ -40,6 +40,22 @@ struct __align__(16) WalkRec2 {   // 32 B: the cell itself - bounds (gravity.c:4
 };
 static_assert(sizeof(WalkRec0) == 32 && sizeof(WalkRec2) == 32, "walk records are 32 bytes");
 
+// The throughput walk's record: EVERYTHING a visit needs in one 32-byte sector, in DEPTH-FIRST (pre-order) numbering of the
+// non-empty nodes - the first non-empty child of node p is p + 1, so only the successor needs a link, and an accepted cell
+// costs one scattered request instead of two (decision record + COM record: profiles/r02_walk_exact_ncu.txt).
+//   a = {COM x, y, z, mass | cell: centre x, y, z; leaf: half edge of the filter cube (-1: single body), -, -}
+//   w = kind << 30 | depth << 24 | successor (RECP_END: none)
+// A cell's width^2 is not stored: every cell of depth d is the root halved d times, so width^2 = root width^2 / 4^d up to the
+// rounding of the split planes.  finalize checks that per node (RECP_TOL); where it holds (RECP_SURE) the walk settles every
+// opening decision farther than RECP_BAND from theta with that value, and only the rest - and the cells where it does not hold
+// (RECP_EXACT) - fetch the exact width^2 from the breadth-first record rec0[bfs_of[p]].
+struct __align__(32) WalkRecP { float a[7]; uint32_t w; };
+static_assert(sizeof(WalkRecP) == 32, "walk records are 32 bytes");
+constexpr uint32_t RECP_END = 0x00FFFFFFu;                 // (also the largest node count the numbering can hold)
+constexpr uint32_t RECP_SINGLE = 0u, RECP_LEAF = 1u, RECP_EXACT = 2u, RECP_SURE = 3u;   // cells have the sign bit set
+constexpr float RECP_TOL = 1.0e-4f, RECP_BAND = 1.0e-3f;
+enum { RP_W0 = 0, RP_KR = 1, RP_BAD = 2, RP_COUNT = 3, RP_WORDS = 4 };   // recp_par[]: root width^2 (bits), rin2 / width^2, fallback flag, records
+
 // One slot of a level's particle order: everything that moves with a particle from level to level, as ONE 32-byte record
 // (= one sector, written with one 256-bit store).  Separate 16 / 8 / 4-byte arrays made every scattered store a partial
 // sector write, which the memory system punishes (measured: 87 us for the top-level scatter against 48 us with the final
@@ -116,9 +132,16 @@ struct TreeDev {
     WalkRec0* rec0;
     float4* rec1;      // {com x, y, z, mass}
     WalkRec2* rec2;
+    WalkRecP* recp;    // pre-order records of the non-empty nodes (walk_p_kernel)
+    uint32_t* bfs_of;  // pre-order id -> node id
+    uint32_t* recp_par;   // RP_*
+    uint32_t* recp_hist;  // [N + 1] per first slot: (nodes starting there) << 16 | sum of their depths; scratch of the numbering
+    uint32_t* recp_pref;  // [N + 1] exclusive prefix of the counts = pre-order id of the shallowest node starting at a slot
 };
 
 TreeDev tree_dev(Ctx* c);
+int walk_publish_recp(Ctx* c, cudaStream_t s, const char* fn);   // sfe_walk.cu: recp_par -> constant memory
+int tree_ensure_recp(Ctx* c, cudaStream_t s, const char* fn);  // builds the pre-order records of the current tree if they do not exist yet
 int tree_root_moments(Ctx* c, const float4* pm4, uint32_t i0, uint32_t ni, float theta, bool force, cudaStream_t s);
 
 }  // namespace sfe

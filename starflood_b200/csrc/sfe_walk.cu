@@ -119,7 +119,7 @@ __device__ __forceinline__ bool opens(float w2, float d2, float theta) {
 // as coherent as on one GPU, which a slice of particle INDICES is not (indices are random in space) - and delivers every
 // result straight into the window of the rank that OWNS the particle (index slice [r*N/world, (r+1)*N/world)), with
 // plain stores over NVLink peer pointers; the arrival flags follow in peer_barrier_kernel.
-struct WalkRoute { char* base[SFE_PEER_MAX]; uint64_t acc_off, pot_off; uint32_t world, N; };
+struct WalkRoute { char* base[SFE_PEER_MAX]; uint64_t acc_off, pot_off; uint32_t world, N; uint32_t fallback; };   // fallback: run only if walk_p_kernel could not
 
 __device__ __forceinline__ void load_rec0(uint32_t (&r)[8], const WalkRec0* p) {
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -137,6 +137,14 @@ __device__ __forceinline__ float4 load_rec1(const float4* p) {
     return v;
 }
 
+// RP_* of the tree the context holds, copied into constant memory behind every build (walk_publish_recp): warp-uniform values
+// the loop reads as constant operands instead of keeping them in (or spilling them from) its 32 registers
+__constant__ uint32_t c_recp_par[RP_WORDS];
+int walk_publish_recp(Ctx* c, cudaStream_t s, const char* fn) {
+    SFE_CUDA(fn, cudaMemcpyToSymbolAsync(c_recp_par, c->tree.recp_par.p, RP_WORDS * 4, 0, cudaMemcpyDeviceToDevice, s));
+    return SFE_SUCCESS;
+}
+
 template <int FLAVOUR, bool ROUTED>
 __global__ void __launch_bounds__(WALK_THREADS, 16)
 walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restrict__ slots /* null: the range from s0 */,
@@ -145,6 +153,7 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nslots) return;
     if (t.meta[M_STATUS] != 0u) return;          // the build failed (tree.c:180-189): nothing consistent to walk; tree_status() raises it
+    if (route.fallback && c_recp_par[RP_BAD] == 0u) return;   // walk_p_kernel, launched in front, has done the work
     const uint32_t M = t.meta[M_NUM_INBOX];
     const uint32_t s = slots ? slots[k] : s0 + k;
     const uint32_t fin = t.meta[M_FINAL];
@@ -253,6 +262,147 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
         while (idx >= (uint32_t)(((uint64_t)route.N * (r + 1u)) / route.world)) r++;
         acc = reinterpret_cast<float*>(route.base[r] + route.acc_off);
         pot = reinterpret_cast<float*>(route.base[r] + route.pot_off);
+    }
+    acc[3u * idx + 0u] = __fmul_rn(gm, fx);
+    acc[3u * idx + 1u] = __fmul_rn(gm, fy);
+    acc[3u * idx + 2u] = __fmul_rn(gm, fz);
+    pot[idx] = __fmul_rn(-G, fp);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// walk_p_kernel: walk_kernel on the pre-order records (WalkRecP, sfe_tree.cuh): ONE 32-byte load per visit.  An accepted cell
+// no longer fetches its COM record (15.9 M of walk_kernel's 34.4 M scattered requests per launch at C2), the first child of an
+// opened cell is the next record, and the cell's width^2 comes from its depth (root width^2 / 4^depth, verified per node by
+// the build to RECP_TOL); an opening test closer than RECP_BAND to theta, a cell the build could not verify, and the
+// self-subtraction test go to the breadth-first records through bfs_of[].  Same visits, same arithmetic, same bits.
+// Returns at once when the build could not number the tree (RP_BAD: degenerate boxes) - walk_kernel is launched behind it and
+// returns at once when it could.
+// RANGE_OK: every q = r^2 + eps^2 this thread can meet lies in the verified range of the Newton sequences (decided once per
+// warp from the root box, as in walk_sp_kernel), so the loop carries no IEEE fallback.
+template <int FLAVOUR, bool RANGE_OK>
+__device__ __forceinline__ void p_loop(const TreeDev& t, uint32_t n, const float x, const float y, const float z, const float mi,
+                                       const float eps2, const float theta, float& fx, float& fy, float& fz, float& fp) {
+    KahanRef2 kxy = {{0.f, 0.f}, {0.f, 0.f}}, kzp = {{0.f, 0.f}, {0.f, 0.f}};   // (acc x, acc y) and (acc z, pot)
+    fx = fy = fz = fp = 0.f;
+    const WalkRecP* __restrict__ recp = t.recp;
+    // an accepted cell has theta d^2 > w^2, a cell that contains its target d^2 <= rin2 = kr w^2: both only if theta kr >= 1
+    const float krx = theta * __uint_as_float(c_recp_par[RP_KR]) >= 0.99f ? __uint_as_float(c_recp_par[RP_KR]) : -1.0f;   // (-1: never)
+    while (n != RECP_END) {
+        uint32_t r[8];
+        load_rec0(r, reinterpret_cast<const WalkRec0*>(recp + n));     // one 256-bit load: the whole visit
+        const uint32_t w = r[7];
+        const float rx0 = __uint_as_float(r[0]), ry0 = __uint_as_float(r[1]), rz0 = __uint_as_float(r[2]), mj0 = __uint_as_float(r[3]);
+        bool maybe_inside = false;
+        if ((int)w < 0) {                                                // a cell: {COM, mass, centre}
+            const float2 oxy = __fadd2_rn(make_float2(__uint_as_float(r[4]), __uint_as_float(r[5])), make_float2(-x, -y));
+            const float2 osq = __fmul2_rn(oxy, oxy);
+            const float oz = __fsub_rn(__uint_as_float(r[6]), z);
+            const float d2 = __fadd_rn(__fadd_rn(osq.x, osq.y), __fmul_rn(oz, oz));
+            float w2 = __uint_as_float(c_recp_par[RP_W0] - (w & 0x1F000000u));   // root width^2 / 4^depth
+            float rin2 = krx * w2;
+            // theta <= fl(w^2 / d^2) (gravity.c:377,448): the sign of w^2 - theta d^2 settles it unless that is within RECP_BAND
+            const float rhs = theta * d2, diff = w2 - rhs;
+            bool open = diff > 0.0f;
+            if (!(w >= 0xC0000000u && fabsf(diff) > rhs * RECP_BAND && 0.0f < d2)) {        // rare: the exact width^2
+                const WalkRec0* e = t.rec0 + t.bfs_of[n];
+                w2 = __ldg(&e->a[3]); rin2 = __ldg(&e->rin2);
+                open = opens(w2, d2, theta);
+            }
+            if (open) { n++; continue; }                                 // gravity.c:448-453: its first non-empty child is the next record
+            maybe_inside = d2 <= rin2;
+        } else {                                                         // a leaf: the record IS the monopole
+            const float ux = x - rx0, uy = y - ry0, uz = z - rz0;
+            maybe_inside = fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz)) <= __uint_as_float(r[4]);   // (-1 for a single body)
+        }
+        float rx = rx0, ry = ry0, rz = rz0, mj = mj0;
+        // monopole (gravity.c:463-548)
+        if (maybe_inside) {
+            float4 lo, hi;                                       // lo = {lo.x, lo.y, lo.z, hi.x}, hi = {hi.y, hi.z, -, -}
+            load_rec2(lo, hi, &t.rec2[t.bfs_of[n]]);
+            if (lo.x <= x && x <= lo.w && lo.y <= y && y <= hi.x && lo.z <= z && z <= hi.y) {
+                rx = __fsub_rn(__fmul_rn(rx, mj), __fmul_rn(mi, x));              // gravity.c:478-484
+                ry = __fsub_rn(__fmul_rn(ry, mj), __fmul_rn(mi, y));
+                rz = __fsub_rn(__fmul_rn(rz, mj), __fmul_rn(mi, z));
+                mj = __fsub_rn(mj, mi);
+                const float inv = 0.0f < mj ? __fdiv_rn(1.0f, mj) : 1.0f;
+                rx = __fmul_rn(rx, inv); ry = __fmul_rn(ry, inv); rz = __fmul_rn(rz, inv);
+            }
+        }
+        if (FLAVOUR == (int)SFE_WALK_EXACT) {
+            const float2 dxy = __fadd2_rn(make_float2(x, y), make_float2(-rx, -ry));
+            const float2 sq = __fmul2_rn(dxy, dxy);
+            const float dz = __fsub_rn(z, rz);
+            const float r2 = __fadd_rn(__fadd_rn(sq.x, sq.y), __fmul_rn(dz, dz));
+            const float q = __fadd_rn(r2, eps2);
+            float inv_r2, inv_r1;
+            if (RANGE_OK || q < SEQ_HI) {    // (q >= eps2 >= SEQ_LO: the caller's business)
+                const float sr = sqrt_rn_seq(q);
+                const float2 nqs = make_float2(-q, -sr), one = make_float2(1.0f, 1.0f);
+                float2 rr = make_float2(rcp_approx(q), rcp_approx(sr));
+                float2 e = __ffma2_rn(nqs, rr, one);
+                rr = __ffma2_rn(rr, e, rr);
+                e = __ffma2_rn(nqs, rr, one);
+                rr = __ffma2_rn(rr, e, rr);
+                inv_r2 = rr.x; inv_r1 = rr.y;
+            } else {
+                inv_r2 = __fdiv_rn(1.0f, q);
+                inv_r1 = __fdiv_rn(1.0f, __fsqrt_rn(q));
+            }
+            const float pj = __fmul_rn(mj, inv_r1);
+            const float wgt = __fmul_rn(pj, inv_r2);
+            // (scalar products on purpose: see walk_kernel)
+            const float2 fxy = make_float2(__fmul_rn(wgt, dxy.x), __fmul_rn(wgt, dxy.y));
+            const float2 fzp = make_float2(__fmul_rn(wgt, dz), pj);
+            kxy.add(fxy); kzp.add(fzp);
+        } else {
+            const float dx = __fsub_rn(x, rx), dy = __fsub_rn(y, ry), dz = __fsub_rn(z, rz);
+            const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            const float q = __fadd_rn(r2, eps2);
+            const float inv = rsqrt_approx(q);
+            const float pj = mj * inv;
+            const float wgt = pj * (inv * inv);
+            fx = fmaf(wgt, dx, fx); fy = fmaf(wgt, dy, fy); fz = fmaf(wgt, dz, fz);
+            fp += pj;
+        }
+        n = w & RECP_END;
+    }
+    if (FLAVOUR == (int)SFE_WALK_EXACT) { fx = kxy.s.x; fy = kxy.s.y; fz = kzp.s.x; fp = kzp.s.y; }
+}
+
+template <int FLAVOUR, bool ROUTED>
+__global__ void __launch_bounds__(WALK_THREADS, 16)
+walk_p_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restrict__ slots /* null: the range from s0 */,
+              uint32_t s0, uint32_t nslots, float G, float eps2, float theta,
+              float* __restrict__ acc, float* __restrict__ pot, WalkRoute route) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nslots) return;
+    if (t.meta[M_STATUS] != 0u || c_recp_par[RP_BAD] != 0u) return;
+    const uint32_t M = t.meta[M_NUM_INBOX];
+    const uint32_t s = slots ? slots[k] : s0 + k;
+    const uint32_t fin = t.meta[M_FINAL];
+    uint32_t idx; float4 me;
+    if (s < M) { const SlotRec r = slot_load(&t.srec[fin][s]); idx = r.idx; me = r.pm; }   // one sector: particle and index
+    else { idx = t.perm_out[s - M]; me = pm4[idx]; }
+    const float x = me.x, y = me.y, z = me.z, mi = me.w;
+    const uint32_t n0 = M == 0u ? RECP_END : 0u;   // an empty root is never evaluated (gravity.c:324-328)
+    // every source (a COM, with or without the target taken out) lies inside the root box: the farthest corner bounds r^2
+    bool range_ok = true;
+    if (FLAVOUR == (int)SFE_WALK_EXACT) {
+        const float ex = fmaxf(fabsf(x - t.bounds[0]), fabsf(x - t.bounds[3]));
+        const float ey = fmaxf(fabsf(y - t.bounds[1]), fabsf(y - t.bounds[4]));
+        const float ez = fmaxf(fabsf(z - t.bounds[2]), fabsf(z - t.bounds[5]));
+        range_ok = eps2 >= SEQ_LO && (ex * ex + ey * ey + ez * ez) * 1.01f + eps2 < 0.5f * SEQ_HI;
+    }
+    float fx, fy, fz, fp;
+    if (__all_sync(__activemask(), range_ok)) p_loop<FLAVOUR, true>(t, n0, x, y, z, mi, eps2, theta, fx, fy, fz, fp);
+    else p_loop<FLAVOUR, false>(t, n0, x, y, z, mi, eps2, theta, fx, fy, fz, fp);
+    const float gm = __fmul_rn(-G, mi);                                            // gravity.c:656-659
+    if (ROUTED) {
+        uint32_t rk = (uint32_t)(((uint64_t)idx * route.world) / route.N);
+        while (idx < (uint32_t)(((uint64_t)route.N * rk) / route.world)) rk--;
+        while (idx >= (uint32_t)(((uint64_t)route.N * (rk + 1u)) / route.world)) rk++;
+        acc = reinterpret_cast<float*>(route.base[rk] + route.acc_off);
+        pot = reinterpret_cast<float*>(route.base[rk] + route.pot_off);
     }
     acc[3u * idx + 0u] = __fmul_rn(gm, fx);
     acc[3u * idx + 1u] = __fmul_rn(gm, fy);
@@ -442,22 +592,39 @@ walk_sp_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __rest
 // visits, which the pipeline shortens), walk_kernel otherwise (fewer loads and registers: more throughput).  Measured at
 // N = 2^20 (profiles/r02_walk_sp.txt): N/16 targets 0.36 -> 0.24 ms, N/8 0.40 -> 0.34, N/4 0.60 -> 0.60, all 1.83 -> 1.95.
 // SFE_WALK_SP=0 / 1 or sfe_walk_select() forces one of them (test / measurement hook).
-static int g_walk_select = -2;     // -2: not read yet, -1: by size, 0 / 1: forced (SFE_WALK_SP or sfe_walk_select())
+static int g_walk_select = -2;     // -2: not read yet, -1: by size and flavour, 0 / 1 / 2: forced (SFE_WALK_SP or sfe_walk_select())
 static bool walk_use_sp(Ctx* c, uint32_t ntargets) {
-    if (g_walk_select == -2) { const char* e = getenv("SFE_WALK_SP"); g_walk_select = e ? (atoi(e) != 0) : -1; }
-    if (g_walk_select >= 0) return g_walk_select != 0;
+    if (g_walk_select == -2) { const char* e = getenv("SFE_WALK_SP"); g_walk_select = e ? atoi(e) : -1; }
+    if (g_walk_select >= 0) return g_walk_select == 1;
     return (uint64_t)ntargets <= (uint64_t)c->sm_count * WALK_SP_CTAS * WALK_THREADS;
 }
 
 template <bool ROUTED>
-static void launch_walk(Ctx* c, uint32_t flavour, uint32_t grid, cudaStream_t s, const TreeDev& dv, const float4* pm4,
+static int launch_walk(Ctx* c, uint32_t flavour, uint32_t grid, cudaStream_t s, const TreeDev& dv, const float4* pm4,
                         const uint32_t* slots, uint32_t s0, uint32_t ns, float G, float eps2, float theta, float* acc, float* pot,
                         const WalkRoute& rt) {
     const bool sp = walk_use_sp(c, ns);
+    // walk_p_kernel (one record per visit, pre-order numbering) for launches of more than one wave: the FAST flavour, which
+    // is bound by the L1 data pipe, gains 11 % (1.50 -> 1.34 ms at C2) and pays ~45 us once per build for the records; the
+    // EXACT flavour, bound by issue slots, gains nothing (1.68 vs 1.68 ms) and stays on walk_kernel.  sfe_walk_select(2)
+    // forces it for both (tests).  walk_kernel follows as the gated fallback for trees the numbering cannot describe.
+    if (!sp && (g_walk_select == 2 || (g_walk_select == -1 && flavour == SFE_WALK_FAST)) && c->tree.nodes_max < RECP_END) {
+        if (tree_ensure_recp(c, s, "sfe_bh")) return SFE_FAILURE;
+        WalkRoute fb = rt; fb.fallback = 1u;
+        if (flavour == SFE_WALK_EXACT) {
+            walk_p_kernel<(int)SFE_WALK_EXACT, ROUTED><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, s0, ns, G, eps2, theta, acc, pot, rt);
+            walk_kernel<(int)SFE_WALK_EXACT, ROUTED><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, s0, ns, G, eps2, theta, acc, pot, fb);
+        } else {
+            walk_p_kernel<(int)SFE_WALK_FAST, ROUTED><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, s0, ns, G, eps2, theta, acc, pot, rt);
+            walk_kernel<(int)SFE_WALK_FAST, ROUTED><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, s0, ns, G, eps2, theta, acc, pot, fb);
+        }
+        return SFE_SUCCESS;
+    }
 #define SFE_WALK_GO(K, FL) K<(int)FL, ROUTED><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, s0, ns, G, eps2, theta, acc, pot, rt)
     if (flavour == SFE_WALK_EXACT) { if (sp) SFE_WALK_GO(walk_sp_kernel, SFE_WALK_EXACT); else SFE_WALK_GO(walk_kernel, SFE_WALK_EXACT); }
     else { if (sp) SFE_WALK_GO(walk_sp_kernel, SFE_WALK_FAST); else SFE_WALK_GO(walk_kernel, SFE_WALK_FAST); }
 #undef SFE_WALK_GO
+    return SFE_SUCCESS;
 }
 
 // slots whose particle index lies in [i0, i0+ni), in slot order (multi-GPU target slices)
@@ -496,8 +663,8 @@ int launch_bh(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, f
     uint32_t* slots = nullptr;
     if (ni != N && walk_slice_slots(c, N, i0, ni, s, &slots)) return SFE_FAILURE;
     const uint32_t grid = (ni + WALK_THREADS - 1) / WALK_THREADS;
-    WalkRoute none; none.world = 0u; none.N = N; none.acc_off = none.pot_off = 0u;
-    launch_walk<false>(c, flavour, grid, s, dv, pm4, slots, 0u, ni, G, eps2, theta, acc, pot, none);
+    WalkRoute none; none.world = 0u; none.N = N; none.acc_off = none.pot_off = 0u; none.fallback = 0u;
+    if (launch_walk<false>(c, flavour, grid, s, dv, pm4, slots, 0u, ni, G, eps2, theta, acc, pot, none)) return SFE_FAILURE;
     return check_launch(fn);
 }
 
@@ -524,10 +691,10 @@ int launch_bh_routed(Ctx* c, const float4* pm4, uint32_t N, uint64_t acc_off, ui
         if (ns) {
             WalkRoute rt;
             for (uint32_t r = 0; r < SFE_PEER_MAX; r++) rt.base[r] = (char*)pr.base[r];
-            rt.acc_off = acc_off; rt.pot_off = pot_off; rt.world = pr.world; rt.N = N;
+            rt.acc_off = acc_off; rt.pot_off = pot_off; rt.world = pr.world; rt.N = N; rt.fallback = 0u;
             const uint32_t grid = (ns + WALK_THREADS - 1) / WALK_THREADS;
             TreeDev dv = tree_dev(c);
-            launch_walk<true>(c, flavour, grid, s, dv, pm4, nullptr, s0, ns, G, eps2, theta, nullptr, nullptr, rt);
+            if (launch_walk<true>(c, flavour, grid, s, dv, pm4, nullptr, s0, ns, G, eps2, theta, nullptr, nullptr, rt)) return SFE_FAILURE;
             if (check_launch(fn)) return SFE_FAILURE;
         }
     }
@@ -543,7 +710,7 @@ extern "C" int sfe_dev_bh_peer(const void* pm4, uint32_t N, uint64_t acc_off, ui
 }
 
 extern "C" int sfe_walk_select(int mode) {
-    if (mode < -1 || mode > 1) { sfe::set_error("sfe_walk_select", "mode %d is not -1, 0 or 1", mode); return SFE_FAILURE; }
+    if (mode < -1 || mode > 2) { sfe::set_error("sfe_walk_select", "mode %d is not -1 .. 2", mode); return SFE_FAILURE; }
     sfe::g_walk_select = mode;
     return SFE_SUCCESS;
 }

@@ -289,7 +289,8 @@ def selftest_exact_math():
 
 
 def walk_select(mode):
-    """Test / measurement hook: 0 forces walk_kernel, 1 walk_sp_kernel (same bits, see sfengine.h), -1 chooses by size."""
+    """Test / measurement hook: 0 forces walk_kernel, 1 walk_sp_kernel, 2 walk_p_kernel (same bits, see sfengine.h), -1
+    chooses by size and flavour."""
     _check(lib().sfe_walk_select(int(mode)), "sfe_walk_select")
 
 

@@ -13,10 +13,11 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.fixture(params=[0, 1], ids=["walk_kernel", "walk_sp_kernel"])
+@pytest.fixture(params=[0, 1, 2], ids=["walk_kernel", "walk_sp_kernel", "walk_p_kernel"])
 def both_kernels(engine, request):
-    """The walk has a throughput kernel and a latency (software-pipelined) kernel, chosen by the number of targets; the tests
-    that use this fixture run with each of them forced, whatever the size."""
+    """The walk has a throughput kernel, a latency (software-pipelined) kernel and a throughput kernel on depth-first node
+    records, chosen by the number of targets and the flavour; the tests that use this fixture run with each of them forced,
+    whatever the size."""
     engine.walk_select(request.param)
     yield request.param
     engine.walk_select(-1)
