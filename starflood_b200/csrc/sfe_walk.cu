@@ -285,8 +285,6 @@ __device__ __forceinline__ void p_loop(const TreeDev& t, uint32_t n, const float
     KahanRef2 kxy = {{0.f, 0.f}, {0.f, 0.f}}, kzp = {{0.f, 0.f}, {0.f, 0.f}};   // (acc x, acc y) and (acc z, pot)
     fx = fy = fz = fp = 0.f;
     const WalkRecP* __restrict__ recp = t.recp;
-    // an accepted cell has theta d^2 > w^2, a cell that contains its target d^2 <= rin2 = kr w^2: both only if theta kr >= 1
-    const float krx = theta * __uint_as_float(c_recp_par[RP_KR]) >= 0.99f ? __uint_as_float(c_recp_par[RP_KR]) : -1.0f;   // (-1: never)
     while (n != RECP_END) {
         uint32_t r[8];
         load_rec0(r, reinterpret_cast<const WalkRec0*>(recp + n));     // one 256-bit load: the whole visit
@@ -299,7 +297,7 @@ __device__ __forceinline__ void p_loop(const TreeDev& t, uint32_t n, const float
             const float oz = __fsub_rn(__uint_as_float(r[6]), z);
             const float d2 = __fadd_rn(__fadd_rn(osq.x, osq.y), __fmul_rn(oz, oz));
             float w2 = __uint_as_float(c_recp_par[RP_W0] - (w & 0x1F000000u));   // root width^2 / 4^depth
-            float rin2 = krx * w2;
+            float rin2 = __uint_as_float(c_recp_par[RP_KR]) * w2;           // (the filter of the self-subtraction: a multiple of width^2)
             // theta <= fl(w^2 / d^2) (gravity.c:377,448): the sign of w^2 - theta d^2 settles it unless that is within RECP_BAND
             const float rhs = theta * d2, diff = w2 - rhs;
             bool open = diff > 0.0f;
