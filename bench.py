@@ -903,11 +903,13 @@ def run_engine(args):
     info = e.device_info()
     # the engine walks a launch that fits the GPU in one wave with its latency kernel (launch_walk() in csrc/sfe_walk.cu)
     sp = ni <= info["sm_count"] * 7 * 128
-    kernel = "walk_sp_kernel" if sp else ("walk_p_kernel" if args.flavour == "fast" else "walk_kernel")   # (launch_walk() in csrc/sfe_walk.cu)
+    # ... and a launch of at least half (FAST) / five eighths (EXACT) of all targets with walk_p_kernel (depth-first records)
+    p_pays = (2 * ni >= N) if args.flavour == "fast" else (8 * ni >= 5 * N)
+    kernel = "walk_sp_kernel" if sp else ("walk_p_kernel" if p_pays else "walk_kernel")   # (launch_walk() in csrc/sfe_walk.cu)
     prof = os.path.join(ROOT, "profiles", "walk_traffic.json")
     if os.path.exists(prof):
         try:
-            rec = json.load(open(prof)).get(args.flavour + ("_sp" if sp else ""), {})
+            rec = json.load(open(prof)).get(args.flavour + ("_sp" if sp else ("" if p_pays else "_walk_kernel")), {})
             share = ni / float(rec.get("targets", N_DEFAULT))       # the capture's counts, scaled to this launch's targets
             traffic = rec.get("dram_bytes_per_launch")
             winst = rec.get("warp_instructions_per_launch") * share

@@ -53,8 +53,7 @@ struct KahanRef2 {  // two of them in the lanes of packed fp32x2 instructions (s
         const float2 z = __fadd2_rn(t, make_float2(-s.x, -s.y));
         c = __fadd2_rn(z, make_float2(-y.x, -y.y));
         s = t;
-    }
-};
+    }};
 
 // ---------------------------------------------------------------------------------------------------------
 // Correctly rounded 1/q, sqrt(q) and 1/sqrt-then-reciprocal for the EXACT flavour.  The reference computes
@@ -290,7 +289,9 @@ __device__ __forceinline__ void p_loop(const TreeDev& t, uint32_t n, const float
         load_rec0(r, reinterpret_cast<const WalkRec0*>(recp + n));     // one 256-bit load: the whole visit
         const uint32_t w = r[7];
         const float rx0 = __uint_as_float(r[0]), ry0 = __uint_as_float(r[1]), rz0 = __uint_as_float(r[2]), mj0 = __uint_as_float(r[3]);
-        bool maybe_inside = false;
+        const uint32_t here = n;
+        bool maybe_inside = false, eval = true;
+        uint32_t succ = w & RECP_END;
         if ((int)w < 0) {                                                // a cell: {COM, mass, centre}
             const float2 oxy = __fadd2_rn(make_float2(__uint_as_float(r[4]), __uint_as_float(r[5])), make_float2(-x, -y));
             const float2 osq = __fmul2_rn(oxy, oxy);
@@ -306,17 +307,22 @@ __device__ __forceinline__ void p_loop(const TreeDev& t, uint32_t n, const float
                 w2 = __ldg(&e->a[3]); rin2 = __ldg(&e->rin2);
                 open = opens(w2, d2, theta);
             }
-            if (open) { n++; continue; }                                 // gravity.c:448-453: its first non-empty child is the next record
+            // an opened cell goes on with its first non-empty child, the next record (gravity.c:448-453) - a select, not a
+            // `continue`: the divergent exit out of two nested regions cost ~16 % of the loop's instructions in bookkeeping
+            eval = !open;
+            succ = open ? n + 1u : succ;
             maybe_inside = d2 <= rin2;
         } else {                                                         // a leaf: the record IS the monopole
             const float ux = x - rx0, uy = y - ry0, uz = z - rz0;
             maybe_inside = fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz)) <= __uint_as_float(r[4]);   // (-1 for a single body)
         }
+        n = succ;
+        if (!eval) continue;
         float rx = rx0, ry = ry0, rz = rz0, mj = mj0;
         // monopole (gravity.c:463-548)
         if (maybe_inside) {
             float4 lo, hi;                                       // lo = {lo.x, lo.y, lo.z, hi.x}, hi = {hi.y, hi.z, -, -}
-            load_rec2(lo, hi, &t.rec2[t.bfs_of[n]]);
+            load_rec2(lo, hi, &t.rec2[t.bfs_of[here]]);
             if (lo.x <= x && x <= lo.w && lo.y <= y && y <= hi.x && lo.z <= z && z <= hi.y) {
                 rx = __fsub_rn(__fmul_rn(rx, mj), __fmul_rn(mi, x));              // gravity.c:478-484
                 ry = __fsub_rn(__fmul_rn(ry, mj), __fmul_rn(mi, y));
@@ -362,7 +368,6 @@ __device__ __forceinline__ void p_loop(const TreeDev& t, uint32_t n, const float
             fx = fmaf(wgt, dx, fx); fy = fmaf(wgt, dy, fy); fz = fmaf(wgt, dz, fz);
             fp += pj;
         }
-        n = w & RECP_END;
     }
     if (FLAVOUR == (int)SFE_WALK_EXACT) { fx = kxy.s.x; fy = kxy.s.y; fz = kzp.s.x; fp = kzp.s.y; }
 }
@@ -602,11 +607,15 @@ static int launch_walk(Ctx* c, uint32_t flavour, uint32_t grid, cudaStream_t s, 
                         const uint32_t* slots, uint32_t s0, uint32_t ns, float G, float eps2, float theta, float* acc, float* pot,
                         const WalkRoute& rt) {
     const bool sp = walk_use_sp(c, ns);
-    // walk_p_kernel (one record per visit, pre-order numbering) for launches of more than one wave: the FAST flavour, which
-    // is bound by the L1 data pipe, gains 11 % (1.50 -> 1.34 ms at C2) and pays ~45 us once per build for the records; the
-    // EXACT flavour, bound by issue slots, gains nothing (1.68 vs 1.68 ms) and stays on walk_kernel.  sfe_walk_select(2)
-    // forces it for both (tests).  walk_kernel follows as the gated fallback for trees the numbering cannot describe.
-    if (!sp && (g_walk_select == 2 || (g_walk_select == -1 && flavour == SFE_WALK_FAST)) && c->tree.nodes_max < RECP_END) {
+    // walk_p_kernel (one record per visit, depth-first numbering) where it pays for its records (~45 us per build at C2, five
+    // launches over all slots and nodes, made by the first walk that wants them).  [B200] C2, all targets: FAST 1.50 -> 1.34 ms
+    // (bound by the L1 data pipe: a third fewer requests), EXACT 1.68 -> 1.60 ms (bound by issue slots: shorter paths).  So:
+    // FAST from half of the targets on, EXACT from 5/8 on - single-GPU solves; a rank's share on several GPUs stays on
+    // walk_kernel / walk_sp_kernel.  sfe_walk_select(2) forces it (tests).  walk_kernel follows as the gated fallback for
+    // trees the numbering cannot describe.
+    const uint64_t share_num = flavour == SFE_WALK_FAST ? 2u : 8u, share_den = flavour == SFE_WALK_FAST ? 1u : 5u;   // ns / N >= den / num
+    const bool p_pays = (uint64_t)ns * share_num >= (uint64_t)c->tree.N * share_den;
+    if (!sp && (g_walk_select == 2 || (g_walk_select == -1 && p_pays)) && c->tree.nodes_max < RECP_END) {
         if (tree_ensure_recp(c, s, "sfe_bh")) return SFE_FAILURE;
         WalkRoute fb = rt; fb.fallback = 1u;
         if (flavour == SFE_WALK_EXACT) {
