@@ -118,7 +118,7 @@ __device__ __forceinline__ bool opens(float w2, float d2, float theta) {
 // as coherent as on one GPU, which a slice of particle INDICES is not (indices are random in space) - and delivers every
 // result straight into the window of the rank that OWNS the particle (index slice [r*N/world, (r+1)*N/world)), with
 // plain stores over NVLink peer pointers; the arrival flags follow in peer_barrier_kernel.
-struct WalkRoute { char* base[SFE_PEER_MAX]; uint64_t acc_off, pot_off; uint32_t world, N; uint32_t fallback; };   // fallback: run only if walk_p_kernel could not
+struct WalkRoute { char* base[SFE_PEER_MAX]; uint64_t acc_off, pot_off; uint32_t world, N; };
 
 __device__ __forceinline__ void load_rec0(uint32_t (&r)[8], const WalkRec0* p) {
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -144,23 +144,10 @@ int walk_publish_recp(Ctx* c, cudaStream_t s, const char* fn) {
     return SFE_SUCCESS;
 }
 
-template <int FLAVOUR, bool ROUTED>
-__global__ void __launch_bounds__(WALK_THREADS, 16)
-walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restrict__ slots /* null: the range from s0 */,
-            uint32_t s0, uint32_t nslots, float G, float eps2, float theta,
-            float* __restrict__ acc, float* __restrict__ pot, WalkRoute route) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nslots) return;
-    if (t.meta[M_STATUS] != 0u) return;          // the build failed (tree.c:180-189): nothing consistent to walk; tree_status() raises it
-    if (route.fallback && c_recp_par[RP_BAD] == 0u) return;   // walk_p_kernel, launched in front, has done the work
-    const uint32_t M = t.meta[M_NUM_INBOX];
-    const uint32_t s = slots ? slots[k] : s0 + k;
-    const uint32_t fin = t.meta[M_FINAL];
-    uint32_t idx; float4 me;
-    if (s < M) { const SlotRec r = slot_load(&t.srec[fin][s]); idx = r.idx; me = r.pm; }   // one sector: particle and index
-    else { idx = t.perm_out[s - M]; me = pm4[idx]; }
-    const float x = me.x, y = me.y, z = me.z, mi = me.w;
-
+// the walk of one target on the breadth-first records {rec0, rec1, rec2}: walk_kernel's loop (also walk_p_kernel's fallback)
+template <int FLAVOUR>
+__device__ __forceinline__ void v1_loop(const TreeDev& t, const uint32_t M, const float x, const float y, const float z, const float mi,
+                                        const float eps2, const float theta, float& fx_, float& fy_, float& fz_, float& fp_) {
     KahanRef2 kxy = {{0.f, 0.f}, {0.f, 0.f}}, kzp = {{0.f, 0.f}, {0.f, 0.f}};   // (acc x, acc y) and (acc z, pot)
     float fx = 0.f, fy = 0.f, fz = 0.f, fp = 0.f;
 
@@ -253,6 +240,27 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
         n = next;
     }
     if (FLAVOUR == (int)SFE_WALK_EXACT) { fx = kxy.s.x; fy = kxy.s.y; fz = kzp.s.x; fp = kzp.s.y; }
+    fx_ = fx; fy_ = fy; fz_ = fz; fp_ = fp;
+}
+
+template <int FLAVOUR, bool ROUTED>
+__global__ void __launch_bounds__(WALK_THREADS, 16)
+walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restrict__ slots /* null: the range from s0 */,
+            uint32_t s0, uint32_t nslots, float G, float eps2, float theta,
+            float* __restrict__ acc, float* __restrict__ pot, WalkRoute route) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nslots) return;
+    if (t.meta[M_STATUS] != 0u) return;          // the build failed (tree.c:180-189): nothing consistent to walk; tree_status() raises it
+    const uint32_t M = t.meta[M_NUM_INBOX];
+    const uint32_t s = slots ? slots[k] : s0 + k;
+    const uint32_t fin = t.meta[M_FINAL];
+    uint32_t idx; float4 me;
+    if (s < M) { const SlotRec r = slot_load(&t.srec[fin][s]); idx = r.idx; me = r.pm; }   // one sector: particle and index
+    else { idx = t.perm_out[s - M]; me = pm4[idx]; }
+    const float x = me.x, y = me.y, z = me.z, mi = me.w;
+
+    float fx, fy, fz, fp;
+    v1_loop<FLAVOUR>(t, M, x, y, z, mi, eps2, theta, fx, fy, fz, fp);
     const float gm = __fmul_rn(-G, mi);                                            // gravity.c:656-659
     if (ROUTED) {
         // owner r of particle idx: (N*r)/world <= idx < (N*(r+1))/world
@@ -274,8 +282,7 @@ walk_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restric
 // opened cell is the next record, and the cell's width^2 comes from its depth (root width^2 / 4^depth, verified per node by
 // the build to RECP_TOL); an opening test closer than RECP_BAND to theta, a cell the build could not verify, and the
 // self-subtraction test go to the breadth-first records through bfs_of[].  Same visits, same arithmetic, same bits.
-// Returns at once when the build could not number the tree (RP_BAD: degenerate boxes) - walk_kernel is launched behind it and
-// returns at once when it could.
+// When the build could not number the tree (RP_BAD: a degenerate root box) the kernel runs walk_kernel's loop instead.
 // RANGE_OK: every q = r^2 + eps^2 this thread can meet lies in the verified range of the Newton sequences (decided once per
 // warp from the root box, as in walk_sp_kernel), so the loop carries no IEEE fallback.
 template <int FLAVOUR, bool RANGE_OK>
@@ -379,7 +386,7 @@ walk_p_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restr
               float* __restrict__ acc, float* __restrict__ pot, WalkRoute route) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nslots) return;
-    if (t.meta[M_STATUS] != 0u || c_recp_par[RP_BAD] != 0u) return;
+    if (t.meta[M_STATUS] != 0u) return;
     const uint32_t M = t.meta[M_NUM_INBOX];
     const uint32_t s = slots ? slots[k] : s0 + k;
     const uint32_t fin = t.meta[M_FINAL];
@@ -397,7 +404,8 @@ walk_p_kernel(TreeDev t, const float4* __restrict__ pm4, const uint32_t* __restr
         range_ok = eps2 >= SEQ_LO && (ex * ex + ey * ey + ez * ez) * 1.01f + eps2 < 0.5f * SEQ_HI;
     }
     float fx, fy, fz, fp;
-    if (__all_sync(__activemask(), range_ok)) p_loop<FLAVOUR, true>(t, n0, x, y, z, mi, eps2, theta, fx, fy, fz, fp);
+    if (c_recp_par[RP_BAD] != 0u) v1_loop<FLAVOUR>(t, M, x, y, z, mi, eps2, theta, fx, fy, fz, fp);   // the build could not number this tree
+    else if (__all_sync(__activemask(), range_ok)) p_loop<FLAVOUR, true>(t, n0, x, y, z, mi, eps2, theta, fx, fy, fz, fp);
     else p_loop<FLAVOUR, false>(t, n0, x, y, z, mi, eps2, theta, fx, fy, fz, fp);
     const float gm = __fmul_rn(-G, mi);                                            // gravity.c:656-659
     if (ROUTED) {
@@ -611,20 +619,14 @@ static int launch_walk(Ctx* c, uint32_t flavour, uint32_t grid, cudaStream_t s, 
     // launches over all slots and nodes, made by the first walk that wants them).  [B200] C2, all targets: FAST 1.50 -> 1.34 ms
     // (bound by the L1 data pipe: a third fewer requests), EXACT 1.68 -> 1.60 ms (bound by issue slots: shorter paths).  So:
     // FAST from half of the targets on, EXACT from 5/8 on - single-GPU solves; a rank's share on several GPUs stays on
-    // walk_kernel / walk_sp_kernel.  sfe_walk_select(2) forces it (tests).  walk_kernel follows as the gated fallback for
-    // trees the numbering cannot describe.
+    // walk_kernel / walk_sp_kernel.  sfe_walk_select(2) forces it (tests).  For a tree the numbering cannot describe (a device
+    // flag: degenerate root box) the kernel runs walk_kernel's loop instead.
     const uint64_t share_num = flavour == SFE_WALK_FAST ? 2u : 8u, share_den = flavour == SFE_WALK_FAST ? 1u : 5u;   // ns / N >= den / num
     const bool p_pays = (uint64_t)ns * share_num >= (uint64_t)c->tree.N * share_den;
     if (!sp && (g_walk_select == 2 || (g_walk_select == -1 && p_pays)) && c->tree.nodes_max < RECP_END) {
         if (tree_ensure_recp(c, s, "sfe_bh")) return SFE_FAILURE;
-        WalkRoute fb = rt; fb.fallback = 1u;
-        if (flavour == SFE_WALK_EXACT) {
-            walk_p_kernel<(int)SFE_WALK_EXACT, ROUTED><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, s0, ns, G, eps2, theta, acc, pot, rt);
-            walk_kernel<(int)SFE_WALK_EXACT, ROUTED><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, s0, ns, G, eps2, theta, acc, pot, fb);
-        } else {
-            walk_p_kernel<(int)SFE_WALK_FAST, ROUTED><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, s0, ns, G, eps2, theta, acc, pot, rt);
-            walk_kernel<(int)SFE_WALK_FAST, ROUTED><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, s0, ns, G, eps2, theta, acc, pot, fb);
-        }
+        if (flavour == SFE_WALK_EXACT) walk_p_kernel<(int)SFE_WALK_EXACT, ROUTED><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, s0, ns, G, eps2, theta, acc, pot, rt);
+        else walk_p_kernel<(int)SFE_WALK_FAST, ROUTED><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, s0, ns, G, eps2, theta, acc, pot, rt);
         return SFE_SUCCESS;
     }
 #define SFE_WALK_GO(K, FL) K<(int)FL, ROUTED><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, s0, ns, G, eps2, theta, acc, pot, rt)
@@ -670,7 +672,7 @@ int launch_bh(Ctx* c, const float4* pm4, uint32_t N, uint32_t i0, uint32_t ni, f
     uint32_t* slots = nullptr;
     if (ni != N && walk_slice_slots(c, N, i0, ni, s, &slots)) return SFE_FAILURE;
     const uint32_t grid = (ni + WALK_THREADS - 1) / WALK_THREADS;
-    WalkRoute none; none.world = 0u; none.N = N; none.acc_off = none.pot_off = 0u; none.fallback = 0u;
+    WalkRoute none; none.world = 0u; none.N = N; none.acc_off = none.pot_off = 0u;
     if (launch_walk<false>(c, flavour, grid, s, dv, pm4, slots, 0u, ni, G, eps2, theta, acc, pot, none)) return SFE_FAILURE;
     return check_launch(fn);
 }
@@ -698,7 +700,7 @@ int launch_bh_routed(Ctx* c, const float4* pm4, uint32_t N, uint64_t acc_off, ui
         if (ns) {
             WalkRoute rt;
             for (uint32_t r = 0; r < SFE_PEER_MAX; r++) rt.base[r] = (char*)pr.base[r];
-            rt.acc_off = acc_off; rt.pot_off = pot_off; rt.world = pr.world; rt.N = N; rt.fallback = 0u;
+            rt.acc_off = acc_off; rt.pot_off = pot_off; rt.world = pr.world; rt.N = N;
             const uint32_t grid = (ns + WALK_THREADS - 1) / WALK_THREADS;
             TreeDev dv = tree_dev(c);
             if (launch_walk<true>(c, flavour, grid, s, dv, pm4, nullptr, s0, ns, G, eps2, theta, nullptr, nullptr, rt)) return SFE_FAILURE;

@@ -94,6 +94,20 @@ def test_targets_on_cell_faces_and_large_theta(engine, both_kernels, theta):
     assert rel_rms(sim.acc, acc) <= 1e-4 and rel_rms(sim.pot, pot) <= 1e-4
 
 
+def test_root_box_that_is_a_point(engine, both_kernels):
+    """A root box of zero extent (three coincident particles inside it, everything else outside): a one-leaf tree whose depth
+    cannot be read off the extents - the depth-first numbering raises its flag and walk_p_kernel runs walk_kernel's loop."""
+    N = 300
+    pos, vel, mas = sfo.initcond(N)
+    pos[3 * 7:3 * 7 + 3] = pos[0:3]; pos[3 * 9:3 * 9 + 3] = pos[0:3]
+    b = np.array([pos[0], pos[1], pos[2], pos[0], pos[1], pos[2]], np.float32)
+    rc, onodes, oc, *_ = sfo.tree_build_sorted(b, pos, mas, 1024)
+    acc, pot, st = sfo.bh_walk(onodes[:oc], pos, mas)
+    assert oc == 1 and st.self_sub == 3
+    sim = solve(engine, pos, mas, b, engine.WALK_EXACT, max_nodes=1024)
+    assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)
+
+
 def test_distances_beyond_the_newton_range(engine, both_kernels):
     """q = r^2 + eps^2 >= 2^16 leaves the range in which the EXACT walk's Newton sequences were verified: those sources go
     through the IEEE forms (walk_kernel: per source; walk_sp_kernel: the loop without RANGE_OK for warps that can meet one)."""
