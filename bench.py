@@ -903,8 +903,8 @@ def run_engine(args):
     info = e.device_info()
     # the engine walks a launch that fits the GPU in one wave with its latency kernel (launch_walk() in csrc/sfe_walk.cu)
     sp = ni <= info["sm_count"] * 7 * 128
-    # ... and a launch of at least half (FAST) / five eighths (EXACT) of all targets with walk_p_kernel (depth-first records)
-    p_pays = (2 * ni >= N) if args.flavour == "fast" else (8 * ni >= 5 * N)
+    # ... and a launch whose gain covers the depth-first records with walk_p_kernel (the rule of launch_walk())
+    p_pays = ni * (2.2e-4 if args.flavour == "fast" else 1.04e-4) > 1.3 * (30.0 + 12.0e-6 * N)
     kernel = "walk_sp_kernel" if sp else ("walk_p_kernel" if p_pays else "walk_kernel")   # (launch_walk() in csrc/sfe_walk.cu)
     prof = os.path.join(ROOT, "profiles", "walk_traffic.json")
     if os.path.exists(prof):

@@ -615,14 +615,16 @@ static int launch_walk(Ctx* c, uint32_t flavour, uint32_t grid, cudaStream_t s, 
                         const uint32_t* slots, uint32_t s0, uint32_t ns, float G, float eps2, float theta, float* acc, float* pot,
                         const WalkRoute& rt) {
     const bool sp = walk_use_sp(c, ns);
-    // walk_p_kernel (one record per visit, depth-first numbering) where it pays for its records (~45 us per build at C2, five
-    // launches over all slots and nodes, made by the first walk that wants them).  [B200] C2, all targets: FAST 1.50 -> 1.34 ms
-    // (bound by the L1 data pipe: a third fewer requests), EXACT 1.68 -> 1.60 ms (bound by issue slots: shorter paths).  So:
-    // FAST from half of the targets on, EXACT from 5/8 on - single-GPU solves; a rank's share on several GPUs stays on
-    // walk_kernel / walk_sp_kernel.  sfe_walk_select(2) forces it (tests).  For a tree the numbering cannot describe (a device
-    // flag: degenerate root box) the kernel runs walk_kernel's loop instead.
-    const uint64_t share_num = flavour == SFE_WALK_FAST ? 2u : 8u, share_den = flavour == SFE_WALK_FAST ? 1u : 5u;   // ns / N >= den / num
-    const bool p_pays = (uint64_t)ns * share_num >= (uint64_t)c->tree.N * share_den;
+    // walk_p_kernel (one record per visit, depth-first numbering) where it pays for its records, which the first walk that
+    // wants them makes: five launches over all slots and nodes, ~45 us per build at C2 (~30 us + 12 us per million particles).
+    // [B200] C2, all targets: FAST 1.50 -> 1.30 ms (bound by the L1 data pipe: a third fewer requests), EXACT 1.68 -> 1.57 ms
+    // (bound by issue slots: shorter paths) - 0.22 / 0.10 ns per target.  Used when that gain is worth 1.3 x the records:
+    // single-GPU solves, FAST shares down to a quarter of C2, EXACT shares of C5 on 2 / 4 GPUs; the rest stays on walk_kernel /
+    // walk_sp_kernel.  sfe_walk_select(2) forces it (tests).  For a tree the numbering cannot describe (a device flag:
+    // degenerate root box) the kernel runs walk_kernel's loop instead.
+    const double records_us = 30.0 + 12.0e-6 * (double)c->tree.N;
+    const double gain_us = (double)ns * (flavour == SFE_WALK_FAST ? 2.2e-4 : 1.04e-4);
+    const bool p_pays = c->tree.recp_ready || gain_us > 1.3 * records_us;          // (records that exist cost nothing more)
     if (!sp && (g_walk_select == 2 || (g_walk_select == -1 && p_pays)) && c->tree.nodes_max < RECP_END) {
         if (tree_ensure_recp(c, s, "sfe_bh")) return SFE_FAILURE;
         if (flavour == SFE_WALK_EXACT) walk_p_kernel<(int)SFE_WALK_EXACT, ROUTED><<<grid, WALK_THREADS, 0, s>>>(dv, pm4, slots, s0, ns, G, eps2, theta, acc, pot, rt);

@@ -20,9 +20,9 @@ def free_port():
         return s.getsockname()[1]
 
 
-def run_world(world, timeout=150):
+def run_world(world, timeout=150, **extra_env):
     port = free_port()
-    env = dict(os.environ, SFE_PEER_TIMEOUT_MS="60000")
+    env = dict(os.environ, SFE_PEER_TIMEOUT_MS="60000", **extra_env)
     procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "peer_worker.py"), str(r), str(world), str(port)],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env) for r in range(world)]
     outs = []
@@ -43,6 +43,13 @@ def test_two_ranks_exchange_and_leapfrog():
 
 def test_three_ranks_uneven_slices():
     run_world(3)
+
+
+@pytest.mark.parametrize("kernel", ["0", "2"], ids=["walk_kernel", "walk_p_kernel"])
+def test_two_ranks_with_the_throughput_walk_kernels(kernel):
+    """The ranks' shares are small here, so the routed walk normally runs walk_sp_kernel; SFE_WALK_SP forces the two
+    throughput kernels (what a rank runs at large N) through the same bit-for-bit leapfrog checks."""
+    run_world(2, SFE_WALK_SP=kernel)
 
 
 def test_single_rank_window_and_errors(engine):
