@@ -21,9 +21,15 @@
 //     same order: acc and pot are bit-identical to the reference;
 //   * SFE_WALK_FAST uses rsqrt.approx and plain fp32 accumulation in the same visit order.
 //
-// Bound: instruction issue (EXACT: 1.6e9 warp instructions per launch at N = 2^20, issue slots 82 % busy, 21 of 32 lanes
-// active; FAST: L1 sector look-ups of divergent node loads) - the node table stays L1/L2 resident, DRAM traffic is 0.4 % of
-// the bytes of SURVEY 8(d)'s HBM model (32 B x node visits + particle I/O), which bench.py reports beside the binding roof.
+// Three kernels walk the same visits in the same order and produce the same bits (launch_walk() chooses):
+//   walk_kernel     the records above in the build's breadth-first numbering; a rank's share of C2 on 2 / 4 GPUs
+//   walk_p_kernel   ONE 32-byte record per visit in depth-first numbering (WalkRecP, made on demand): single-GPU solves
+//   walk_sp_kernel  software-pipelined, for launches that fit the GPU in one wave (a rank's share on 8 GPUs, small N)
+//
+// Bound: on the SM.  EXACT: instruction issue (walk_p_kernel: 1.38e9 warp instructions per launch at N = 2^20, issue slots 82 %
+// busy, 22 of 32 lanes active); FAST: the L1 data pipe (82 %: every lane fetches its own node).  The node table stays L1/L2
+// resident, DRAM traffic is 0.4 % of the bytes of SURVEY 8(d)'s HBM model (32 B x node visits + particle I/O), which bench.py
+// reports beside the binding roof.
 #include "sfe_internal.cuh"
 #include "sfe_tree.cuh"
 #include "sfe_scan.cuh"
