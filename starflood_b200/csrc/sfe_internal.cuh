@@ -50,6 +50,9 @@ struct Tree {
     uint32_t level0_range_len = 0;       // non-zero: the last build took the one-pass top levels and left srec[0] unwritten (top_level0_kernel)
     const float* bounds_dev = nullptr;   // the root box of the last build (bounds_buf or the root-box kernel's output)
     bool valid = false;
+    // what the top-level pass of the last build told the host (mapped memory, read while the host waits for that pass anyway):
+    // valid only for that build; lets tree_root_moments() skip the root gate's nine launches when no target can accept the root
+    bool gate_hint = false; uint32_t hint_inbox = 0; float hint_kr = 0.f;
     bool recp_ready = false;   // the pre-order walk records (WalkRecP) of this build exist (made on demand: tree_ensure_recp)
     // results, fetched lazily by tree_status()
     uint32_t num_nodes = 0, num_inbox = 0, depth = 0;

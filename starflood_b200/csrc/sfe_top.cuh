@@ -151,6 +151,11 @@ __global__ void __launch_bounds__(TP_THREADS, 4) top_rank_kernel(TreeDev t, cons
                 if (in_box(t.bounds, p)) {
                     uint32_t ties;
                     c = top_code(t.bounds, p, &ties);
+                    if (ties & 1u) {                                // on a split plane of the root: is it the root's very centre?
+                        const float* b = t.bounds;                  // (d^2 = 0 there: the one in-box point that does NOT open the
+                        if (p.x == __fmul_rn(0.5f, __fadd_rn(b[0], b[3])) && p.y == __fmul_rn(0.5f, __fadd_rn(b[1], b[4])) &&   // root,
+                            p.z == __fmul_rn(0.5f, __fadd_rn(b[2], b[5]))) t.top_flag[2] = 1u;                                 // gravity.c:377)
+                    }
                     for (; ties; ties &= ties - 1u) {              // on a split plane: top_nodes_kernel checks its rank there
                         const uint32_t k = atomicAdd(&t.top_flag[1], 1u);
                         if (k < TOP_CAND_MAX) t.top_cand[k] = make_uint2(i, (uint32_t)__ffs(ties) - 1u);
@@ -535,6 +540,17 @@ __global__ void __launch_bounds__(TN_THREADS) top_nodes_kernel(TreeDev t, int de
         t.meta[M_COUNT] = s_lvb[TOP_L + 2];
         *t.sub_count = exs[TOP_COLS] >> 16;                       // the subtree roots of the top levels (later levels append)
         hs[1] = 0u; hs[2] = 0u; hs[3] = s_lvb[TOP_L + 2];
+        {   // what lets the HOST close the walk's root gate without a launch (tree_root_moments): the in-box bodies and the root's
+            // filter radius^2 over its width^2, computed like finalize_kernel's (gravity.c:368-372)
+            volatile uint32_t* hh = t.summary + 4 * (TOP_SUMMARY_SLOT + 1u);
+            const float* b = t.bounds;
+            const float ex = __fsub_rn(b[3], b[0]), ey = __fsub_rn(b[4], b[1]), ez = __fsub_rn(b[5], b[2]);
+            const float slack = 4e-6f * (fabsf(b[0]) + fabsf(b[1]) + fabsf(b[2]) + fabsf(b[3]) + fabsf(b[4]) + fabsf(b[5]));
+            const float diag = sqrtf(ex * ex + ey * ey + ez * ez);
+            const float w = __fmul_rn((float)(1.0 / 3.0), __fadd_rn(__fadd_rn(ex, ey), ez));
+            const float rin2 = (0.5f * diag + slack) * (0.5f * diag + slack) * 1.0001f + 1e-30f;
+            hh[0] = M; hh[1] = __float_as_uint(rin2 / __fmul_rn(w, w)); hh[2] = t.top_flag[2];   // [2]: a body at the root's very centre
+        }
         __threadfence_system();
         for (int d = 0; d <= TOP_L; d++) t.summary[4 * d] = t.build_id;
         hs[0] = t.build_id;

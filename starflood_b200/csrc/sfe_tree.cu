@@ -1492,7 +1492,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
                       uint32_t nodes_max, cudaStream_t s, const float* bounds_dev) {
     const char* fn = "sfe_tree_build";
     Tree& t = c->tree;
-    t.valid = false; t.status_fetched = false; t.recp_ready = false;
+    t.valid = false; t.status_fetched = false; t.recp_ready = false; t.gate_hint = false;
     t.level0_range_len = 0u;
     if (depth_max < 0 || depth_max > SFE_MAX_LEVELS) { set_error(fn, "depth_max %d outside [0,%d]", depth_max, SFE_MAX_LEVELS); return SFE_FAILURE; }
     if (nodes_max < 1) { set_error(fn, "nodes_max must be at least 1"); return SFE_FAILURE; }
@@ -1524,8 +1524,8 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         return SFE_FAILURE;
     if (!t.meta_host) SFE_CUDA(fn, cudaMallocHost(&t.meta_host, sizeof(uint32_t) * M_WORDS));
     if (!t.summary_host) {
-        SFE_CUDA(fn, cudaHostAlloc(&t.summary_host, sizeof(uint32_t) * 4 * (SFE_MAX_LEVELS + 4), cudaHostAllocMapped));
-        memset(t.summary_host, 0, sizeof(uint32_t) * 4 * (SFE_MAX_LEVELS + 4));
+        SFE_CUDA(fn, cudaHostAlloc(&t.summary_host, sizeof(uint32_t) * 4 * (SFE_MAX_LEVELS + 6), cudaHostAllocMapped));
+        memset(t.summary_host, 0, sizeof(uint32_t) * 4 * (SFE_MAX_LEVELS + 6));
         SFE_CUDA(fn, cudaHostGetDevicePointer(&t.summary_dev, t.summary_host, 0));
     }
     if (!t.ev_init) {
@@ -1597,7 +1597,7 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
             SFE_CUDA(fn, cudaFuncSetAttribute(top_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tn_smem));
             tn_attr = true;
         }
-        SFE_CUDA(fn, cudaMemsetAsync(dv.top_flag, 0, 8, s));
+        SFE_CUDA(fn, cudaMemsetAsync(dv.top_flag, 0, 16, s));
         if (trace_enabled()) cudaEventRecord(t.ev_perm[0], s);
         top_rank_kernel<<<ranges, TP_THREADS, 0, s>>>(dv, pm4, N, range_len);
         if (check_launch(fn)) return SFE_FAILURE;
@@ -1611,6 +1611,12 @@ int launch_tree_build(Ctx* c, const float bounds[6], const float4* pm4, uint32_t
         uint32_t not_applicable = 0, status = 0;
         if (wait_summary((int)TOP_SUMMARY_SLOT, &not_applicable, &status)) return SFE_FAILURE;
         if (!not_applicable) {
+            {   // (written in front of the summary's build id: visible by now)
+                volatile uint32_t* hh = t.summary_host + 4 * (TOP_SUMMARY_SLOT + 1u);
+                const uint32_t krb = hh[1];
+                float kr; memcpy(&kr, &krb, 4);
+                t.gate_hint = hh[2] == 0u; t.hint_inbox = hh[0]; t.hint_kr = kr;   // (no hint with a body at the root's very centre)
+            }
             first_level = TOP_L;
             t.level0_range_len = range_len;
             // the folds of levels 1 .. TOP_L: one launch of each fold kernel for all of them, the chunked fold of the very
@@ -1800,6 +1806,11 @@ int tree_root_moments(Ctx* c, const float4* pm4, uint32_t i0, uint32_t ni, float
     Tree& t = c->tree;
     TreeDev dv = make_dev(t);
     uint32_t* gate = t.root_gate.as<uint32_t>();
+    // Nobody accepts the ROOT as a monopole when every particle - hence every possible target - lies inside the root box, the
+    // root is a cell, and a point inside the box opens it: theta <= w^2 / d^2 holds for all d^2 <= rin2 = kr w^2 when theta kr < 1.
+    // The top-level pass has told the host both numbers, so the gate's nine launches (the pre-pass over the targets and eight
+    // kernels that would return at once: ~28 us per walk at C2) are not made at all.
+    if (!force && t.gate_hint && t.hint_inbox == t.N && t.N > 8u && theta > 0.0f && theta * t.hint_kr < 0.99f) return SFE_SUCCESS;
     if (force) root_force_kernel<<<1, 1, 0, s>>>(gate);
     else root_gate_kernel<<<(ni + 255) / 256, 256, 0, s>>>(dv, pm4, i0, ni, theta, gate);
     if (check_launch(fn)) return SFE_FAILURE;

@@ -108,6 +108,27 @@ def test_root_box_that_is_a_point(engine, both_kernels):
     assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)
 
 
+def test_body_at_the_very_centre_of_the_root_box(engine, both_kernels):
+    """d^2 = 0 makes the reference's opening ratio 0 (gravity.c:377): the one in-box point that does NOT open the root but takes it
+    as a monopole (minus itself).  At this size the build's top-level pass tells the host whether the root's deferred fold can be
+    needed at all (every body in the box, theta * rin2 / w^2 < 1): a body at the exact centre must keep the gate's pre-pass."""
+    N = 70000                                                          # (>= 65536: the one-pass top levels)
+    pos, vel, mas = sfo.initcond(N)
+    b = np.array([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], np.float32)        # every body inside, centre (0, 0, 0)
+    pos[3 * 1234:3 * 1234 + 3] = [0.0, 0.0, 0.0]
+    rc, onodes, oc, _, _, nin = sfo.tree_build_sorted(b, pos, mas, 2 * N)
+    assert nin == N
+    acc, pot, st = sfo.bh_walk(onodes[:oc], pos, mas)
+    sim = solve(engine, pos, mas, b, engine.WALK_EXACT, max_nodes=2 * N)
+    assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)
+    # ... and without it the gate is closed on the host: same parity, no root fold
+    pos[3 * 1234:3 * 1234 + 3] = [0.01, 0.0, 0.0]
+    rc, onodes, oc, *_ = sfo.tree_build_sorted(b, pos, mas, 2 * N)
+    acc, pot, st = sfo.bh_walk(onodes[:oc], pos, mas)
+    sim = solve(engine, pos, mas, b, engine.WALK_EXACT, max_nodes=2 * N)
+    assert np.array_equal(sim.acc, acc) and np.array_equal(sim.pot, pot)
+
+
 def test_distances_beyond_the_newton_range(engine, both_kernels):
     """q = r^2 + eps^2 >= 2^16 leaves the range in which the EXACT walk's Newton sequences were verified: those sources go
     through the IEEE forms (walk_kernel: per source; walk_sp_kernel: the loop without RANGE_OK for warps that can meet one)."""
